@@ -1,0 +1,134 @@
+/*
+ * tfhe_b200.h -- C ABI of the B200-native TFHE gate-bootstrapping engine (librustfhe_b200.so).
+ *
+ * Drop-in boundary for the bootstrapped-HomNAND path of hideki1217/rusTfhe.  In the reference the only
+ * language boundary is the FFT binding
+ *     utils/src/spqlios.rs:18-32  <->  utils/src/spqlios/spqlios-wrapper.cpp:4-53   (8 functions, opaque handle)
+ * crossed 5080 times per gate.  Here the boundary moves up: ONE call submits a BATCH of gates and everything
+ * under hom_nand::tfhe::TFHE::{hom_nand,hom_and,hom_or,hom_xor,hom_not,hom_mux} (hom_nand/src/tfhe.rs:27-113) runs
+ * in CUDA on sm_100a.  Same style as the reference binding: plain pointers and sizes, opaque handle, caller
+ * owns every buffer.  Differences, on purpose: every function returns an int status (the reference returns void
+ * and abort()s, spqlios-fft-impl.cpp:92-97) and destroy really frees (the reference leaks,
+ * spqlios-wrapper.cpp:14-16).  There is NO CPU fallback: every compute entry fails with TFHE_B200_ERR_CUDA when no
+ * sm_100 device is usable.
+ *
+ * Flat little-endian u32 layouts (Torus32 = u32, wrapping arithmetic, utils/src/math.rs:489-539):
+ *   TLWE lv0 ciphertext : [n+1]      word 0 = b ("cipher"), words 1..n = a ("p_key")       hom_nand/src/tlwe.rs:19-22
+ *   TLWE lv1 ciphertext : [N+1]      same, dimension N                                      hom_nand/src/trlwe.rs:110-121
+ *   TRLWE               : [2][N]     poly 0 = b ("cipher"), poly 1 = a ("p_key")            hom_nand/src/trlwe.rs:13-16
+ *   TRGSW               : [2l][2][N] rows 0..l carry mu/Bg^(j+1) on b, rows l..2l on a      hom_nand/src/trgsw.rs:23-26,213-229
+ *   bootstrapping key   : [n][2l][2][N]   BK_i = TRGSW_{s1}(s0_i), TORUS domain            hom_nand/src/tfhe.rs:116-126
+ *   key-switching key   : [N][t][3][n+1]  entry (i,l,d-1) = TLWE_{s0}(d*s1_i / 2^(2(l+1))), d=1..3
+ *                                         (the reference also stores an unreachable d=4)   hom_nand/src/tlwe.rs:243-283
+ * Default parameters: n=635, N=1024, l=3, Bgbit=6, t=8, basebit=2, mu=1/8 (tlwe.rs:175-186, trlwe.rs:76,
+ * trgsw.rs:112-115, tfhe.rs:16-17).  This build is specialised for exactly these (other values -> ERR_PARAM).
+ *
+ * Threading: a ctx may be used by one host thread at a time (the reference handle is not thread safe either,
+ * spqlios-fft.h:25-30).  "_device" variants take device pointers and a cudaStream_t (as void*), enqueue
+ * asynchronously and never synchronise; the host-pointer variants copy in, run, copy out and synchronise.
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFHE_B200_OK 0
+#define TFHE_B200_ERR_PARAM 1    /* bad argument / unsupported parameter set */
+#define TFHE_B200_ERR_CUDA 2     /* CUDA runtime error (see tfhe_b200_last_error) */
+#define TFHE_B200_ERR_STATE 3    /* keys not loaded */
+#define TFHE_B200_ERR_NOMEM 4
+
+/* gate opcodes: the linear pre-combination applied before the bootstrap (hom_nand/src/tfhe.rs:27-71) */
+#define TFHE_B200_NAND 0   /* (1/8,0) - (c0+c1)          tfhe.rs:41-47 */
+#define TFHE_B200_AND 1    /* (c0+c1) - (1/8,0)          tfhe.rs:48-54 */
+#define TFHE_B200_OR 2     /* (c0+c1) + (1/8,0)          tfhe.rs:55-61 */
+#define TFHE_B200_XOR 3    /* 2(c0+c1) + (1/4,0)         tfhe.rs:62-68 */
+#define TFHE_B200_NOT 4    /* -c0 (still bootstrapped)   tfhe.rs:69-71 */
+#define TFHE_B200_COPY 5   /* bootstrap(c0)              tfhe.rs:73-80 */
+#define TFHE_B200_ANDNY 6  /* hom_and(-c0, c1)           tfhe.rs:34    */
+
+#define TFHE_B200_MASK_FAITHFUL 0x02084000u /* Torus32::make_decomp_mask(3,6) as it evaluates, math.rs:542-560 */
+#define TFHE_B200_MASK_CORRECTED 0x02082000u /* the mask the reference's decomposition KATs pin, math.rs:582-591 */
+
+typedef struct tfhe_b200_ctx tfhe_b200_ctx;
+
+typedef struct {
+    int32_t n, N, l, bgbit, ks_t, ks_basebit;
+    uint32_t mu;          /* test-vector coefficient / message amplitude, 0x20000000 = 1/8 */
+    uint32_t decomp_mask; /* TFHE_B200_MASK_FAITHFUL by default */
+} tfhe_b200_params;
+
+typedef struct {
+    uint64_t kernel_launches;  /* kernels of this library launched since ctx creation */
+    float last_blind_rotate_ms; /* device time of the most recent blind-rotate kernel (CUDA events on its stream) */
+    float last_keyswitch_ms;
+    uint64_t last_batch;
+    int32_t gates_per_cta, sm_count;
+    uint64_t device_key_bytes;
+} tfhe_b200_stats;
+
+/* ---- lifecycle (replaces Spqlios_new / Spqlios_destructor, spqlios-wrapper.cpp:9-16) ---- */
+int tfhe_b200_default_params(tfhe_b200_params* p);
+int tfhe_b200_ctx_create(const tfhe_b200_params* p /* NULL = defaults */, int device, tfhe_b200_ctx** out);
+int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx);
+const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx /* NULL = last error of a failed ctx_create */);
+int tfhe_b200_set_decomp_mask(tfhe_b200_ctx* ctx, uint32_t mask);
+int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out); /* synchronises the ctx stream */
+
+/* ---- keys: BootstrappingKey::new / KeySwitchingKey::new products (tfhe.rs:119-126, tlwe.rs:247-277) ----
+ * load_bk transforms the torus-domain key on the device into the NTT domain (replaces TRGSWRepF::from,
+ * trgsw.rs:68-76).  The *_device variants read device memory (e.g. the destination of an NCCL broadcast). */
+int tfhe_b200_load_bk(tfhe_b200_ctx* ctx, const uint32_t* bk_host);
+int tfhe_b200_load_bk_device(tfhe_b200_ctx* ctx, const uint32_t* bk_dev, void* stream);
+int tfhe_b200_load_ksk(tfhe_b200_ctx* ctx, const uint32_t* ksk_host);
+int tfhe_b200_load_ksk_device(tfhe_b200_ctx* ctx, const uint32_t* ksk_dev, void* stream);
+
+/* ---- the hot path: batched bootstrapped gates (TFHE::hom_* , tfhe.rs:27-80) ----
+ * in0,in1,out : [B][n+1].  in1 is ignored (may be NULL) for NOT/COPY.  out may alias an input. */
+int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B);
+int tfhe_b200_gate_batch_device(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out,
+                                size_t B, void* stream);
+int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t B); /* TFHE::bootstrap */
+/* hom_mux(control, input_0, input_1) = (input_1 & control) | (input_0 & !control): three bootstraps, tfhe.rs:27-40 */
+int tfhe_b200_mux_batch(tfhe_b200_ctx* ctx, const uint32_t* control, const uint32_t* in0, const uint32_t* in1,
+                        uint32_t* out, size_t B);
+int tfhe_b200_mux_batch_device(tfhe_b200_ctx* ctx, const uint32_t* control, const uint32_t* in0, const uint32_t* in1,
+                               uint32_t* out, size_t B, void* stream);
+
+/* ---- step-level entries (parity ladder, micro-benchmarks; host pointers) ---- */
+/* TFHE::blind_rotate restricted to the first nsteps key elements (nsteps = n for the full rotation): [B][2][N] */
+int tfhe_b200_blind_rotate_batch(tfhe_b200_ctx* ctx, const uint32_t* in /*[B][n+1]*/, int nsteps, uint32_t* out_trlwe,
+                                 size_t B);
+/* blind_rotate + sample_extract_index(0): [B][N+1]  (tfhe.rs:81-88) */
+int tfhe_b200_bootstrap_lv1_batch(tfhe_b200_ctx* ctx, const uint32_t* in, uint32_t* out_lwe1, size_t B);
+/* TLWERep::identity_key_switch: [B][N+1] -> [B][n+1]  (tlwe.rs:43-73) */
+int tfhe_b200_keyswitch_batch(tfhe_b200_ctx* ctx, const uint32_t* lwe1, uint32_t* out, size_t B);
+/* TRGSWRepF::cross: out[g] = trgsw[g % ntrgsw] (x) trlwe[g]   (trgsw.rs:264-306); trgsw in the torus domain */
+int tfhe_b200_external_product_batch(tfhe_b200_ctx* ctx, const uint32_t* trgsw /*[ntrgsw][2l][2][N]*/, size_t ntrgsw,
+                                     const uint32_t* trlwe /*[B][2][N]*/, uint32_t* out /*[B][2][N]*/, size_t B);
+/* Polynomial::fft_cross / Spqlios_poly_mul replacement (math.rs:337-347, spqlios-wrapper.cpp:38-53), exact:
+ * out[g] = a[g] * d[g] mod (X^N+1, 2^32), a torus, |d| <= 192 */
+int tfhe_b200_negacyclic_mul_batch(tfhe_b200_ctx* ctx, const uint32_t* a /*[B][N]*/, const int32_t* d /*[B][N]*/,
+                                   uint32_t* out /*[B][N]*/, size_t B);
+
+/* ---- host-side key generation / encryption (TFHE::new, Cryptor::{encrypto,decrypto}; tfhe.rs:21-25,
+ * tlwe.rs:197-241,247-277, trgsw.rs:117-139,213-229, trlwe.rs:127-137, digest.rs:14-33).  Seeded counter-based
+ * generator (the reference uses thread_rng and cannot be seeded, math.rs:421-476). */
+int tfhe_b200_keygen_secret(uint64_t seed, uint8_t* s0 /*[n]*/, uint8_t* s1 /*[N]*/);
+int tfhe_b200_keygen_bk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uint32_t* bk);
+int tfhe_b200_keygen_ksk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uint32_t* ksk);
+int tfhe_b200_encrypt_bits(uint64_t seed, uint64_t ct_index0, const uint8_t* s0, const uint8_t* bits, size_t B,
+                           uint32_t* out /*[B][n+1]*/);
+int tfhe_b200_phase(const uint8_t* s0, const uint32_t* ct, size_t B, uint32_t* phase);
+int tfhe_b200_decrypt_bits(const uint8_t* s0, const uint32_t* ct, size_t B, uint8_t* bits);
+
+const char* tfhe_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,100 @@
+"""ctypes binding of include/tfhe_b200.h (the C ABI is the product boundary; this file is only glue)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+OK, ERR_PARAM, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
+NAND, AND, OR, XOR, NOT, COPY, ANDNY = range(7)
+MASK_FAITHFUL, MASK_CORRECTED = 0x02084000, 0x02082000
+n, N, L, KS_T = 635, 1024, 3, 8
+BK_WORDS = n * 2 * L * 2 * N
+KSK_WORDS = N * KS_T * 3 * (n + 1)
+
+# every symbol include/tfhe_b200.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "tfhe_b200_default_params", "tfhe_b200_ctx_create", "tfhe_b200_ctx_destroy", "tfhe_b200_last_error",
+    "tfhe_b200_set_decomp_mask", "tfhe_b200_get_stats", "tfhe_b200_load_bk", "tfhe_b200_load_bk_device",
+    "tfhe_b200_load_ksk", "tfhe_b200_load_ksk_device", "tfhe_b200_gate_batch", "tfhe_b200_gate_batch_device",
+    "tfhe_b200_bootstrap_batch", "tfhe_b200_mux_batch", "tfhe_b200_mux_batch_device", "tfhe_b200_blind_rotate_batch",
+    "tfhe_b200_bootstrap_lv1_batch", "tfhe_b200_keyswitch_batch", "tfhe_b200_external_product_batch",
+    "tfhe_b200_negacyclic_mul_batch", "tfhe_b200_keygen_secret", "tfhe_b200_keygen_bk", "tfhe_b200_keygen_ksk",
+    "tfhe_b200_encrypt_bits", "tfhe_b200_phase", "tfhe_b200_decrypt_bits", "tfhe_b200_version",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("n", C.c_int32), ("N", C.c_int32), ("l", C.c_int32), ("bgbit", C.c_int32), ("ks_t", C.c_int32),
+                ("ks_basebit", C.c_int32), ("mu", C.c_uint32), ("decomp_mask", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("last_blind_rotate_ms", C.c_float), ("last_keyswitch_ms", C.c_float),
+                ("last_batch", C.c_uint64), ("gates_per_cta", C.c_int32), ("sm_count", C.c_int32),
+                ("device_key_bytes", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load librustfhe_b200.so (building it in-tree when sources are newer). Raises if it cannot be loaded: there is
+    no Python/CPU fallback for the compute path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    l = C.CDLL(path)
+    vp, sz, u64, i32, u32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32
+    sig = {
+        "tfhe_b200_default_params": (i32, [C.POINTER(Params)]),
+        "tfhe_b200_ctx_create": (i32, [C.POINTER(Params), i32, C.POINTER(vp)]),
+        "tfhe_b200_ctx_destroy": (i32, [vp]),
+        "tfhe_b200_last_error": (C.c_char_p, [vp]),
+        "tfhe_b200_set_decomp_mask": (i32, [vp, u32]),
+        "tfhe_b200_get_stats": (i32, [vp, C.POINTER(Stats)]),
+        "tfhe_b200_load_bk": (i32, [vp, vp]),
+        "tfhe_b200_load_bk_device": (i32, [vp, vp, vp]),
+        "tfhe_b200_load_ksk": (i32, [vp, vp]),
+        "tfhe_b200_load_ksk_device": (i32, [vp, vp, vp]),
+        "tfhe_b200_gate_batch": (i32, [vp, i32, vp, vp, vp, sz]),
+        "tfhe_b200_gate_batch_device": (i32, [vp, i32, vp, vp, vp, sz, vp]),
+        "tfhe_b200_bootstrap_batch": (i32, [vp, vp, vp, sz]),
+        "tfhe_b200_mux_batch": (i32, [vp, vp, vp, vp, vp, sz]),
+        "tfhe_b200_mux_batch_device": (i32, [vp, vp, vp, vp, vp, sz, vp]),
+        "tfhe_b200_blind_rotate_batch": (i32, [vp, vp, i32, vp, sz]),
+        "tfhe_b200_bootstrap_lv1_batch": (i32, [vp, vp, vp, sz]),
+        "tfhe_b200_keyswitch_batch": (i32, [vp, vp, vp, sz]),
+        "tfhe_b200_external_product_batch": (i32, [vp, vp, sz, vp, vp, sz]),
+        "tfhe_b200_negacyclic_mul_batch": (i32, [vp, vp, vp, vp, sz]),
+        "tfhe_b200_keygen_secret": (i32, [u64, vp, vp]),
+        "tfhe_b200_keygen_bk": (i32, [u64, vp, vp, vp]),
+        "tfhe_b200_keygen_ksk": (i32, [u64, vp, vp, vp]),
+        "tfhe_b200_encrypt_bits": (i32, [u64, u64, vp, vp, sz, vp]),
+        "tfhe_b200_phase": (i32, [vp, vp, sz, vp]),
+        "tfhe_b200_decrypt_bits": (i32, [vp, vp, sz, vp]),
+        "tfhe_b200_version": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(l, name)
+        f.restype, f.argtypes = res, args
+    _lib = l
+    return l
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class TfheError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tfhe_b200 error {code}: {msg}")
+        self.code = code

@@ -1,0 +1,145 @@
+// cmux_steps.cuh -- the per-warp pieces of one CMUX step (TRGSW (x) TRLWE external product + accumulate).
+//
+// Reference semantics: hom_nand/src/tfhe.rs:103-110 (one fold step of blind_rotate), hom_nand/src/trgsw.rs:264-306
+// (TRGSWRepF::cross), utils/src/math.rs:85-113 (rotate), utils/src/math.rs:300-326 (decomposition_i32_).
+//
+// Work split of one gate: 6 warps.  Warp w = 3*poly + k.
+//   phase 1 (digit side)  : warp (poly,k) builds digit k of (X^abar * acc - acc)[poly], forward-NTTs it and leaves
+//                           the spectrum in plane dh[3*poly+k]        (decomposition order = b-digits first, F10)
+//   phase 2 (key side)    : warp (poly,k) computes sum_j dh[j] * BKpart_k[poly][j] (11-bit key slice k), inverse-NTTs
+//                           it, lifts to the exact integer, shifts by 11k and leaves it in plane sp[3*poly+k]
+//   phase 3               : acc[poly] += sp[3*poly+0] + sp[3*poly+1] + sp[3*poly+2]      (mod 2^32)
+// Each function below is what ONE lane does between two warp-level synchronisation points; the CUDA kernel calls
+// them with real shared memory and __syncwarp(), the CPU emulation (host_emul.cu) loops over the 32 lanes.
+#pragma once
+#include "ntt32.cuh"
+
+namespace tfhe {
+
+constexpr int NPOLY = 1024;
+constexpr int LWE_N = 635;
+constexpr int GADGET_L = 3;
+constexpr int BK_ROWS = 6;                               // 2 * L
+constexpr size_t BK_POLY_WORDS = 1024;                   // one transformed key-slice polynomial
+constexpr size_t BK_SLAB_WORDS = BK_ROWS * 1024;         // [j][q][lane][4] : what one phase-2 warp streams per step
+constexpr size_t BK_STEP_WORDS = 2 * 3 * BK_SLAB_WORDS;  // [poly][part] slabs of one TRGSW = 36 polys = 147,456 B
+
+// device BK layout: word offset of (step i, output poly, key slice part, row j, chunk q, lane, e)
+TFHE_HD size_t bk_off(int i, int poly, int part, int j, int q, int lane) {
+    return ((((((size_t)i * 2 + poly) * 3 + part) * BK_ROWS + j) * 8 + q) * 32 + lane) * 4;
+}
+
+// value of (X^abar * A - A)[k], abar in [0, 2048)
+TFHE_HD uint32_t rot_diff(const uint32_t* A, uint32_t k, uint32_t abar) {
+    const uint32_t ap = abar & 1023u;
+    const uint32_t v = A[k];
+    uint32_t rv = A[(k - ap) & 1023u];
+    const bool neg = (k < ap) != ((abar >> 10) != 0);
+    rv = neg ? 0u - rv : rv;
+    return rv - v;
+}
+
+// ---- phase 1a: lane = column c.  Build digit `dw` of the source polynomial, column NTT, scatter into tile S ----
+// ROTATE=true : source = X^abar * A - A   (blind rotation step);  ROTATE=false : source = A (plain external product)
+template <bool ROTATE>
+TFHE_HD void p1a(int lane, const uint32_t* A, uint32_t abar, uint32_t mask, int dw, uint32_t* S) {
+    uint32_t x[32];
+#pragma unroll
+    for (int r = 0; r < 32; r++) {
+        const uint32_t k = 32u * r + lane;
+        const uint32_t src = ROTATE ? rot_diff(A, k, abar) : A[k];
+        x[r] = to_residue(gadget_digit(src, mask, dw));
+    }
+    ct32(x, TwUniform<false>());
+#pragma unroll
+    for (int r = 0; r < 32; r++) S[swz(r, lane)] = x[r];
+}
+// generic forward column pass for an already prepared residue column (used by the key transform / poly-mul entry)
+TFHE_HD void fwd_cols(int lane, uint32_t (&x)[32], uint32_t* S) {
+    ct32(x, TwUniform<false>());
+#pragma unroll
+    for (int r = 0; r < 32; r++) S[swz(r, lane)] = x[r];
+}
+// ---- phase 1b: lane = row r.  Row NTT with this lane's twiddle row, full reduction, store back (row layout) ----
+TFHE_HD void fwd_rows(int lane, uint32_t* S, const uint32_t* twF, uint32_t (&x)[32]) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(S + swz_chunk(lane, q));
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+    ct32(x, TwRow{twF + lane * TWB_STRIDE});
+#pragma unroll
+    for (int c = 0; c < 32; c++) x[c] = csub(csub(x[c], P2), P);
+}
+TFHE_HD void p1b(int lane, uint32_t* S, const uint32_t* twF) {
+    uint32_t x[32];
+    fwd_rows(lane, S, twF, x);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+}
+
+// ---- phase 2a: lane = row r.  MAC over the 6 digit spectra against this warp's key slab, row INTT, store ----
+// dh: 6 planes of 1024 words (row layout written by p1b); slab: BK_SLAB_WORDS words for (step, poly, part)
+TFHE_HD void p2a(int lane, const uint32_t* slab, const uint32_t* dh, const uint32_t* twI, uint32_t* S) {
+    uint32_t x[32];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int j = 0; j < BK_ROWS; j++) {
+#if defined(__CUDA_ARCH__)
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
+#else
+            const uint4 b = *(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
+#endif
+            const uint4 d = *reinterpret_cast<const uint4*>(dh + j * NPOLY + swz_chunk(lane, q));
+            a0 += (uint64_t)d.x * b.x; a1 += (uint64_t)d.y * b.y; a2 += (uint64_t)d.z * b.z; a3 += (uint64_t)d.w * b.w;
+        }
+        x[4 * q] = redc64(a0); x[4 * q + 1] = redc64(a1); x[4 * q + 2] = redc64(a2); x[4 * q + 3] = redc64(a3);
+    }
+    gs32(x, TwRow{twI + lane * TWB_STRIDE});
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+}
+// inverse row pass for a row already in registers (poly-mul entry)
+TFHE_HD void inv_rows(int lane, uint32_t (&x)[32], const uint32_t* twI, uint32_t* S) {
+    gs32(x, TwRow{twI + lane * TWB_STRIDE});
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+}
+// ---- phase 2b: lane = column c.  Column INTT -> exact signed integers, shifted by 11*part (kept in registers) ----
+TFHE_HD void p2b(int lane, const uint32_t* S, int part, uint32_t (&x)[32]) {
+#pragma unroll
+    for (int r = 0; r < 32; r++) x[r] = S[swz(r, lane)];
+    gs32(x, TwUniform<true>());
+#pragma unroll
+    for (int r = 0; r < 32; r++) x[r] = (uint32_t)lift(csub(x[r], P)) << (11 * part);
+}
+// ---- phase 2c: plain (unswizzled) store: coefficient k = 32 r + lane ----
+TFHE_HD void p2c(int lane, uint32_t* S, const uint32_t (&x)[32]) {
+#pragma unroll
+    for (int r = 0; r < 32; r++) S[32 * r + lane] = x[r];
+}
+
+// ---- key transform: column `lane` of key slice `part` of a torus polynomial ----
+TFHE_HD void key_cols(int lane, const uint32_t* src, int part, uint32_t* S) {
+    uint32_t x[32];
+#pragma unroll
+    for (int r = 0; r < 32; r++) x[r] = to_residue(key_slice(src[32 * r + lane], part));
+    fwd_cols(lane, x, S);
+}
+// row pass + fold 2^32/N (Montgomery factor and the inverse transform's 1/N), store in the device BK layout
+TFHE_HD void key_rows(int lane, uint32_t* S, const uint32_t* twF, uint32_t* dst /* one BK poly: [q][lane][4] */) {
+    uint32_t x[32];
+    fwd_rows(lane, S, twF, x);
+#pragma unroll
+    for (int c = 0; c < 32; c++) x[c] = csub(shoup_mul(x[c], NTT_MONT_NINV, NTT_MONT_NINV_SHOUP), P);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        *reinterpret_cast<uint4*>(dst + (q * 32 + lane) * 4) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+}
+
+}  // namespace tfhe

@@ -1,0 +1,65 @@
+// host_emul.cpp -- CPU execution of the SAME per-lane arithmetic the CUDA kernels run (ntt32.cuh / cmux_steps.cuh),
+// lane by lane, with the same shared-memory tiles, swizzles and device key layout.  Built as libhostemul.so and used
+// only by the CPU test-suite (tests/test_host_emul.py) to pin the kernel math against the oracle without a GPU.
+// It is NOT a fallback: the product C-ABI never calls it.
+#include <vector_types.h>
+#include <vector_functions.h>
+#include <cstring>
+#include <vector>
+#include "cmux_steps.cuh"
+
+using namespace tfhe;
+
+extern "C" {
+
+// TRGSW torus polys [row j][poly][1024] (reference order: rows b-first, poly 0 = cipher, 1 = p_key) -> device layout
+void emul_key_transform(const uint32_t* trgsw, uint32_t* dev) {
+    std::vector<uint32_t> S(1024);
+    for (int j = 0; j < BK_ROWS; j++)
+        for (int poly = 0; poly < 2; poly++)
+            for (int part = 0; part < 3; part++) {
+                const uint32_t* src = trgsw + (size_t)(j * 2 + poly) * 1024;
+                for (int lane = 0; lane < 32; lane++) key_cols(lane, src, part, S.data());
+                for (int lane = 0; lane < 32; lane++) key_rows(lane, S.data(), h_fwdB, dev + bk_off(0, poly, part, j, 0, 0));
+            }
+}
+
+static void cmux_core(const uint32_t* dev, const uint32_t* acc, bool rotate, uint32_t abar, uint32_t mask, uint32_t* sp) {
+    std::vector<uint32_t> dh(6 * 1024);
+    for (int w = 0; w < 6; w++) {
+        const int poly = w / 3, k = w % 3;
+        uint32_t* S = dh.data() + w * 1024;
+        for (int lane = 0; lane < 32; lane++) {
+            if (rotate) p1a<true>(lane, acc + poly * 1024, abar, mask, k, S);
+            else p1a<false>(lane, acc + poly * 1024, abar, mask, k, S);
+        }
+        for (int lane = 0; lane < 32; lane++) p1b(lane, S, h_fwdB);
+    }
+    for (int w = 0; w < 6; w++) {
+        const int poly = w / 3, k = w % 3;
+        uint32_t* S = sp + w * 1024;
+        uint32_t x[32][32];
+        for (int lane = 0; lane < 32; lane++) p2a(lane, dev + bk_off(0, poly, k, 0, 0, 0), dh.data(), h_invB, S);
+        for (int lane = 0; lane < 32; lane++) p2b(lane, S, k, x[lane]);
+        for (int lane = 0; lane < 32; lane++) p2c(lane, S, x[lane]);
+    }
+}
+// plain external product: out = TRGSW (x) trlwe  (hom_nand/src/trgsw.rs:264-306)
+void emul_external_product(const uint32_t* dev, const uint32_t* trlwe, uint32_t mask, uint32_t* out) {
+    std::vector<uint32_t> sp(6 * 1024);
+    cmux_core(dev, trlwe, false, 0, mask, sp.data());
+    for (int poly = 0; poly < 2; poly++)
+        for (int k = 0; k < 1024; k++)
+            out[poly * 1024 + k] = sp[(3 * poly) * 1024 + k] + sp[(3 * poly + 1) * 1024 + k] + sp[(3 * poly + 2) * 1024 + k];
+}
+// one blind-rotation step: acc <- BK (x) (X^abar acc - acc) + acc   (hom_nand/src/tfhe.rs:103-110)
+void emul_cmux_rotate(const uint32_t* dev, uint32_t* acc, uint32_t abar, uint32_t mask) {
+    std::vector<uint32_t> sp(6 * 1024);
+    cmux_core(dev, acc, true, abar, mask, sp.data());
+    for (int poly = 0; poly < 2; poly++)
+        for (int k = 0; k < 1024; k++)
+            acc[poly * 1024 + k] += sp[(3 * poly) * 1024 + k] + sp[(3 * poly + 1) * 1024 + k] + sp[(3 * poly + 2) * 1024 + k];
+}
+uint32_t emul_prime(void) { return P; }
+int32_t emul_key_slice(uint32_t c, int part) { return key_slice(c, part); }
+}

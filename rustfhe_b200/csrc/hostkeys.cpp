@@ -1,0 +1,144 @@
+// hostkeys.cpp -- host-side key generation, encryption and decryption of the product library.
+//
+// API surface kept from the reference: TFHE::new = KeySwitchingKey::new + BootstrappingKey::new
+// (hom_nand/src/tfhe.rs:21-25,119-126; tlwe.rs:247-277; trgsw.rs:117-139,213-229; trlwe.rs:127-137) and
+// Cryptor::{encrypto,decrypto} for TLWE bits (digest.rs:14-33; tlwe.rs:181-240).  One-off, host side, like the reference.
+// Deliberate differences: a seeded counter-based generator (the reference cannot be seeded), full 32-bit uniform masks
+// (the reference samples Uniform<f32>, 24 random bits, math.rs:425-432) and an exact a*s product (the reference uses its FFT).
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include "../../include/tfhe_b200.h"
+
+namespace {
+constexpr int n = 635, N = 1024, L = 3, BGBIT = 6, KS_T = 8, KS_BB = 2;
+constexpr uint32_t MU = 0x20000000u;
+enum Stream : uint64_t { S0 = 1, S1 = 2, BK_A = 3, BK_E = 4, KSK_A = 5, KSK_E = 6, ENC_A = 7, ENC_E = 8 };
+
+inline uint64_t mix(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+struct Rng {  // counter based: value = f(seed, stream, index)
+    uint64_t h;
+    Rng(uint64_t seed, uint64_t stream) : h(mix(seed ^ mix(stream * 0xD6E8FEB86659FD93ull + 0x1234567ull))) {}
+    uint64_t u64(uint64_t idx) const { return mix(h + idx * 0x9E3779B97F4A7C15ull); }
+    uint32_t u32(uint64_t idx) const { return (uint32_t)(u64(idx) >> 32); }
+    // round(N(0, alpha) * 2^32), Box-Muller
+    uint32_t gauss(uint64_t idx, double alpha) const {
+        const double k = 1.0 / 9007199254740992.0;
+        const double u1 = (double)((u64(2 * idx) >> 11) + 1) * k, u2 = (double)(u64(2 * idx + 1) >> 11) * k;
+        const double g = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925 * u2);
+        return (uint32_t)(int32_t)std::llrint(g * alpha * 4294967296.0);
+    }
+};
+template <class F>
+void parallel_for(int count, F f) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > 32) nt = 32;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([=] { for (int i = (int)t; i < count; i += (int)nt) f(i); });
+    for (auto& x : th) x.join();
+}
+// b += a * s mod (X^N + 1) for a binary s given as the list of its set positions
+void add_mul_binary(const uint32_t* a, const std::vector<int>& ones, uint32_t* b) {
+    for (int j : ones) {
+        for (int k = j; k < N; k++) b[k] += a[k - j];
+        for (int k = 0; k < j; k++) b[k] -= a[N + k - j];
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int tfhe_b200_keygen_secret(uint64_t seed, uint8_t* s0, uint8_t* s1) {
+    if (!s0 || !s1) return TFHE_B200_ERR_PARAM;
+    Rng r0(seed, S0), r1(seed, S1);
+    for (int i = 0; i < n; i++) s0[i] = (uint8_t)(r0.u64(i) >> 63);
+    for (int i = 0; i < N; i++) s1[i] = (uint8_t)(r1.u64(i) >> 63);
+    return TFHE_B200_OK;
+}
+
+// BK_i = TRGSW_{s1}(s0_i): 2l fresh TRLWE_{s1}(0) rows (B = A*s1 + e, A), then mu/Bg^(j+1) added on B[0] of rows j<l and on
+// A[0] of rows l+j (trgsw.rs:118-138,213-229); alpha_bk = 2^-25 (trlwe.rs:77)
+int tfhe_b200_keygen_bk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uint32_t* bk) {
+    if (!s0 || !s1 || !bk) return TFHE_B200_ERR_PARAM;
+    std::vector<int> ones;
+    for (int j = 0; j < N; j++) if (s1[j]) ones.push_back(j);
+    const Rng ra(seed, BK_A), re(seed, BK_E);
+    parallel_for(n * 2 * L, [&](int row) {
+        const int i = row / (2 * L), j = row % (2 * L);
+        uint32_t* B = bk + ((size_t)row * 2 + 0) * N;
+        uint32_t* A = bk + ((size_t)row * 2 + 1) * N;
+        const uint64_t base = (uint64_t)row * N;
+        for (int k = 0; k < N; k++) { A[k] = ra.u32(base + k); B[k] = re.gauss(base + k, 1.0 / 33554432.0); }
+        add_mul_binary(A, ones, B);
+        const uint32_t mu = (uint32_t)s0[i] << (32 - BGBIT * ((j % L) + 1));
+        if (j < L) B[0] += mu; else A[0] += mu;
+    });
+    return TFHE_B200_OK;
+}
+
+// KS[i][l][d-1] = TLWE_{s0}(d * s1_i / 2^(2(l+1))), d = 1..3 (tlwe.rs:247-283; the unreachable d=4 entry is not stored);
+// alpha = 2^-15 (tlwe.rs:176)
+int tfhe_b200_keygen_ksk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uint32_t* ksk) {
+    if (!s0 || !s1 || !ksk) return TFHE_B200_ERR_PARAM;
+    const Rng ra(seed, KSK_A), re(seed, KSK_E);
+    parallel_for(N * KS_T * 3, [&](int rowid) {
+        const int i = rowid / (KS_T * 3), l = (rowid / 3) % KS_T, d = rowid % 3 + 1;
+        uint32_t* row = ksk + (size_t)rowid * (n + 1);
+        uint32_t b = ((uint32_t)(d * s1[i]) << (32 - KS_BB * (l + 1))) + re.gauss((uint64_t)rowid, 1.0 / 32768.0);
+        for (int c = 0; c < n; c++) {
+            const uint32_t a = ra.u32((uint64_t)rowid * n + c);
+            row[1 + c] = a;
+            if (s0[c]) b += a;
+        }
+        row[0] = b;
+    });
+    return TFHE_B200_OK;
+}
+
+// Cryptor::encrypto(TLWE, &s0, Binary): One -> +1/8, Zero -> -1/8 (tlwe.rs:181-186), b = <a,s> + e + m (tlwe.rs:213-228)
+int tfhe_b200_encrypt_bits(uint64_t seed, uint64_t ct_index0, const uint8_t* s0, const uint8_t* bits, size_t B, uint32_t* out) {
+    if (!s0 || (!bits && B) || (!out && B)) return TFHE_B200_ERR_PARAM;
+    const Rng ra(seed, ENC_A), re(seed, ENC_E);
+    for (size_t g = 0; g < B; g++) {
+        uint32_t* ct = out + g * (n + 1);
+        const uint64_t id = ct_index0 + g;
+        uint32_t b = (bits[g] ? MU : 0u - MU) + re.gauss(id, 1.0 / 32768.0);
+        for (int i = 0; i < n; i++) {
+            const uint32_t a = ra.u32(id * n + i);
+            ct[1 + i] = a;
+            if (s0[i]) b += a;
+        }
+        ct[0] = b;
+    }
+    return TFHE_B200_OK;
+}
+// phase = b - <a, s> (tlwe.rs:230-240)
+int tfhe_b200_phase(const uint8_t* s0, const uint32_t* ct, size_t B, uint32_t* phase) {
+    if (!s0 || (!ct && B) || (!phase && B)) return TFHE_B200_ERR_PARAM;
+    for (size_t g = 0; g < B; g++) {
+        const uint32_t* c = ct + g * (n + 1);
+        uint32_t acc = c[0];
+        for (int i = 0; i < n; i++) if (s0[i]) acc -= c[1 + i];
+        phase[g] = acc;
+    }
+    return TFHE_B200_OK;
+}
+// torus2binary: f32(phase) < 0.5 -> One (tlwe.rs:187-194, math.rs:684-690)
+int tfhe_b200_decrypt_bits(const uint8_t* s0, const uint32_t* ct, size_t B, uint8_t* bits) {
+    if (!s0 || (!ct && B) || (!bits && B)) return TFHE_B200_ERR_PARAM;
+    for (size_t g = 0; g < B; g++) {
+        uint32_t ph;
+        tfhe_b200_phase(s0, ct + g * (n + 1), 1, &ph);
+        bits[g] = ((float)ph * (1.0f / 4294967296.0f)) < 0.5f ? 1 : 0;
+    }
+    return TFHE_B200_OK;
+}
+}

@@ -1,0 +1,192 @@
+// ntt32.cuh -- arithmetic core of the B200 TFHE engine: exact negacyclic NTT over Z_p[X]/(X^1024+1).
+//
+// Replaces the reference's f64 spqlios FFT (utils/src/spqlios/spqlios-{fft,ifft}-avx.s driven by
+// utils/src/spqlios/fft_processor_spqlios.cpp:58-183) with exact modular integer arithmetic.
+//
+// Design:
+//  * one prime p < 2^29 (8p < 2^32): Shoup multiplication (2 IMAD + 1 IMAD.HI) with lazy Harvey ranges; the only
+//    correction per butterfly is min(x, x-2p) which sm_100a executes as ONE instruction (VIADDMNMX.U32) on the ALU
+//    pipe, off the FMA pipe that bounds the kernel (profiles/intpipe_r01.json).
+//  * 1024 = 32 x 32: one WARP owns one polynomial, each thread holds 32 coefficients in registers and runs a fully
+//    unrolled 32-point network twice (columns with warp-uniform twiddles read from the constant bank, rows with
+//    per-thread twiddles read from shared memory), with a single swizzled shared-memory transpose in between.
+//    No block-level barrier is needed inside a transform.
+//  * forward = merged-twist Cooley-Tukey (natural in, bit-reversed out), inverse = Gentleman-Sande (mirror image);
+//    the pointwise stage does not care about the order, 1/N and the Montgomery 2^32 are folded into the key.
+//
+// Everything here is __host__ __device__ so tests/host_emul can run the identical arithmetic on the CPU.
+#pragma once
+#include <stdint.h>
+#include "ntt_tables.h"
+
+#if defined(__CUDACC__)
+#define TFHE_HD __host__ __device__ __forceinline__
+#else
+#define TFHE_HD inline
+#endif
+
+namespace tfhe {
+
+constexpr uint32_t P = NTT_P;
+constexpr uint32_t P2 = NTT_2P;
+constexpr int TWB_STRIDE = NTT_TWB_STRIDE;
+
+static const uint32_t h_fwdA[64] = {NTT_FWD_A_LIST};
+static const uint32_t h_invA[64] = {NTT_INV_A_LIST};
+static const uint32_t h_fwdB[32 * NTT_TWB_STRIDE] = {NTT_FWD_B_LIST};
+static const uint32_t h_invB[32 * NTT_TWB_STRIDE] = {NTT_INV_B_LIST};
+#if defined(__CUDACC__)
+static __constant__ uint32_t c_fwdA[64] = {NTT_FWD_A_LIST};
+static __constant__ uint32_t c_invA[64] = {NTT_INV_A_LIST};
+static __device__ const uint32_t g_fwdB[32 * NTT_TWB_STRIDE] = {NTT_FWD_B_LIST};
+static __device__ const uint32_t g_invB[32 * NTT_TWB_STRIDE] = {NTT_INV_B_LIST};
+#endif
+
+TFHE_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+// min(x, x - m) for unsigned x: conditional subtraction without a branch (VIADDMNMX.U32 on sm_100a)
+TFHE_HD uint32_t csub(uint32_t x, uint32_t m) {
+    uint32_t y = x - m;
+#if defined(__CUDA_ARCH__)
+    return min(x, y);
+#else
+    return y < x ? y : x;
+#endif
+}
+// Shoup: y * w mod p for ANY 32-bit y, ws = floor(w * 2^32 / p); result in [0, 2p)
+TFHE_HD uint32_t shoup_mul(uint32_t y, uint32_t w, uint32_t ws) { return y * w - mulhi32(y, ws) * P; }
+// Montgomery reduction of S < p * 2^32 : returns S * 2^-32 mod p in (0, 2p)
+TFHE_HD uint32_t redc64(uint64_t s) {
+    uint32_t m = (uint32_t)s * NTT_PINV;
+    return (uint32_t)(s >> 32) + P - mulhi32(m, P);
+}
+// centred lift of v in [0,p) to the exact signed integer (|true value| < p/2 by construction)
+TFHE_HD int32_t lift(uint32_t v) { return v > (P - 1) / 2 ? (int32_t)(v - P) : (int32_t)v; }
+
+// ---- twiddle providers: entry q in [1,32) = (w, shoup(w)) ----
+template <bool INV>
+struct TwUniform {  // pass A: same for every lane -> constant-bank operands
+    TFHE_HD void get(int q, uint32_t& w, uint32_t& ws) const {
+#if defined(__CUDA_ARCH__)
+        w = INV ? c_invA[2 * q] : c_fwdA[2 * q];
+        ws = INV ? c_invA[2 * q + 1] : c_fwdA[2 * q + 1];
+#else
+        w = INV ? h_invA[2 * q] : h_fwdA[2 * q];
+        ws = INV ? h_invA[2 * q + 1] : h_fwdA[2 * q + 1];
+#endif
+    }
+    TFHE_HD void get2(int q, uint32_t& w0, uint32_t& ws0, uint32_t& w1, uint32_t& ws1) const {
+        get(q, w0, ws0);
+        get(q + 1, w1, ws1);
+    }
+};
+struct TwRow {  // pass B: per-thread row (shared memory on the device), 16-byte aligned
+    const uint32_t* row;
+    TFHE_HD void get(int q, uint32_t& w, uint32_t& ws) const {
+        const uint2 v = *reinterpret_cast<const uint2*>(row + 2 * q);
+        w = v.x;
+        ws = v.y;
+    }
+    TFHE_HD void get2(int q, uint32_t& w0, uint32_t& ws0, uint32_t& w1, uint32_t& ws1) const {  // q even
+        const uint4 v = *reinterpret_cast<const uint4*>(row + 2 * q);
+        w0 = v.x; ws0 = v.y; w1 = v.z; ws1 = v.w;
+    }
+};
+
+// ---- 32-point merged-twist Cooley-Tukey network on registers; values stay in [0,4p) ----
+TFHE_HD void ct_bfly(uint32_t& a, uint32_t& b, uint32_t w, uint32_t ws) {
+    const uint32_t X = csub(a, P2);
+    const uint32_t T = shoup_mul(b, w, ws);
+    a = X + T;
+    b = X - T + P2;
+}
+template <int S, class TW>
+TFHE_HD void ct_stage(uint32_t (&x)[32], const TW& tw) {  // stage S = 1..4: m = 2^S blocks of half-width t = 16 >> S
+    constexpr int m = 1 << S, t = 16 >> S;
+#pragma unroll
+    for (int i = 0; i < m; i += 2) {
+        uint32_t w0, ws0, w1, ws1;
+        tw.get2(m + i, w0, ws0, w1, ws1);
+#pragma unroll
+        for (int j = 0; j < t; j++) ct_bfly(x[2 * i * t + j], x[2 * i * t + j + t], w0, ws0);
+#pragma unroll
+        for (int j = 0; j < t; j++) ct_bfly(x[2 * (i + 1) * t + j], x[2 * (i + 1) * t + j + t], w1, ws1);
+    }
+}
+template <class TW>
+TFHE_HD void ct32(uint32_t (&x)[32], const TW& tw) {
+    {
+        uint32_t w, ws;
+        tw.get(1, w, ws);
+#pragma unroll
+        for (int j = 0; j < 16; j++) ct_bfly(x[j], x[j + 16], w, ws);
+    }
+    ct_stage<1>(x, tw);
+    ct_stage<2>(x, tw);
+    ct_stage<3>(x, tw);
+    ct_stage<4>(x, tw);
+}
+// ---- 32-point Gentleman-Sande network (exact mirror); values stay in [0,2p) ----
+TFHE_HD void gs_bfly(uint32_t& a, uint32_t& b, uint32_t w, uint32_t ws) {
+    const uint32_t U = a, V = b;
+    a = csub(U + V, P2);
+    b = shoup_mul(U - V + P2, w, ws);
+}
+template <int S, class TW>
+TFHE_HD void gs_stage(uint32_t (&x)[32], const TW& tw) {  // stage S = 0..3: h = 16 >> S blocks of half-width t = 2^S
+    constexpr int t = 1 << S, h = 16 >> S;
+#pragma unroll
+    for (int i = 0; i < h; i += 2) {
+        uint32_t w0, ws0, w1, ws1;
+        tw.get2(h + i, w0, ws0, w1, ws1);
+#pragma unroll
+        for (int j = 0; j < t; j++) gs_bfly(x[2 * i * t + j], x[2 * i * t + j + t], w0, ws0);
+#pragma unroll
+        for (int j = 0; j < t; j++) gs_bfly(x[2 * (i + 1) * t + j], x[2 * (i + 1) * t + j + t], w1, ws1);
+    }
+}
+template <class TW>
+TFHE_HD void gs32(uint32_t (&x)[32], const TW& tw) {
+    gs_stage<0>(x, tw);
+    gs_stage<1>(x, tw);
+    gs_stage<2>(x, tw);
+    gs_stage<3>(x, tw);
+    {
+        uint32_t w, ws;
+        tw.get(1, w, ws);
+#pragma unroll
+        for (int j = 0; j < 16; j++) gs_bfly(x[j], x[j + 16], w, ws);
+    }
+}
+
+// swizzled position of element (row r, column c) in a 32x32 word tile: 16-byte chunks are XOR-permuted with the
+// row so that both "lane = column, loop over rows" word accesses and "lane = row" 128-bit accesses are
+// bank-conflict free.
+TFHE_HD int swz(int r, int c) { return r * 32 + ((((c >> 2) ^ (r & 7)) << 2) | (c & 3)); }
+TFHE_HD int swz_chunk(int r, int q) { return r * 32 + ((q ^ (r & 7)) << 2); }
+
+// ---- decomposition pieces (reference: utils/src/math.rs:300-326 with the mask of math.rs:542-560) ----
+// digit `dw` (0 = most significant) of x after the mask trick, sign-extended from 6 bits
+TFHE_HD int32_t gadget_digit(uint32_t x, uint32_t mask, int dw) {
+    const uint32_t u = (x + mask) ^ mask;
+    return ((int32_t)(u << (6 * dw))) >> 26;
+}
+TFHE_HD uint32_t to_residue(int32_t v) { return (uint32_t)v + (v < 0 ? P : 0u); }
+
+// centred 11/11/10-bit slices of a torus word: c0 + 2^11 c1 + 2^22 c2 == C (mod 2^32), |c0|,|c1| <= 1024, |c2| <= 512
+TFHE_HD int32_t key_slice(uint32_t C, int part) {
+    const int32_t c0 = (int32_t)((C & 0x7FFu) ^ 0x400u) - 0x400;
+    if (part == 0) return c0;
+    const uint32_t C1 = (C - (uint32_t)c0) >> 11;
+    const int32_t c1 = (int32_t)((C1 & 0x7FFu) ^ 0x400u) - 0x400;
+    if (part == 1) return c1;
+    const uint32_t C2 = ((C1 - (uint32_t)c1) >> 11) & 0x3FFu;
+    return (int32_t)((C2 & 0x3FFu) ^ 0x200u) - 0x200;
+}
+
+}  // namespace tfhe

@@ -1,0 +1,5 @@
+#!/bin/bash
+# first-contact script for a GPU box: run the GPU parity tests, log to gpurun_out/
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
+python -m pytest tests -m gpu -x -q 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log

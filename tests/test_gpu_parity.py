@@ -1,0 +1,227 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical seeded inputs.
+
+Parity ladder:
+  P0  kernel vs exact-integer oracle ........ BIT-EXACT (poly mul, external product, blind rotate, extract, key switch,
+                                               whole gate ciphertext)
+  P1  single external product vs the reference's own FFT ... every coefficient within +-2 ulp (2^-32)
+  P2  whole gate vs reference-FFT gate path .. identical decrypted bit, |e_gpu| < 3/32, |e_gpu - e_ref| < 1/16
+"""
+import numpy as np
+import pytest
+
+from conftest import phase_err
+
+pytestmark = pytest.mark.gpu
+
+N, n = 1024, 635
+
+
+def u32(rng, *shape):
+    return rng.integers(0, 2 ** 32, size=shape, dtype=np.uint64).astype(np.uint32)
+
+
+def test_negacyclic_mul_exact(engine, oracle, rng):
+    """config 3(i): torus x small-int polynomial, bit-exact vs schoolbook (math.rs:761-843 / 905-952 semantics)."""
+    B = 33
+    a = u32(rng, B, N)
+    d = rng.integers(-32, 32, size=(B, N)).astype(np.int32)
+    d[1] = rng.integers(0, 2, size=N)                # binary variant mirroring math.rs:934-951
+    a[2], d[2] = 0xFFFFFFFF, 31                      # extreme magnitudes
+    a[3], d[3] = 0x80000000, -32
+    d[4] = rng.integers(-192, 193, size=N)           # documented bound of the entry
+    out = engine.negacyclic_mul_batch(a, d)
+    for g in range(B):
+        ref = np.zeros(N, np.uint32)
+        oracle.lib().orc_negacyclic_mul_schoolbook(a[g], d[g], N, ref)
+        assert np.array_equal(out[g], ref), g
+
+
+def test_negacyclic_mul_kat_via_device(engine):
+    """reference KAT math.rs:761-843: [2,3,4]*[4,5,6] = [-30,-2,43] mod X^3+1 embeds in N=1024 only as a linear product;
+    use the N-independent identities X^k * a instead: a * X^1023 * X = -a."""
+    a = np.arange(1, N + 1, dtype=np.uint32).reshape(1, N)
+    d = np.zeros((1, N), np.int32)
+    d[0, 1] = 1                                       # multiply by X == rotate(1) (math.rs:75-84)
+    out = engine.negacyclic_mul_batch(a, d)[0]
+    assert out[0] == np.uint32(-int(a[0, N - 1]) & 0xFFFFFFFF) and np.array_equal(out[1:], a[0, :-1])
+
+
+@pytest.mark.parametrize("mask", [0x02084000, 0x02082000])
+def test_external_product_exact(engine, oracle, rng, mask):
+    """config 3(ii): TRGSW (x) TRLWE, shared and per-item TRGSW, bit-exact vs the integer oracle (trgsw.rs:264-306)."""
+    engine.set_decomp_mask(mask)
+    try:
+        B = 5
+        trlwe = u32(rng, B, 2, N)
+        trlwe[1] = 0x7DF7C000  # all digits -32
+        for ntr in (1, B):
+            trgsw = u32(rng, ntr, 6, 2, N)
+            if ntr == B:
+                trgsw[1] = 0x7FFFFFFF
+            out = engine.external_product_batch(trgsw, trlwe)
+            for g in range(B):
+                ref = np.zeros(2 * N, np.uint32)
+                oracle.lib().orc_external_product_exact(trgsw[g % ntr].reshape(-1), trlwe[g].reshape(-1), mask, ref)
+                assert np.array_equal(out[g].reshape(-1), ref), (ntr, g)
+    finally:
+        engine.set_decomp_mask(0x02084000)
+
+
+def test_external_product_vs_reference_fft(engine, oracle, rng):
+    """P1: against the reference's own FFT (oracle/_ref): |diff| <= 2 ulp per coefficient (measured -1/0/+1)."""
+    if not oracle.ref_init():
+        pytest.skip("oracle/_ref/libspqlios_ref.so not built")
+    B = 4
+    trgsw = u32(rng, 1, 6, 2, N)
+    trlwe = u32(rng, B, 2, N)
+    out = engine.external_product_batch(trgsw, trlwe)
+    worst = 0
+    for g in range(B):
+        ref = np.zeros(2 * N, np.uint32)
+        oracle.lib().orc_ref_external_product_torus(trgsw.reshape(-1), trlwe[g].reshape(-1), 0x02084000, ref)
+        diff = (out[g].reshape(-1).astype(np.int64) - ref.astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+        worst = max(worst, int(np.abs(diff).max()))
+    assert worst <= 2, worst
+
+
+@pytest.mark.parametrize("nsteps", [0, 1, 2, 17, 635])
+def test_blind_rotate_exact(engine, oracle, keys, rng, nsteps):
+    """blind_rotate prefix of nsteps CMUXes, raw TRLWE accumulator bit-exact vs the integer oracle (tfhe.rs:89-113)."""
+    B = 3 if nsteps == 635 else 5
+    bits = rng.integers(0, 2, B).astype(np.uint8)
+    lin = oracle.gate_linear(oracle.NAND, keys.encrypt(bits, 0), keys.encrypt(1 - bits, 1000))
+    lin[0, 0] = 0                      # bbar = 0
+    if B > 3:
+        lin[3, 0] = 0xFFE00000         # bbar = 2047
+        lin[4, 0] = 0x80000000         # bbar = 1024
+        lin[4, 1] = 0xFFF00000         # abar rounds up to 2048 -> 0
+        lin[4, 2] = 0x7FF00000         # abar = 1024
+    out = engine.blind_rotate_batch(lin, nsteps)
+    for g in range(B):
+        ref = np.zeros(2 * N, np.uint32)
+        oracle.lib().orc_blind_rotate_exact(keys.exact_handle(), lin[g], 0x02084000, nsteps, ref)
+        assert np.array_equal(out[g].reshape(-1), ref), (nsteps, g)
+
+
+def test_sample_extract_and_keyswitch_exact(engine, oracle, keys, rng):
+    """sample_extract_index(0) (trlwe.rs:110-121) and identity_key_switch (tlwe.rs:43-73), bit-exact."""
+    B = 19  # not a multiple of the key-switch gate tile
+    bits = rng.integers(0, 2, B).astype(np.uint8)
+    lin = oracle.gate_linear(oracle.COPY, keys.encrypt(bits, 50))
+    lwe1 = engine.bootstrap_lv1_batch(lin)
+    trl = engine.blind_rotate_batch(lin, 635)
+    for g in range(B):
+        ref = np.zeros(N + 1, np.uint32)
+        oracle.lib().orc_sample_extract0(trl[g].reshape(-1), ref)
+        assert np.array_equal(lwe1[g], ref)
+    # key switch on arbitrary level-1 samples, including digit edge cases
+    x = u32(rng, B, N + 1)
+    x[0, 1:] = 0               # all digits zero
+    x[1, 1:] = 0xFFFF8000      # rounding carries out of the top
+    x[2, 1:] = 0x55555555
+    out = engine.keyswitch_batch(x)
+    for g in range(B):
+        ref = np.zeros(n + 1, np.uint32)
+        oracle.lib().orc_key_switch(keys.ksk, x[g], ref)
+        assert np.array_equal(out[g], ref), g
+    # and the real thing decrypts
+    out = engine.keyswitch_batch(lwe1)
+    assert np.array_equal(keys.decrypt(out), bits)
+
+
+OPS = ["NAND", "AND", "OR", "XOR", "NOT"]
+
+
+def truth(op, x, y):
+    return {"NAND": 1 - (x & y), "AND": x & y, "OR": x | y, "XOR": x ^ y, "NOT": 1 - x}[op]
+
+
+@pytest.mark.parametrize("op", OPS)
+def test_gate_truth_tables_exact_and_reference(engine, oracle, keys, op):
+    """config 1 workload (examples/homnand-bench.rs:22-136, tfhe.rs:147-279): truth tables of nand/and/or/xor/not with fresh
+    encryptions.  P0: whole output ciphertext bit-exact vs the integer oracle.  P2: vs the reference-FFT gate path."""
+    x = np.array([0, 1, 0, 1], np.uint8)
+    y = np.array([0, 0, 1, 1], np.uint8)
+    if op == "NOT":
+        x, y = np.array([0, 1], np.uint8), None
+    c0 = keys.encrypt(x, 7000)
+    c1 = keys.encrypt(y, 7100) if y is not None else None
+    code = getattr(oracle, op)
+    out = engine.gate_batch(code, c0, c1)
+    want = truth(op, x, y if y is not None else x)
+    assert np.array_equal(keys.decrypt(out), want)
+    exact = oracle.gate_exact(keys, code, c0, c1)
+    assert np.array_equal(out, exact), "ciphertext differs from the exact-integer oracle"
+    if oracle.ref_init():
+        ref = oracle.gate_ref(keys, code, c0, c1)
+        assert np.array_equal(keys.decrypt(ref), want)
+        e_gpu, e_ref = phase_err(keys, out, want), phase_err(keys, ref, want)
+        assert np.abs(e_gpu).max() < 3 / 32
+        assert np.abs(e_gpu - e_ref).max() < 1 / 16
+
+
+def test_mux(engine, oracle, keys):
+    """hom_mux = bootstrap(AND(c,i1) + AND(-c,i0) + 1/8): all 8 input combinations (tfhe.rs:27-40)."""
+    c = np.array([0, 0, 0, 0, 1, 1, 1, 1], np.uint8)
+    i0 = np.array([0, 0, 1, 1, 0, 0, 1, 1], np.uint8)
+    i1 = np.array([0, 1, 0, 1, 0, 1, 0, 1], np.uint8)
+    cc, c0, c1 = keys.encrypt(c, 9000), keys.encrypt(i0, 9100), keys.encrypt(i1, 9200)
+    out = engine.mux_batch(cc, c0, c1)
+    assert np.array_equal(keys.decrypt(out), np.where(c == 1, i1, i0))
+    t1 = oracle.gate_exact(keys, oracle.AND, cc, c1)
+    t0 = oracle.gate_exact(keys, oracle.ANDNY, cc, c0)
+    assert np.array_equal(out, oracle.gate_exact(keys, oracle.OR, t1, t0))
+
+
+def test_batch_1024_nand(engine, oracle, keys, rng):
+    """config 2: 1024 independent NAND gates; all decrypts correct, a 64-gate subset bit-exact vs the oracle and within
+    the P2 phase bounds vs the reference-FFT path; phase-noise std within 15% of the reference's."""
+    B = 1024
+    x = rng.integers(0, 2, B).astype(np.uint8)
+    y = rng.integers(0, 2, B).astype(np.uint8)
+    c0, c1 = keys.encrypt(x, 100000), keys.encrypt(y, 200000)
+    out = engine.gate_batch(oracle.NAND, c0, c1)
+    want = 1 - (x & y)
+    assert np.array_equal(keys.decrypt(out), want)
+    sub = np.arange(0, B, 16)
+    assert np.array_equal(out[sub], oracle.gate_exact(keys, oracle.NAND, c0[sub], c1[sub]))
+    e_gpu = phase_err(keys, out, want)
+    assert np.abs(e_gpu).max() < 3 / 32
+    if oracle.ref_init():
+        ref = oracle.gate_ref(keys, oracle.NAND, c0[sub], c1[sub])
+        e_ref = phase_err(keys, ref, want[sub])
+        assert np.abs(e_gpu[sub] - e_ref).max() < 1 / 16
+        assert 0.85 < e_gpu.std() / e_ref.std() < 1.15, (e_gpu.std(), e_ref.std())
+
+
+def test_ragged_and_edge_batches(engine, oracle, keys, rng):
+    """empty batch, batch of one (latency path, 1 gate per CTA), odd sizes around the CTA pairing and the SM count."""
+    assert engine.gate_batch(oracle.NAND, np.zeros((0, n + 1), np.uint32), np.zeros((0, n + 1), np.uint32)).shape == (0, n + 1)
+    for B in (1, 2, 3, 149, 151):
+        x = rng.integers(0, 2, B).astype(np.uint8)
+        y = rng.integers(0, 2, B).astype(np.uint8)
+        out = engine.gate_batch(oracle.XOR, keys.encrypt(x, 300000), keys.encrypt(y, 400000))
+        assert np.array_equal(keys.decrypt(out), x ^ y), B
+
+
+def test_trivial_inputs_like_nander(engine, oracle, keys):
+    """nander's leaves are TRIVIAL ciphertexts TLWERep::logic_true/false (tlwe.rs:80-87, nander/src/lib.rs:150-151)."""
+    import rustfhe_b200 as R
+    t, f = R.TLWERep.logic_true(), R.TLWERep.logic_false()
+    for a, b, abit, bbit in ((t, t, 1, 1), (t, f, 1, 0), (f, f, 0, 0)):
+        out = engine.gate_batch(oracle.NAND, a, b)
+        assert keys.decrypt(out)[0] == 1 - (abit & bbit)
+        assert np.array_equal(out, oracle.gate_exact(keys, oracle.NAND, a, b))
+
+
+def test_error_paths(engine):
+    import rustfhe_b200 as R
+    with pytest.raises(R.TfheError):
+        engine._ck(engine._l.tfhe_b200_gate_batch(engine._ctx, 99, None, None, None, 1))
+    fresh = R.DeviceEngine(0)
+    try:
+        with pytest.raises(R.TfheError) as ei:
+            fresh.gate_batch(R.NAND, np.zeros((1, n + 1), np.uint32), np.zeros((1, n + 1), np.uint32))
+        assert ei.value.code == 3  # TFHE_B200_ERR_STATE: keys not loaded
+    finally:
+        fresh.close()
