@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""bench.py -- bootstrapped HomNAND gates/s on N B200s (BASELINE.json metric), one process per GPU.
+
+A "step" = one pass of the hot path (gate pre-combination -> 635 x CMUX blind rotation -> sample extract -> LWE key
+switch) over one batch of 1024 independent NAND gates per GPU (BASELINE.json configs[1]); weak scaling: every rank
+owns its own 1024-gate shard, keys are replicated once by an NCCL broadcast, no collective per gate.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          GPU arm (this repo's CUDA path through the C ABI)
+  python bench.py --impl reference ...                         reference arm: the reference's CPU gate path (its own FFT
+                                                               library oracle/_ref + restated glue) on the host cores
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0x5EED0001
+BATCH = 1024                     # gates per GPU per step (configs[1])
+N_LWE, N_POLY = 635, 1024
+CT_WORDS = N_LWE + 1
+NROT = 32                        # distinct input batches rotated through: 32 x 5.2 MB = 167 MB > 126 MB L2
+# algorithmic figures (SURVEY.md section 8d / DESIGN.md section "Roofline")
+BK_BYTES_ALGO = 62_423_040       # 635 x 12 x 1024 coefficients x 8 B (SURVEY's single-modulus basis)
+BK_BYTES_DEVICE = 635 * 36 * 1024 * 4  # this design: 3 key slices x 4 B = 12 B / coefficient
+KSK_BYTES = 1024 * 8 * 3 * 636 * 4
+MODMUL_PER_GATE = 33.81e6        # 635 x (8 x 5120 butterflies + 12288 MACs), single-modulus basis
+# this design per gate: 635 x (12 transforms x 5120 Shoup butterflies + 36864 wide MACs + 6144 REDC)
+BUTTERFLIES_PER_GATE = 635 * 12 * 5120
+FMA_SLOTS_PER_GATE = 635 * (12 * 5120 * 4 + 36864 * 2.5 + 6144 * 3)   # IMAD-issue-slot equivalents, see DESIGN.md
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def int_peak():
+    """IMAD issue-slot peak measured on this pool's B200 by tools/microbench/intpipe.cu (profiles/intpipe_r01.json)."""
+    p = os.path.join(ROOT, "profiles", "intpipe_r01.json")
+    try:
+        return json.load(open(p))["imad_lo"]["Gops_per_s"] * 1e9, "measured (profiles/intpipe_r01.json)"
+    except Exception:
+        return 148 * 64 * 1.965e9, "nominal 148 SM x 64 lanes x 1.965 GHz"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_reference_run(nthreads, gates_per_thread, keys=None):
+    """Time the reference-equivalent CPU gate path (reference FFT library + restated glue) on `nthreads` host threads."""
+    from oracle import oracle as O
+    O.lib()
+    if not O.ref_init():
+        raise RuntimeError("oracle/_ref/libspqlios_ref.so missing (build it where /root/reference exists: make -C oracle ref)")
+    K = keys or O.Keys(SEED)
+    B = nthreads * gates_per_thread
+    rng = np.random.default_rng(SEED + 1)
+    x = rng.integers(0, 2, B).astype(np.uint8)
+    y = rng.integers(0, 2, B).astype(np.uint8)
+    c0, c1 = K.encrypt(x, 0), K.encrypt(y, 10_000_000)
+    K.fourier_handle()
+    O.bench_ref_gates(K, O.NAND, c0[:nthreads], c1[:nthreads], nthreads)  # warm-up: one gate per thread
+    secs, out = O.bench_ref_gates(K, O.NAND, c0, c1, nthreads)
+    ok = bool(np.array_equal(K.decrypt(out), 1 - (x & y)))
+    return B / secs, secs, B, ok, K
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nthreads = os.cpu_count() or 1
+    gpt = 2  # gates per thread per step: bounded sample of the 1024-gate batch
+    from oracle import oracle as O
+    K = None
+    vals = []
+    for it in range(args.warmup + args.steps):
+        gps, secs, B, ok, K = cpu_reference_run(nthreads, gpt, K)
+        if it >= args.warmup:
+            vals.append((gps, secs))
+        if not ok:
+            print(json.dumps({"impl": "reference", "error": "reference CPU path decrypted a wrong bit"}))
+            return 1
+    total_gates = nthreads * gpt * args.steps
+    total_secs = sum(s for _, s in vals)
+    v = total_gates / total_secs
+    line = {
+        "impl": "reference", "metric": "bootstrapped HomNAND gates/sec", "value": v, "unit": "gates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_secs / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 FFT + u32 torus", "data": "synthetic",
+        "config": {"workload": "batched independent HomNAND gates, default TFHE parameters (n=635,N=1024,l=3,Bg=64,t=8)",
+                   "batch_per_step": nthreads * gpt, "note": "bounded sample of the 1024-gate batch; CPU time per gate is batch independent"},
+        "cpu_baseline": {"value": v, "unit": "gates/s", "cores": nthreads, "kind": "port",
+                         "sample": f"{nthreads * gpt} NAND gates per step on {nthreads} threads; reference's own spqlios FFT "
+                                   f"(oracle/_ref, compiled from /root/reference) + C restatement of the Rust glue (Rust toolchain absent)"},
+        "e2e": {"value": v, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import rustfhe_b200 as R
+    from rustfhe_b200 import _capi as K
+
+    # ---- keys: generated once on rank 0 (host, product keygen), replicated with ONE NCCL broadcast each ----
+    t_key0 = time.time()
+    bk_d = torch.empty(K.BK_WORDS, dtype=torch.int32, device=dev)
+    ksk_d = torch.empty(K.KSK_WORDS, dtype=torch.int32, device=dev)
+    s0 = torch.zeros(N_LWE, dtype=torch.uint8)
+    if rank == 0:
+        sk = R.SecretKeys.generate(SEED)
+        bk = R.BootstrappingKey.new(sk.s_key_tlwelv0, sk.s_key_tlwelv1, SEED)
+        ksk = R.KeySwitchingKey.new(sk.s_key_tlwelv1, sk.s_key_tlwelv0, SEED)
+        bk_d.copy_(torch.from_numpy(bk.words.view(np.int32)))
+        ksk_d.copy_(torch.from_numpy(ksk.words.view(np.int32)))
+        s0 = torch.from_numpy(sk.s_key_tlwelv0.copy())
+    if world > 1:
+        dist.broadcast(bk_d, 0)
+        dist.broadcast(ksk_d, 0)
+        s0d = s0.to(dev)
+        dist.broadcast(s0d, 0)
+        s0 = s0d.cpu()
+    s0 = s0.numpy()
+    eng = R.DeviceEngine(local)
+    stream = torch.cuda.current_stream()
+    eng.load_ksk_device(ksk_d.data_ptr(), stream.cuda_stream)
+    eng.load_bk_device(bk_d.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    del bk_d, ksk_d
+    key_s = time.time() - t_key0
+
+    # ---- synthetic inputs: NROT distinct batches of random-bit encryptions per rank, resident in HBM ----
+    rng = np.random.default_rng(SEED + 17 * rank)
+    nct = NROT * BATCH
+    bx = rng.integers(0, 2, nct).astype(np.uint8)
+    by = rng.integers(0, 2, nct).astype(np.uint8)
+    cx = R.Cryptor.encrypto(R.TLWE, s0, bx, seed=SEED + 100 + rank, ct_index0=0)
+    cy = R.Cryptor.encrypto(R.TLWE, s0, by, seed=SEED + 200 + rank, ct_index0=0)
+    hx = torch.from_numpy(cx.view(np.int32)).pin_memory()
+    hy = torch.from_numpy(cy.view(np.int32)).pin_memory()
+    dx, dy = hx.to(dev), hy.to(dev)
+    dout = torch.empty((BATCH, CT_WORDS), dtype=torch.int32, device=dev)
+    hout = torch.empty((BATCH, CT_WORDS), dtype=torch.int32).pin_memory()
+
+    def step_device(it):
+        o = (it % NROT) * BATCH
+        eng.gate_batch_device(K.NAND, dx[o:o + BATCH].data_ptr(), dy[o:o + BATCH].data_ptr(), dout.data_ptr(), BATCH,
+                              stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for it in range(args.warmup):
+        step_device(it)
+    torch.cuda.synchronize()
+    # correctness of the last warm-up batch (decrypt all 1024 outputs)
+    o = ((args.warmup - 1) % NROT) * BATCH if args.warmup > 0 else 0
+    if args.warmup == 0:
+        step_device(0); torch.cuda.synchronize()
+    got = R.Cryptor.decrypto(R.TLWE, s0, dout.cpu().numpy().view(np.uint32))
+    wrong = int((got != (1 - (bx[o:o + BATCH] & by[o:o + BATCH]))).sum())
+
+    # ---- timed region: exactly K steps, device-resident inputs ----
+    eng.reset_stats()
+    launches0 = eng.stats()["kernel_launches"]
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize()
+    e0.record(stream)
+    for it in range(args.steps):
+        step_device(args.warmup + it)
+    e1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    ms = e0.elapsed_time(e1)
+    st = eng.stats()
+    launches = st["kernel_launches"] - launches0
+
+    # ---- e2e: same steps through the host-buffer C ABI call, pinned host memory, H2D + D2H inside the timed region ----
+    hx_np, hy_np, hout_np = hx.numpy().view(np.uint32), hy.numpy().view(np.uint32), hout.numpy().view(np.uint32)
+    import ctypes as C
+    lib = K.lib()
+
+    def step_host(it):
+        o = (it % NROT) * BATCH
+        rc = lib.tfhe_b200_gate_batch(eng._ctx, K.NAND, K.ptr(hx_np[o:o + BATCH]), K.ptr(hy_np[o:o + BATCH]), K.ptr(hout_np), BATCH)
+        if rc:
+            raise RuntimeError(lib.tfhe_b200_last_error(eng._ctx))
+
+    step_host(0)
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for it in range(args.steps):
+        step_host(args.warmup + it)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    got = R.Cryptor.decrypto(R.TLWE, s0, hout_np)
+    o = ((args.warmup + args.steps - 1) % NROT) * BATCH
+    wrong += int((got != (1 - (bx[o:o + BATCH] & by[o:o + BATCH]))).sum())
+
+    # max over ranks
+    t = torch.tensor([ms, e2e_s * 1e3, float(wrong)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, wrong = float(t[0]), float(t[1]), int(t[2])
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        p_int, p_int_src = int_peak()
+        gates = BATCH * world * args.steps
+        value = gates / (ms * 1e-3)
+        br_ms, ks_ms = st["avg_blind_rotate_ms"], st["avg_keyswitch_ms"]
+        # dominant kernel = blind_rotate_kernel: algorithmic bytes per launch = BK once + ciphertext I/O of the batch
+        algo_bytes = BK_BYTES_ALGO + BATCH * (2 * CT_WORDS * 4 + CT_WORDS * 4 + N_POLY * 2)
+        achieved = algo_bytes / (br_ms * 1e-3) / 1e9 if br_ms > 0 else 0.0
+        per_gpu_gps_kernel = BATCH / (br_ms * 1e-3) if br_ms > 0 else 0.0
+        line = {
+            "metric": "bootstrapped HomNAND gates/sec", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 (torus mod 2^32; NTT over a 29-bit prime)", "data": "synthetic",
+            "config": {"workload": "batched 1024 independent HomNAND gates per GPU (BASELINE configs[1]), default TFHE parameters "
+                                   "n=635 N=1024 l=3 Bg=64 t=8 basebit=2, decomposition mask 0x02084000 (reference-faithful)",
+                       "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world} (independent gate shards, keys replicated)",
+                       "l2": f"inputs rotate over {NROT} batches ({NROT * BATCH * 2 * CT_WORDS * 4 / 1e6:.0f} MB) > L2; keys "
+                             f"{(BK_BYTES_DEVICE + KSK_BYTES) / 1e6:.0f} MB > L2; no explicit flush",
+                       "gates_per_cta": st["gates_per_cta"]},
+            "latency_us_per_gate_amortised": 1e3 * ms / args.steps / BATCH,
+            "wrong_bits": wrong,
+            "e2e": {"value": gates / (e2e_ms * 1e-3), "unit": "gates/s", "h2d_bytes_per_step": 2 * BATCH * CT_WORDS * 4,
+                    "d2h_bytes_per_step": BATCH * CT_WORDS * 4, "ms_per_step": e2e_ms / args.steps,
+                    "api": "tfhe_b200_gate_batch (host pointers, pinned)"},
+            "gpu_launches": int(launches),
+            "kernels": {"blind_rotate_ms": br_ms, "keyswitch_ms": ks_ms, "timed_launches": st["timed_launches"]},
+            "roofline": {"bound": "hbm", "kernel": "blind_rotate_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                         "algorithmic_bytes_per_launch": algo_bytes, "traffic": None,
+                         "note": "HBM is NOT the binding roof of this kernel (key bytes are read once per 1024-gate launch); "
+                                 "the binding roof is the integer FMA pipe, see int_roofline"},
+            "int_roofline": {"bound": "integer FMA pipe (IMAD issue slots)", "kernel": "blind_rotate_kernel",
+                             "achieved": per_gpu_gps_kernel * FMA_SLOTS_PER_GATE / 1e12, "peak": p_int / 1e12, "unit": "T IMAD-slots/s",
+                             "frac": per_gpu_gps_kernel * FMA_SLOTS_PER_GATE / p_int, "peak_kind": p_int_src,
+                             "slots_per_gate": FMA_SLOTS_PER_GATE, "butterflies_per_gate": BUTTERFLIES_PER_GATE,
+                             "modmul_per_gate_single_modulus_basis": MODMUL_PER_GATE,
+                             "note": "slot weights measured on B200: IMAD 1, IMAD.HI 2, IMAD.WIDE 2.5 (profiles/intpipe_r01.json); "
+                                     "butterfly = 2 IMAD + 1 IMAD.HI = 4 slots; this design runs 12 transforms per CMUX"},
+            "clocks": clocks,
+            "key_setup_s": key_s,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                nthreads = os.cpu_count() or 1
+                gps1, secs1, B1, ok1, Kc = cpu_reference_run(1, 16)
+                gpsN, secsN, BN, okN, _ = cpu_reference_run(nthreads, 16, Kc)
+                line["cpu_baseline"] = {"value": gpsN, "unit": "gates/s", "cores": nthreads, "kind": "port",
+                                        "value_1core": gps1, "ms_per_gate_1core": 1e3 / gps1, "decrypt_ok": bool(ok1 and okN),
+                                        "sample": f"{BN} NAND gates on {nthreads} threads ({secsN:.1f} s) and {B1} gates on 1 thread "
+                                                  f"({secs1:.1f} s); reference's own spqlios FFT (oracle/_ref) + C restatement of the "
+                                                  f"Rust glue (no Rust toolchain in the image)"}
+            except Exception as ex:  # the GPU numbers stand on their own
+                line["cpu_baseline"] = {"value": None, "unit": "gates/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0 if wrong == 0 else 1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        sys.exit(run_reference(args))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29541", os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
+               str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+        sys.exit(subprocess.call(cmd))
+    sys.exit(run_gpu(args))
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,9 @@ typedef struct {
     uint64_t kernel_launches;  /* kernels of this library launched since ctx creation */
     float last_blind_rotate_ms; /* device time of the most recent blind-rotate kernel (CUDA events on its stream) */
     float last_keyswitch_ms;
+    float avg_blind_rotate_ms;  /* mean over the last timed_launches (<= 64) gate batches since reset_stats */
+    float avg_keyswitch_ms;
+    uint64_t timed_launches;
     uint64_t last_batch;
     int32_t gates_per_cta, sm_count;
     uint64_t device_key_bytes;
@@ -77,7 +80,8 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p /* NULL = defaults */, int de
 int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx);
 const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx /* NULL = last error of a failed ctx_create */);
 int tfhe_b200_set_decomp_mask(tfhe_b200_ctx* ctx, uint32_t mask);
-int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out); /* synchronises the ctx stream */
+int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out); /* waits for the recorded events */
+int tfhe_b200_reset_stats(tfhe_b200_ctx* ctx);
 
 /* ---- keys: BootstrappingKey::new / KeySwitchingKey::new products (tfhe.rs:119-126, tlwe.rs:247-277) ----
  * load_bk transforms the torus-domain key on the device into the NTT domain (replaces TRGSWRepF::from,

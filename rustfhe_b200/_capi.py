@@ -18,7 +18,7 @@ KSK_WORDS = N * KS_T * 3 * (n + 1)
 # every symbol include/tfhe_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "tfhe_b200_default_params", "tfhe_b200_ctx_create", "tfhe_b200_ctx_destroy", "tfhe_b200_last_error",
-    "tfhe_b200_set_decomp_mask", "tfhe_b200_get_stats", "tfhe_b200_load_bk", "tfhe_b200_load_bk_device",
+    "tfhe_b200_set_decomp_mask", "tfhe_b200_get_stats", "tfhe_b200_reset_stats", "tfhe_b200_load_bk", "tfhe_b200_load_bk_device",
     "tfhe_b200_load_ksk", "tfhe_b200_load_ksk_device", "tfhe_b200_gate_batch", "tfhe_b200_gate_batch_device",
     "tfhe_b200_bootstrap_batch", "tfhe_b200_mux_batch", "tfhe_b200_mux_batch_device", "tfhe_b200_blind_rotate_batch",
     "tfhe_b200_bootstrap_lv1_batch", "tfhe_b200_keyswitch_batch", "tfhe_b200_external_product_batch",
@@ -34,6 +34,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("last_blind_rotate_ms", C.c_float), ("last_keyswitch_ms", C.c_float),
+                ("avg_blind_rotate_ms", C.c_float), ("avg_keyswitch_ms", C.c_float), ("timed_launches", C.c_uint64),
                 ("last_batch", C.c_uint64), ("gates_per_cta", C.c_int32), ("sm_count", C.c_int32),
                 ("device_key_bytes", C.c_uint64)]
 
@@ -57,6 +58,7 @@ def lib():
         "tfhe_b200_last_error": (C.c_char_p, [vp]),
         "tfhe_b200_set_decomp_mask": (i32, [vp, u32]),
         "tfhe_b200_get_stats": (i32, [vp, C.POINTER(Stats)]),
+        "tfhe_b200_reset_stats": (i32, [vp]),
         "tfhe_b200_load_bk": (i32, [vp, vp]),
         "tfhe_b200_load_bk_device": (i32, [vp, vp, vp]),
         "tfhe_b200_load_ksk": (i32, [vp, vp]),

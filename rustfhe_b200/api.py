@@ -232,6 +232,9 @@ class DeviceEngine:
     def set_decomp_mask(self, mask):
         self._ck(self._l.tfhe_b200_set_decomp_mask(self._ctx, mask))
 
+    def reset_stats(self):
+        self._ck(self._l.tfhe_b200_reset_stats(self._ctx))
+
     def stats(self):
         s = K.Stats()
         self._ck(self._l.tfhe_b200_get_stats(self._ctx, C.byref(s)))

@@ -299,8 +299,9 @@ struct tfhe_b200_ctx {
     uint16_t* ksdig = nullptr; size_t ksdig_cap = 0;
     uint32_t* tmp[4] = {nullptr, nullptr, nullptr, nullptr}; size_t tmp_cap[4] = {0, 0, 0, 0};
     uint32_t* xbk = nullptr; size_t xbk_cap = 0;  // external-product scratch keys
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool ev_valid = false;
+    static constexpr int RING = 64;          // event ring: per-launch device times of the last RING timed gate batches
+    cudaEvent_t ev[RING][4] = {};
+    uint64_t timed = 0;
     uint64_t launches = 0;
     uint64_t last_batch = 0;
     int gates_per_cta = 2;
@@ -367,7 +368,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     auto bail = [&](const char* what, cudaError_t ee) { g_create_err = std::string(what) + ": " + cudaGetErrorString(ee); delete ctx; return TFHE_B200_ERR_CUDA; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (auto& slot : ctx->ev) for (auto& ev : slot) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->bkdev, (size_t)LWE_N * BK_STEP_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc(bk)", e);
     if ((e = cudaMalloc(&ctx->kskdev, (size_t)1024 * 8 * 3 * (LWE_N + 1) * 4)) != cudaSuccess) return bail("cudaMalloc(ksk)", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(2))) != cudaSuccess) return bail("smem attr", e);
@@ -383,7 +384,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->bkdev); cudaFree(ctx->kskdev); cudaFree(ctx->ksdig); cudaFree(ctx->xbk);
     for (auto p : ctx->tmp) cudaFree(p);
-    for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& slot : ctx->ev) for (auto ev : slot) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TFHE_B200_OK;
@@ -397,6 +398,11 @@ int tfhe_b200_set_decomp_mask(tfhe_b200_ctx* ctx, uint32_t mask) {
     return TFHE_B200_OK;
 }
 
+int tfhe_b200_reset_stats(tfhe_b200_ctx* ctx) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ctx->timed = 0;
+    return TFHE_B200_OK;
+}
 int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out) {
     if (!ctx || !out) return TFHE_B200_ERR_PARAM;
     memset(out, 0, sizeof *out);
@@ -405,11 +411,19 @@ int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out) {
     out->gates_per_cta = ctx->gates_per_cta;
     out->sm_count = ctx->sm_count;
     out->device_key_bytes = (uint64_t)LWE_N * BK_STEP_WORDS * 4 + (uint64_t)1024 * 8 * 3 * (LWE_N + 1) * 4;
-    if (ctx->ev_valid) {
-        CK(cudaEventSynchronize(ctx->ev[3]));
-        CK(cudaEventElapsedTime(&out->last_blind_rotate_ms, ctx->ev[0], ctx->ev[1]));
-        CK(cudaEventElapsedTime(&out->last_keyswitch_ms, ctx->ev[2], ctx->ev[3]));
+    const uint64_t cnt = ctx->timed < (uint64_t)tfhe_b200_ctx::RING ? ctx->timed : (uint64_t)tfhe_b200_ctx::RING;
+    double sb = 0, sk = 0;
+    for (uint64_t k = 0; k < cnt; k++) {
+        const int slot = (int)((ctx->timed - 1 - k) % tfhe_b200_ctx::RING);
+        float b = 0, s = 0;
+        CK(cudaEventSynchronize(ctx->ev[slot][3]));
+        CK(cudaEventElapsedTime(&b, ctx->ev[slot][0], ctx->ev[slot][1]));
+        CK(cudaEventElapsedTime(&s, ctx->ev[slot][2], ctx->ev[slot][3]));
+        if (k == 0) { out->last_blind_rotate_ms = b; out->last_keyswitch_ms = s; }
+        sb += b; sk += s;
     }
+    out->timed_launches = cnt;
+    if (cnt) { out->avg_blind_rotate_ms = (float)(sb / cnt); out->avg_keyswitch_ms = (float)(sk / cnt); }
     return TFHE_B200_OK;
 }
 
@@ -475,7 +489,8 @@ static void op_coeffs(int op, uint32_t mu, int32_t* c0, int32_t* c1, uint32_t* c
 }
 static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, bool timed) {
     a.bkdev = ctx->bkdev; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu;
-    if (timed) CK(cudaEventRecord(ctx->ev[0], st));
+    const int slot = (int)(ctx->timed % tfhe_b200_ctx::RING);
+    if (timed) CK(cudaEventRecord(ctx->ev[slot][0], st));
     // one gate per CTA when the batch cannot fill the machine with pairs (latency case), else two
     const bool pair = a.B > (long)ctx->sm_count;
     if (pair) {
@@ -488,16 +503,17 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
     }
     ctx->launches++;
     CK(cudaGetLastError());
-    if (timed) CK(cudaEventRecord(ctx->ev[1], st));
+    if (timed) CK(cudaEventRecord(ctx->ev[slot][1], st));
     return TFHE_B200_OK;
 }
 static int launch_keyswitch(tfhe_b200_ctx* ctx, const uint16_t* dig, uint32_t* out, long B, cudaStream_t st, bool timed) {
-    if (timed) CK(cudaEventRecord(ctx->ev[2], st));
+    const int slot = (int)(ctx->timed % tfhe_b200_ctx::RING);
+    if (timed) CK(cudaEventRecord(ctx->ev[slot][2], st));
     dim3 grid((unsigned)((B + KS_GT - 1) / KS_GT), KS_ISPLIT);
     keyswitch_kernel<<<grid, KS_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B);
     ctx->launches++;
     CK(cudaGetLastError());
-    if (timed) { CK(cudaEventRecord(ctx->ev[3], st)); ctx->ev_valid = true; }
+    if (timed) { CK(cudaEventRecord(ctx->ev[slot][3], st)); ctx->timed++; }
     return TFHE_B200_OK;
 }
 static const size_t CT_BYTES = (size_t)(LWE_N + 1) * 4;
