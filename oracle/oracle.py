@@ -60,6 +60,9 @@ def lib():
         "orc_tested_decomp_mask": (u32, [u32, u32]),
         "orc_decompose_scalar": (None, [u32, u32, u32, u32, i32p]),
         "orc_decompose": (None, [u32p, u32, i32p]),
+        "orc_decompose_u32_scalar": (None, [u32, u32, u32, u32p]),
+        "orc_ref_roundtrip_n": (None, [i32, u32p, u32p]),
+        "orc_ref_poly_mul_n": (None, [i32, u32p, u32p, u32p]),
         "orc_torus_from_f32": (u32, [C.c_float]),
         "orc_torus_to_f32": (C.c_float, [u32]),
         "orc_gate_linear": (None, [i32, u32p, vp, sz, u32p]),

@@ -117,6 +117,12 @@ void orc_decompose_scalar(uint32_t x, uint32_t l, uint32_t bits, uint32_t mask, 
         out[i] = (int32_t)((v & (1u << (bits - 1))) * 0xfffffffeu + v);
     }
 }
+/* Torus32::decomposition_u32, utils/src/math.rs:596-614 : unsigned digits after adding the rounding bit */
+void orc_decompose_u32_scalar(uint32_t x, uint32_t l, uint32_t bits, uint32_t* out) {
+    uint32_t u = x + ((32 - l * bits != 0) ? (1u << (32 - l * bits - 1)) : 0u);
+    uint32_t m = (1u << bits) - 1;
+    for (uint32_t i = 0; i < l; i++) out[i] = (u >> (32 - bits * (i + 1))) & m;
+}
 /* Polynomial::decomposition_i32_, utils/src/math.rs:300-326 : out[i][k] = digit i of coefficient k */
 void orc_decompose(const uint32_t* p, uint32_t mask, int32_t* out) {
     int32_t d[L_];
@@ -513,6 +519,16 @@ void orc_ref_ifft_fft_roundtrip(const uint32_t* a, uint32_t* out) {
     R.ifft_u32(h, f, a);
     R.fft_u32(h, out, f);
 }
+/* spqlios.rs fft_test (utils/src/spqlios.rs:243-276) needs N=16; because of the latched 2/N call these only in
+ * a process that never touches N=1024. */
+void orc_ref_roundtrip_n(int n, const uint32_t* a, uint32_t* out) {
+    void* h = R.mk(n);
+    double* f = malloc(sizeof(double) * n);
+    R.ifft_u32(h, f, a);
+    R.fft_u32(h, out, f);
+    free(f);
+}
+void orc_ref_poly_mul_n(int n, const uint32_t* a, const uint32_t* b, uint32_t* out) { R.poly_mul(R.mk(n), out, a, b); }
 void orc_ref_free(void* p) { free(p); }
 /* TRGSWRepF::from, hom_nand/src/trgsw.rs:68-76 : struct { cipher_f[2L], pkey_f[2L] }, each ifft_torus of the torus poly */
 static void trgsw_to_fourier(const uint32_t* trgsw, double* out) {

@@ -60,6 +60,7 @@ uint32_t orc_make_decomp_mask(uint32_t l, uint32_t bits);
 uint32_t orc_tested_decomp_mask(uint32_t l, uint32_t bits);
 void orc_decompose_scalar(uint32_t x, uint32_t l, uint32_t bits, uint32_t mask, int32_t* out /*[l]*/);
 void orc_decompose(const uint32_t* p, uint32_t mask, int32_t* out /*[L][N]*/);
+void orc_decompose_u32_scalar(uint32_t x, uint32_t l, uint32_t bits, uint32_t* out /*[l]*/);
 uint32_t orc_torus_from_f32(float v);
 float orc_torus_to_f32(uint32_t t);
 void orc_gate_linear(int op, const uint32_t* in0, const uint32_t* in1, size_t B, uint32_t* out);
@@ -86,6 +87,8 @@ void orc_ref_poly_mul(const uint32_t* a, const uint32_t* b, uint32_t* out); /* S
 void orc_ref_ifft_fft_roundtrip(const uint32_t* a, uint32_t* out);
 double* orc_ref_bk_fourier(const uint32_t* bk); /* [n][cipher_f[2L], pkey_f[2L]][N] doubles; free with orc_ref_free */
 void orc_ref_free(void* p);
+void orc_ref_roundtrip_n(int n, const uint32_t* a, uint32_t* out); /* separate process only (F6) */
+void orc_ref_poly_mul_n(int n, const uint32_t* a, const uint32_t* b, uint32_t* out);
 void orc_ref_external_product(const double* trgswF /*[2][2L][N]*/, const uint32_t* trlwe, uint32_t mask, uint32_t* out);
 void orc_ref_external_product_torus(const uint32_t* trgsw, const uint32_t* trlwe, uint32_t mask, uint32_t* out);
 void orc_ref_blind_rotate(const double* bkF, const uint32_t* tlwe, uint32_t mask, int nsteps, uint32_t* out_trlwe);

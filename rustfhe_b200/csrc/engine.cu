@@ -9,6 +9,7 @@
 //   polymul_kernel         : exact negacyclic product micro-entry (math.rs:337-347)
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -69,8 +70,8 @@ struct BrArgs {
     long ntrgsw;
 };
 
-template <int G, bool EXTPROD>
-__global__ void __launch_bounds__(G* THREADS_PER_GATE, 1) blind_rotate_kernel(const BrArgs a) {
+template <int G, bool EXTPROD, int MINB>
+__global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel(const BrArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* twF = smem;
     uint32_t* twI = smem + 32 * TWB_STRIDE;
@@ -305,6 +306,7 @@ struct tfhe_b200_ctx {
     uint64_t launches = 0;
     uint64_t last_batch = 0;
     int gates_per_cta = 2;
+    int variant = 3;  // blind-rotate launch shape: 0 = 2 gates/CTA x 1 CTA/SM, 2 = 1 gate/CTA x 2 CTA/SM, 3 = 1 gate/CTA x 3 CTA/SM
     std::string err;
 };
 static thread_local std::string g_create_err;
@@ -371,9 +373,12 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     for (auto& slot : ctx->ev) for (auto& ev : slot) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->bkdev, (size_t)LWE_N * BK_STEP_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc(bk)", e);
     if ((e = cudaMalloc(&ctx->kskdev, (size_t)1024 * 8 * 3 * (LWE_N + 1) * 4)) != cudaSuccess) return bail("cudaMalloc(ksk)", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(2))) != cudaSuccess) return bail("smem attr", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(2))) != cudaSuccess) return bail("smem attr", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(2))) != cudaSuccess) return bail("smem attr", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(2))) != cudaSuccess) return bail("smem attr", e);
+    if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
     *out = ctx;
     return TFHE_B200_OK;
 }
@@ -493,12 +498,18 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
     if (timed) CK(cudaEventRecord(ctx->ev[slot][0], st));
     // one gate per CTA when the batch cannot fill the machine with pairs (latency case), else two
     const bool pair = a.B > (long)ctx->sm_count;
-    if (pair) {
+    if (pair && ctx->variant == 0) {
         const unsigned grid = (unsigned)((a.B + 1) / 2);
-        blind_rotate_kernel<2, false><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
+        blind_rotate_kernel<2, false, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
         ctx->gates_per_cta = 2;
+    } else if (pair && ctx->variant == 2) {
+        blind_rotate_kernel<1, false, 2><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
+        ctx->gates_per_cta = 1;
+    } else if (pair && ctx->variant == 3) {
+        blind_rotate_kernel<1, false, 3><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
+        ctx->gates_per_cta = 1;
     } else {
-        blind_rotate_kernel<1, false><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
+        blind_rotate_kernel<1, false, 1><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
         ctx->gates_per_cta = 1;
     }
     ctx->launches++;
@@ -673,7 +684,7 @@ int tfhe_b200_external_product_batch(tfhe_b200_ctx* ctx, const uint32_t* trgsw, 
                             a.bkdev = c->xbk; a.mask = c->prm.decomp_mask; a.mu = c->prm.mu; a.B = (long)x->B; a.nsteps = 1;
                             a.trlwe_in = di[0]; a.trlwe_out = dout; a.ntrgsw = (long)x->ntrgsw;
                             const unsigned grid = (unsigned)((x->B + 1) / 2);
-                            blind_rotate_kernel<2, true><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), c->stream>>>(a);
+                            blind_rotate_kernel<2, true, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), c->stream>>>(a);
                             c->launches++;
                             cudaError_t e = cudaGetLastError();
                             if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return TFHE_B200_ERR_CUDA; }

@@ -40,8 +40,18 @@ static __constant__ uint32_t c_fwdA[64] = {NTT_FWD_A_LIST};
 static __constant__ uint32_t c_invA[64] = {NTT_INV_A_LIST};
 static __device__ const uint32_t g_fwdB[32 * NTT_TWB_STRIDE] = {NTT_FWD_B_LIST};
 static __device__ const uint32_t g_invB[32 * NTT_TWB_STRIDE] = {NTT_INV_B_LIST};
+static __constant__ uint32_t c_zero = 0;  // opaque to ptxas (a __constant__ may be rewritten by the host)
 #endif
 
+// a + b as a THREE-input add with an opaque zero: keeps ptxas from emitting IMAD.IADD, i.e. keeps plain additions on
+// the ALU pipe and off the FMA-heavy pipe that bounds the transforms (profiles/r01_ncu_blind_rotate_v1.txt).
+TFHE_HD uint32_t add_alu(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return a + b + c_zero;
+#else
+    return a + b;
+#endif
+}
 TFHE_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
     return __umulhi(a, b);
@@ -102,7 +112,7 @@ struct TwRow {  // pass B: per-thread row (shared memory on the device), 16-byte
 TFHE_HD void ct_bfly(uint32_t& a, uint32_t& b, uint32_t w, uint32_t ws) {
     const uint32_t X = csub(a, P2);
     const uint32_t T = shoup_mul(b, w, ws);
-    a = X + T;
+    a = add_alu(X, T);
     b = X - T + P2;
 }
 template <int S, class TW>
@@ -134,7 +144,7 @@ TFHE_HD void ct32(uint32_t (&x)[32], const TW& tw) {
 // ---- 32-point Gentleman-Sande network (exact mirror); values stay in [0,2p) ----
 TFHE_HD void gs_bfly(uint32_t& a, uint32_t& b, uint32_t w, uint32_t ws) {
     const uint32_t U = a, V = b;
-    a = csub(U + V, P2);
+    a = csub(add_alu(U, V), P2);
     b = shoup_mul(U - V + P2, w, ws);
 }
 template <int S, class TW>

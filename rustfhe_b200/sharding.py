@@ -1,0 +1,56 @@
+"""Multi-GPU plumbing for the gate path: one process per GPU, keys replicated once, independent gate shards.
+
+SURVEY.md section 8(e): every gate of a batch is independent and the only shared state is the read-only key material, so
+the batch is cut into contiguous shards of ceil(B/g) gates, BK and KSK are broadcast ONCE (NCCL over NVLink on GPUs) and no
+collective runs per gate.  The reference has no parallel path at all (single thread, F11); this module is the host logic
+of ours and is backend-agnostic so that it is covered by world_size-2 `gloo` tests on CPU.
+"""
+import numpy as np
+
+
+def shard_bounds(batch, world):
+    """Contiguous shards of ceil(batch/world) gates: [(start, end)] per rank (trailing ranks may be empty)."""
+    per = -(-batch // world) if batch > 0 else 0
+    return [(min(r * per, batch), min((r + 1) * per, batch)) for r in range(world)]
+
+
+def replicate_keys(bk_words, ksk_words, rank, world, device=None):
+    """Broadcast the torus-domain bootstrapping key and the key-switching key from rank 0.
+
+    Returns int32 torch tensors (bk, ksk) on `device` (CUDA for NCCL, None/cpu for gloo).  Rank 0 passes numpy uint32
+    arrays, the other ranks pass None."""
+    import torch
+    import torch.distributed as dist
+    from . import _capi as K
+    bk = torch.empty(K.BK_WORDS, dtype=torch.int32, device=device)
+    ksk = torch.empty(K.KSK_WORDS, dtype=torch.int32, device=device)
+    if rank == 0:
+        bk.copy_(torch.from_numpy(np.ascontiguousarray(bk_words, np.uint32).reshape(-1).view(np.int32)))
+        ksk.copy_(torch.from_numpy(np.ascontiguousarray(ksk_words, np.uint32).reshape(-1).view(np.int32)))
+    if world > 1:
+        dist.broadcast(bk, 0)
+        dist.broadcast(ksk, 0)
+    return bk, ksk
+
+
+def evaluate_sharded(gate_fn, in0, in1, rank, world, gather=True):
+    """Evaluate one batch of gates split across ranks.  `gate_fn(in0_shard, in1_shard) -> out_shard` is the per-rank
+    engine call (tfhe_b200_gate_batch).  With gather=True every rank returns the whole output batch (one all_gather of
+    2544 B per ciphertext -- the per-LEVEL exchange of a levelised circuit, never per gate)."""
+    import torch
+    import torch.distributed as dist
+    B = len(in0)
+    bounds = shard_bounds(B, world)
+    s, e = bounds[rank]
+    width = in0.shape[1]
+    out_shard = gate_fn(in0[s:e], None if in1 is None else in1[s:e]) if e > s else np.zeros((0, width), np.uint32)
+    if not gather or world == 1:
+        return out_shard
+    per = bounds[0][1] - bounds[0][0]
+    pad = np.zeros((per, width), np.uint32)
+    pad[:e - s] = out_shard
+    mine = torch.from_numpy(pad.view(np.int32))
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    out = np.concatenate([p.numpy().view(np.uint32)[:b[1] - b[0]] for p, b in zip(parts, bounds)], axis=0)
+    return out
