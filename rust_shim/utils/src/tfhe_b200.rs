@@ -1,0 +1,42 @@
+//! utils/src/tfhe_b200.rs -- the `extern "C"` block that replaces utils/src/spqlios.rs:18-32.
+//! One call per BATCH of gates instead of 8 FFT entry points crossed 5080 times per gate.
+//! Mirrors include/tfhe_b200.h one to one.  NOT COMPILED in this repository's image (no Rust toolchain).
+use std::os::raw::{c_char, c_int, c_void};
+
+pub enum Ctx {}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct Params {
+    pub n: i32,
+    pub big_n: i32,
+    pub l: i32,
+    pub bgbit: i32,
+    pub ks_t: i32,
+    pub ks_basebit: i32,
+    pub mu: u32,
+    pub decomp_mask: u32,
+}
+
+pub const NAND: c_int = 0;
+pub const AND: c_int = 1;
+pub const OR: c_int = 2;
+pub const XOR: c_int = 3;
+pub const NOT: c_int = 4;
+pub const COPY: c_int = 5;
+
+extern "C" {
+    pub fn tfhe_b200_default_params(p: *mut Params) -> c_int;
+    pub fn tfhe_b200_ctx_create(p: *const Params, device: c_int, out: *mut *mut Ctx) -> c_int;
+    pub fn tfhe_b200_ctx_destroy(ctx: *mut Ctx) -> c_int;
+    pub fn tfhe_b200_last_error(ctx: *const Ctx) -> *const c_char;
+    pub fn tfhe_b200_load_bk(ctx: *mut Ctx, bk: *const u32) -> c_int;
+    pub fn tfhe_b200_load_ksk(ctx: *mut Ctx, ksk: *const u32) -> c_int;
+    pub fn tfhe_b200_gate_batch(ctx: *mut Ctx, op: c_int, in0: *const u32, in1: *const u32, out: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_gate_batch_device(ctx: *mut Ctx, op: c_int, in0: *const u32, in1: *const u32, out: *mut u32, b: usize, stream: *mut c_void) -> c_int;
+    pub fn tfhe_b200_mux_batch(ctx: *mut Ctx, c: *const u32, in0: *const u32, in1: *const u32, out: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_blind_rotate_batch(ctx: *mut Ctx, input: *const u32, nsteps: c_int, out_trlwe: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_keyswitch_batch(ctx: *mut Ctx, lwe1: *const u32, out: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_external_product_batch(ctx: *mut Ctx, trgsw: *const u32, ntrgsw: usize, trlwe: *const u32, out: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_negacyclic_mul_batch(ctx: *mut Ctx, a: *const u32, d: *const i32, out: *mut u32, b: usize) -> c_int;
+}
