@@ -249,6 +249,18 @@ def run_gpu(args):
     st = eng.stats()
     launches = st["kernel_launches"] - launches0
 
+    # ---- B = 1 latency (SURVEY 8d "latency metric"): one gate per call, median of 30 after 3 warm-ups, CUDA events ----
+    lat = []
+    for rep in range(33):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        eng.gate_batch_device(K.NAND, dx[rep:rep + 1].data_ptr(), dy[rep:rep + 1].data_ptr(), dout.data_ptr(), 1, stream.cuda_stream)
+        a1.record(stream)
+        a1.synchronize()
+        if rep >= 3:
+            lat.append(a0.elapsed_time(a1) * 1e3)
+    latency_us = float(np.median(lat))
+
     # ---- e2e: same steps through the host-buffer C ABI call, pinned host memory, H2D + D2H inside the timed region ----
     hx_np, hy_np, hout_np = hx.numpy().view(np.uint32), hy.numpy().view(np.uint32), hout.numpy().view(np.uint32)
     import ctypes as C
@@ -300,6 +312,7 @@ def run_gpu(args):
                              f"{(BK_BYTES_DEVICE + KSK_BYTES) / 1e6:.0f} MB > L2; no explicit flush",
                        "gates_per_cta": st["gates_per_cta"]},
             "latency_us_per_gate_amortised": 1e3 * ms / args.steps / BATCH,
+            "latency_us_single_gate": latency_us,
             "wrong_bits": wrong,
             "e2e": {"value": gates / (e2e_ms * 1e-3), "unit": "gates/s", "h2d_bytes_per_step": 2 * BATCH * CT_WORDS * 4,
                     "d2h_bytes_per_step": BATCH * CT_WORDS * 4, "ms_per_step": e2e_ms / args.steps,

@@ -13,9 +13,10 @@ All compute goes through the C ABI in include/tfhe_b200.h (librustfhe_b200.so, C
 without the library or without a B200 the compute calls raise.
 """
 from ._capi import (AND, ANDNY, COPY, MASK_CORRECTED, MASK_FAITHFUL, NAND, NOT, OR, XOR, BK_WORDS, KSK_WORDS, TfheError)
+from . import circuit
 from .api import (TFHE, TLWE, BootstrappingKey, Cryptor, KeySwitchingKey, SecretKeys, TFHEHelper, TLWEHelper, TLWERep,
                   TRGSWHelper, TRLWEHelper, DeviceEngine)
 
-__all__ = ["TFHE", "TLWE", "BootstrappingKey", "Cryptor", "KeySwitchingKey", "SecretKeys", "TFHEHelper", "TLWEHelper",
+__all__ = ["circuit", "TFHE", "TLWE", "BootstrappingKey", "Cryptor", "KeySwitchingKey", "SecretKeys", "TFHEHelper", "TLWEHelper",
            "TLWERep", "TRGSWHelper", "TRLWEHelper", "DeviceEngine", "TfheError", "NAND", "AND", "OR", "XOR", "NOT", "COPY",
            "ANDNY", "MASK_FAITHFUL", "MASK_CORRECTED", "BK_WORDS", "KSK_WORDS"]

@@ -1,0 +1,225 @@
+"""Circuit front-end over the batched gate engine (BASELINE config 4).
+
+The reference evaluates logic expressions depth-first, ONE bootstrapped gate at a time (`eval_logic_expr`,
+nander/src/lib.rs:72-89).  Independent gates are where the GPU's throughput comes from, so this module levelises a gate
+netlist and submits every level as batched calls (one `tfhe_b200_gate_batch*` per opcode per level).
+
+Mirrored reference interface (nander/src/lib.rs):
+  parse_logic_expr(str) -> LogicExpr        grammar `0 1 & | ^ ! $ ( )`, left-assoc, no precedence   lib.rs:90-172
+  eval_logic_expr(pros, expr)               pros = TFHE (native gates, lib.rs:40-62)                    lib.rs:72-89
+  Logip mapping for TFHE: nand/not/and/or/xor -> hom_nand/hom_not/hom_and/hom_or/hom_xor               lib.rs:40-62
+Leaves are TRIVIAL ciphertexts TLWERep::logic_true/false (tlwe.rs:80-87), as in the reference.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi as K
+
+NAND, AND, OR, XOR, NOT = K.NAND, K.AND, K.OR, K.XOR, K.NOT
+_SYM = {"&": AND, "|": OR, "^": XOR, "$": NAND}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# nander grammar
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class LogicExpr:
+    """LogicExpr<R> (nander/src/lib.rs:64-71): kind in {'nand','not','and','or','xor','leaf'}."""
+    kind: str
+    lhs: "LogicExpr" = None
+    rhs: "LogicExpr" = None
+    value: int = 0
+
+
+def parse_logic_expr(text):
+    """nander/src/lib.rs:90-172.  Whitespace is dropped; binary operators are left-associative without precedence; `!`
+    binds to the following element; input after a complete expression is ignored, like the reference.
+    Raises ValueError with the reference's messages."""
+    s = [c for c in text.strip() if not c.isspace()]
+    pos = 0
+
+    def peek():
+        return s[pos] if pos < len(s) else None
+
+    def parse_elem():
+        nonlocal pos
+        c = peek()
+        if c is None:
+            raise ValueError("invalid element. this is none")
+        pos += 1
+        if c == "0":
+            return LogicExpr("leaf", value=0)
+        if c == "1":
+            return LogicExpr("leaf", value=1)
+        if c == "(":
+            e = parse_binary()
+            if peek() != ")":
+                raise ValueError("braket is not closed")
+            pos += 1
+            return e
+        raise ValueError("invalid element")
+
+    def parse_mono():
+        nonlocal pos
+        if peek() == "!":
+            pos += 1
+            return LogicExpr("not", lhs=parse_mono())
+        return parse_elem()
+
+    def parse_binary():
+        nonlocal pos
+        lhs = parse_mono()
+        while peek() in _SYM:
+            op = {"&": "and", "|": "or", "^": "xor", "$": "nand"}[peek()]
+            pos += 1
+            lhs = LogicExpr(op, lhs=lhs, rhs=parse_mono())
+        return lhs
+
+    return parse_binary()
+
+
+def eval_logic_expr_plain(expr):
+    """Cleartext semantics of a LogicExpr (what the decrypted result must equal)."""
+    k = expr.kind
+    if k == "leaf":
+        return expr.value
+    a = eval_logic_expr_plain(expr.lhs)
+    if k == "not":
+        return 1 - a
+    b = eval_logic_expr_plain(expr.rhs)
+    return {"nand": 1 - (a & b), "and": a & b, "or": a | b, "xor": a ^ b}[k]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# netlists
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class Netlist:
+    """Gate netlist over wires 0..n_wires-1. Wires [0, n_inputs) are primary inputs; `consts` maps wire -> 0/1 (trivial
+    ciphertexts).  gates: (op, in0, in1 or -1, out)."""
+    n_inputs: int = 0
+    n_wires: int = 0
+    gates: list = field(default_factory=list)
+    consts: dict = field(default_factory=dict)
+    outputs: list = field(default_factory=list)
+
+    def new_wire(self):
+        self.n_wires += 1
+        return self.n_wires - 1
+
+    def add_inputs(self, k):
+        assert self.n_wires == self.n_inputs, "declare inputs first"
+        first = self.n_wires
+        self.n_inputs += k
+        self.n_wires += k
+        return list(range(first, first + k))
+
+    def const(self, bit):
+        w = self.new_wire()
+        self.consts[w] = int(bit)
+        return w
+
+    def gate(self, op, a, b=-1):
+        out = self.new_wire()
+        self.gates.append((op, a, b, out))
+        return out
+
+    def nand(self, a, b):
+        return self.gate(NAND, a, b)
+
+    def levels(self):
+        """ASAP levelisation: level(g) = 1 + max(level of its inputs); inputs and constants are level 0.
+        Returns a list of levels, each a dict op -> (in0 idx array, in1 idx array, out idx array)."""
+        lvl = np.zeros(self.n_wires, np.int64)
+        per = {}
+        for op, a, b, out in self.gates:
+            l = 1 + max(lvl[a], lvl[b] if b >= 0 else 0)
+            lvl[out] = l
+            per.setdefault(int(l), {}).setdefault(op, []).append((a, b if b >= 0 else a, out))
+        res = []
+        for l in sorted(per):
+            res.append({op: tuple(np.array(col, np.int64) for col in zip(*g)) for op, g in per[l].items()})
+        return res
+
+    def simulate(self, input_bits):
+        """Cleartext evaluation (oracle for the tests)."""
+        v = np.zeros(self.n_wires, np.uint8)
+        v[:self.n_inputs] = np.asarray(input_bits, np.uint8)
+        for w, bit in self.consts.items():
+            v[w] = bit
+        for op, a, b, out in self.gates:
+            x, y = int(v[a]), int(v[b]) if b >= 0 else 0
+            v[out] = {NAND: 1 - (x & y), AND: x & y, OR: x | y, XOR: x ^ y, NOT: 1 - x}[op]
+        return v[self.outputs] if self.outputs else v
+
+
+def ripple_carry_adder(nbits=32):
+    """NAND-only ripple-carry adder (BASELINE config 4): bit 0 = 5-NAND half adder, bits 1.. = 9-NAND full adders.
+    Inputs: x[0..nbits), y[0..nbits) little endian; outputs: nbits sum bits + carry out."""
+    nl = Netlist()
+    x = nl.add_inputs(nbits)
+    y = nl.add_inputs(nbits)
+    t = nl.nand(x[0], y[0])
+    s = nl.nand(nl.nand(x[0], t), nl.nand(t, y[0]))
+    c = nl.nand(t, t)
+    outs = [s]
+    for i in range(1, nbits):
+        x1 = nl.nand(x[i], y[i])
+        s1 = nl.nand(nl.nand(x[i], x1), nl.nand(y[i], x1))   # x ^ y
+        x4 = nl.nand(s1, c)
+        outs.append(nl.nand(nl.nand(s1, x4), nl.nand(c, x4)))  # x ^ y ^ c
+        c = nl.nand(x1, x4)                                    # majority
+    outs.append(c)
+    nl.outputs = outs
+    return nl
+
+
+def expr_to_netlist(expr):
+    """Compile a LogicExpr with the TFHE Logip mapping (native and/or/xor/not gates, nander/src/lib.rs:40-62)."""
+    nl = Netlist()
+
+    def rec(e):
+        if e.kind == "leaf":
+            return nl.const(e.value)
+        a = rec(e.lhs)
+        if e.kind == "not":
+            return nl.gate(NOT, a)
+        b = rec(e.rhs)
+        return nl.gate({"nand": NAND, "and": AND, "or": OR, "xor": XOR}[e.kind], a, b)
+
+    nl.outputs = [rec(expr)]
+    return nl
+
+
+# ------------------------------------------------------------------------------------------------------------
+# batched evaluation
+# ------------------------------------------------------------------------------------------------------------
+def evaluate(engine, netlist, inputs=None, stats=None):
+    """Level-synchronous evaluation on one device context.  `inputs`: uint32 [n_inputs][n+1] ciphertexts.
+    Host-side wire table + one engine.gate_batch call per (level, opcode).  Returns the output ciphertexts."""
+    W = K.n + 1
+    wires = np.zeros((netlist.n_wires, W), np.uint32)
+    if netlist.n_inputs:
+        wires[:netlist.n_inputs] = np.ascontiguousarray(inputs, np.uint32).reshape(netlist.n_inputs, W)
+    for w, bit in netlist.consts.items():
+        wires[w, 0] = 0x20000000 if bit else 0xE0000000
+    levels = netlist.levels()
+    hist = []
+    for lev in levels:
+        width = 0
+        for op, (i0, i1, o) in lev.items():
+            out = engine.gate_batch(op, wires[i0], None if op == NOT else wires[i1])
+            wires[o] = out
+            width += len(o)
+        hist.append(width)
+    if stats is not None:
+        stats["levels"] = len(levels)
+        stats["width_histogram"] = hist
+        stats["gates"] = len(netlist.gates)
+    return wires[netlist.outputs] if netlist.outputs else wires
+
+
+def eval_logic_expr(pros, expr):
+    """eval_logic_expr(&pros, exp) (nander/src/lib.rs:72-89) for pros = TFHE, evaluated level by level in batches."""
+    return evaluate(pros.engine, expr_to_netlist(expr))

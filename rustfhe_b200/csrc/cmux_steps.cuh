@@ -33,10 +33,9 @@ TFHE_HD size_t bk_off(int i, int poly, int part, int j, int q, int lane) {
 TFHE_HD uint32_t rot_diff(const uint32_t* A, uint32_t k, uint32_t abar) {
     const uint32_t ap = abar & 1023u;
     const uint32_t v = A[k];
-    uint32_t rv = A[(k - ap) & 1023u];
-    const bool neg = (k < ap) != ((abar >> 10) != 0);
-    rv = neg ? 0u - rv : rv;
-    return rv - v;
+    const uint32_t rv = A[(k - ap) & 1023u];
+    const uint32_t m = ((k < ap) != ((abar >> 10) != 0)) ? 0xFFFFFFFFu : 0u;  // negate rv when m = ~0:  -rv = (rv ^ m) - m
+    return (rv ^ m) - m - v;
 }
 
 // ---- phase 1a: lane = column c.  Build digit `dw` of the source polynomial, column NTT, scatter into tile S ----
@@ -67,9 +66,11 @@ TFHE_HD void fwd_rows(int lane, uint32_t* S, const uint32_t* twF, uint32_t (&x)[
         const uint4 v = *reinterpret_cast<const uint4*>(S + swz_chunk(lane, q));
         x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
     }
+#pragma unroll
+    for (int c = 0; c < 32; c++) x[c] = csub(csub(x[c], 2u * P2), P2);  // column pass leaves < 8p; row pass wants < 2p
     ct32(x, TwRow{twF + lane * TWB_STRIDE});
 #pragma unroll
-    for (int c = 0; c < 32; c++) x[c] = csub(csub(x[c], P2), P);
+    for (int c = 0; c < 32; c++) x[c] = csub(csub(csub(x[c], 2u * P2), P2), P);  // < 8p -> [0,p)
 }
 TFHE_HD void p1b(int lane, uint32_t* S, const uint32_t* twF) {
     uint32_t x[32];
@@ -81,8 +82,7 @@ TFHE_HD void p1b(int lane, uint32_t* S, const uint32_t* twF) {
 
 // ---- phase 2a: lane = row r.  MAC over the 6 digit spectra against this warp's key slab, row INTT, store ----
 // dh: 6 planes of 1024 words (row layout written by p1b); slab: BK_SLAB_WORDS words for (step, poly, part)
-TFHE_HD void p2a(int lane, const uint32_t* slab, const uint32_t* dh, const uint32_t* twI, uint32_t* S) {
-    uint32_t x[32];
+TFHE_HD void p2a_mac(int lane, const uint32_t* slab, const uint32_t* dh, uint32_t (&x)[32]) {
 #pragma unroll
     for (int q = 0; q < 8; q++) {
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
@@ -98,6 +98,10 @@ TFHE_HD void p2a(int lane, const uint32_t* slab, const uint32_t* dh, const uint3
         }
         x[4 * q] = redc64(a0); x[4 * q + 1] = redc64(a1); x[4 * q + 2] = redc64(a2); x[4 * q + 3] = redc64(a3);
     }
+}
+TFHE_HD void p2a(int lane, const uint32_t* slab, const uint32_t* dh, const uint32_t* twI, uint32_t* S) {
+    uint32_t x[32];
+    p2a_mac(lane, slab, dh, x);
     gs32(x, TwRow{twI + lane * TWB_STRIDE});
 #pragma unroll
     for (int q = 0; q < 8; q++)

@@ -70,6 +70,22 @@ struct BrArgs {
     long ntrgsw;
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
 template <int G, bool EXTPROD, int MINB>
 __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel(const BrArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -83,6 +99,7 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     uint32_t* dh = acc + 2 * 1024;
     uint32_t* sp = dh + 6 * 1024;
     uint16_t* abar = reinterpret_cast<uint16_t*>(sp + 6 * 1024);
+    uint64_t* macdone = reinterpret_cast<uint64_t*>(sp + 6 * 1024 + 318);  // abar uses 635 u16 = 317.5 words of its 320
 
     const long gate_raw = (long)blockIdx.x * G + gl;
     const bool active = gate_raw < a.B;
@@ -92,6 +109,7 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         twF[t] = g_fwdB[t];
         twI[t] = g_invB[t];
     }
+    if (tid6 == 0) mbar_init(macdone, WARPS_PER_GATE);
     // ---- prologue: gate pre-combination (tfhe.rs:27-71), rounding of (b, a) (tfhe.rs:97,107-108), acc_0 ----
     int nsteps = a.nsteps;
     if (EXTPROD) {
@@ -121,34 +139,47 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     __syncthreads();
 
     // ---- 635 x CMUX ----
+    // Synchronisation per step (named barriers, so gates sharing a CTA and the two polynomials of a gate decouple):
+    //   macdone (mbarrier, 6 arrivals) : every warp finished READING the digit spectra dh[] of the previous step
+    //   B1 gate barrier (192 threads)  : the 6 digit spectra of this step are complete
+    //   B2 poly barrier (96 threads)   : the 3 key-slice outputs of this polynomial are complete
+    //   B3 poly barrier (96 threads)   : acc[poly] is updated
+    const int bar_gate = 1 + gl, bar_poly = 1 + G + 2 * gl + pw;
+    const int tid3 = tid6 - pw * 96;
+    uint32_t mac_parity = 0;
 #pragma unroll 1
     for (int i = 0; i < nsteps; i++) {
         const uint32_t* step_bk = a.bkdev + (EXTPROD ? (size_t)(gate % a.ntrgsw) : (size_t)i) * BK_STEP_WORDS;
+        if (i > 0) { mbar_wait(macdone, mac_parity); mac_parity ^= 1u; }
         {   // phase 1: digit kw of poly pw -> spectrum plane dh[w6]
             uint32_t* S = dh + w6 * 1024;
             p1a<!EXTPROD>(lane, acc + pw * 1024, EXTPROD ? 0u : (uint32_t)abar[i], a.mask, kw, S);
             __syncwarp();
             p1b(lane, S, twF);
         }
-        __syncthreads();
+        bar_sync(bar_gate, THREADS_PER_GATE);
         {   // phase 2: key slice kw of output poly pw
             uint32_t* S = sp + w6 * 1024;
             uint32_t x[32];
-            p2a(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, dh, twI, S);
+            p2a_mac(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, dh, x);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(macdone);
+            inv_rows(lane, x, twI, S);
             __syncwarp();
             p2b(lane, S, kw, x);
             __syncwarp();
             p2c(lane, S, x);
         }
-        __syncthreads();
-        // phase 3: acc += sum of the three slices (EXTPROD: acc = sum)
-        for (int k = tid6; k < 2048; k += THREADS_PER_GATE) {
-            const int p = k >> 10, kk = k & 1023;
-            const uint32_t s = sp[(3 * p) * 1024 + kk] + sp[(3 * p + 1) * 1024 + kk] + sp[(3 * p + 2) * 1024 + kk];
-            acc[k] = EXTPROD ? s : acc[k] + s;
+        bar_sync(bar_poly, 96);
+        // phase 3: acc[pw] += sum of its three slices (EXTPROD: acc = sum), done by the 3 warps of this polynomial
+        for (int k = tid3; k < 1024; k += 96) {
+            const uint32_t* q = sp + (3 * pw) * 1024 + k;
+            const uint32_t sum = q[0] + q[1024] + q[2048];
+            acc[pw * 1024 + k] = EXTPROD ? sum : acc[pw * 1024 + k] + sum;
         }
-        __syncthreads();
+        bar_sync(bar_poly, 96);
     }
+    bar_sync(bar_gate, THREADS_PER_GATE);
 
     // ---- epilogue: sample_extract_index(0) (trlwe.rs:110-121) + key-switch digits (tlwe.rs:47-64) ----
     if (!active) return;
@@ -377,6 +408,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<3, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(3))) != cudaSuccess) return bail("smem attr", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_kernel<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(2))) != cudaSuccess) return bail("smem attr", e);
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
     *out = ctx;
@@ -505,6 +537,10 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
     } else if (pair && ctx->variant == 2) {
         blind_rotate_kernel<1, false, 2><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
         ctx->gates_per_cta = 1;
+    } else if (pair && ctx->variant == 4) {
+        const unsigned grid = (unsigned)((a.B + 2) / 3);
+        blind_rotate_kernel<3, false, 1><<<grid, 3 * THREADS_PER_GATE, br_smem_bytes(3), st>>>(a);
+        ctx->gates_per_cta = 3;
     } else if (pair && ctx->variant == 3) {
         blind_rotate_kernel<1, false, 3><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
         ctx->gates_per_cta = 1;

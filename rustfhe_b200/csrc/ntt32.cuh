@@ -109,13 +109,17 @@ struct TwRow {  // pass B: per-thread row (shared memory on the device), 16-byte
 };
 
 // ---- 32-point merged-twist Cooley-Tukey network on registers; values stay in [0,4p) ----
+// CORR = 0: no correction (bound grows by 2p), CORR = 4: conditional subtraction of 4p first.  Any 32-bit value is a
+// legal Shoup input, so only the pass-through operand needs its range watched; 8p < 2^32 leaves room for three
+// uncorrected stages.  Range bookkeeping (upper bounds, in units of p) is in ct32 below.
+template <int CORR>
 TFHE_HD void ct_bfly(uint32_t& a, uint32_t& b, uint32_t w, uint32_t ws) {
-    const uint32_t X = csub(a, P2);
+    const uint32_t X = CORR ? csub(a, 2u * P2) : a;
     const uint32_t T = shoup_mul(b, w, ws);
     a = add_alu(X, T);
     b = X - T + P2;
 }
-template <int S, class TW>
+template <int S, int CORR, class TW>
 TFHE_HD void ct_stage(uint32_t (&x)[32], const TW& tw) {  // stage S = 1..4: m = 2^S blocks of half-width t = 16 >> S
     constexpr int m = 1 << S, t = 16 >> S;
 #pragma unroll
@@ -123,23 +127,25 @@ TFHE_HD void ct_stage(uint32_t (&x)[32], const TW& tw) {  // stage S = 1..4: m =
         uint32_t w0, ws0, w1, ws1;
         tw.get2(m + i, w0, ws0, w1, ws1);
 #pragma unroll
-        for (int j = 0; j < t; j++) ct_bfly(x[2 * i * t + j], x[2 * i * t + j + t], w0, ws0);
+        for (int j = 0; j < t; j++) ct_bfly<CORR>(x[2 * i * t + j], x[2 * i * t + j + t], w0, ws0);
 #pragma unroll
-        for (int j = 0; j < t; j++) ct_bfly(x[2 * (i + 1) * t + j], x[2 * (i + 1) * t + j + t], w1, ws1);
+        for (int j = 0; j < t; j++) ct_bfly<CORR>(x[2 * (i + 1) * t + j], x[2 * (i + 1) * t + j + t], w1, ws1);
     }
 }
+// Input bound: x < 2p.  Bounds after each stage (a butterfly outputs < X + 2p, csub(.,4p) maps [0,8p) to [0,4p)):
+//   s0: 4p   s1: 6p   s2: 8p   s3 (corrected to 4p): 6p   s4: 8p        -> output < 8p < 2^32
 template <class TW>
 TFHE_HD void ct32(uint32_t (&x)[32], const TW& tw) {
     {
         uint32_t w, ws;
         tw.get(1, w, ws);
 #pragma unroll
-        for (int j = 0; j < 16; j++) ct_bfly(x[j], x[j + 16], w, ws);
+        for (int j = 0; j < 16; j++) ct_bfly<0>(x[j], x[j + 16], w, ws);
     }
-    ct_stage<1>(x, tw);
-    ct_stage<2>(x, tw);
-    ct_stage<3>(x, tw);
-    ct_stage<4>(x, tw);
+    ct_stage<1, 0>(x, tw);
+    ct_stage<2, 0>(x, tw);
+    ct_stage<3, 4>(x, tw);
+    ct_stage<4, 0>(x, tw);
 }
 // ---- 32-point Gentleman-Sande network (exact mirror); values stay in [0,2p) ----
 TFHE_HD void gs_bfly(uint32_t& a, uint32_t& b, uint32_t w, uint32_t ws) {
@@ -183,10 +189,12 @@ TFHE_HD int swz_chunk(int r, int q) { return r * 32 + ((q ^ (r & 7)) << 2); }
 // ---- decomposition pieces (reference: utils/src/math.rs:300-326 with the mask of math.rs:542-560) ----
 // digit `dw` (0 = most significant) of x after the mask trick, sign-extended from 6 bits
 TFHE_HD int32_t gadget_digit(uint32_t x, uint32_t mask, int dw) {
-    const uint32_t u = (x + mask) ^ mask;
+    const uint32_t u = add_alu(x, mask) ^ mask;
     return ((int32_t)(u << (6 * dw))) >> 26;
 }
-TFHE_HD uint32_t to_residue(int32_t v) { return (uint32_t)v + (v < 0 ? P : 0u); }
+// residue of a small signed integer: for v < 0 the unsigned value is huge and v + p wraps to the residue, so it is
+// min(v, v + p) in unsigned arithmetic -- one VIADDMNMX
+TFHE_HD uint32_t to_residue(int32_t v) { return csub((uint32_t)v, 0u - P); }
 
 // centred 11/11/10-bit slices of a torus word: c0 + 2^11 c1 + 2^22 c2 == C (mod 2^32), |c0|,|c1| <= 1024, |c2| <= 512
 TFHE_HD int32_t key_slice(uint32_t C, int part) {

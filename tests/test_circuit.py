@@ -1,0 +1,96 @@
+"""Circuit front-end: nander grammar (nander/src/lib.rs:90-172), netlist levelisation, 32-bit ripple-carry adder (config 4).
+CPU tests check the host logic against cleartext simulation; the GPU test evaluates the encrypted adder."""
+import numpy as np
+import pytest
+
+from rustfhe_b200 import circuit as Cq
+
+
+def test_parse_examples_from_the_repl_banner():
+    """examples printed by nander_console (nander/src/main.rs:27-31): 1&1 => 1 ; !(1|0)$0 => 1 ; 1&1$0 => (1&1)$0"""
+    assert Cq.eval_logic_expr_plain(Cq.parse_logic_expr("1&1")) == 1
+    assert Cq.eval_logic_expr_plain(Cq.parse_logic_expr("!(1|0)$0")) == 1
+    e = Cq.parse_logic_expr(" 1 & 1 $ 0 ")
+    assert e.kind == "nand" and e.lhs.kind == "and" and Cq.eval_logic_expr_plain(e) == 1
+    assert Cq.eval_logic_expr_plain(Cq.parse_logic_expr("!!1^1|0")) == 0      # ((!!1)^1)|0, no precedence
+    assert Cq.eval_logic_expr_plain(Cq.parse_logic_expr("1)garbage")) == 1    # trailing input ignored like the reference
+
+
+@pytest.mark.parametrize("bad,msg", [("(1&0", "braket is not closed"), ("1&", "invalid element. this is none"),
+                                     ("a", "invalid element"), ("", "invalid element. this is none")])
+def test_parse_errors(bad, msg):
+    with pytest.raises(ValueError) as ei:
+        Cq.parse_logic_expr(bad)
+    assert str(ei.value) == msg
+
+
+def test_adder_netlist_and_levels(rng):
+    nl = Cq.ripple_carry_adder(32)
+    assert len(nl.gates) == 5 + 31 * 9 and nl.n_inputs == 64 and len(nl.outputs) == 33
+    assert all(op == Cq.NAND for op, *_ in nl.gates)
+    for _ in range(20):
+        x, y = int(rng.integers(0, 2 ** 32)), int(rng.integers(0, 2 ** 32))
+        bits = [(x >> i) & 1 for i in range(32)] + [(y >> i) & 1 for i in range(32)]
+        out = nl.simulate(bits)
+        assert sum(int(b) << i for i, b in enumerate(out)) == x + y
+    lv = nl.levels()
+    widths = [sum(len(o) for (_, _, o) in l.values()) for l in lv]
+    assert sum(widths) == len(nl.gates)
+    assert widths[0] == 32                        # every x_i NAND y_i is independent of the carry chain
+    assert len(lv) < 2 * 32 + 8                   # carry chain: ~2 levels per bit
+    # a level only reads wires produced by earlier levels
+    ready = set(range(nl.n_inputs)) | set(nl.consts)
+    for l in lv:
+        outs = set()
+        for (i0, i1, o) in l.values():
+            assert set(i0.tolist()) <= ready and set(i1.tolist()) <= ready
+            outs |= set(o.tolist())
+        ready |= outs
+
+
+def test_expr_netlist_matches_plain(rng):
+    for text in ("1&0|1^1", "!(1$1)&(0|!0)", "((1^1)^(1^0))$!(0&1)", "1"):
+        e = Cq.parse_logic_expr(text)
+        nl = Cq.expr_to_netlist(e)
+        assert int(nl.simulate([])[0]) == Cq.eval_logic_expr_plain(e)
+
+
+def test_evaluate_with_oracle_engine(oracle, keys):
+    """the level-synchronous evaluator driven by the CPU oracle standing in for the device engine (host logic only)"""
+    class OracleEngine:
+        def gate_batch(self, op, a, b=None):
+            return oracle.gate_exact(keys, op, a, b)
+    nl = Cq.ripple_carry_adder(2)
+    x, y = 3, 2
+    bits = np.array([(x >> i) & 1 for i in range(2)] + [(y >> i) & 1 for i in range(2)], np.uint8)
+    st = {}
+    out = Cq.evaluate(OracleEngine(), nl, keys.encrypt(bits, 555), st)
+    got = keys.decrypt(out)
+    assert sum(int(b) << i for i, b in enumerate(got)) == x + y
+    assert st["gates"] == 14 and sum(st["width_histogram"]) == 14
+
+
+@pytest.mark.gpu
+def test_encrypted_32bit_adder_on_gpu(engine, keys, rng):
+    """config 4: two encrypted u32 (seed S+2), 284 NAND gates levelised; 33 output bits must equal x + y"""
+    r = np.random.default_rng(0x5EED0001 + 2)
+    x, y = int(r.integers(0, 2 ** 32)), int(r.integers(0, 2 ** 32))
+    bits = np.array([(x >> i) & 1 for i in range(32)] + [(y >> i) & 1 for i in range(32)], np.uint8)
+    nl = Cq.ripple_carry_adder(32)
+    st = {}
+    out = Cq.evaluate(engine, nl, keys.encrypt(bits, 31337), st)
+    got = keys.decrypt(out)
+    assert sum(int(b) << i for i, b in enumerate(got)) == x + y
+    assert st["levels"] == len(st["width_histogram"])
+
+
+@pytest.mark.gpu
+def test_nander_expressions_on_gpu(engine, keys):
+    class P:  # minimal `pros` carrying the engine, as TFHE does
+        pass
+    p = P()
+    p.engine = engine
+    for text in ("1&1", "!(1|0)$0", "1&1$0", "!(1$1)&(0|!0)^1"):
+        e = Cq.parse_logic_expr(text)
+        out = Cq.eval_logic_expr(p, e)
+        assert int(keys.decrypt(out)[0]) == Cq.eval_logic_expr_plain(e), text
