@@ -1,0 +1,117 @@
+#!/usr/bin/env python3
+"""Secondary measurements for BASELINE.json configs 3, 4 and 5 (bench.py covers configs 1-2).  GPU box only.
+
+  config 3: negacyclic poly-mul and external-product micro-bench, N=1024, batch sweep          (host-buffer C ABI calls)
+  config 4: 32-bit ripple-carry adder (284 NAND gates, levelised) wall time + level-width histogram
+  config 5: throughput of large random-bit NAND batches (device-resident), 2^12 .. 2^17 gates on this GPU
+Writes one JSON document to stdout / --out.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--max-log2", type=int, default=17)
+    args = ap.parse_args()
+    import torch
+    import rustfhe_b200 as R
+    from rustfhe_b200 import _capi as K
+    from rustfhe_b200 import circuit as Cq
+
+    seed = 0x5EED0001
+    sk = R.SecretKeys.generate(seed)
+    tfhe = R.TFHE.new(sk.s_key_tlwelv0, sk.s_key_tlwelv1, seed)
+    eng = tfhe.engine
+    rng = np.random.default_rng(seed + 3)
+    res = {"gpu": torch.cuda.get_device_name(0)}
+
+    def timed(fn, reps=3):
+        fn()
+        best = 1e30
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        return best
+
+    # ---- config 3 ----
+    pm, xp = [], []
+    for lb in range(0, 17, 2):
+        B = 1 << lb
+        a = rng.integers(0, 2 ** 32, (B, 1024), dtype=np.uint64).astype(np.uint32)
+        d = rng.integers(-32, 32, (B, 1024)).astype(np.int32)
+        t = timed(lambda: eng.negacyclic_mul_batch(a, d))
+        pm.append({"batch": B, "seconds": t, "products_per_s": B / t})
+        if B <= 16384:
+            trl = rng.integers(0, 2 ** 32, (B, 2, 1024), dtype=np.uint64).astype(np.uint32)
+            trg = rng.integers(0, 2 ** 32, (1, 6, 2, 1024), dtype=np.uint64).astype(np.uint32)
+            t = timed(lambda: eng.external_product_batch(trg, trl))
+            xp.append({"batch": B, "shared_trgsw": True, "seconds": t, "external_products_per_s": B / t})
+    res["config3_negacyclic_mul_host_io"] = pm
+    res["config3_external_product_host_io"] = xp
+
+    # ---- config 4 ----
+    r = np.random.default_rng(seed + 2)
+    x, y = int(r.integers(0, 2 ** 32)), int(r.integers(0, 2 ** 32))
+    bits = np.array([(x >> i) & 1 for i in range(32)] + [(y >> i) & 1 for i in range(32)], np.uint8)
+    nl = Cq.ripple_carry_adder(32)
+    cts = R.Cryptor.encrypto(R.TLWE, sk.s_key_tlwelv0, bits, seed=seed + 2, ct_index0=0)
+    st = {}
+    Cq.evaluate(eng, nl, cts, st)
+    t0 = time.perf_counter()
+    out = Cq.evaluate(eng, nl, cts, st)
+    wall = time.perf_counter() - t0
+    got = R.Cryptor.decrypto(R.TLWE, sk.s_key_tlwelv0, out)
+    res["config4_adder32"] = {"gates": st["gates"], "levels": st["levels"], "width_histogram": st["width_histogram"],
+                              "wall_seconds_1gpu": wall, "correct": bool(sum(int(b) << i for i, b in enumerate(got)) == x + y),
+                              "note": "latency bound: carry chain gives ~2 levels per bit of width <= 3; does not scale with GPUs"}
+
+    # ---- config 5 (single GPU part) ----
+    sweep = []
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    for lb in range(12, args.max_log2 + 1):
+        B = 1 << lb
+        base = 4096
+        bx = rng.integers(0, 2, base).astype(np.uint8)
+        by = rng.integers(0, 2, base).astype(np.uint8)
+        cx = R.Cryptor.encrypto(R.TLWE, sk.s_key_tlwelv0, bx, seed=seed + 5, ct_index0=0)
+        cy = R.Cryptor.encrypto(R.TLWE, sk.s_key_tlwelv0, by, seed=seed + 6, ct_index0=0)
+        reps = B // base
+        dx = torch.from_numpy(np.tile(cx, (reps, 1)).view(np.int32)).to(dev)
+        dy = torch.from_numpy(np.tile(cy, (reps, 1)).view(np.int32)).to(dev)
+        do = torch.empty_like(dx)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.gate_batch_device(K.NAND, dx.data_ptr(), dy.data_ptr(), do.data_ptr(), B, stream.cuda_stream)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        eng.gate_batch_device(K.NAND, dx.data_ptr(), dy.data_ptr(), do.data_ptr(), B, stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        idx = rng.choice(B, 4096, replace=False)
+        got = R.Cryptor.decrypto(R.TLWE, sk.s_key_tlwelv0, do[torch.from_numpy(idx).to(dev)].cpu().numpy().view(np.uint32))
+        want = 1 - (np.tile(bx, reps)[idx] & np.tile(by, reps)[idx])
+        sweep.append({"gates": B, "ms": ms, "gates_per_s": B / (ms * 1e-3), "wrong_in_4096_sample": int((got != want).sum())})
+        del dx, dy, do
+    res["config5_sweep_1gpu"] = sweep
+    txt = json.dumps(res, indent=1)
+    if args.out:
+        open(args.out, "w").write(txt)
+    print(txt)
+
+
+if __name__ == "__main__":
+    main()
