@@ -48,7 +48,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    path = os.environ.get("TFHE_B200_LIB") or _build.build()  # override: experiment builds of the same sources
     l = C.CDLL(path)
     vp, sz, u64, i32, u32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32
     sig = {

@@ -88,12 +88,14 @@ TFHE_HD void p2a_mac(int lane, const uint32_t* slab, const uint32_t* dh, uint32_
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
         for (int j = 0; j < BK_ROWS; j++) {
-#if defined(__CUDA_ARCH__)
+            const uint4 d = *reinterpret_cast<const uint4*>(dh + j * NPOLY + swz_chunk(lane, q));
+#if defined(TFHE_EXP_NOBK)   /* timing experiment only: no key traffic */
+            const uint4 b = make_uint4(d.y, d.z, d.w, d.x);
+#elif defined(__CUDA_ARCH__)
             const uint4 b = __ldg(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
 #else
             const uint4 b = *(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
 #endif
-            const uint4 d = *reinterpret_cast<const uint4*>(dh + j * NPOLY + swz_chunk(lane, q));
             a0 += (uint64_t)d.x * b.x; a1 += (uint64_t)d.y * b.y; a2 += (uint64_t)d.z * b.z; a3 += (uint64_t)d.w * b.w;
         }
         x[4 * q] = redc64(a0); x[4 * q + 1] = redc64(a1); x[4 * q + 2] = redc64(a2); x[4 * q + 3] = redc64(a3);

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) bk_transform_kernel(const uint3
 // =====================================================================================================
 constexpr int WARPS_PER_GATE = 6;
 constexpr int THREADS_PER_GATE = WARPS_PER_GATE * 32;
-constexpr int GATE_SMEM_WORDS = 2 * 1024 /*acc*/ + 6 * 1024 /*dh*/ + 6 * 1024 /*sp*/ + 320 /*abar u16[640]*/;
+constexpr int GATE_SMEM_WORDS = 2 * 1024 /*acc*/ + 6 * 1024 /*dh: digit spectra / transpose scratch*/ + 320 /*abar u16[640]*/;
 constexpr int TW_SMEM_WORDS = 2 * 32 * TWB_STRIDE;
 constexpr size_t br_smem_bytes(int G) { return (size_t)(TW_SMEM_WORDS + G * GATE_SMEM_WORDS) * 4; }
 
@@ -71,7 +71,11 @@ struct BrArgs {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+#if !defined(TFHE_EXP_NOBAR)   /* timing experiment only */
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
@@ -79,6 +83,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+#if defined(TFHE_EXP_NOBAR)
+    return;
+#endif
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -97,9 +104,8 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     const int tid6 = threadIdx.x - gl * THREADS_PER_GATE;
     uint32_t* acc = smem + TW_SMEM_WORDS + gl * GATE_SMEM_WORDS;
     uint32_t* dh = acc + 2 * 1024;
-    uint32_t* sp = dh + 6 * 1024;
-    uint16_t* abar = reinterpret_cast<uint16_t*>(sp + 6 * 1024);
-    uint64_t* macdone = reinterpret_cast<uint64_t*>(sp + 6 * 1024 + 318);  // abar uses 635 u16 = 317.5 words of its 320
+    uint16_t* abar = reinterpret_cast<uint16_t*>(dh + 6 * 1024);
+    uint64_t* macdone = reinterpret_cast<uint64_t*>(dh + 6 * 1024 + 318);  // abar uses 635 u16 = 317.5 words of its 320
 
     const long gate_raw = (long)blockIdx.x * G + gl;
     const bool active = gate_raw < a.B;
@@ -140,44 +146,47 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
 
     // ---- 635 x CMUX ----
     // Synchronisation per step (named barriers, so gates sharing a CTA and the two polynomials of a gate decouple):
-    //   macdone (mbarrier, 6 arrivals) : every warp finished READING the digit spectra dh[] of the previous step
     //   B1 gate barrier (192 threads)  : the 6 digit spectra of this step are complete
-    //   B2 poly barrier (96 threads)   : the 3 key-slice outputs of this polynomial are complete
-    //   B3 poly barrier (96 threads)   : acc[poly] is updated
+    //   macdone (mbarrier, 6 arrivals) : every warp finished READING the digit spectra dh[] -> a warp may reuse its own
+    //                                    plane dh[w6] as the transpose scratch of its inverse transform
+    //   3 poly barriers (96 threads)   : the three key-slice warps of a polynomial add their exact slice into acc[poly]
+    //                                    one after the other (no separate output planes: 24 KB less shared memory per gate)
     const int bar_gate = 1 + gl, bar_poly = 1 + G + 2 * gl + pw;
-    const int tid3 = tid6 - pw * 96;
     uint32_t mac_parity = 0;
 #pragma unroll 1
     for (int i = 0; i < nsteps; i++) {
         const uint32_t* step_bk = a.bkdev + (EXTPROD ? (size_t)(gate % a.ntrgsw) : (size_t)i) * BK_STEP_WORDS;
-        if (i > 0) { mbar_wait(macdone, mac_parity); mac_parity ^= 1u; }
+        uint32_t* S = dh + w6 * 1024;
         {   // phase 1: digit kw of poly pw -> spectrum plane dh[w6]
-            uint32_t* S = dh + w6 * 1024;
             p1a<!EXTPROD>(lane, acc + pw * 1024, EXTPROD ? 0u : (uint32_t)abar[i], a.mask, kw, S);
             __syncwarp();
             p1b(lane, S, twF);
         }
         bar_sync(bar_gate, THREADS_PER_GATE);
+        uint32_t x[32];
         {   // phase 2: key slice kw of output poly pw
-            uint32_t* S = sp + w6 * 1024;
-            uint32_t x[32];
             p2a_mac(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, dh, x);
             __syncwarp();
             if (lane == 0) mbar_arrive(macdone);
-            inv_rows(lane, x, twI, S);
+            gs32(x, TwRow{twI + lane * TWB_STRIDE});
+            mbar_wait(macdone, mac_parity);
+            mac_parity ^= 1u;
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
             __syncwarp();
-            p2b(lane, S, kw, x);
-            __syncwarp();
-            p2c(lane, S, x);
+            p2b(lane, S, kw, x);   // x[r] = exact slice value (already shifted) of coefficient 32 r + lane
         }
-        bar_sync(bar_poly, 96);
-        // phase 3: acc[pw] += sum of its three slices (EXTPROD: acc = sum), done by the 3 warps of this polynomial
-        for (int k = tid3; k < 1024; k += 96) {
-            const uint32_t* q = sp + (3 * pw) * 1024 + k;
-            const uint32_t sum = q[0] + q[1024] + q[2048];
-            acc[pw * 1024 + k] = EXTPROD ? sum : acc[pw * 1024 + k] + sum;
+        // phase 3: acc[pw] += x, slice warps take turns (EXTPROD: the first turn overwrites)
+        uint32_t* A = acc + pw * 1024 + lane;
+#pragma unroll
+        for (int turn = 0; turn < 3; turn++) {
+            if (kw == turn) {
+#pragma unroll
+                for (int r = 0; r < 32; r++) A[32 * r] = (EXTPROD && turn == 0) ? x[r] : A[32 * r] + x[r];
+            }
+            bar_sync(bar_poly, 96);
         }
-        bar_sync(bar_poly, 96);
     }
     bar_sync(bar_gate, THREADS_PER_GATE);
 
@@ -408,6 +417,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_kernel<3, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(3))) != cudaSuccess) return bail("smem attr", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_kernel<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(2))) != cudaSuccess) return bail("smem attr", e);
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
@@ -541,6 +551,9 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         const unsigned grid = (unsigned)((a.B + 2) / 3);
         blind_rotate_kernel<3, false, 1><<<grid, 3 * THREADS_PER_GATE, br_smem_bytes(3), st>>>(a);
         ctx->gates_per_cta = 3;
+    } else if (pair && ctx->variant == 5) {
+        blind_rotate_kernel<1, false, 4><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
+        ctx->gates_per_cta = 1;
     } else if (pair && ctx->variant == 3) {
         blind_rotate_kernel<1, false, 3><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
         ctx->gates_per_cta = 1;
