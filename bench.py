@@ -215,10 +215,14 @@ def run_gpu(args):
     dout = torch.empty((BATCH, CT_WORDS), dtype=torch.int32, device=dev)
     hout = torch.empty((BATCH, CT_WORDS), dtype=torch.int32).pin_memory()
 
-    def step_device(it):
+    streams = [stream, torch.cuda.Stream(device=dev)]   # consecutive steps alternate streams: independent batches overlap
+    douts = [dout, torch.empty_like(dout)]
+
+    def step_device(it, st=None, o_buf=None):
         o = (it % NROT) * BATCH
-        eng.gate_batch_device(K.NAND, dx[o:o + BATCH].data_ptr(), dy[o:o + BATCH].data_ptr(), dout.data_ptr(), BATCH,
-                              stream.cuda_stream)
+        st = st or stream
+        eng.gate_batch_device(K.NAND, dx[o:o + BATCH].data_ptr(), dy[o:o + BATCH].data_ptr(), (o_buf if o_buf is not None else dout).data_ptr(),
+                              BATCH, st.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -234,20 +238,38 @@ def run_gpu(args):
     got = R.Cryptor.decrypto(R.TLWE, s0, dout.cpu().numpy().view(np.uint32))
     wrong = int((got != (1 - (bx[o:o + BATCH] & by[o:o + BATCH]))).sum())
 
-    # ---- timed region: exactly K steps, device-resident inputs ----
+    # ---- serial region (one stream, K steps): isolated per-launch kernel durations for the roofline ----
     eng.reset_stats()
+    s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize()
+    s0e.record(stream)
+    for it in range(args.steps):
+        step_device(args.warmup + it)
+    s1e.record(stream)
+    torch.cuda.synchronize(); barrier()
+    serial_ms = s0e.elapsed_time(s1e)
+    st = eng.stats()
+
+    # ---- timed region: exactly K steps, device-resident inputs, steps alternate between two streams so the tail of one
+    #      batch's blind rotation and its key switch run under the head of the next batch (independent batches) ----
     launches0 = eng.stats()["kernel_launches"]
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    join = torch.cuda.Event()
     barrier(); torch.cuda.synchronize()
     e0.record(stream)
+    streams[1].wait_event(e0)
     for it in range(args.steps):
-        step_device(args.warmup + it)
+        step_device(args.warmup + it, streams[it % 2], douts[it % 2])
+    join.record(streams[1])
+    stream.wait_event(join)
     e1.record(stream)
     torch.cuda.synchronize(); barrier()
     ms = e0.elapsed_time(e1)
-    st = eng.stats()
-    launches = st["kernel_launches"] - launches0
+    launches = eng.stats()["kernel_launches"] - launches0
+    o = ((args.warmup + args.steps - 1) % NROT) * BATCH
+    got = R.Cryptor.decrypto(R.TLWE, s0, douts[(args.steps - 1) % 2].cpu().numpy().view(np.uint32))
+    wrong += int((got != (1 - (bx[o:o + BATCH] & by[o:o + BATCH]))).sum())
 
     # ---- B = 1 latency (SURVEY 8d "latency metric"): one gate per call, median of 30 after 3 warm-ups, CUDA events ----
     lat = []
@@ -261,35 +283,40 @@ def run_gpu(args):
             lat.append(a0.elapsed_time(a1) * 1e3)
     latency_us = float(np.median(lat))
 
-    # ---- e2e: same steps through the host-buffer C ABI call, pinned host memory, H2D + D2H inside the timed region ----
-    hx_np, hy_np, hout_np = hx.numpy().view(np.uint32), hy.numpy().view(np.uint32), hout.numpy().view(np.uint32)
-    import ctypes as C
+    # ---- e2e: the same K steps through the host-buffer C ABI (tfhe_b200_gate_batch_async + tfhe_b200_sync), pinned host
+    #      memory, H2D of both input batches and D2H of the output batch inside the timed region, every step ----
+    hx_np, hy_np = hx.numpy().view(np.uint32), hy.numpy().view(np.uint32)
+    NOUT = 4
+    houts = [torch.empty((BATCH, CT_WORDS), dtype=torch.int32).pin_memory() for _ in range(NOUT)]
+    houts_np = [h.numpy().view(np.uint32) for h in houts]
     lib = K.lib()
 
     def step_host(it):
         o = (it % NROT) * BATCH
-        rc = lib.tfhe_b200_gate_batch(eng._ctx, K.NAND, K.ptr(hx_np[o:o + BATCH]), K.ptr(hy_np[o:o + BATCH]), K.ptr(hout_np), BATCH)
+        rc = lib.tfhe_b200_gate_batch_async(eng._ctx, K.NAND, K.ptr(hx_np[o:o + BATCH]), K.ptr(hy_np[o:o + BATCH]),
+                                            K.ptr(houts_np[it % NOUT]), BATCH)
         if rc:
             raise RuntimeError(lib.tfhe_b200_last_error(eng._ctx))
 
-    step_host(0)
+    step_host(0); eng.sync()
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for it in range(args.steps):
         step_host(args.warmup + it)
-    torch.cuda.synchronize()
+    eng.sync()
     e2e_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
-    got = R.Cryptor.decrypto(R.TLWE, s0, hout_np)
-    o = ((args.warmup + args.steps - 1) % NROT) * BATCH
+    last = args.warmup + args.steps - 1
+    got = R.Cryptor.decrypto(R.TLWE, s0, houts_np[last % NOUT])
+    o = (last % NROT) * BATCH
     wrong += int((got != (1 - (bx[o:o + BATCH] & by[o:o + BATCH]))).sum())
 
     # max over ranks
-    t = torch.tensor([ms, e2e_s * 1e3, float(wrong)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, float(wrong), serial_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, wrong = float(t[0]), float(t[1]), int(t[2])
+    ms, e2e_ms, wrong, serial_ms = float(t[0]), float(t[1]), int(t[2]), float(t[3])
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -310,15 +337,18 @@ def run_gpu(args):
                        "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world} (independent gate shards, keys replicated)",
                        "l2": f"inputs rotate over {NROT} batches ({NROT * BATCH * 2 * CT_WORDS * 4 / 1e6:.0f} MB) > L2; keys "
                              f"{(BK_BYTES_DEVICE + KSK_BYTES) / 1e6:.0f} MB > L2; no explicit flush",
-                       "gates_per_cta": st["gates_per_cta"]},
+                       "gates_per_cta": st["gates_per_cta"], "streams": 2},
+            "value_serial": gates / (serial_ms * 1e-3),
             "latency_us_per_gate_amortised": 1e3 * ms / args.steps / BATCH,
             "latency_us_single_gate": latency_us,
             "wrong_bits": wrong,
             "e2e": {"value": gates / (e2e_ms * 1e-3), "unit": "gates/s", "h2d_bytes_per_step": 2 * BATCH * CT_WORDS * 4,
                     "d2h_bytes_per_step": BATCH * CT_WORDS * 4, "ms_per_step": e2e_ms / args.steps,
-                    "api": "tfhe_b200_gate_batch (host pointers, pinned)"},
+                    "api": "tfhe_b200_gate_batch_async x K + tfhe_b200_sync (host pointers, pinned)"},
             "gpu_launches": int(launches),
-            "kernels": {"blind_rotate_ms": br_ms, "keyswitch_ms": ks_ms, "timed_launches": st["timed_launches"]},
+            "kernels": {"blind_rotate_ms": br_ms, "keyswitch_ms": ks_ms, "timed_launches": st["timed_launches"],
+                        "note": "isolated per-launch durations (CUDA events on the launching stream) from a serial K-step region of "
+                                "this same run; in the timed region consecutive batches overlap on two streams"},
             "roofline": {"bound": "hbm", "kernel": "blind_rotate_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                          "algorithmic_bytes_per_launch": algo_bytes, "traffic": None,

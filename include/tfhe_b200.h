@@ -25,7 +25,8 @@
  *
  * Threading: a ctx may be used by one host thread at a time (the reference handle is not thread safe either,
  * spqlios-fft.h:25-30).  "_device" variants take device pointers and a cudaStream_t (as void*), enqueue
- * asynchronously and never synchronise; the host-pointer variants copy in, run, copy out and synchronise.
+ * asynchronously and never synchronise; calls issued on different streams may overlap on the device (workspaces are
+ * handed out from an event-guarded ring).  The host-pointer variants copy in, run, copy out and synchronise.
  */
 #ifndef TFHE_B200_H
 #define TFHE_B200_H
@@ -96,6 +97,11 @@ int tfhe_b200_load_ksk_device(tfhe_b200_ctx* ctx, const uint32_t* ksk_dev, void*
 int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B);
 int tfhe_b200_gate_batch_device(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out,
                                 size_t B, void* stream);
+/* Asynchronous host-pointer form: H2D copy, gate batch and D2H copy are enqueued on one of the context's internal
+ * streams and the call returns; buffers must stay valid (and should be pinned) until tfhe_b200_sync returns.
+ * Consecutive async batches overlap on the device (the tail of one blind rotation runs under the head of the next). */
+int tfhe_b200_gate_batch_async(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B);
+int tfhe_b200_sync(tfhe_b200_ctx* ctx); /* waits for every batch this context has enqueued (any stream) */
 int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t B); /* TFHE::bootstrap */
 /* hom_mux(control, input_0, input_1) = (input_1 & control) | (input_0 & !control): three bootstraps, tfhe.rs:27-40 */
 int tfhe_b200_mux_batch(tfhe_b200_ctx* ctx, const uint32_t* control, const uint32_t* in0, const uint32_t* in1,

@@ -250,6 +250,15 @@ class DeviceEngine:
         self._ck(self._l.tfhe_b200_gate_batch(self._ctx, op, ptr(in0), ptr(in1), ptr(out), len(in0)))
         return out
 
+    def gate_batch_async(self, op, in0, in1, out):
+        """Asynchronous form: `in0`, `in1`, `out` are caller-owned (pinned) uint32 arrays [B][n+1] that must stay
+        alive until `sync()`; consecutive calls overlap on the device."""
+        assert in0.dtype == np.uint32 and out.dtype == np.uint32 and in0.shape == out.shape and in0.shape[1] == K.n + 1
+        self._ck(self._l.tfhe_b200_gate_batch_async(self._ctx, op, ptr(in0), ptr(in1), ptr(out), len(in0)))
+
+    def sync(self):
+        self._ck(self._l.tfhe_b200_sync(self._ctx))
+
     def mux_batch(self, control, in0, in1):
         control, in0, in1 = (_u32_batch(x, K.n + 1) for x in (control, in0, in1))
         out = np.empty_like(in0)

@@ -57,6 +57,12 @@ struct BrArgs {
     const uint32_t* in1;     // [B][n+1] or null
     int32_t c0, c1;          // lin = c0*in0 + c1*in1 + (cb, 0, ...)
     uint32_t cb;
+    // second operand set for gates >= split (fused hom_mux first stage: two different gates in one launch); split = B when unused
+    long split;
+    const uint32_t* in0b;
+    const uint32_t* in1b;
+    int32_t c0b, c1b;
+    uint32_t cbb;
     uint32_t mu, mask;
     int nsteps;
     long B;
@@ -68,6 +74,9 @@ struct BrArgs {
     // external-product mode
     const uint32_t* trlwe_in;  // [B][2][N]
     long ntrgsw;
+    int stagger_cycles;
+    // gate -> CTA distribution (see the kernel prologue)
+    int cta_base, cta_rem;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,9 +116,12 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     uint16_t* abar = reinterpret_cast<uint16_t*>(dh + 6 * 1024);
     uint64_t* macdone = reinterpret_cast<uint64_t*>(dh + 6 * 1024 + 318);  // abar uses 635 u16 = 317.5 words of its 320
 
-    const long gate_raw = (long)blockIdx.x * G + gl;
-    const bool active = gate_raw < a.B;
-    const long gate = active ? gate_raw : a.B - 1;
+    // gates are dealt out evenly: the first cta_rem CTAs own cta_base+1 consecutive gates, the others cta_base (<= G)
+    const long cta = blockIdx.x;
+    const long first = cta * a.cta_base + (cta < a.cta_rem ? cta : a.cta_rem);
+    const int cnt = a.cta_base + (cta < a.cta_rem ? 1 : 0);
+    const bool active = gl < cnt;
+    const long gate = active ? first + gl : a.B - 1;
 
     for (int t = threadIdx.x; t < 32 * TWB_STRIDE; t += blockDim.x) {
         twF[t] = g_fwdB[t];
@@ -124,12 +136,17 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         for (int k = tid6; k < 2048; k += THREADS_PER_GATE) acc[k] = src[k];
     } else {
         uint32_t* lin = dh;
-        const uint32_t* p0 = a.in0 + (size_t)gate * (LWE_N + 1);
-        const uint32_t* p1 = a.in1 ? a.in1 + (size_t)gate * (LWE_N + 1) : nullptr;
+        const bool second = gate >= a.split;
+        const long gsrc = second ? gate - a.split : gate;
+        const uint32_t* q0 = second ? a.in0b : a.in0;
+        const uint32_t* q1 = second ? a.in1b : a.in1;
+        const uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
+        const uint32_t* p0 = q0 + (size_t)gsrc * (LWE_N + 1);
+        const uint32_t* p1 = q1 ? q1 + (size_t)gsrc * (LWE_N + 1) : nullptr;
         for (int c = tid6; c <= LWE_N; c += THREADS_PER_GATE) {
-            uint32_t v = (uint32_t)a.c0 * p0[c];
-            if (p1) v += (uint32_t)a.c1 * p1[c];
-            if (c == 0) v += a.cb;
+            uint32_t v = k0 * p0[c];
+            if (p1) v += k1 * p1[c];
+            if (c == 0) v += kb;
             lin[c] = v;
         }
         __syncthreads();
@@ -143,6 +160,13 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         }
     }
     __syncthreads();
+    if (!active) return;   // gate slots without a gate leave here: every barrier below is private to one gate
+    // optional start offset between the gates of a CTA (TFHE_B200_STAGGER, cycles per step; measured: no effect, default 0)
+    if (!EXTPROD && a.stagger_cycles > 0) {
+        const long long wait = (long long)gl * a.stagger_cycles / G;
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) __nanosleep(200);
+    }
 
     // ---- 635 x CMUX ----
     // Synchronisation per step (named barriers, so gates sharing a CTA and the two polynomials of a gate decouple):
@@ -157,6 +181,12 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     for (int i = 0; i < nsteps; i++) {
         const uint32_t* step_bk = a.bkdev + (EXTPROD ? (size_t)(gate % a.ntrgsw) : (size_t)i) * BK_STEP_WORDS;
         uint32_t* S = dh + w6 * 1024;
+#if defined(TFHE_EXP_PF)   /* experiment: sparse L2 prefetch of the next step's key, 1/64 of the slab per CTA */
+        if (!EXTPROD && i + 1 < nsteps && tid6 < 18) {
+            const char* nxt = reinterpret_cast<const char*>(step_bk + BK_STEP_WORDS);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)((blockIdx.x & 63) * 18 + tid6) * 128));
+        }
+#endif
         {   // phase 1: digit kw of poly pw -> spectrum plane dh[w6]
             p1a<!EXTPROD>(lane, acc + pw * 1024, EXTPROD ? 0u : (uint32_t)abar[i], a.mask, kw, S);
             __syncwarp();
@@ -191,7 +221,6 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     bar_sync(bar_gate, THREADS_PER_GATE);
 
     // ---- epilogue: sample_extract_index(0) (trlwe.rs:110-121) + key-switch digits (tlwe.rs:47-64) ----
-    if (!active) return;
     if (a.trlwe_out) {
         uint32_t* dst = a.trlwe_out + (size_t)gate * 2048;
         for (int k = tid6; k < 2048; k += THREADS_PER_GATE) dst[k] = acc[k];
@@ -328,25 +357,37 @@ __global__ void __launch_bounds__(PM_WARPS * 32) polymul_kernel(const uint32_t* 
 // =====================================================================================================
 // host side: context + C ABI
 // =====================================================================================================
+// Work slots: every gate-batch call borrows one slot (key-switch digit workspace, staging buffers, scratch) from a
+// small ring.  A slot is guarded by an event recorded behind the last operation that touches its buffers, so calls
+// issued on DIFFERENT streams (or back-to-back asynchronous host calls) may overlap on the device: the tail of one
+// batch's blind rotation and its key switch run under the head of the next batch.
+struct Slot {
+    cudaStream_t stream = nullptr;   // internal stream, used by the host-pointer entry points
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+    uint16_t* ksdig = nullptr; size_t ksdig_cap = 0;
+    uint32_t* tmp[4] = {nullptr, nullptr, nullptr, nullptr}; size_t tmp_cap[4] = {0, 0, 0, 0};
+    uint32_t* scratch = nullptr; size_t scratch_cap = 0;   // hom_mux intermediates / transformed TRGSWs of step-level calls
+};
+
 struct tfhe_b200_ctx {
     tfhe_b200_params prm;
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
     uint32_t* bkdev = nullptr;   // n * BK_STEP_WORDS
     uint32_t* kskdev = nullptr;  // [N][t][3][n+1]
+    int stagger_cycles = 0;
     bool have_bk = false, have_ksk = false;
-    // workspaces (grown on demand)
-    uint16_t* ksdig = nullptr; size_t ksdig_cap = 0;
-    uint32_t* tmp[4] = {nullptr, nullptr, nullptr, nullptr}; size_t tmp_cap[4] = {0, 0, 0, 0};
-    uint32_t* xbk = nullptr; size_t xbk_cap = 0;  // external-product scratch keys
+    static constexpr int NSLOT = 4;
+    Slot slots[NSLOT];
+    unsigned next_slot = 0;
     static constexpr int RING = 64;          // event ring: per-launch device times of the last RING timed gate batches
     cudaEvent_t ev[RING][4] = {};
     uint64_t timed = 0;
     uint64_t launches = 0;
     uint64_t last_batch = 0;
-    int gates_per_cta = 2;
-    int variant = 3;  // blind-rotate launch shape: 0 = 2 gates/CTA x 1 CTA/SM, 2 = 1 gate/CTA x 2 CTA/SM, 3 = 1 gate/CTA x 3 CTA/SM
+    int gates_per_cta = 1;
+    int variant = 7;  // blind-rotate launch shape, see launch_blind_rotate
     std::string err;
 };
 static thread_local std::string g_create_err;
@@ -359,6 +400,11 @@ static thread_local std::string g_create_err;
             return TFHE_B200_ERR_CUDA;                                                                    \
         }                                                                                                 \
     } while (0)
+#define RC(call)                                                                                          \
+    do {                                                                                                  \
+        int rc_ = (call);                                                                                 \
+        if (rc_) return rc_;                                                                              \
+    } while (0)
 
 static int fail(tfhe_b200_ctx* ctx, int code, const char* msg) {
     if (ctx) ctx->err = msg; else g_create_err = msg;
@@ -366,16 +412,32 @@ static int fail(tfhe_b200_ctx* ctx, int code, const char* msg) {
 }
 static int grow(tfhe_b200_ctx* ctx, void** p, size_t* cap, size_t bytes) {
     if (*cap >= bytes) return TFHE_B200_OK;
-    if (*p) CK(cudaFree(*p));
+    if (*p) CK(cudaFree(*p));   // cudaFree waits for the device: nothing in flight can still use the old buffer
     *p = nullptr; *cap = 0;
     CK(cudaMalloc(p, bytes));
     *cap = bytes;
     return TFHE_B200_OK;
 }
+// borrow the next slot of the ring for work that will be enqueued on `st` (nullptr = the slot's own stream)
+static int slot_acquire(tfhe_b200_ctx* ctx, cudaStream_t* st, bool own_stream, Slot** out) {
+    Slot& s = ctx->slots[ctx->next_slot++ % tfhe_b200_ctx::NSLOT];
+    if (own_stream) *st = s.stream;
+    if (s.pending) CK(cudaStreamWaitEvent(*st, s.done, 0));
+    *out = &s;
+    return TFHE_B200_OK;
+}
+static int slot_release(tfhe_b200_ctx* ctx, Slot* s, cudaStream_t st) {
+    CK(cudaEventRecord(s->done, st));
+    s->pending = true;
+    return TFHE_B200_OK;
+}
+
+template <class Kern>
+static cudaError_t set_smem(Kern k, int G) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(G)); }
 
 extern "C" {
 
-const char* tfhe_b200_version(void) { return "rustfhe_b200 0.1 (sm_100a, p=536856577, 3x11-bit key slices)"; }
+const char* tfhe_b200_version(void) { return "rustfhe_b200 0.2 (sm_100a, p=536856577, 3x11-bit key slices)"; }
 
 int tfhe_b200_default_params(tfhe_b200_params* p) {
     if (!p) return TFHE_B200_ERR_PARAM;
@@ -407,20 +469,26 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     }
     tfhe_b200_ctx* ctx = new tfhe_b200_ctx();
     ctx->prm = prm; ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
-    auto bail = [&](const char* what, cudaError_t ee) { g_create_err = std::string(what) + ": " + cudaGetErrorString(ee); delete ctx; return TFHE_B200_ERR_CUDA; };
+    auto bail = [&](const char* what, cudaError_t ee) { g_create_err = std::string(what) + ": " + cudaGetErrorString(ee); tfhe_b200_ctx_destroy(ctx); return TFHE_B200_ERR_CUDA; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (auto& s : ctx->slots) {
+        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+        if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
     for (auto& slot : ctx->ev) for (auto& ev : slot) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->bkdev, (size_t)LWE_N * BK_STEP_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc(bk)", e);
     if ((e = cudaMalloc(&ctx->kskdev, (size_t)1024 * 8 * 3 * (LWE_N + 1) * 4)) != cudaSuccess) return bail("cudaMalloc(ksk)", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(2))) != cudaSuccess) return bail("smem attr", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(1))) != cudaSuccess) return bail("smem attr", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<3, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(3))) != cudaSuccess) return bail("smem attr", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(2))) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<2, false, 1>, 2)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<1, false, 1>, 1)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<1, false, 2>, 1)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<1, false, 3>, 1)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<1, false, 4>, 1)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<3, false, 1>, 3)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<2, false, 2>, 2)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<4, false, 1>, 4)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<2, true, 1>, 2)) != cudaSuccess) return bail("smem attr", e);
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
+    if (const char* v = getenv("TFHE_B200_STAGGER")) ctx->stagger_cycles = atoi(v);
     *out = ctx;
     return TFHE_B200_OK;
 }
@@ -428,11 +496,15 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
 int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     if (!ctx) return TFHE_B200_ERR_PARAM;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->bkdev); cudaFree(ctx->kskdev); cudaFree(ctx->ksdig); cudaFree(ctx->xbk);
-    for (auto p : ctx->tmp) cudaFree(p);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->bkdev); cudaFree(ctx->kskdev);
+    for (auto& s : ctx->slots) {
+        cudaFree(s.ksdig); cudaFree(s.scratch);
+        for (auto p : s.tmp) cudaFree(p);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
     for (auto& slot : ctx->ev) for (auto ev : slot) if (ev) cudaEventDestroy(ev);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TFHE_B200_OK;
 }
@@ -442,6 +514,14 @@ const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx) { return ctx ? ctx->e
 int tfhe_b200_set_decomp_mask(tfhe_b200_ctx* ctx, uint32_t mask) {
     if (!ctx) return TFHE_B200_ERR_PARAM;
     ctx->prm.decomp_mask = mask;
+    return TFHE_B200_OK;
+}
+
+int tfhe_b200_sync(tfhe_b200_ctx* ctx) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    CK(cudaSetDevice(ctx->device));
+    for (auto& s : ctx->slots)
+        if (s.pending) { CK(cudaEventSynchronize(s.done)); s.pending = false; }
     return TFHE_B200_OK;
 }
 
@@ -485,8 +565,7 @@ static int transform_keys(tfhe_b200_ctx* ctx, const uint32_t* src_dev, uint32_t*
 int tfhe_b200_load_bk_device(tfhe_b200_ctx* ctx, const uint32_t* bk_dev, void* stream) {
     if (!ctx || !bk_dev) return fail(ctx, TFHE_B200_ERR_PARAM, "load_bk_device: null argument");
     CK(cudaSetDevice(ctx->device));
-    int rc = transform_keys(ctx, bk_dev, ctx->bkdev, LWE_N, (cudaStream_t)stream);
-    if (rc) return rc;
+    RC(transform_keys(ctx, bk_dev, ctx->bkdev, LWE_N, (cudaStream_t)stream));
     ctx->have_bk = true;
     return TFHE_B200_OK;
 }
@@ -494,13 +573,14 @@ int tfhe_b200_load_bk(tfhe_b200_ctx* ctx, const uint32_t* bk_host) {
     if (!ctx || !bk_host) return fail(ctx, TFHE_B200_ERR_PARAM, "load_bk: null argument");
     CK(cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)LWE_N * 12 * 1024 * 4;
+    cudaStream_t st = ctx->slots[0].stream;
     uint32_t* staging = nullptr;
     CK(cudaMalloc(&staging, bytes));
-    cudaError_t e = cudaMemcpyAsync(staging, bk_host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(staging, bk_host, bytes, cudaMemcpyHostToDevice, st);
     int rc = TFHE_B200_OK;
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = TFHE_B200_ERR_CUDA; }
-    if (!rc) rc = tfhe_b200_load_bk_device(ctx, staging, ctx->stream);
-    e = cudaStreamSynchronize(ctx->stream);
+    if (!rc) rc = tfhe_b200_load_bk_device(ctx, staging, st);
+    e = cudaStreamSynchronize(st);
     if (!rc && e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = TFHE_B200_ERR_CUDA; }
     cudaFree(staging);
     return rc;
@@ -515,11 +595,14 @@ int tfhe_b200_load_ksk_device(tfhe_b200_ctx* ctx, const uint32_t* ksk_dev, void*
 int tfhe_b200_load_ksk(tfhe_b200_ctx* ctx, const uint32_t* ksk_host) {
     if (!ctx || !ksk_host) return fail(ctx, TFHE_B200_ERR_PARAM, "load_ksk: null argument");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(ctx->kskdev, ksk_host, (size_t)1024 * 8 * 3 * (LWE_N + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    cudaStream_t st = ctx->slots[0].stream;
+    CK(cudaMemcpyAsync(ctx->kskdev, ksk_host, (size_t)1024 * 8 * 3 * (LWE_N + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
     ctx->have_ksk = true;
     return TFHE_B200_OK;
 }
+
+}  // extern "C" (helpers below are internal)
 
 // ---- launches ----
 static void op_coeffs(int op, uint32_t mu, int32_t* c0, int32_t* c1, uint32_t* cb, bool* two) {
@@ -536,30 +619,54 @@ static void op_coeffs(int op, uint32_t mu, int32_t* c0, int32_t* c1, uint32_t* c
 }
 static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, bool timed) {
     a.bkdev = ctx->bkdev; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu;
+    if (a.split <= 0) a.split = a.B;
     const int slot = (int)(ctx->timed % tfhe_b200_ctx::RING);
     if (timed) CK(cudaEventRecord(ctx->ev[slot][0], st));
-    // one gate per CTA when the batch cannot fill the machine with pairs (latency case), else two
-    const bool pair = a.B > (long)ctx->sm_count;
-    if (pair && ctx->variant == 0) {
-        const unsigned grid = (unsigned)((a.B + 1) / 2);
+    // Launch shapes.  B <= #SMs: one gate per CTA, 254 registers (latency shape).  Larger batches: CTAs of up to G gates
+    // (default G = 4: 24 warps = 6 per SM sub-partition, 80 registers, one CTA per SM -- measured 57.6 k gates/s against
+    // 50.7 k for three 1-gate CTAs per SM whose 18 warps load the four sub-partitions 5/5/4/4); the batch is dealt out
+    // evenly over rounds * #SMs CTAs so that a batch that is not a multiple of G * #SMs ends with 3-gate CTAs instead of
+    // a half-empty last wave.
+    const bool full = a.B > (long)ctx->sm_count;
+    a.stagger_cycles = full ? ctx->stagger_cycles : 0;
+    auto deal = [&](int G) {
+        const long cap = (long)G * ctx->sm_count;
+        const long rounds = (a.B + cap - 1) / cap;
+        long nctas = rounds * ctx->sm_count;
+        if (nctas > a.B) nctas = a.B;
+        a.cta_base = (int)(a.B / nctas); a.cta_rem = (int)(a.B % nctas);
+        ctx->gates_per_cta = G;
+        return (unsigned)nctas;
+    };
+    auto fixed = [&](int G) {   // every CTA owns exactly G gates (the last one possibly fewer)
+        const long nctas = (a.B + G - 1) / G;
+        a.cta_base = (int)(a.B / nctas); a.cta_rem = (int)(a.B % nctas);
+        ctx->gates_per_cta = G;
+        return (unsigned)nctas;
+    };
+    if (full && ctx->variant == 0) {
+        const unsigned grid = fixed(2);
         blind_rotate_kernel<2, false, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
-        ctx->gates_per_cta = 2;
-    } else if (pair && ctx->variant == 2) {
-        blind_rotate_kernel<1, false, 2><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-        ctx->gates_per_cta = 1;
-    } else if (pair && ctx->variant == 4) {
-        const unsigned grid = (unsigned)((a.B + 2) / 3);
+    } else if (full && ctx->variant == 2) {
+        blind_rotate_kernel<1, false, 2><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
+    } else if (full && ctx->variant == 3) {
+        blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
+    } else if (full && ctx->variant == 4) {
+        const unsigned grid = fixed(3);
         blind_rotate_kernel<3, false, 1><<<grid, 3 * THREADS_PER_GATE, br_smem_bytes(3), st>>>(a);
-        ctx->gates_per_cta = 3;
-    } else if (pair && ctx->variant == 5) {
-        blind_rotate_kernel<1, false, 4><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-        ctx->gates_per_cta = 1;
-    } else if (pair && ctx->variant == 3) {
-        blind_rotate_kernel<1, false, 3><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-        ctx->gates_per_cta = 1;
+    } else if (full && ctx->variant == 5) {
+        blind_rotate_kernel<1, false, 4><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
+    } else if (full && ctx->variant == 6) {
+        const unsigned grid = fixed(2);
+        blind_rotate_kernel<2, false, 2><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
+    } else if (full && ctx->variant == 8) {
+        const unsigned grid = fixed(4);
+        blind_rotate_kernel<4, false, 1><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
+    } else if (full) {   // default (variant 7)
+        const unsigned grid = deal(4);
+        blind_rotate_kernel<4, false, 1><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
     } else {
-        blind_rotate_kernel<1, false, 1><<<(unsigned)a.B, THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-        ctx->gates_per_cta = 1;
+        blind_rotate_kernel<1, false, 1><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -576,62 +683,90 @@ static int launch_keyswitch(tfhe_b200_ctx* ctx, const uint16_t* dig, uint32_t* o
     if (timed) { CK(cudaEventRecord(ctx->ev[slot][3], st)); ctx->timed++; }
     return TFHE_B200_OK;
 }
-static const size_t CT_BYTES = (size_t)(LWE_N + 1) * 4;
+static const size_t CT_WORDS = (size_t)(LWE_N + 1);
+static const size_t CT_BYTES = CT_WORDS * 4;
+
+// one bootstrapped gate batch on `st` with the workspaces of slot `s` (device pointers)
+static int run_gates(tfhe_b200_ctx* ctx, Slot* s, BrArgs& a, uint32_t* out, cudaStream_t st) {
+    RC(grow(ctx, (void**)&s->ksdig, &s->ksdig_cap, (size_t)a.B * 1024 * sizeof(uint16_t)));
+    a.nsteps = LWE_N; a.out_init = out; a.ksdig = s->ksdig;
+    RC(launch_blind_rotate(ctx, a, st, true));
+    RC(launch_keyswitch(ctx, s->ksdig, out, a.B, st, true));
+    ctx->last_batch = (uint64_t)a.B;
+    return TFHE_B200_OK;
+}
+static int gate_args(tfhe_b200_ctx* ctx, const char* who, int op, const uint32_t* in0, const uint32_t* in1, size_t B, BrArgs* a) {
+    if (op < 0 || op > TFHE_B200_ANDNY) return fail(ctx, TFHE_B200_ERR_PARAM, "gate_batch: bad opcode");
+    if (!ctx->have_bk || !ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "gate_batch: keys not loaded");
+    bool two;
+    op_coeffs(op, ctx->prm.mu, &a->c0, &a->c1, &a->cb, &two);
+    if (two && !in1) return fail(ctx, TFHE_B200_ERR_PARAM, "gate_batch: in1 required for this opcode");
+    a->in0 = in0; a->in1 = two ? in1 : nullptr; a->B = (long)B;
+    (void)who;
+    return TFHE_B200_OK;
+}
+// hom_mux on device pointers: stage 1 = ONE launch of 2B gates (AND(control, in1) | AND(-control, in0)), stage 2 = OR
+static int run_mux(tfhe_b200_ctx* ctx, Slot* s, const uint32_t* control, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B,
+                   cudaStream_t st) {
+    if (!ctx->have_bk || !ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "mux_batch: keys not loaded");
+    RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, 2 * B * CT_BYTES));
+    uint32_t* t = s->scratch;   // [0,B) = i_1 = hom_and(control, input_1); [B,2B) = i_0 = hom_and(-control, input_0)   (tfhe.rs:33-34)
+    BrArgs a{};
+    bool two;
+    op_coeffs(TFHE_B200_AND, ctx->prm.mu, &a.c0, &a.c1, &a.cb, &two);
+    op_coeffs(TFHE_B200_ANDNY, ctx->prm.mu, &a.c0b, &a.c1b, &a.cbb, &two);
+    a.in0 = control; a.in1 = in1; a.in0b = control; a.in1b = in0; a.split = (long)B; a.B = (long)(2 * B);
+    RC(run_gates(ctx, s, a, t, st));
+    BrArgs b{};
+    op_coeffs(TFHE_B200_OR, ctx->prm.mu, &b.c0, &b.c1, &b.cb, &two);   // bootstrap(i_1 + i_0 + 1/8)   (tfhe.rs:35-39)
+    b.in0 = t; b.in1 = t + B * CT_WORDS; b.B = (long)B;
+    return run_gates(ctx, s, b, out, st);
+}
+
+extern "C" {
 
 int tfhe_b200_gate_batch_device(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B,
                                 void* stream) {
     if (!ctx || !in0 || !out) return fail(ctx, TFHE_B200_ERR_PARAM, "gate_batch: null argument");
-    if (op < 0 || op > TFHE_B200_ANDNY) return fail(ctx, TFHE_B200_ERR_PARAM, "gate_batch: bad opcode");
-    if (!ctx->have_bk || !ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "gate_batch: keys not loaded");
+    BrArgs a{};
+    RC(gate_args(ctx, "gate_batch_device", op, in0, in1, B, &a));
     if (B == 0) return TFHE_B200_OK;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = grow(ctx, (void**)&ctx->ksdig, &ctx->ksdig_cap, B * 1024 * sizeof(uint16_t));
-    if (rc) return rc;
-    BrArgs a{};
-    bool two;
-    op_coeffs(op, ctx->prm.mu, &a.c0, &a.c1, &a.cb, &two);
-    if (two && !in1) return fail(ctx, TFHE_B200_ERR_PARAM, "gate_batch: in1 required for this opcode");
-    a.in0 = in0; a.in1 = two ? in1 : nullptr; a.nsteps = LWE_N; a.B = (long)B;
-    a.out_init = out; a.ksdig = ctx->ksdig;
-    if ((rc = launch_blind_rotate(ctx, a, st, true))) return rc;
-    if ((rc = launch_keyswitch(ctx, ctx->ksdig, out, (long)B, st, true))) return rc;
-    ctx->last_batch = B;
-    return TFHE_B200_OK;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, false, &s));
+    RC(run_gates(ctx, s, a, out, st));
+    return slot_release(ctx, s, st);
 }
 
-// host-pointer wrapper: H2D, run, D2H on the ctx stream
-static int with_host_io(tfhe_b200_ctx* ctx, const void* const* ins, const size_t* in_bytes, int nin, void* outp, size_t out_bytes,
-                        int (*fn)(tfhe_b200_ctx*, uint32_t* const* dev_in, uint32_t* dev_out, void* user), void* user) {
-    CK(cudaSetDevice(ctx->device));
-    uint32_t* dev_in[3] = {nullptr, nullptr, nullptr};
-    for (int k = 0; k < nin; k++) {
-        if (!ins[k]) continue;
-        int rc = grow(ctx, (void**)&ctx->tmp[k], &ctx->tmp_cap[k], in_bytes[k]);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(ctx->tmp[k], ins[k], in_bytes[k], cudaMemcpyHostToDevice, ctx->stream));
-        dev_in[k] = ctx->tmp[k];
-    }
-    int rc = grow(ctx, (void**)&ctx->tmp[3], &ctx->tmp_cap[3], out_bytes);
-    if (rc) return rc;
-    if ((rc = fn(ctx, dev_in, ctx->tmp[3], user))) return rc;
-    CK(cudaMemcpyAsync(outp, ctx->tmp[3], out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return TFHE_B200_OK;
-}
-
-struct GateCall { int op; size_t B; };
-int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B) {
+// host pointers, asynchronous: H2D, gate batch, D2H are enqueued on one of the ctx's internal streams and the call
+// returns; tfhe_b200_sync waits.  Host buffers should be pinned (pageable memory makes the copies synchronous).
+int tfhe_b200_gate_batch_async(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B) {
     if (!ctx || !in0 || !out) return fail(ctx, TFHE_B200_ERR_PARAM, "gate_batch: null argument");
+    BrArgs a{};
+    RC(gate_args(ctx, "gate_batch", op, in0, in1, B, &a));
     if (B == 0) return TFHE_B200_OK;
-    const void* ins[2] = {in0, in1};
-    const size_t nb[2] = {B * CT_BYTES, B * CT_BYTES};
-    GateCall gc{op, B};
-    return with_host_io(ctx, ins, nb, 2, out, B * CT_BYTES,
-                        [](tfhe_b200_ctx* c, uint32_t* const* di, uint32_t* dout, void* u) {
-                            GateCall* g = (GateCall*)u;
-                            return tfhe_b200_gate_batch_device(c, g->op, di[0], di[1], dout, g->B, c->stream);
-                        }, &gc);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = nullptr;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, true, &s));
+    const size_t bytes = B * CT_BYTES;
+    RC(grow(ctx, (void**)&s->tmp[0], &s->tmp_cap[0], bytes));
+    RC(grow(ctx, (void**)&s->tmp[3], &s->tmp_cap[3], bytes));
+    CK(cudaMemcpyAsync(s->tmp[0], in0, bytes, cudaMemcpyHostToDevice, st));
+    a.in0 = s->tmp[0];
+    if (a.in1) {
+        RC(grow(ctx, (void**)&s->tmp[1], &s->tmp_cap[1], bytes));
+        CK(cudaMemcpyAsync(s->tmp[1], in1, bytes, cudaMemcpyHostToDevice, st));
+        a.in1 = s->tmp[1];
+    }
+    RC(run_gates(ctx, s, a, s->tmp[3], st));
+    CK(cudaMemcpyAsync(out, s->tmp[3], bytes, cudaMemcpyDeviceToHost, st));
+    return slot_release(ctx, s, st);
+}
+int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B) {
+    RC(tfhe_b200_gate_batch_async(ctx, op, in0, in1, out, B));
+    return tfhe_b200_sync(ctx);
 }
 int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t B) {
     return tfhe_b200_gate_batch(ctx, TFHE_B200_COPY, in, nullptr, out, B);
@@ -642,120 +777,128 @@ int tfhe_b200_mux_batch_device(tfhe_b200_ctx* ctx, const uint32_t* control, cons
     if (!ctx || !control || !in0 || !in1 || !out) return fail(ctx, TFHE_B200_ERR_PARAM, "mux_batch: null argument");
     if (B == 0) return TFHE_B200_OK;
     CK(cudaSetDevice(ctx->device));
-    // i_1 = hom_and(control, input_1); i_0 = hom_and(-control, input_0); out = bootstrap(i_1 + i_0 + 1/8)  (tfhe.rs:27-40)
-    uint32_t *t1 = nullptr, *t0 = nullptr;
-    static_assert(sizeof(void*) == 8, "64-bit only");
-    int rc;
-    // scratch for the two intermediate batches lives in xbk-independent buffers
-    if ((rc = grow(ctx, (void**)&ctx->xbk, &ctx->xbk_cap, 2 * B * CT_BYTES))) return rc;
-    t1 = ctx->xbk; t0 = ctx->xbk + B * (LWE_N + 1);
-    if ((rc = tfhe_b200_gate_batch_device(ctx, TFHE_B200_AND, control, in1, t1, B, stream))) return rc;
-    if ((rc = tfhe_b200_gate_batch_device(ctx, TFHE_B200_ANDNY, control, in0, t0, B, stream))) return rc;
-    return tfhe_b200_gate_batch_device(ctx, TFHE_B200_OR, t1, t0, out, B, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, false, &s));
+    RC(run_mux(ctx, s, control, in0, in1, out, B, st));
+    return slot_release(ctx, s, st);
 }
 int tfhe_b200_mux_batch(tfhe_b200_ctx* ctx, const uint32_t* control, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B) {
     if (!ctx || !control || !in0 || !in1 || !out) return fail(ctx, TFHE_B200_ERR_PARAM, "mux_batch: null argument");
     if (B == 0) return TFHE_B200_OK;
-    const void* ins[3] = {control, in0, in1};
-    const size_t nb[3] = {B * CT_BYTES, B * CT_BYTES, B * CT_BYTES};
-    size_t Bc = B;
-    return with_host_io(ctx, ins, nb, 3, out, B * CT_BYTES,
-                        [](tfhe_b200_ctx* c, uint32_t* const* di, uint32_t* dout, void* u) {
-                            return tfhe_b200_mux_batch_device(c, di[0], di[1], di[2], dout, *(size_t*)u, c->stream);
-                        }, &Bc);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = nullptr;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, true, &s));
+    const size_t bytes = B * CT_BYTES;
+    const uint32_t* src[3] = {control, in0, in1};
+    for (int k = 0; k < 3; k++) {
+        RC(grow(ctx, (void**)&s->tmp[k], &s->tmp_cap[k], bytes));
+        CK(cudaMemcpyAsync(s->tmp[k], src[k], bytes, cudaMemcpyHostToDevice, st));
+    }
+    RC(grow(ctx, (void**)&s->tmp[3], &s->tmp_cap[3], bytes));
+    RC(run_mux(ctx, s, s->tmp[0], s->tmp[1], s->tmp[2], s->tmp[3], B, st));
+    CK(cudaMemcpyAsync(out, s->tmp[3], bytes, cudaMemcpyDeviceToHost, st));
+    RC(slot_release(ctx, s, st));
+    return tfhe_b200_sync(ctx);
 }
 
-// ---- step-level entries ----
-struct BrCall { int nsteps; size_t B; int what; };  // what: 0 = trlwe, 1 = lwe1
+}  // extern "C"
+
+// ---- step-level entries: host pointers, synchronous.  `fn` enqueues the device work on (slot, stream). ----
+struct HostIo {
+    const void* in[3] = {nullptr, nullptr, nullptr};
+    size_t in_bytes[3] = {0, 0, 0};
+    void* out = nullptr;
+    size_t out_bytes = 0;
+};
+template <class F>
+static int with_host_io(tfhe_b200_ctx* ctx, const HostIo& io, F fn) {
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = nullptr;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, true, &s));
+    uint32_t* dev_in[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3; k++) {
+        if (!io.in[k]) continue;
+        RC(grow(ctx, (void**)&s->tmp[k], &s->tmp_cap[k], io.in_bytes[k]));
+        CK(cudaMemcpyAsync(s->tmp[k], io.in[k], io.in_bytes[k], cudaMemcpyHostToDevice, st));
+        dev_in[k] = s->tmp[k];
+    }
+    RC(grow(ctx, (void**)&s->tmp[3], &s->tmp_cap[3], io.out_bytes));
+    RC(fn(s, st, dev_in, s->tmp[3]));
+    CK(cudaMemcpyAsync(io.out, s->tmp[3], io.out_bytes, cudaMemcpyDeviceToHost, st));
+    RC(slot_release(ctx, s, st));
+    return tfhe_b200_sync(ctx);
+}
+
+extern "C" {
+
 int tfhe_b200_blind_rotate_batch(tfhe_b200_ctx* ctx, const uint32_t* in, int nsteps, uint32_t* out_trlwe, size_t B) {
     if (!ctx || !in || !out_trlwe) return fail(ctx, TFHE_B200_ERR_PARAM, "blind_rotate_batch: null argument");
     if (nsteps < 0 || nsteps > LWE_N) return fail(ctx, TFHE_B200_ERR_PARAM, "blind_rotate_batch: nsteps out of range");
     if (!ctx->have_bk) return fail(ctx, TFHE_B200_ERR_STATE, "blind_rotate_batch: bootstrapping key not loaded");
     if (B == 0) return TFHE_B200_OK;
-    const void* ins[1] = {in};
-    const size_t nb[1] = {B * CT_BYTES};
-    BrCall bc{nsteps, B, 0};
-    return with_host_io(ctx, ins, nb, 1, out_trlwe, B * 2048 * 4,
-                        [](tfhe_b200_ctx* c, uint32_t* const* di, uint32_t* dout, void* u) {
-                            BrCall* b = (BrCall*)u;
-                            BrArgs a{};
-                            a.c0 = 1; a.in0 = di[0]; a.nsteps = b->nsteps; a.B = (long)b->B; a.trlwe_out = dout;
-                            return launch_blind_rotate(c, a, c->stream, false);
-                        }, &bc);
+    HostIo io; io.in[0] = in; io.in_bytes[0] = B * CT_BYTES; io.out = out_trlwe; io.out_bytes = B * 2048 * 4;
+    return with_host_io(ctx, io, [&](Slot*, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
+        BrArgs a{};
+        a.c0 = 1; a.in0 = di[0]; a.nsteps = nsteps; a.B = (long)B; a.trlwe_out = dout;
+        return launch_blind_rotate(ctx, a, st, false);
+    });
 }
 int tfhe_b200_bootstrap_lv1_batch(tfhe_b200_ctx* ctx, const uint32_t* in, uint32_t* out_lwe1, size_t B) {
     if (!ctx || !in || !out_lwe1) return fail(ctx, TFHE_B200_ERR_PARAM, "bootstrap_lv1_batch: null argument");
     if (!ctx->have_bk) return fail(ctx, TFHE_B200_ERR_STATE, "bootstrap_lv1_batch: bootstrapping key not loaded");
     if (B == 0) return TFHE_B200_OK;
-    const void* ins[1] = {in};
-    const size_t nb[1] = {B * CT_BYTES};
-    BrCall bc{LWE_N, B, 1};
-    return with_host_io(ctx, ins, nb, 1, out_lwe1, B * 1025 * 4,
-                        [](tfhe_b200_ctx* c, uint32_t* const* di, uint32_t* dout, void* u) {
-                            BrCall* b = (BrCall*)u;
-                            BrArgs a{};
-                            a.c0 = 1; a.in0 = di[0]; a.nsteps = b->nsteps; a.B = (long)b->B; a.lwe1_out = dout;
-                            return launch_blind_rotate(c, a, c->stream, false);
-                        }, &bc);
+    HostIo io; io.in[0] = in; io.in_bytes[0] = B * CT_BYTES; io.out = out_lwe1; io.out_bytes = B * 1025 * 4;
+    return with_host_io(ctx, io, [&](Slot*, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
+        BrArgs a{};
+        a.c0 = 1; a.in0 = di[0]; a.nsteps = LWE_N; a.B = (long)B; a.lwe1_out = dout;
+        return launch_blind_rotate(ctx, a, st, false);
+    });
 }
 int tfhe_b200_keyswitch_batch(tfhe_b200_ctx* ctx, const uint32_t* lwe1, uint32_t* out, size_t B) {
     if (!ctx || !lwe1 || !out) return fail(ctx, TFHE_B200_ERR_PARAM, "keyswitch_batch: null argument");
     if (!ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "keyswitch_batch: key-switching key not loaded");
     if (B == 0) return TFHE_B200_OK;
-    const void* ins[1] = {lwe1};
-    const size_t nb[1] = {B * 1025 * 4};
-    size_t Bc = B;
-    return with_host_io(ctx, ins, nb, 1, out, B * CT_BYTES,
-                        [](tfhe_b200_ctx* c, uint32_t* const* di, uint32_t* dout, void* u) {
-                            const size_t Bn = *(size_t*)u;
-                            int rc = grow(c, (void**)&c->ksdig, &c->ksdig_cap, Bn * 1024 * sizeof(uint16_t));
-                            if (rc) return rc;
-                            lwe1_prepare_kernel<<<(unsigned)Bn, 256, 0, c->stream>>>(di[0], c->ksdig, dout, (long)Bn);
-                            c->launches++;
-                            return launch_keyswitch(c, c->ksdig, dout, (long)Bn, c->stream, false);
-                        }, &Bc);
+    HostIo io; io.in[0] = lwe1; io.in_bytes[0] = B * 1025 * 4; io.out = out; io.out_bytes = B * CT_BYTES;
+    return with_host_io(ctx, io, [&](Slot* s, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
+        RC(grow(ctx, (void**)&s->ksdig, &s->ksdig_cap, B * 1024 * sizeof(uint16_t)));
+        lwe1_prepare_kernel<<<(unsigned)B, 256, 0, st>>>(di[0], s->ksdig, dout, (long)B);
+        ctx->launches++;
+        return launch_keyswitch(ctx, s->ksdig, dout, (long)B, st, false);
+    });
 }
-struct XpCall { const uint32_t* trgsw; size_t ntrgsw; size_t B; };
 int tfhe_b200_external_product_batch(tfhe_b200_ctx* ctx, const uint32_t* trgsw, size_t ntrgsw, const uint32_t* trlwe, uint32_t* out,
                                      size_t B) {
     if (!ctx || !trgsw || !trlwe || !out || ntrgsw == 0) return fail(ctx, TFHE_B200_ERR_PARAM, "external_product_batch: bad argument");
     if (B == 0) return TFHE_B200_OK;
-    const void* ins[2] = {trlwe, trgsw};
-    const size_t nb[2] = {B * 2048 * 4, ntrgsw * 12 * 1024 * 4};
-    XpCall xc{trgsw, ntrgsw, B};
-    return with_host_io(ctx, ins, nb, 2, out, B * 2048 * 4,
-                        [](tfhe_b200_ctx* c, uint32_t* const* di, uint32_t* dout, void* u) {
-                            XpCall* x = (XpCall*)u;
-                            int rc = grow(c, (void**)&c->xbk, &c->xbk_cap, x->ntrgsw * BK_STEP_WORDS * 4);
-                            if (rc) return rc;
-                            if ((rc = transform_keys(c, di[1], c->xbk, (int)x->ntrgsw, c->stream))) return rc;
-                            BrArgs a{};
-                            a.bkdev = c->xbk; a.mask = c->prm.decomp_mask; a.mu = c->prm.mu; a.B = (long)x->B; a.nsteps = 1;
-                            a.trlwe_in = di[0]; a.trlwe_out = dout; a.ntrgsw = (long)x->ntrgsw;
-                            const unsigned grid = (unsigned)((x->B + 1) / 2);
-                            blind_rotate_kernel<2, true, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), c->stream>>>(a);
-                            c->launches++;
-                            cudaError_t e = cudaGetLastError();
-                            if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return TFHE_B200_ERR_CUDA; }
-                            return TFHE_B200_OK;
-                        }, &xc);
+    HostIo io; io.in[0] = trlwe; io.in_bytes[0] = B * 2048 * 4; io.in[1] = trgsw; io.in_bytes[1] = ntrgsw * 12 * 1024 * 4;
+    io.out = out; io.out_bytes = B * 2048 * 4;
+    return with_host_io(ctx, io, [&](Slot* s, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
+        RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, ntrgsw * BK_STEP_WORDS * 4));
+        RC(transform_keys(ctx, di[1], s->scratch, (int)ntrgsw, st));
+        BrArgs a{};
+        a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
+        a.trlwe_in = di[0]; a.trlwe_out = dout; a.ntrgsw = (long)ntrgsw;
+        const unsigned grid = (unsigned)((B + 1) / 2);
+        a.cta_base = (int)(B / grid); a.cta_rem = (int)(B % grid);
+        blind_rotate_kernel<2, true, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return TFHE_B200_OK;
+    });
 }
 int tfhe_b200_negacyclic_mul_batch(tfhe_b200_ctx* ctx, const uint32_t* a, const int32_t* d, uint32_t* out, size_t B) {
     if (!ctx || !a || !d || !out) return fail(ctx, TFHE_B200_ERR_PARAM, "negacyclic_mul_batch: null argument");
     if (B == 0) return TFHE_B200_OK;
-    const void* ins[2] = {a, d};
-    const size_t nb[2] = {B * 4096, B * 4096};
-    size_t Bc = B;
-    return with_host_io(ctx, ins, nb, 2, out, B * 4096,
-                        [](tfhe_b200_ctx* c, uint32_t* const* di, uint32_t* dout, void* u) {
-                            const size_t Bn = *(size_t*)u;
-                            polymul_kernel<<<(unsigned)((Bn + PM_WARPS - 1) / PM_WARPS), PM_WARPS * 32, 0, c->stream>>>(
-                                di[0], (const int32_t*)di[1], dout, (long)Bn);
-                            c->launches++;
-                            cudaError_t e = cudaGetLastError();
-                            if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return TFHE_B200_ERR_CUDA; }
-                            return TFHE_B200_OK;
-                        }, &Bc);
+    HostIo io; io.in[0] = a; io.in_bytes[0] = B * 4096; io.in[1] = d; io.in_bytes[1] = B * 4096; io.out = out; io.out_bytes = B * 4096;
+    return with_host_io(ctx, io, [&](Slot*, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
+        polymul_kernel<<<(unsigned)((B + PM_WARPS - 1) / PM_WARPS), PM_WARPS * 32, 0, st>>>(di[0], (const int32_t*)di[1], dout, (long)B);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return TFHE_B200_OK;
+    });
 }
 
 }  // extern "C"
