@@ -29,13 +29,15 @@ TFHE_HD size_t bk_off(int i, int poly, int part, int j, int q, int lane) {
     return ((((((size_t)i * 2 + poly) * 3 + part) * BK_ROWS + j) * 8 + q) * 32 + lane) * 4;
 }
 
-// value of (X^abar * A - A)[k], abar in [0, 2048)
+// value of (X^abar * A - A)[k], abar in [0, 2048).  Written with explicit sign masks (no predicated negate) so that every
+// operation is a LOP3 / SHF / 3-input IADD3 on the ALU pipe: the FMA-heavy pipe is the one that bounds the kernel.
 TFHE_HD uint32_t rot_diff(const uint32_t* A, uint32_t k, uint32_t abar) {
     const uint32_t ap = abar & 1023u;
-    const uint32_t v = A[k];
-    const uint32_t rv = A[(k - ap) & 1023u];
-    const uint32_t m = ((k < ap) != ((abar >> 10) != 0)) ? 0xFFFFFFFFu : 0u;  // negate rv when m = ~0:  -rv = (rv ^ m) - m
-    return (rv ^ m) - m - v;
+    const uint32_t flip = 0u - (abar >> 10);                 // ~0 when abar >= N: one more factor X^N = -1
+    const uint32_t t = k - ap;                               // wraps below zero when the rotated index folds around
+    const uint32_t m = (uint32_t)((int32_t)t >> 31) ^ flip;  // ~0 -> take -A[...]:  -x = (x ^ m) - m
+    const uint32_t rv = A[t & 1023u];
+    return (rv ^ m) - m - A[k];
 }
 
 // ---- phase 1a: lane = column c.  Build digit `dw` of the source polynomial, column NTT, scatter into tile S ----
@@ -101,10 +103,31 @@ TFHE_HD void p2a_mac(int lane, const uint32_t* slab, const uint32_t* dh, uint32_
         x[4 * q] = redc64(a0); x[4 * q + 1] = redc64(a1); x[4 * q + 2] = redc64(a2); x[4 * q + 3] = redc64(a3);
     }
 }
+// same, with the first two inverse row stages of each chunk folded into the MAC loop (see gs32_head4): butterfly work
+// fills the wait for the next chunk's loads.  Finish with gs32_tail.
+TFHE_HD void p2a_mac_head(int lane, const uint32_t* slab, const uint32_t* dh, const uint32_t* twI, uint32_t (&x)[32]) {
+    const TwRow tw{twI + lane * TWB_STRIDE};
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int j = 0; j < BK_ROWS; j++) {
+            const uint4 d = *reinterpret_cast<const uint4*>(dh + j * NPOLY + swz_chunk(lane, q));
+#if defined(__CUDA_ARCH__)
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
+#else
+            const uint4 b = *(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
+#endif
+            a0 += (uint64_t)d.x * b.x; a1 += (uint64_t)d.y * b.y; a2 += (uint64_t)d.z * b.z; a3 += (uint64_t)d.w * b.w;
+        }
+        x[4 * q] = redc64(a0); x[4 * q + 1] = redc64(a1); x[4 * q + 2] = redc64(a2); x[4 * q + 3] = redc64(a3);
+        gs32_head4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3], q, tw);
+    }
+}
 TFHE_HD void p2a(int lane, const uint32_t* slab, const uint32_t* dh, const uint32_t* twI, uint32_t* S) {
     uint32_t x[32];
-    p2a_mac(lane, slab, dh, x);
-    gs32(x, TwRow{twI + lane * TWB_STRIDE});
+    p2a_mac_head(lane, slab, dh, twI, x);
+    gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
 #pragma unroll
     for (int q = 0; q < 8; q++)
         *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);

@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     //   B1 gate barrier (192 threads)  : the 6 digit spectra of this step are complete
     //   macdone (mbarrier, 6 arrivals) : every warp finished READING the digit spectra dh[] -> a warp may reuse its own
     //                                    plane dh[w6] as the transpose scratch of its inverse transform
-    //   3 poly barriers (96 threads)   : the three key-slice warps of a polynomial add their exact slice into acc[poly]
-    //                                    one after the other (no separate output planes: 24 KB less shared memory per gate)
+    //   poly barrier (96 threads)      : the three key-slice warps of a polynomial have added their exact slices into
+    //                                    acc[poly] (red.shared, no output planes: 24 KB less shared memory per gate)
     const int bar_gate = 1 + gl, bar_poly = 1 + G + 2 * gl + pw;
     uint32_t mac_parity = 0;
 #pragma unroll 1
@@ -195,10 +195,14 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         bar_sync(bar_gate, THREADS_PER_GATE);
         uint32_t x[32];
         {   // phase 2: key slice kw of output poly pw
-            p2a_mac(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, dh, x);
+            p2a_mac_head(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, dh, twI, x);
+            if (EXTPROD) {   // plain external product: the result replaces acc; every warp clears its share before it arrives
+#pragma unroll
+                for (int r = kw; r < 32; r += 3) acc[pw * 1024 + 32 * r + lane] = 0u;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(macdone);
-            gs32(x, TwRow{twI + lane * TWB_STRIDE});
+            gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
             mbar_wait(macdone, mac_parity);
             mac_parity ^= 1u;
 #pragma unroll
@@ -207,16 +211,13 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
             __syncwarp();
             p2b(lane, S, kw, x);   // x[r] = exact slice value (already shifted) of coefficient 32 r + lane
         }
-        // phase 3: acc[pw] += x, slice warps take turns (EXTPROD: the first turn overwrites)
-        uint32_t* A = acc + pw * 1024 + lane;
+        // phase 3: acc[pw] += x by shared-memory reductions (the three slice warps of a polynomial add concurrently)
+        {
+            const uint32_t A = smem_u32(acc + pw * 1024 + lane);
 #pragma unroll
-        for (int turn = 0; turn < 3; turn++) {
-            if (kw == turn) {
-#pragma unroll
-                for (int r = 0; r < 32; r++) A[32 * r] = (EXTPROD && turn == 0) ? x[r] : A[32 * r] + x[r];
-            }
-            bar_sync(bar_poly, 96);
+            for (int r = 0; r < 32; r++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(A + 128u * r), "r"(x[r]) : "memory");
         }
+        bar_sync(bar_poly, 96);   // acc[pw] is complete before the next step decomposes it
     }
     bar_sync(bar_gate, THREADS_PER_GATE);
 

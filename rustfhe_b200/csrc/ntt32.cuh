@@ -183,6 +183,31 @@ TFHE_HD void gs32(uint32_t (&x)[32], const TW& tw) {
     }
 }
 
+// Gentleman-Sande network split for software pipelining: stages 0 and 1 only touch the four values of one 16-byte chunk,
+// so the pointwise stage can run them chunk by chunk while it still waits for the next chunk's key and spectrum loads
+// (gs32_head4), and the transform proper starts at stage 2 (gs32_tail).  gs32 == 8 x gs32_head4 + gs32_tail.
+template <class TW>
+TFHE_HD void gs32_head4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, int q, const TW& tw) {
+    uint32_t w0, ws0, w1, ws1, w2, ws2;
+    tw.get2(16 + 2 * q, w0, ws0, w1, ws1);
+    tw.get(8 + q, w2, ws2);
+    gs_bfly(x0, x1, w0, ws0);
+    gs_bfly(x2, x3, w1, ws1);
+    gs_bfly(x0, x2, w2, ws2);
+    gs_bfly(x1, x3, w2, ws2);
+}
+template <class TW>
+TFHE_HD void gs32_tail(uint32_t (&x)[32], const TW& tw) {
+    gs_stage<2>(x, tw);
+    gs_stage<3>(x, tw);
+    {
+        uint32_t w, ws;
+        tw.get(1, w, ws);
+#pragma unroll
+        for (int j = 0; j < 16; j++) gs_bfly(x[j], x[j + 16], w, ws);
+    }
+}
+
 // swizzled position of element (row r, column c) in a 32x32 word tile: 16-byte chunks are XOR-permuted with the
 // row so that both "lane = column, loop over rows" word accesses and "lane = row" 128-bit accesses are
 // bank-conflict free.

@@ -33,6 +33,19 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
                 a[i] = x + t;
                 w[i] = x - t + 2u * 536813569u;
             }
+            if (MODE >= 9) {  // lazy butterfly + (MODE-8) extra independent ALU instructions: does the issue port keep up?
+                uint32_t x = a[i], y = (uint32_t)w[i], q, t;
+                asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(q) : "r"(y), "r"(b));
+                asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(y), "r"(c));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t) : "r"(q), "r"(0u - 536813569u));
+                uint32_t e = (uint32_t)(w[i] >> 32);
+                if (MODE >= 9) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(e) : "r"(b), "r"(c));
+                if (MODE >= 10) asm volatile("min.u32 %0, %0, %1;" : "+r"(e) : "r"(x));
+                if (MODE >= 11) asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(e) : "r"(y), "r"(c));
+                if (MODE >= 12) asm volatile("shf.l.wrap.b32 %0, %0, %1, 3;" : "+r"(e) : "r"(x));
+                a[i] = x + t;
+                w[i] = ((uint64_t)e << 32) | (uint32_t)(x - t + 2u * 536813569u);
+            }
             if (MODE == 8) {  // same + Harvey correction of x (min trick)
                 uint32_t x = a[i], y = (uint32_t)w[i], q, t;
                 x = min(x, x - 2u * 536813569u);
@@ -79,6 +92,10 @@ int main() {
     run<6>("dfma", blocks, out, 1);
     run<7>("shoup_ct_butterfly_lazy", blocks, out, 1);
     run<8>("shoup_ct_butterfly_harvey", blocks, out, 1);
+    run<9>("butterfly_plus1_alu", blocks, out, 1);
+    run<10>("butterfly_plus2_alu", blocks, out, 1);
+    run<11>("butterfly_plus3_alu", blocks, out, 1);
+    run<12>("butterfly_plus4_alu", blocks, out, 1);
     cudaError_t err = cudaDeviceSynchronize();
     printf("  \"cuda_error\": \"%s\"\n}\n", cudaGetErrorString(err));
     return err != cudaSuccess;
