@@ -42,6 +42,7 @@ extern "C" {
 #define TFHE_B200_ERR_CUDA 2     /* CUDA runtime error (see tfhe_b200_last_error) */
 #define TFHE_B200_ERR_STATE 3    /* keys not loaded */
 #define TFHE_B200_ERR_NOMEM 4
+#define TFHE_B200_ERR_IO 5       /* file format / I/O error (see tfhe_b200_file_last_error) */
 
 /* gate opcodes: the linear pre-combination applied before the bootstrap (hom_nand/src/tfhe.rs:27-71) */
 #define TFHE_B200_NAND 0   /* (1/8,0) - (c0+c1)          tfhe.rs:41-47 */
@@ -135,6 +136,40 @@ int tfhe_b200_encrypt_bits(uint64_t seed, uint64_t ct_index0, const uint8_t* s0,
                            uint32_t* out /*[B][n+1]*/);
 int tfhe_b200_phase(const uint8_t* s0, const uint32_t* ct, size_t B, uint32_t* phase);
 int tfhe_b200_decrypt_bits(const uint8_t* s0, const uint32_t* ct, size_t B, uint8_t* bits);
+
+/* ---- device-side key generation / encryption / decryption (same seeded generator as the host functions above: the
+ * results are bit-identical to tfhe_b200_keygen_bk / _keygen_ksk / _encrypt_bits with the same seed).  Replaces the
+ * host loops of BootstrappingKey::new (3810 TRLWE encryptions, tfhe.rs:119-126, trgsw.rs:117-139) and
+ * KeySwitchingKey::new (24576 TLWE encryptions, tlwe.rs:247-277) that the reference marks "TODO: parallelise". ---- */
+int tfhe_b200_keygen_device(tfhe_b200_ctx* ctx, uint64_t seed, const uint8_t* s0 /*[n] host*/, const uint8_t* s1 /*[N] host*/);
+int tfhe_b200_export_bk(tfhe_b200_ctx* ctx, uint32_t* bk_host /*[n][2l][2][N] torus domain*/);
+int tfhe_b200_export_ksk(tfhe_b200_ctx* ctx, uint32_t* ksk_host /*[N][t][3][n+1]*/);
+int tfhe_b200_encrypt_bits_device(tfhe_b200_ctx* ctx, uint64_t seed, uint64_t ct_index0, const uint8_t* s0 /*host*/,
+                                  const uint8_t* bits_dev /*[B] device*/, size_t B, uint32_t* out_dev /*[B][n+1] device*/,
+                                  void* stream);
+int tfhe_b200_decrypt_bits_device(tfhe_b200_ctx* ctx, const uint8_t* s0 /*host*/, const uint32_t* ct_dev, size_t B,
+                                  uint8_t* bits_dev /*[B] or NULL*/, uint32_t* phase_dev /*[B] or NULL*/, void* stream);
+
+/* ---- remaining scheme surface below the gate level (host pointers, synchronous) ---- */
+/* TRGSWRep::cmux(rep_1, rep_0) = cross(rep_1 - rep_0) + rep_0  (trgsw.rs:315-330); out[g] uses trgsw[g % ntrgsw] */
+int tfhe_b200_cmux_batch(tfhe_b200_ctx* ctx, const uint32_t* trgsw /*[ntrgsw][2l][2][N]*/, size_t ntrgsw,
+                         const uint32_t* rep1 /*[B][2][N]*/, const uint32_t* rep0 /*[B][2][N]*/, uint32_t* out, size_t B);
+/* TRLWERep::sample_extract_index(index) (trlwe.rs:110-121): [B][2][N] -> [B][N+1] */
+int tfhe_b200_sample_extract_batch(tfhe_b200_ctx* ctx, const uint32_t* trlwe, int index, uint32_t* out_lwe1, size_t B);
+
+/* ---- flat little-endian file format for keys and ciphertexts (the reference has no serialisation; layout in
+ * rustfhe_b200/csrc/wire.cpp: 64-byte header + the C-ABI layouts above + FNV-1a checksum) ---- */
+#define TFHE_B200_FILE_SECRET 1 /* s0[n] bytes then s1[N] bytes */
+#define TFHE_B200_FILE_BK 2     /* torus-domain bootstrapping key */
+#define TFHE_B200_FILE_KSK 3
+#define TFHE_B200_FILE_TLWE0 4  /* count x [n+1] */
+#define TFHE_B200_FILE_TLWE1 5  /* count x [N+1] */
+#define TFHE_B200_FILE_TRLWE 6  /* count x [2][N] */
+#define TFHE_B200_FILE_TRGSW 7  /* count x [2l][2][N] */
+int tfhe_b200_file_write(const char* path, int kind, const void* payload, uint64_t count);
+int tfhe_b200_file_info(const char* path, int* kind, uint64_t* count, uint64_t* payload_bytes);
+int tfhe_b200_file_read(const char* path, int kind, void* payload, uint64_t payload_bytes);
+const char* tfhe_b200_file_last_error(void);
 
 const char* tfhe_b200_version(void);
 

@@ -34,12 +34,47 @@ uint64_t orc_rnd64(uint64_t seed, uint64_t stream, uint64_t idx) {
     uint64_t h = fmix64(seed ^ fmix64(stream * 0xD6E8FEB86659FD93ull + 0x1234567ull));
     return fmix64(h + idx * 0x9E3779B97F4A7C15ull);
 }
-/* round(N(0,alpha) * 2^32) as a wrapping torus increment (reference: Normal<f32> -> torus!, math.rs:411-432) */
+/* round(N(0,alpha) * 2^32) as a wrapping torus increment (reference: Normal<f32> -> torus!, math.rs:411-432).
+ * Box-Muller evaluated with correctly rounded IEEE-754 double operations only (+ - * / sqrt, fixed order, no libm, no
+ * fused multiply-add: this file is compiled as ISO C, where GCC does not contract, and the volatile temporaries pin
+ * it), so that any conforming CPU -- and the product's device keygen -- produce the same bits from the same seed. */
+static inline double o_mul(double a, double b) { volatile double r = a * b; return r; }
+static inline double o_add(double a, double b) { volatile double r = a + b; return r; }
+static inline double o_div(double a, double b) { volatile double r = a / b; return r; }
+static double o_log(double u) { /* u normal, in (0,1] */
+    uint64_t b; memcpy(&b, &u, 8);
+    int e = (int)((b >> 52) & 0x7FF) - 1022;
+    uint64_t mb = (b & 0x000FFFFFFFFFFFFFull) | 0x3FE0000000000000ull;
+    double m; memcpy(&m, &mb, 8);
+    if (m < 0.70710678118654752440) { m = o_mul(m, 2.0); e -= 1; }
+    const double s = o_div(o_add(m, -1.0), o_add(m, 1.0));
+    const double z = o_mul(s, s);
+    double p = 1.0 / 23.0;
+    for (int k = 21; k >= 1; k -= 2) p = o_add(o_mul(p, z), 1.0 / (double)k);
+    return o_add(o_mul((double)e, 0.69314718055994530942), o_mul(o_mul(2.0, s), p));
+}
+static double o_cos2pi(double v) { /* v in [0,1) */
+    static const double CF[10] = {-1.0 / 6402373705728000.0, 1.0 / 20922789888000.0, -1.0 / 87178291200.0, 1.0 / 479001600.0,
+                                  -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -0.5, 1.0};
+    static const double SF[10] = {-1.0 / 121645100408832000.0, 1.0 / 355687428096000.0, -1.0 / 1307674368000.0, 1.0 / 6227020800.0,
+                                  -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0, 1.0};
+    const double t = o_mul(v, 4.0);
+    const int q = (int)t;
+    double r = o_add(t, -(double)q);
+    const int fold = r > 0.5;
+    if (fold) r = o_add(1.0, -r);
+    const double x = o_mul(r, 1.57079632679489661923), z = o_mul(x, x);
+    double c = CF[0], s = SF[0];
+    for (int k = 1; k < 10; k++) { c = o_add(o_mul(c, z), CF[k]); s = o_add(o_mul(s, z), SF[k]); }
+    s = o_mul(s, x);
+    const double cq = fold ? s : c, sq = fold ? c : s;
+    return q == 0 ? cq : q == 1 ? -sq : q == 2 ? -cq : sq;
+}
 int32_t orc_gauss_torus(uint64_t seed, uint64_t stream, uint64_t idx, double alpha) {
-    double u1 = ((double)((orc_rnd64(seed, stream, 2 * idx) >> 11) + 1)) * (1.0 / 9007199254740992.0);
-    double u2 = ((double)(orc_rnd64(seed, stream, 2 * idx + 1) >> 11)) * (1.0 / 9007199254740992.0);
-    double g = sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
-    return (int32_t)llrint(g * alpha * 4294967296.0);
+    double u1 = o_mul((double)((orc_rnd64(seed, stream, 2 * idx) >> 11) + 1), 1.0 / 9007199254740992.0);
+    double u2 = o_mul((double)(orc_rnd64(seed, stream, 2 * idx + 1) >> 11), 1.0 / 9007199254740992.0);
+    double g = o_mul(sqrt(o_mul(-2.0, o_log(u1))), o_cos2pi(u2));
+    return (int32_t)llrint(o_mul(g, alpha * 4294967296.0));
 }
 enum { ST_S0 = 1, ST_S1 = 2, ST_BK_A = 3, ST_BK_E = 4, ST_KSK_A = 5, ST_KSK_E = 6, ST_ENC_A = 7, ST_ENC_E = 8 };
 

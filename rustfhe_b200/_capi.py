@@ -25,7 +25,12 @@ SYMBOLS = [
     "tfhe_b200_bootstrap_lv1_batch", "tfhe_b200_keyswitch_batch", "tfhe_b200_external_product_batch",
     "tfhe_b200_negacyclic_mul_batch", "tfhe_b200_keygen_secret", "tfhe_b200_keygen_bk", "tfhe_b200_keygen_ksk",
     "tfhe_b200_encrypt_bits", "tfhe_b200_phase", "tfhe_b200_decrypt_bits", "tfhe_b200_version",
+    "tfhe_b200_keygen_device", "tfhe_b200_export_bk", "tfhe_b200_export_ksk", "tfhe_b200_encrypt_bits_device",
+    "tfhe_b200_decrypt_bits_device", "tfhe_b200_cmux_batch", "tfhe_b200_sample_extract_batch",
+    "tfhe_b200_file_write", "tfhe_b200_file_info", "tfhe_b200_file_read", "tfhe_b200_file_last_error",
 ]
+FILE_SECRET, FILE_BK, FILE_KSK, FILE_TLWE0, FILE_TLWE1, FILE_TRLWE, FILE_TRGSW = range(1, 8)
+ERR_IO = 5
 
 
 class Params(C.Structure):
@@ -83,6 +88,17 @@ def lib():
         "tfhe_b200_phase": (i32, [vp, vp, sz, vp]),
         "tfhe_b200_decrypt_bits": (i32, [vp, vp, sz, vp]),
         "tfhe_b200_version": (C.c_char_p, []),
+        "tfhe_b200_keygen_device": (i32, [vp, u64, vp, vp]),
+        "tfhe_b200_export_bk": (i32, [vp, vp]),
+        "tfhe_b200_export_ksk": (i32, [vp, vp]),
+        "tfhe_b200_encrypt_bits_device": (i32, [vp, u64, u64, vp, vp, sz, vp, vp]),
+        "tfhe_b200_decrypt_bits_device": (i32, [vp, vp, vp, sz, vp, vp, vp]),
+        "tfhe_b200_cmux_batch": (i32, [vp, vp, sz, vp, vp, vp, sz]),
+        "tfhe_b200_sample_extract_batch": (i32, [vp, vp, i32, vp, sz]),
+        "tfhe_b200_file_write": (i32, [C.c_char_p, i32, vp, u64]),
+        "tfhe_b200_file_info": (i32, [C.c_char_p, C.POINTER(i32), C.POINTER(u64), C.POINTER(u64)]),
+        "tfhe_b200_file_read": (i32, [C.c_char_p, i32, vp, u64]),
+        "tfhe_b200_file_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         f = getattr(l, name)

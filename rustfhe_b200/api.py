@@ -187,6 +187,63 @@ class Cryptor:
         return ph
 
 
+# ---- flat file format (the reference has no serialisation) ----
+_FILE_SHAPES = {K.FILE_SECRET: (np.uint8, (K.n + K.N,)), K.FILE_BK: (np.uint32, (K.BK_WORDS,)), K.FILE_KSK: (np.uint32, (K.KSK_WORDS,)),
+                K.FILE_TLWE0: (np.uint32, (K.n + 1,)), K.FILE_TLWE1: (np.uint32, (K.N + 1,)), K.FILE_TRLWE: (np.uint32, (2, K.N)),
+                K.FILE_TRGSW: (np.uint32, (2 * K.L, 2, K.N))}
+
+
+def _file_check(rc):
+    if rc != K.OK:
+        msg = lib().tfhe_b200_file_last_error()
+        raise TfheError(rc, msg.decode() if msg else "")
+
+
+def save(path, kind, array):
+    """Write keys / ciphertext batches in the flat little-endian format of rustfhe_b200/csrc/wire.cpp."""
+    dtype, shape = _FILE_SHAPES[kind]
+    a = np.ascontiguousarray(array, dtype)
+    rec = int(np.prod(shape))
+    if a.size % rec:
+        raise ValueError(f"array of {a.size} elements is not a whole number of records of {rec}")
+    _file_check(lib().tfhe_b200_file_write(str(path).encode(), kind, ptr(a.reshape(-1)), a.size // rec))
+
+
+def load(path, kind=None):
+    """Read a file written by `save`; returns (kind, array[count, *record shape]) (keys: the single record)."""
+    k, cnt, nbytes = C.c_int(), C.c_uint64(), C.c_uint64()
+    _file_check(lib().tfhe_b200_file_info(str(path).encode(), C.byref(k), C.byref(cnt), C.byref(nbytes)))
+    if kind is not None and k.value != kind:
+        raise TfheError(K.ERR_IO, f"{path}: holds kind {k.value}, expected {kind}")
+    dtype, shape = _FILE_SHAPES[k.value]
+    out = np.empty(nbytes.value // np.dtype(dtype).itemsize, dtype)
+    _file_check(lib().tfhe_b200_file_read(str(path).encode(), k.value, ptr(out), nbytes.value))
+    out = out.reshape((cnt.value,) + shape)
+    if k.value in (K.FILE_SECRET, K.FILE_BK, K.FILE_KSK):
+        out = out[0]
+    return k.value, out
+
+
+class TRLWERep:
+    """Level-1 ring ciphertexts [B][2][N] (trlwe.rs:13-16): the operations the reference exposes below the gate level."""
+
+    @staticmethod
+    def sample_extract_index(engine, rep, index):   # trlwe.rs:110-121
+        return engine.sample_extract_batch(rep, index)
+
+
+class TRGSWRep:
+    """Torus-domain TRGSW samples [ntrgsw][2l][2][N] (trgsw.rs:23-26)."""
+
+    @staticmethod
+    def cross(engine, trgsw, rhs):                  # trgsw.rs:264-314
+        return engine.external_product_batch(trgsw, rhs)
+
+    @staticmethod
+    def cmux(engine, trgsw, rep_1, rep_0):          # trgsw.rs:315-330
+        return engine.cmux_batch(trgsw, rep_1, rep_0)
+
+
 class DeviceEngine:
     """Owner of one tfhe_b200_ctx (one CUDA device). Thin, explicit wrapper of the C ABI."""
 
@@ -228,6 +285,29 @@ class DeviceEngine:
 
     def load_ksk_device(self, dev_ptr, stream=0):
         self._ck(self._l.tfhe_b200_load_ksk_device(self._ctx, C.c_void_p(dev_ptr), C.c_void_p(stream)))
+
+    def keygen_device(self, seed, s_key_tlwelv0, s_key_tlwelv1):
+        """BootstrappingKey::new + KeySwitchingKey::new on the device (bit-identical to the host keygen with this seed)."""
+        self._ck(self._l.tfhe_b200_keygen_device(self._ctx, seed, ptr(np.ascontiguousarray(s_key_tlwelv0, np.uint8)),
+                                                 ptr(np.ascontiguousarray(s_key_tlwelv1, np.uint8))))
+
+    def export_bk(self):
+        w = np.empty(K.BK_WORDS, np.uint32)
+        self._ck(self._l.tfhe_b200_export_bk(self._ctx, ptr(w)))
+        return BootstrappingKey(w)
+
+    def export_ksk(self):
+        w = np.empty(K.KSK_WORDS, np.uint32)
+        self._ck(self._l.tfhe_b200_export_ksk(self._ctx, ptr(w)))
+        return KeySwitchingKey(w)
+
+    def encrypt_bits_device(self, seed, ct_index0, s_key, bits_ptr, B, out_ptr, stream=0):
+        self._ck(self._l.tfhe_b200_encrypt_bits_device(self._ctx, seed, ct_index0, ptr(np.ascontiguousarray(s_key, np.uint8)),
+                                                       C.c_void_p(bits_ptr), B, C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def decrypt_bits_device(self, s_key, ct_ptr, B, bits_ptr=None, phase_ptr=None, stream=0):
+        self._ck(self._l.tfhe_b200_decrypt_bits_device(self._ctx, ptr(np.ascontiguousarray(s_key, np.uint8)), C.c_void_p(ct_ptr), B,
+                                                       C.c_void_p(bits_ptr or None), C.c_void_p(phase_ptr or None), C.c_void_p(stream)))
 
     def set_decomp_mask(self, mask):
         self._ck(self._l.tfhe_b200_set_decomp_mask(self._ctx, mask))
@@ -300,6 +380,21 @@ class DeviceEngine:
         self._ck(self._l.tfhe_b200_external_product_batch(self._ctx, ptr(trgsw), len(trgsw), ptr(trlwe), ptr(out), len(trlwe)))
         return out
 
+    def cmux_batch(self, trgsw, rep_1, rep_0):
+        trgsw = np.ascontiguousarray(trgsw, np.uint32).reshape(-1, 2 * K.L, 2, K.N)
+        rep_1 = np.ascontiguousarray(rep_1, np.uint32).reshape(-1, 2, K.N)
+        rep_0 = np.ascontiguousarray(rep_0, np.uint32).reshape(-1, 2, K.N)
+        assert rep_1.shape == rep_0.shape
+        out = np.empty_like(rep_1)
+        self._ck(self._l.tfhe_b200_cmux_batch(self._ctx, ptr(trgsw), len(trgsw), ptr(rep_1), ptr(rep_0), ptr(out), len(rep_1)))
+        return out
+
+    def sample_extract_batch(self, trlwe, index=0):
+        trlwe = np.ascontiguousarray(trlwe, np.uint32).reshape(-1, 2, K.N)
+        out = np.empty((len(trlwe), K.N + 1), np.uint32)
+        self._ck(self._l.tfhe_b200_sample_extract_batch(self._ctx, ptr(trlwe), index, ptr(out), len(trlwe)))
+        return out
+
     def negacyclic_mul_batch(self, a, d):
         a = np.ascontiguousarray(a, np.uint32).reshape(-1, K.N)
         d = np.ascontiguousarray(d, np.int32).reshape(-1, K.N)
@@ -313,11 +408,22 @@ class TFHE:
     """`TFHE<TLWE_N, TRLWE_N>`: owns the bootstrapping and key-switching keys and evaluates bootstrapped gates
     (hom_nand/src/tfhe.rs:9-113). Gates take and return TLWERep batches [B][n+1]."""
 
-    def __init__(self, bk, ksk, device=0, decomp_mask=K.MASK_FAITHFUL):
+    def __init__(self, bk, ksk, device=0, decomp_mask=K.MASK_FAITHFUL, engine=None):
         self.bk, self.ksk = bk, ksk
+        if engine is not None:           # keys already on the device (TFHE.new_on_device)
+            self.engine = engine
+            return
         self.engine = DeviceEngine(device, decomp_mask)
         self.engine.load_ksk(ksk.words)
         self.engine.load_bk(bk.words)
+
+    @staticmethod
+    def new_on_device(s_key_tlwelv0, s_key_tlwelv1, seed=0, device=0, decomp_mask=K.MASK_FAITHFUL):
+        """TFHE::new with both keys generated ON the device (same seed -> same keys as `TFHE.new`); `bk` / `ksk` stay None
+        until exported with `engine.export_bk()` / `engine.export_ksk()`."""
+        eng = DeviceEngine(device, decomp_mask)
+        eng.keygen_device(seed, s_key_tlwelv0, s_key_tlwelv1)
+        return TFHE(None, None, device, decomp_mask, engine=eng)
 
     @staticmethod
     def new(s_key_tlwelv0, s_key_tlwelv1, seed=0, device=0, decomp_mask=K.MASK_FAITHFUL):

@@ -23,7 +23,8 @@ def _newer(target, sources):
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("engine.cu", "hostkeys.cpp", "ntt32.cuh", "cmux_steps.cuh", "ntt_tables.h")] + [
+    return [os.path.join(CSRC, f) for f in ("engine.cu", "hostkeys.cpp", "wire.cpp", "ntt32.cuh", "cmux_steps.cuh", "ntt_tables.h",
+                                            "tfhe_rng.cuh")] + [
         os.path.join(HERE, "..", "include", "tfhe_b200.h")]
 
 
@@ -35,7 +36,7 @@ def build(force=False, verbose=False):
                 return LIB  # GPU box without a toolkit: use the prebuilt library that travelled with the snapshot
             raise RuntimeError("nvcc not found and librustfhe_b200.so is not built")
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-            os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "hostkeys.cpp"), "-o", LIB]
+            os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "hostkeys.cpp"), os.path.join(CSRC, "wire.cpp"), "-o", LIB]
         subprocess.check_call(cmd)
     emul_src = [os.path.join(CSRC, f) for f in ("host_emul.cpp", "ntt32.cuh", "cmux_steps.cuh", "ntt_tables.h")]
     if force or not _newer(EMUL, emul_src):

@@ -15,6 +15,7 @@
 #include <vector>
 #include "../../include/tfhe_b200.h"
 #include "cmux_steps.cuh"
+#include "tfhe_rng.cuh"
 
 using namespace tfhe;
 
@@ -73,6 +74,7 @@ struct BrArgs {
     uint32_t* lwe1_out;      // [B][N+1]
     // external-product mode
     const uint32_t* trlwe_in;  // [B][2][N]
+    const uint32_t* trlwe_in0; // [B][2][N] or null: cmux, the product is taken of (trlwe_in - trlwe_in0) and trlwe_in0 is added back
     long ntrgsw;
     int stagger_cycles;
     // gate -> CTA distribution (see the kernel prologue)
@@ -133,7 +135,8 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     if (EXTPROD) {
         nsteps = 1;
         const uint32_t* src = a.trlwe_in + (size_t)gate * 2048;
-        for (int k = tid6; k < 2048; k += THREADS_PER_GATE) acc[k] = src[k];
+        const uint32_t* sub = a.trlwe_in0 ? a.trlwe_in0 + (size_t)gate * 2048 : nullptr;   // cmux: rep_1 - rep_0 (trgsw.rs:315-322)
+        for (int k = tid6; k < 2048; k += THREADS_PER_GATE) acc[k] = sub ? src[k] - sub[k] : src[k];
     } else {
         uint32_t* lin = dh;
         const bool second = gate >= a.split;
@@ -224,7 +227,8 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     // ---- epilogue: sample_extract_index(0) (trlwe.rs:110-121) + key-switch digits (tlwe.rs:47-64) ----
     if (a.trlwe_out) {
         uint32_t* dst = a.trlwe_out + (size_t)gate * 2048;
-        for (int k = tid6; k < 2048; k += THREADS_PER_GATE) dst[k] = acc[k];
+        const uint32_t* add = (EXTPROD && a.trlwe_in0) ? a.trlwe_in0 + (size_t)gate * 2048 : nullptr;   // cmux: ... + rep_0
+        for (int k = tid6; k < 2048; k += THREADS_PER_GATE) dst[k] = add ? acc[k] + add[k] : acc[k];
     }
     if (a.ksdig || a.lwe1_out) {
         for (int i = tid6; i < 1024; i += THREADS_PER_GATE) {
@@ -308,8 +312,11 @@ __global__ void lwe1_prepare_kernel(const uint32_t* __restrict__ lwe1, uint16_t*
 // exact negacyclic product a (torus) * d (small ints): one warp per product, 7 transforms
 // =====================================================================================================
 constexpr int PM_WARPS = 2;
+// product g reads a = A + g*a_stride, d = D + g*d_stride (d_stride 0: one multiplier shared by the batch) and writes
+// out + g*o_stride (accumulate: += instead of =)
 __global__ void __launch_bounds__(PM_WARPS * 32) polymul_kernel(const uint32_t* __restrict__ A, const int32_t* __restrict__ D,
-                                                               uint32_t* __restrict__ out, long B) {
+                                                               uint32_t* __restrict__ out, long B, long a_stride, long d_stride,
+                                                               long o_stride, int accumulate) {
     __shared__ __align__(16) uint32_t twF[32 * TWB_STRIDE];
     __shared__ __align__(16) uint32_t twI[32 * TWB_STRIDE];
     __shared__ __align__(16) uint32_t scratch[PM_WARPS][2][1024];
@@ -318,8 +325,8 @@ __global__ void __launch_bounds__(PM_WARPS * 32) polymul_kernel(const uint32_t* 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long g = (long)blockIdx.x * PM_WARPS + warp;
     if (g >= B) return;
-    const uint32_t* a = A + (size_t)g * 1024;
-    const int32_t* d = D + (size_t)g * 1024;
+    const uint32_t* a = A + (size_t)g * a_stride;
+    const int32_t* d = D + (size_t)g * d_stride;
     uint32_t* S = scratch[warp][0];
     uint32_t* T = scratch[warp][1];
     uint32_t dh[32], x[32], res[32];
@@ -351,8 +358,92 @@ __global__ void __launch_bounds__(PM_WARPS * 32) polymul_kernel(const uint32_t* 
 #pragma unroll
         for (int r = 0; r < 32; r++) res[r] += x[r];
     }
+    uint32_t* o = out + (size_t)g * o_stride;
 #pragma unroll
-    for (int r = 0; r < 32; r++) out[(size_t)g * 1024 + 32 * r + lane] = res[r];
+    for (int r = 0; r < 32; r++) o[32 * r + lane] = accumulate ? o[32 * r + lane] + res[r] : res[r];
+}
+
+// =====================================================================================================
+// Device-side key generation and encryption.  Same seeded counter generator and the same operation
+// order as the host keygen (hostkeys.cpp, tfhe_rng.cuh): the device keys are bit-identical to the host keys.
+// Reference: BootstrappingKey::new (tfhe.rs:119-126), TRGSW/TRLWE encrypt (trgsw.rs:117-139,213-229; trlwe.rs:127-137),
+// KeySwitchingKey::new (tlwe.rs:247-277), TLWE encrypt / decrypt (tlwe.rs:213-240).
+// =====================================================================================================
+using tfhe_rng::Rng;
+// rows of the bootstrapping key before the a*s product: A = uniform, B = noise      bk: [n][2l][2][N], poly 0 = B, poly 1 = A
+__global__ void bk_fill_kernel(uint32_t* __restrict__ bk, uint64_t seed, long nwords /* = rows * N */) {
+    const Rng ra(seed, tfhe_rng::BK_A), re(seed, tfhe_rng::BK_E);
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < nwords; t += (long)gridDim.x * blockDim.x) {
+        const long row = t >> 10;
+        const int k = (int)(t & 1023);
+        bk[(size_t)(row * 2 + 1) * 1024 + k] = ra.u32((uint64_t)t);
+        bk[(size_t)(row * 2 + 0) * 1024 + k] = re.gauss((uint64_t)t, tfhe_rng::SCALE_BK);
+    }
+}
+// gadget term of TRGSW_{s1}(s0_i): s0_i / Bg^(j+1) on B[0] of rows j < l and on A[0] of rows l + j (trgsw.rs:213-229)
+__global__ void bk_gadget_kernel(uint32_t* __restrict__ bk, const uint8_t* __restrict__ s0, int rows) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const int i = row / 6, j = row % 6;
+    const uint32_t mu = (uint32_t)s0[i] << (32 - 6 * ((j % 3) + 1));
+    bk[(size_t)(row * 2 + (j < 3 ? 0 : 1)) * 1024] += mu;
+}
+// one warp per LWE row under s0: a = uniform, b = <a, s0> + noise + message.
+//   mode 0: key-switching key, row id = (i, l, d-1), message = d * s1_i / 2^(2(l+1))      (tlwe.rs:247-283)
+//   mode 1: encryption of bits[g], row id = ct_index0 + g, message = +-1/8                  (tlwe.rs:181-186,213-228)
+__global__ void lwe_rows_kernel(uint32_t* __restrict__ out, long rows, uint64_t seed, uint64_t index0, const uint8_t* __restrict__ s0,
+                                const uint8_t* __restrict__ s1, const uint8_t* __restrict__ bits, int mode) {
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const Rng ra(seed, mode == 0 ? tfhe_rng::KSK_A : tfhe_rng::ENC_A), re(seed, mode == 0 ? tfhe_rng::KSK_E : tfhe_rng::ENC_E);
+    const uint64_t id = index0 + (uint64_t)row;
+    uint32_t* ct = out + (size_t)row * (LWE_N + 1);
+    uint32_t part = 0;
+    for (int c = lane; c < LWE_N; c += 32) {
+        const uint32_t av = ra.u32(id * LWE_N + c);
+        ct[1 + c] = av;
+        if (s0[c]) part += av;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+    if (lane == 0) {
+        uint32_t msg;
+        if (mode == 0) {
+            const int i = (int)(row / 24), l = (int)((row / 3) % 8), d = (int)(row % 3) + 1;
+            msg = (uint32_t)(d * s1[i]) << (32 - 2 * (l + 1));
+        } else {
+            msg = bits[row] ? 0x20000000u : 0xE0000000u;
+        }
+        ct[0] = msg + re.gauss(id, tfhe_rng::SCALE_LV0) + part;
+    }
+}
+// phase = b - <a, s0> and the decoded bit (tlwe.rs:187-194,230-240); one warp per ciphertext
+__global__ void lwe_phase_kernel(const uint32_t* __restrict__ ct, long rows, const uint8_t* __restrict__ s0, uint32_t* __restrict__ phase,
+                                 uint8_t* __restrict__ bits) {
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const uint32_t* c = ct + (size_t)row * (LWE_N + 1);
+    uint32_t part = 0;
+    for (int k = lane; k < LWE_N; k += 32) if (s0[k]) part += c[1 + k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+    if (lane == 0) {
+        const uint32_t ph = c[0] - part;
+        if (phase) phase[row] = ph;
+        if (bits) bits[row] = ((float)ph * (1.0f / 4294967296.0f)) < 0.5f ? 1 : 0;   // torus2binary, math.rs:684-690
+    }
+}
+// TRLWERep::sample_extract_index(index) (trlwe.rs:110-121): b' = b[index]; a'_i = a[index-i] (i <= index), -a[N+index-i] otherwise
+__global__ void sample_extract_kernel(const uint32_t* __restrict__ trlwe, uint32_t* __restrict__ out, long B, int index) {
+    const long g = blockIdx.x;
+    if (g >= B) return;
+    const uint32_t* b = trlwe + (size_t)g * 2048;
+    const uint32_t* a = b + 1024;
+    uint32_t* o = out + (size_t)g * 1025;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) o[1 + i] = (i <= index) ? a[index - i] : 0u - a[1024 + index - i];
+    if (threadIdx.x == 0) o[0] = b[index];
 }
 
 // =====================================================================================================
@@ -369,14 +460,20 @@ struct Slot {
     uint16_t* ksdig = nullptr; size_t ksdig_cap = 0;
     uint32_t* tmp[4] = {nullptr, nullptr, nullptr, nullptr}; size_t tmp_cap[4] = {0, 0, 0, 0};
     uint32_t* scratch = nullptr; size_t scratch_cap = 0;   // hom_mux intermediates / transformed TRGSWs of step-level calls
+    uint8_t* s0buf = nullptr;                               // [1024] device copy of a caller's lv0 secret key (encrypt / decrypt)
 };
 
+static const size_t BK_TORUS_BYTES = (size_t)LWE_N * 12 * 1024 * 4;
+static const size_t KSK_BYTES = (size_t)1024 * 8 * 3 * (LWE_N + 1) * 4;
 struct tfhe_b200_ctx {
     tfhe_b200_params prm;
     int device = 0;
     int sm_count = 0;
     uint32_t* bkdev = nullptr;   // n * BK_STEP_WORDS
     uint32_t* kskdev = nullptr;  // [N][t][3][n+1]
+    uint32_t* bk_torus = nullptr;  // [n][2l][2][N] torus-domain key as loaded / generated (kept for export: 31 MB)
+    uint8_t* keybits = nullptr;    // device copy of (s0[n] | pad to 1024 | s1[N]) during device keygen
+    int32_t* s1poly = nullptr;     // s1 as a polynomial of small integers, the multiplier of the a*s products
     int stagger_cycles = 0;
     bool have_bk = false, have_ksk = false;
     static constexpr int NSLOT = 4;
@@ -479,6 +576,10 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     for (auto& slot : ctx->ev) for (auto& ev : slot) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->bkdev, (size_t)LWE_N * BK_STEP_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc(bk)", e);
     if ((e = cudaMalloc(&ctx->kskdev, (size_t)1024 * 8 * 3 * (LWE_N + 1) * 4)) != cudaSuccess) return bail("cudaMalloc(ksk)", e);
+    if ((e = cudaMalloc(&ctx->bk_torus, BK_TORUS_BYTES)) != cudaSuccess) return bail("cudaMalloc(bk_torus)", e);
+    if ((e = cudaMalloc(&ctx->keybits, 2048)) != cudaSuccess) return bail("cudaMalloc(keybits)", e);
+    if ((e = cudaMalloc(&ctx->s1poly, 1024 * 4)) != cudaSuccess) return bail("cudaMalloc(s1poly)", e);
+    for (auto& s : ctx->slots) if ((e = cudaMalloc(&s.s0buf, 1024)) != cudaSuccess) return bail("cudaMalloc(s0buf)", e);
     if ((e = set_smem(blind_rotate_kernel<2, false, 1>, 2)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<1, false, 1>, 1)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<1, false, 2>, 1)) != cudaSuccess) return bail("smem attr", e);
@@ -498,9 +599,9 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     if (!ctx) return TFHE_B200_ERR_PARAM;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->bkdev); cudaFree(ctx->kskdev);
+    cudaFree(ctx->bkdev); cudaFree(ctx->kskdev); cudaFree(ctx->bk_torus); cudaFree(ctx->keybits); cudaFree(ctx->s1poly);
     for (auto& s : ctx->slots) {
-        cudaFree(s.ksdig); cudaFree(s.scratch);
+        cudaFree(s.ksdig); cudaFree(s.scratch); cudaFree(s.s0buf);
         for (auto p : s.tmp) cudaFree(p);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -566,25 +667,19 @@ static int transform_keys(tfhe_b200_ctx* ctx, const uint32_t* src_dev, uint32_t*
 int tfhe_b200_load_bk_device(tfhe_b200_ctx* ctx, const uint32_t* bk_dev, void* stream) {
     if (!ctx || !bk_dev) return fail(ctx, TFHE_B200_ERR_PARAM, "load_bk_device: null argument");
     CK(cudaSetDevice(ctx->device));
-    RC(transform_keys(ctx, bk_dev, ctx->bkdev, LWE_N, (cudaStream_t)stream));
+    if (bk_dev != ctx->bk_torus) CK(cudaMemcpyAsync(ctx->bk_torus, bk_dev, BK_TORUS_BYTES, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    RC(transform_keys(ctx, ctx->bk_torus, ctx->bkdev, LWE_N, (cudaStream_t)stream));
     ctx->have_bk = true;
     return TFHE_B200_OK;
 }
 int tfhe_b200_load_bk(tfhe_b200_ctx* ctx, const uint32_t* bk_host) {
     if (!ctx || !bk_host) return fail(ctx, TFHE_B200_ERR_PARAM, "load_bk: null argument");
     CK(cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)LWE_N * 12 * 1024 * 4;
     cudaStream_t st = ctx->slots[0].stream;
-    uint32_t* staging = nullptr;
-    CK(cudaMalloc(&staging, bytes));
-    cudaError_t e = cudaMemcpyAsync(staging, bk_host, bytes, cudaMemcpyHostToDevice, st);
-    int rc = TFHE_B200_OK;
-    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = TFHE_B200_ERR_CUDA; }
-    if (!rc) rc = tfhe_b200_load_bk_device(ctx, staging, st);
-    e = cudaStreamSynchronize(st);
-    if (!rc && e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = TFHE_B200_ERR_CUDA; }
-    cudaFree(staging);
-    return rc;
+    CK(cudaMemcpyAsync(ctx->bk_torus, bk_host, BK_TORUS_BYTES, cudaMemcpyHostToDevice, st));
+    RC(tfhe_b200_load_bk_device(ctx, ctx->bk_torus, st));
+    CK(cudaStreamSynchronize(st));
+    return TFHE_B200_OK;
 }
 int tfhe_b200_load_ksk_device(tfhe_b200_ctx* ctx, const uint32_t* ksk_dev, void* stream) {
     if (!ctx || !ksk_dev) return fail(ctx, TFHE_B200_ERR_PARAM, "load_ksk_device: null argument");
@@ -806,6 +901,87 @@ int tfhe_b200_mux_batch(tfhe_b200_ctx* ctx, const uint32_t* control, const uint3
 
 }  // extern "C"
 
+// ---- device-side key generation, encryption, decryption ----
+extern "C" {
+
+int tfhe_b200_keygen_device(tfhe_b200_ctx* ctx, uint64_t seed, const uint8_t* s0, const uint8_t* s1) {
+    if (!ctx || !s0 || !s1) return fail(ctx, TFHE_B200_ERR_PARAM, "keygen_device: null argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    uint8_t hb[2048];
+    int32_t hp[1024];
+    memset(hb, 0, sizeof hb);
+    memcpy(hb, s0, LWE_N);
+    memcpy(hb + 1024, s1, 1024);
+    for (int k = 0; k < 1024; k++) hp[k] = s1[k] ? 1 : 0;
+    CK(cudaMemcpyAsync(ctx->keybits, hb, sizeof hb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->s1poly, hp, sizeof hp, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // hb / hp live on this stack frame
+    const int rows = LWE_N * 6;
+    // BK rows: A uniform, B = noise; B += A * s1 (exact negacyclic product); gadget term; NTT-domain transform
+    bk_fill_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->bk_torus, seed, (long)rows * 1024);
+    polymul_kernel<<<(rows + PM_WARPS - 1) / PM_WARPS, PM_WARPS * 32, 0, st>>>(ctx->bk_torus + 1024, ctx->s1poly, ctx->bk_torus, rows, 2048, 0,
+                                                                                 2048, 1);
+    bk_gadget_kernel<<<(rows + 255) / 256, 256, 0, st>>>(ctx->bk_torus, ctx->keybits, rows);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    RC(transform_keys(ctx, ctx->bk_torus, ctx->bkdev, LWE_N, st));
+    // KSK rows straight into the device key
+    const long krows = 1024L * 8 * 3;
+    lwe_rows_kernel<<<(unsigned)((krows + 7) / 8), 256, 0, st>>>(ctx->kskdev, krows, seed, 0, ctx->keybits, ctx->keybits + 1024, nullptr, 0);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ctx->have_bk = ctx->have_ksk = true;
+    return TFHE_B200_OK;
+}
+int tfhe_b200_export_bk(tfhe_b200_ctx* ctx, uint32_t* bk_host) {
+    if (!ctx || !bk_host) return fail(ctx, TFHE_B200_ERR_PARAM, "export_bk: null argument");
+    if (!ctx->have_bk) return fail(ctx, TFHE_B200_ERR_STATE, "export_bk: bootstrapping key not loaded");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(bk_host, ctx->bk_torus, BK_TORUS_BYTES, cudaMemcpyDeviceToHost));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_export_ksk(tfhe_b200_ctx* ctx, uint32_t* ksk_host) {
+    if (!ctx || !ksk_host) return fail(ctx, TFHE_B200_ERR_PARAM, "export_ksk: null argument");
+    if (!ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "export_ksk: key-switching key not loaded");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(ksk_host, ctx->kskdev, KSK_BYTES, cudaMemcpyDeviceToHost));
+    return TFHE_B200_OK;
+}
+// bits_dev: [B] bytes on the device; out_dev: [B][n+1] on the device; s0: host
+int tfhe_b200_encrypt_bits_device(tfhe_b200_ctx* ctx, uint64_t seed, uint64_t ct_index0, const uint8_t* s0, const uint8_t* bits_dev,
+                                  size_t B, uint32_t* out_dev, void* stream) {
+    if (!ctx || !s0 || (B && (!bits_dev || !out_dev))) return fail(ctx, TFHE_B200_ERR_PARAM, "encrypt_bits_device: null argument");
+    if (B == 0) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, false, &s));
+    CK(cudaMemcpyAsync(s->s0buf, s0, LWE_N, cudaMemcpyHostToDevice, st));
+    lwe_rows_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(out_dev, (long)B, seed, ct_index0, s->s0buf, nullptr, bits_dev, 1);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return slot_release(ctx, s, st);
+}
+// phase_dev / bits_dev: either may be NULL
+int tfhe_b200_decrypt_bits_device(tfhe_b200_ctx* ctx, const uint8_t* s0, const uint32_t* ct_dev, size_t B, uint8_t* bits_dev,
+                                  uint32_t* phase_dev, void* stream) {
+    if (!ctx || !s0 || (B && !ct_dev)) return fail(ctx, TFHE_B200_ERR_PARAM, "decrypt_bits_device: null argument");
+    if (B == 0) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, false, &s));
+    CK(cudaMemcpyAsync(s->s0buf, s0, LWE_N, cudaMemcpyHostToDevice, st));
+    lwe_phase_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(ct_dev, (long)B, s->s0buf, phase_dev, bits_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return slot_release(ctx, s, st);
+}
+
+}  // extern "C"
+
 // ---- step-level entries: host pointers, synchronous.  `fn` enqueues the device work on (slot, stream). ----
 struct HostIo {
     const void* in[3] = {nullptr, nullptr, nullptr};
@@ -895,7 +1071,43 @@ int tfhe_b200_negacyclic_mul_batch(tfhe_b200_ctx* ctx, const uint32_t* a, const 
     if (B == 0) return TFHE_B200_OK;
     HostIo io; io.in[0] = a; io.in_bytes[0] = B * 4096; io.in[1] = d; io.in_bytes[1] = B * 4096; io.out = out; io.out_bytes = B * 4096;
     return with_host_io(ctx, io, [&](Slot*, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
-        polymul_kernel<<<(unsigned)((B + PM_WARPS - 1) / PM_WARPS), PM_WARPS * 32, 0, st>>>(di[0], (const int32_t*)di[1], dout, (long)B);
+        polymul_kernel<<<(unsigned)((B + PM_WARPS - 1) / PM_WARPS), PM_WARPS * 32, 0, st>>>(di[0], (const int32_t*)di[1], dout, (long)B, 1024, 1024,
+                                                                                             1024, 0);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return TFHE_B200_OK;
+    });
+}
+
+// TRGSWRep::cmux(rep_1, rep_0) = cross(rep_1 - rep_0) + rep_0  (trgsw.rs:315-322, 323-330); trgsw in the torus domain
+int tfhe_b200_cmux_batch(tfhe_b200_ctx* ctx, const uint32_t* trgsw, size_t ntrgsw, const uint32_t* rep1, const uint32_t* rep0,
+                         uint32_t* out, size_t B) {
+    if (!ctx || !trgsw || !rep1 || !rep0 || !out || ntrgsw == 0) return fail(ctx, TFHE_B200_ERR_PARAM, "cmux_batch: bad argument");
+    if (B == 0) return TFHE_B200_OK;
+    HostIo io; io.in[0] = rep1; io.in_bytes[0] = B * 2048 * 4; io.in[1] = trgsw; io.in_bytes[1] = ntrgsw * 12 * 1024 * 4;
+    io.in[2] = rep0; io.in_bytes[2] = B * 2048 * 4; io.out = out; io.out_bytes = B * 2048 * 4;
+    return with_host_io(ctx, io, [&](Slot* s, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
+        RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, ntrgsw * BK_STEP_WORDS * 4));
+        RC(transform_keys(ctx, di[1], s->scratch, (int)ntrgsw, st));
+        BrArgs a{};
+        a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
+        a.trlwe_in = di[0]; a.trlwe_in0 = di[2]; a.trlwe_out = dout; a.ntrgsw = (long)ntrgsw;
+        const unsigned grid = (unsigned)((B + 1) / 2);
+        a.cta_base = (int)(B / grid); a.cta_rem = (int)(B % grid);
+        blind_rotate_kernel<2, true, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return TFHE_B200_OK;
+    });
+}
+// TRLWERep::sample_extract_index(index) (trlwe.rs:110-121): [B][2][N] -> [B][N+1]
+int tfhe_b200_sample_extract_batch(tfhe_b200_ctx* ctx, const uint32_t* trlwe, int index, uint32_t* out_lwe1, size_t B) {
+    if (!ctx || !trlwe || !out_lwe1) return fail(ctx, TFHE_B200_ERR_PARAM, "sample_extract_batch: null argument");
+    if (index < 0 || index >= 1024) return fail(ctx, TFHE_B200_ERR_PARAM, "sample_extract_batch: index out of range");
+    if (B == 0) return TFHE_B200_OK;
+    HostIo io; io.in[0] = trlwe; io.in_bytes[0] = B * 2048 * 4; io.out = out_lwe1; io.out_bytes = B * 1025 * 4;
+    return with_host_io(ctx, io, [&](Slot*, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
+        sample_extract_kernel<<<(unsigned)B, 256, 0, st>>>(di[0], dout, (long)B, index);
         ctx->launches++;
         CK(cudaGetLastError());
         return TFHE_B200_OK;

@@ -10,31 +10,13 @@
 #include <thread>
 #include <vector>
 #include "../../include/tfhe_b200.h"
+#include "tfhe_rng.cuh"
 
 namespace {
 constexpr int n = 635, N = 1024, L = 3, BGBIT = 6, KS_T = 8, KS_BB = 2;
 constexpr uint32_t MU = 0x20000000u;
-enum Stream : uint64_t { S0 = 1, S1 = 2, BK_A = 3, BK_E = 4, KSK_A = 5, KSK_E = 6, ENC_A = 7, ENC_E = 8 };
+using namespace tfhe_rng;   // seeded counter-based generator + deterministic Gaussian shared with the device kernels
 
-inline uint64_t mix(uint64_t z) {
-    z += 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-struct Rng {  // counter based: value = f(seed, stream, index)
-    uint64_t h;
-    Rng(uint64_t seed, uint64_t stream) : h(mix(seed ^ mix(stream * 0xD6E8FEB86659FD93ull + 0x1234567ull))) {}
-    uint64_t u64(uint64_t idx) const { return mix(h + idx * 0x9E3779B97F4A7C15ull); }
-    uint32_t u32(uint64_t idx) const { return (uint32_t)(u64(idx) >> 32); }
-    // round(N(0, alpha) * 2^32), Box-Muller
-    uint32_t gauss(uint64_t idx, double alpha) const {
-        const double k = 1.0 / 9007199254740992.0;
-        const double u1 = (double)((u64(2 * idx) >> 11) + 1) * k, u2 = (double)(u64(2 * idx + 1) >> 11) * k;
-        const double g = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925 * u2);
-        return (uint32_t)(int32_t)std::llrint(g * alpha * 4294967296.0);
-    }
-};
 template <class F>
 void parallel_for(int count, F f) {
     unsigned nt = std::thread::hardware_concurrency();
@@ -76,7 +58,7 @@ int tfhe_b200_keygen_bk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uin
         uint32_t* B = bk + ((size_t)row * 2 + 0) * N;
         uint32_t* A = bk + ((size_t)row * 2 + 1) * N;
         const uint64_t base = (uint64_t)row * N;
-        for (int k = 0; k < N; k++) { A[k] = ra.u32(base + k); B[k] = re.gauss(base + k, 1.0 / 33554432.0); }
+        for (int k = 0; k < N; k++) { A[k] = ra.u32(base + k); B[k] = re.gauss(base + k, SCALE_BK); }
         add_mul_binary(A, ones, B);
         const uint32_t mu = (uint32_t)s0[i] << (32 - BGBIT * ((j % L) + 1));
         if (j < L) B[0] += mu; else A[0] += mu;
@@ -92,7 +74,7 @@ int tfhe_b200_keygen_ksk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, ui
     parallel_for(N * KS_T * 3, [&](int rowid) {
         const int i = rowid / (KS_T * 3), l = (rowid / 3) % KS_T, d = rowid % 3 + 1;
         uint32_t* row = ksk + (size_t)rowid * (n + 1);
-        uint32_t b = ((uint32_t)(d * s1[i]) << (32 - KS_BB * (l + 1))) + re.gauss((uint64_t)rowid, 1.0 / 32768.0);
+        uint32_t b = ((uint32_t)(d * s1[i]) << (32 - KS_BB * (l + 1))) + re.gauss((uint64_t)rowid, SCALE_LV0);
         for (int c = 0; c < n; c++) {
             const uint32_t a = ra.u32((uint64_t)rowid * n + c);
             row[1 + c] = a;
@@ -110,7 +92,7 @@ int tfhe_b200_encrypt_bits(uint64_t seed, uint64_t ct_index0, const uint8_t* s0,
     for (size_t g = 0; g < B; g++) {
         uint32_t* ct = out + g * (n + 1);
         const uint64_t id = ct_index0 + g;
-        uint32_t b = (bits[g] ? MU : 0u - MU) + re.gauss(id, 1.0 / 32768.0);
+        uint32_t b = (bits[g] ? MU : 0u - MU) + re.gauss(id, SCALE_LV0);
         for (int i = 0; i < n; i++) {
             const uint32_t a = ra.u32(id * n + i);
             ct[1 + i] = a;

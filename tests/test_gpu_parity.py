@@ -225,3 +225,85 @@ def test_error_paths(engine):
         assert ei.value.code == 3  # TFHE_B200_ERR_STATE: keys not loaded
     finally:
         fresh.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device-side key generation / encryption, scheme surface below the gate level
+# ---------------------------------------------------------------------------------------------------------------
+def test_device_keygen_bit_identical_to_host_and_oracle(oracle, keys):
+    """BootstrappingKey::new / KeySwitchingKey::new on the device (tfhe.rs:119-126, tlwe.rs:247-277): same seeded counter
+    generator and the same deterministic Gaussian as the host keygen and the oracle keygen -> identical keys, bit for bit."""
+    import rustfhe_b200 as R
+    eng = R.DeviceEngine(0)
+    try:
+        eng.keygen_device(keys.seed, keys.s0, keys.s1)
+        bk, ksk = eng.export_bk().words, eng.export_ksk().words
+        assert np.array_equal(ksk, keys.ksk.reshape(-1))
+        assert np.array_equal(bk, keys.bk.reshape(-1))
+        # and the device-generated keys evaluate gates: NAND truth table, bit-exact against the oracle with the oracle's keys
+        x, y = np.array([0, 0, 1, 1], np.uint8), np.array([0, 1, 0, 1], np.uint8)
+        c0, c1 = keys.encrypt(x, 1200), keys.encrypt(y, 1300)
+        out = eng.gate_batch(R.NAND, c0, c1)
+        assert np.array_equal(keys.decrypt(out), 1 - (x & y))
+        assert np.array_equal(out, oracle.gate_exact(keys, oracle.NAND, c0, c1))
+    finally:
+        eng.close()
+
+
+def test_device_encrypt_decrypt_bit_identical(engine, oracle, keys, rng):
+    """Cryptor::encrypto / decrypto (TLWE, bits) on the device (tlwe.rs:181-240) vs the oracle's encryption, same seed."""
+    import torch
+    B = 777
+    bits = rng.integers(0, 2, B).astype(np.uint8)
+    dbits = torch.from_numpy(bits).cuda()
+    dct = torch.empty((B, n + 1), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    engine.encrypt_bits_device(keys.seed, 4242, keys.s0, dbits.data_ptr(), B, dct.data_ptr(), st)
+    torch.cuda.synchronize()
+    ct = dct.cpu().numpy().view(np.uint32)
+    assert np.array_equal(ct, keys.encrypt(bits, 4242, seed=keys.seed))
+    dout = torch.empty(B, dtype=torch.uint8, device="cuda")
+    dph = torch.empty(B, dtype=torch.int32, device="cuda")
+    engine.decrypt_bits_device(keys.s0, dct.data_ptr(), B, dout.data_ptr(), dph.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert np.array_equal(dout.cpu().numpy(), bits)
+    assert np.array_equal(dph.cpu().numpy().view(np.uint32), keys.phase(ct))
+
+
+@pytest.mark.parametrize("index", [0, 1, 511, 1023])
+def test_sample_extract_index(engine, oracle, rng, index):
+    """TRLWERep::sample_extract_index(i) for i != 0 too (trlwe.rs:110-121), bit-exact."""
+    B = 7
+    trl = u32(rng, B, 2, N)
+    out = engine.sample_extract_batch(trl, index)
+    for g in range(B):
+        ref = np.zeros(N + 1, np.uint32)
+        oracle.lib().orc_sample_extract(trl[g].reshape(-1), index, ref)
+        assert np.array_equal(out[g], ref), (index, g)
+
+
+def test_cmux_exact_and_selects(engine, oracle, keys, rng):
+    """TRGSWRep::cmux(rep_1, rep_0) = cross(rep_1 - rep_0) + rep_0 (trgsw.rs:315-330): bit-exact vs the integer oracle, and
+    with real TRGSW(0) / TRGSW(1) samples (two elements of the bootstrapping key) it selects rep_0 / rep_1 up to noise."""
+    B = 6
+    rep1, rep0 = u32(rng, B, 2, N), u32(rng, B, 2, N)
+    trgsw = u32(rng, 2, 6, 2, N)
+    out = engine.cmux_batch(trgsw, rep1, rep0)
+    for g in range(B):
+        ref = np.zeros(2 * N, np.uint32)
+        oracle.lib().orc_external_product_exact(trgsw[g % 2].reshape(-1), (rep1[g] - rep0[g]).reshape(-1), 0x02084000, ref)
+        assert np.array_equal(out[g].reshape(-1), ref + rep0[g].reshape(-1)), g
+    # selection with real TRGSW encryptions of the lv0 key bits: BK_i = TRGSW_{s1}(s0_i)
+    i0 = int(np.flatnonzero(keys.s0 == 0)[0])
+    i1 = int(np.flatnonzero(keys.s0 == 1)[0])
+    bk = keys.bk.reshape(n, 6, 2, N)
+    m1 = np.full(N, 0x20000000, np.uint32)
+    m0 = np.full(N, 0xE0000000, np.uint32)
+    t1 = np.stack([m1, np.zeros(N, np.uint32)])[None]      # trivial TRLWE(+1/8), TRLWE(-1/8)
+    t0 = np.stack([m0, np.zeros(N, np.uint32)])[None]
+    for idx, want in ((i0, m0), (i1, m1)):
+        res = engine.cmux_batch(bk[idx][None], t1, t0)[0]
+        ph = np.zeros(N, np.uint32)
+        oracle.lib().orc_trlwe_phase(keys.s1, res.reshape(-1), ph)
+        err = (ph.astype(np.int64) - want.astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+        assert np.abs(err).max() < 2 ** 32 / 64, idx

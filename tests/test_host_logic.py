@@ -153,3 +153,64 @@ def test_golden_fixtures(oracle, keys):
     assert np.array_equal(ex, g["xp_exact"])
     d = (g["xp_ref"].astype(np.int64) - ex.astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
     assert np.abs(d).max() <= 1
+
+
+def test_wire_format_roundtrip_and_corruption(tmp_path, keys, rng):
+    """Flat file format (the reference has no serialisation): round trips for every kind, checksum and
+    header validation, empty batches."""
+    import rustfhe_b200 as R
+    cts = keys.encrypt(rng.integers(0, 2, 5).astype(np.uint8), 10)
+    cases = [(R.FILE_SECRET, np.concatenate([keys.s0, keys.s1])), (R.FILE_KSK, keys.ksk.reshape(-1)), (R.FILE_BK, keys.bk.reshape(-1)),
+             (R.FILE_TLWE0, cts), (R.FILE_TLWE1, rng.integers(0, 2 ** 32, (3, 1025), dtype=np.uint64).astype(np.uint32)),
+             (R.FILE_TRLWE, rng.integers(0, 2 ** 32, (2, 2, 1024), dtype=np.uint64).astype(np.uint32)),
+             (R.FILE_TRGSW, rng.integers(0, 2 ** 32, (2, 6, 2, 1024), dtype=np.uint64).astype(np.uint32)),
+             (R.FILE_TLWE0, np.zeros((0, 636), np.uint32))]
+    for k, (kind, arr) in enumerate(cases):
+        p = tmp_path / f"obj{k}.tfb"
+        R.save(p, kind, arr)
+        kind2, back = R.load(p)
+        assert kind2 == kind and np.array_equal(back.reshape(-1), np.asarray(arr).reshape(-1))
+        assert p.stat().st_size == 64 + np.asarray(arr).nbytes
+    # wrong expected kind, flipped payload byte, truncated file, bad magic
+    p = tmp_path / "obj3.tfb"
+    with pytest.raises(R.TfheError):
+        R.load(p, R.FILE_TLWE1)
+    raw = bytearray(p.read_bytes())
+    raw[100] ^= 1
+    (tmp_path / "bad1.tfb").write_bytes(raw)
+    with pytest.raises(R.TfheError, match="checksum"):
+        R.load(tmp_path / "bad1.tfb")
+    (tmp_path / "bad2.tfb").write_bytes(p.read_bytes()[:-4])
+    with pytest.raises(R.TfheError):
+        R.load(tmp_path / "bad2.tfb")
+    raw = bytearray(p.read_bytes())
+    raw[0] = ord("X")
+    (tmp_path / "bad3.tfb").write_bytes(raw)
+    with pytest.raises(R.TfheError, match="magic"):
+        R.load(tmp_path / "bad3.tfb")
+    with pytest.raises(R.TfheError):
+        R.load(tmp_path / "missing.tfb")
+    with pytest.raises(ValueError):
+        R.save(tmp_path / "x.tfb", R.FILE_TLWE0, np.zeros(7, np.uint32))
+
+
+def test_deterministic_gaussian_matches_libm_and_is_gaussian(oracle):
+    """The seeded noise sampler is a Box-Muller transform built from correctly rounded IEEE operations only (so that the
+    device keygen reproduces it bit for bit); check it against libm and check its moments."""
+    import ctypes as C
+    import math
+    l = oracle.lib()
+    l.orc_gauss_torus.restype = C.c_int32
+    l.orc_gauss_torus.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_double]
+    l.orc_rnd64.restype = C.c_uint64
+    l.orc_rnd64.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+    xs = []
+    for i in range(4000):
+        u1 = ((l.orc_rnd64(9, 4, 2 * i) >> 11) + 1) / 2.0 ** 53
+        u2 = (l.orc_rnd64(9, 4, 2 * i + 1) >> 11) / 2.0 ** 53
+        want = math.sqrt(-2.0 * math.log(u1)) * math.cos(2 * math.pi * u2) * 2.0 ** 17
+        got = l.orc_gauss_torus(9, 4, i, 2.0 ** -15)
+        assert abs(got - want) <= 1.0, (i, got, want)     # same value up to the final rounding
+        xs.append(got / 2.0 ** 17)
+    xs = np.array(xs)
+    assert abs(xs.mean()) < 0.06 and abs(xs.std() - 1) < 0.05
