@@ -195,6 +195,7 @@ def run_gpu(args):
         s0 = s0d.cpu()
     s0 = s0.numpy()
     eng = R.DeviceEngine(local)
+    eng.reserve(BATCH)
     stream = torch.cuda.current_stream()
     eng.load_ksk_device(ksk_d.data_ptr(), stream.cuda_stream)
     eng.load_bk_device(bk_d.data_ptr(), stream.cuda_stream)

@@ -103,6 +103,9 @@ int tfhe_b200_gate_batch_device(tfhe_b200_ctx* ctx, int op, const uint32_t* in0,
  * Consecutive async batches overlap on the device (the tail of one blind rotation runs under the head of the next). */
 int tfhe_b200_gate_batch_async(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B);
 int tfhe_b200_sync(tfhe_b200_ctx* ctx); /* waits for every batch this context has enqueued (any stream) */
+/* optional: pre-allocate all internal workspaces for batches of up to max_batch gates (otherwise they grow on demand,
+ * and cudaMalloc blocks while earlier batches are still running) */
+int tfhe_b200_reserve(tfhe_b200_ctx* ctx, size_t max_batch);
 int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t B); /* TFHE::bootstrap */
 /* hom_mux(control, input_0, input_1) = (input_1 & control) | (input_0 & !control): three bootstraps, tfhe.rs:27-40 */
 int tfhe_b200_mux_batch(tfhe_b200_ctx* ctx, const uint32_t* control, const uint32_t* in0, const uint32_t* in1,

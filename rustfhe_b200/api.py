@@ -339,6 +339,10 @@ class DeviceEngine:
     def sync(self):
         self._ck(self._l.tfhe_b200_sync(self._ctx))
 
+    def reserve(self, max_batch):
+        """Pre-allocate the internal workspaces for batches of up to `max_batch` gates."""
+        self._ck(self._l.tfhe_b200_reserve(self._ctx, max_batch))
+
     def mux_batch(self, control, in0, in1):
         control, in0, in1 = (_u32_batch(x, K.n + 1) for x in (control, in0, in1))
         out = np.empty_like(in0)

@@ -250,32 +250,38 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
 // 636-word rows (159 chunks).  Every KSK row is read once per CTA and applied to all gates of the tile; the digit
 // is CTA-uniform so the select is a uniform branch.  Partial sums are merged with red.global.add.u32.
 // =====================================================================================================
-constexpr int KS_GT = 16;
-constexpr int KS_ISPLIT = 8;
-constexpr int KS_ICHUNK = 1024 / KS_ISPLIT;
+constexpr int KS_GT = 16;           // gates per thread group (accumulators live in registers: 16 x uint4)
+#if !defined(KS_NG)
+#define KS_NG 2
+#endif
+constexpr int KS_GROUPS = KS_NG;    // thread groups per CTA: they walk the same key rows, the second one hits L1
+constexpr int KS_ISPLIT_MIN = 8;    // key indices are split over gridDim.y CTAs: 8 for large batches, up to 128 for small ones
+constexpr int KS_ICHUNK = 1024 / KS_ISPLIT_MIN;   // largest slice of key indices one CTA walks
 constexpr int KS_CHUNKS = (LWE_N + 1) / 4;  // 159
 constexpr int KS_THREADS = 160;
-__global__ void __launch_bounds__(KS_THREADS) keyswitch_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
-                                                              uint32_t* __restrict__ out, long B) {
-    __shared__ __align__(16) uint16_t dg[KS_ICHUNK][KS_GT];
-    const long g0 = (long)blockIdx.x * KS_GT;
-    const int i0 = blockIdx.y * KS_ICHUNK;
-    for (int t = threadIdx.x; t < KS_ICHUNK * KS_GT; t += blockDim.x) {
-        const int g = t / KS_ICHUNK, ii = t % KS_ICHUNK;
-        dg[ii][g] = (g0 + g < B) ? dig[(size_t)(g0 + g) * 1024 + i0 + ii] : (uint16_t)0;
+__global__ void __launch_bounds__(KS_THREADS* KS_GROUPS) keyswitch_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
+                                                                         uint32_t* __restrict__ out, long B) {
+    __shared__ __align__(16) uint16_t dg[KS_GROUPS][KS_ICHUNK][KS_GT];
+    const int grp = threadIdx.y;
+    const long g0 = ((long)blockIdx.x * KS_GROUPS + grp) * KS_GT;
+    const int ichunk = 1024 / (int)gridDim.y;
+    const int i0 = blockIdx.y * ichunk;
+    for (int t = threadIdx.x; t < ichunk * KS_GT; t += KS_THREADS) {
+        const int g = t / ichunk, ii = t % ichunk;
+        dg[grp][ii][g] = (g0 + g < B) ? dig[(size_t)(g0 + g) * 1024 + i0 + ii] : (uint16_t)0;
     }
     __syncthreads();
     const int t = threadIdx.x;
-    if (t >= KS_CHUNKS) return;
+    if (t >= KS_CHUNKS || g0 >= B) return;
     uint4 acc[KS_GT];
 #pragma unroll
     for (int g = 0; g < KS_GT; g++) acc[g] = make_uint4(0, 0, 0, 0);
     const uint4* base = ksk + (size_t)i0 * 8 * 3 * KS_CHUNKS + t;
 #pragma unroll 1
-    for (int ii = 0; ii < KS_ICHUNK; ii++) {
+    for (int ii = 0; ii < ichunk; ii++) {
         uint32_t dw[KS_GT / 2];
 #pragma unroll
-        for (int g = 0; g < KS_GT / 2; g++) dw[g] = reinterpret_cast<const uint32_t*>(dg[ii])[g];  // two gates per word
+        for (int g = 0; g < KS_GT / 2; g++) dw[g] = reinterpret_cast<const uint32_t*>(dg[grp][ii])[g];  // two gates per word
 #pragma unroll
         for (int l = 0; l < 8; l++) {
             const uint4* row = base + (size_t)(ii * 8 + l) * 3 * KS_CHUNKS;
@@ -619,6 +625,21 @@ int tfhe_b200_set_decomp_mask(tfhe_b200_ctx* ctx, uint32_t mask) {
     return TFHE_B200_OK;
 }
 
+// Pre-allocate every work slot for batches of up to max_batch gates (hom_mux needs twice the key-switch workspace), so
+// that no call in a latency- or throughput-critical region ever reaches cudaMalloc (which blocks while the GPU is busy).
+int tfhe_b200_reserve(tfhe_b200_ctx* ctx, size_t max_batch) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    if (max_batch == 0) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t ct = max_batch * (size_t)(LWE_N + 1) * 4;
+    for (auto& s : ctx->slots) {
+        RC(grow(ctx, (void**)&s.ksdig, &s.ksdig_cap, 2 * max_batch * 1024 * sizeof(uint16_t)));
+        for (int k = 0; k < 4; k++) RC(grow(ctx, (void**)&s.tmp[k], &s.tmp_cap[k], ct));
+        RC(grow(ctx, (void**)&s.scratch, &s.scratch_cap, 2 * ct));
+    }
+    return TFHE_B200_OK;
+}
+
 int tfhe_b200_sync(tfhe_b200_ctx* ctx) {
     if (!ctx) return TFHE_B200_ERR_PARAM;
     CK(cudaSetDevice(ctx->device));
@@ -772,8 +793,12 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
 static int launch_keyswitch(tfhe_b200_ctx* ctx, const uint16_t* dig, uint32_t* out, long B, cudaStream_t st, bool timed) {
     const int slot = (int)(ctx->timed % tfhe_b200_ctx::RING);
     if (timed) CK(cudaEventRecord(ctx->ev[slot][2], st));
-    dim3 grid((unsigned)((B + KS_GT - 1) / KS_GT), KS_ISPLIT);
-    keyswitch_kernel<<<grid, KS_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B);
+    const long tile = (long)KS_GT * KS_GROUPS;
+    const long tiles = (B + tile - 1) / tile;
+    int isplit = KS_ISPLIT_MIN;   // small batches (latency path, narrow circuit levels): split the key indices further to fill the SMs
+    while (isplit < 128 && tiles * isplit < 2L * ctx->sm_count) isplit *= 2;
+    dim3 grid((unsigned)tiles, isplit);
+    keyswitch_kernel<<<grid, dim3(KS_THREADS, KS_GROUPS), 0, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B);
     ctx->launches++;
     CK(cudaGetLastError());
     if (timed) { CK(cudaEventRecord(ctx->ev[slot][3], st)); ctx->timed++; }
