@@ -175,46 +175,49 @@ def run_gpu(args):
     import rustfhe_b200 as R
     from rustfhe_b200 import _capi as K
 
-    # ---- keys: generated once on rank 0 (host, product keygen), replicated with ONE NCCL broadcast each ----
+    # ---- keys: generated once on rank 0 ON THE DEVICE (tfhe_b200_keygen_device), replicated with ONE NCCL broadcast each;
+    #      the other ranks transform the received torus-domain bootstrapping key locally ----
     t_key0 = time.time()
-    bk_d = torch.empty(K.BK_WORDS, dtype=torch.int32, device=dev)
-    ksk_d = torch.empty(K.KSK_WORDS, dtype=torch.int32, device=dev)
-    s0 = torch.zeros(N_LWE, dtype=torch.uint8)
-    if rank == 0:
-        sk = R.SecretKeys.generate(SEED)
-        bk = R.BootstrappingKey.new(sk.s_key_tlwelv0, sk.s_key_tlwelv1, SEED)
-        ksk = R.KeySwitchingKey.new(sk.s_key_tlwelv1, sk.s_key_tlwelv0, SEED)
-        bk_d.copy_(torch.from_numpy(bk.words.view(np.int32)))
-        ksk_d.copy_(torch.from_numpy(ksk.words.view(np.int32)))
-        s0 = torch.from_numpy(sk.s_key_tlwelv0.copy())
-    if world > 1:
-        dist.broadcast(bk_d, 0)
-        dist.broadcast(ksk_d, 0)
-        s0d = s0.to(dev)
-        dist.broadcast(s0d, 0)
-        s0 = s0d.cpu()
-    s0 = s0.numpy()
     eng = R.DeviceEngine(local)
     eng.reserve(BATCH)
     stream = torch.cuda.current_stream()
-    eng.load_ksk_device(ksk_d.data_ptr(), stream.cuda_stream)
-    eng.load_bk_device(bk_d.data_ptr(), stream.cuda_stream)
+    sk = R.SecretKeys.generate(SEED)            # seeded: every rank derives the same secret keys (needed for the decrypt checks)
+    s0 = sk.s_key_tlwelv0
+    if world == 1:
+        eng.keygen_device(SEED, sk.s_key_tlwelv0, sk.s_key_tlwelv1)
+    else:
+        bk_d = torch.empty(K.BK_WORDS, dtype=torch.int32, device=dev)
+        ksk_d = torch.empty(K.KSK_WORDS, dtype=torch.int32, device=dev)
+        if rank == 0:
+            eng.keygen_device(SEED, sk.s_key_tlwelv0, sk.s_key_tlwelv1)
+            eng.export_bk_device(bk_d.data_ptr(), stream.cuda_stream)
+            eng.export_ksk_device(ksk_d.data_ptr(), stream.cuda_stream)
+        dist.broadcast(bk_d, 0)
+        dist.broadcast(ksk_d, 0)
+        if rank != 0:
+            eng.load_ksk_device(ksk_d.data_ptr(), stream.cuda_stream)
+            eng.load_bk_device(bk_d.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        del bk_d, ksk_d
     torch.cuda.synchronize()
-    del bk_d, ksk_d
     key_s = time.time() - t_key0
 
-    # ---- synthetic inputs: NROT distinct batches of random-bit encryptions per rank, resident in HBM ----
+    # ---- synthetic inputs: NROT distinct batches of random-bit encryptions per rank, encrypted on the device, resident in
+    #      HBM; a pinned host copy feeds the end-to-end leg ----
     rng = np.random.default_rng(SEED + 17 * rank)
     nct = NROT * BATCH
     bx = rng.integers(0, 2, nct).astype(np.uint8)
     by = rng.integers(0, 2, nct).astype(np.uint8)
-    cx = R.Cryptor.encrypto(R.TLWE, s0, bx, seed=SEED + 100 + rank, ct_index0=0)
-    cy = R.Cryptor.encrypto(R.TLWE, s0, by, seed=SEED + 200 + rank, ct_index0=0)
-    hx = torch.from_numpy(cx.view(np.int32)).pin_memory()
-    hy = torch.from_numpy(cy.view(np.int32)).pin_memory()
-    dx, dy = hx.to(dev), hy.to(dev)
+    dx = torch.empty((nct, CT_WORDS), dtype=torch.int32, device=dev)
+    dy = torch.empty((nct, CT_WORDS), dtype=torch.int32, device=dev)
+    dbx, dby = torch.from_numpy(bx).to(dev), torch.from_numpy(by).to(dev)
+    eng.encrypt_bits_device(SEED + 100 + rank, 0, s0, dbx.data_ptr(), nct, dx.data_ptr(), stream.cuda_stream)
+    eng.encrypt_bits_device(SEED + 200 + rank, 0, s0, dby.data_ptr(), nct, dy.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    hx = torch.empty((nct, CT_WORDS), dtype=torch.int32).pin_memory()
+    hy = torch.empty((nct, CT_WORDS), dtype=torch.int32).pin_memory()
+    hx.copy_(dx); hy.copy_(dy)
     dout = torch.empty((BATCH, CT_WORDS), dtype=torch.int32, device=dev)
-    hout = torch.empty((BATCH, CT_WORDS), dtype=torch.int32).pin_memory()
 
     streams = [stream, torch.cuda.Stream(device=dev)]   # consecutive steps alternate streams: independent batches overlap
     douts = [dout, torch.empty_like(dout)]

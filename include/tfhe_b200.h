@@ -147,6 +147,9 @@ int tfhe_b200_decrypt_bits(const uint8_t* s0, const uint32_t* ct, size_t B, uint
 int tfhe_b200_keygen_device(tfhe_b200_ctx* ctx, uint64_t seed, const uint8_t* s0 /*[n] host*/, const uint8_t* s1 /*[N] host*/);
 int tfhe_b200_export_bk(tfhe_b200_ctx* ctx, uint32_t* bk_host /*[n][2l][2][N] torus domain*/);
 int tfhe_b200_export_ksk(tfhe_b200_ctx* ctx, uint32_t* ksk_host /*[N][t][3][n+1]*/);
+/* device-to-device forms (e.g. into the send buffer of the NCCL broadcast that replicates the keys) */
+int tfhe_b200_export_bk_device(tfhe_b200_ctx* ctx, uint32_t* bk_dev, void* stream);
+int tfhe_b200_export_ksk_device(tfhe_b200_ctx* ctx, uint32_t* ksk_dev, void* stream);
 int tfhe_b200_encrypt_bits_device(tfhe_b200_ctx* ctx, uint64_t seed, uint64_t ct_index0, const uint8_t* s0 /*host*/,
                                   const uint8_t* bits_dev /*[B] device*/, size_t B, uint32_t* out_dev /*[B][n+1] device*/,
                                   void* stream);

@@ -25,7 +25,8 @@ SYMBOLS = [
     "tfhe_b200_bootstrap_lv1_batch", "tfhe_b200_keyswitch_batch", "tfhe_b200_external_product_batch",
     "tfhe_b200_negacyclic_mul_batch", "tfhe_b200_keygen_secret", "tfhe_b200_keygen_bk", "tfhe_b200_keygen_ksk",
     "tfhe_b200_encrypt_bits", "tfhe_b200_phase", "tfhe_b200_decrypt_bits", "tfhe_b200_version",
-    "tfhe_b200_keygen_device", "tfhe_b200_export_bk", "tfhe_b200_export_ksk", "tfhe_b200_encrypt_bits_device",
+    "tfhe_b200_keygen_device", "tfhe_b200_export_bk", "tfhe_b200_export_ksk", "tfhe_b200_export_bk_device",
+    "tfhe_b200_export_ksk_device", "tfhe_b200_encrypt_bits_device",
     "tfhe_b200_decrypt_bits_device", "tfhe_b200_cmux_batch", "tfhe_b200_sample_extract_batch",
     "tfhe_b200_file_write", "tfhe_b200_file_info", "tfhe_b200_file_read", "tfhe_b200_file_last_error",
 ]
@@ -92,6 +93,8 @@ def lib():
         "tfhe_b200_keygen_device": (i32, [vp, u64, vp, vp]),
         "tfhe_b200_export_bk": (i32, [vp, vp]),
         "tfhe_b200_export_ksk": (i32, [vp, vp]),
+        "tfhe_b200_export_bk_device": (i32, [vp, vp, vp]),
+        "tfhe_b200_export_ksk_device": (i32, [vp, vp, vp]),
         "tfhe_b200_encrypt_bits_device": (i32, [vp, u64, u64, vp, vp, sz, vp, vp]),
         "tfhe_b200_decrypt_bits_device": (i32, [vp, vp, vp, sz, vp, vp, vp]),
         "tfhe_b200_cmux_batch": (i32, [vp, vp, sz, vp, vp, vp, sz]),

@@ -301,6 +301,12 @@ class DeviceEngine:
         self._ck(self._l.tfhe_b200_export_ksk(self._ctx, ptr(w)))
         return KeySwitchingKey(w)
 
+    def export_bk_device(self, dev_ptr, stream=0):
+        self._ck(self._l.tfhe_b200_export_bk_device(self._ctx, C.c_void_p(dev_ptr), C.c_void_p(stream)))
+
+    def export_ksk_device(self, dev_ptr, stream=0):
+        self._ck(self._l.tfhe_b200_export_ksk_device(self._ctx, C.c_void_p(dev_ptr), C.c_void_p(stream)))
+
     def encrypt_bits_device(self, seed, ct_index0, s_key, bits_ptr, B, out_ptr, stream=0):
         self._ck(self._l.tfhe_b200_encrypt_bits_device(self._ctx, seed, ct_index0, ptr(np.ascontiguousarray(s_key, np.uint8)),
                                                        C.c_void_p(bits_ptr), B, C.c_void_p(out_ptr), C.c_void_p(stream)))

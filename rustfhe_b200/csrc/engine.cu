@@ -967,6 +967,21 @@ int tfhe_b200_export_bk(tfhe_b200_ctx* ctx, uint32_t* bk_host) {
     CK(cudaMemcpy(bk_host, ctx->bk_torus, BK_TORUS_BYTES, cudaMemcpyDeviceToHost));
     return TFHE_B200_OK;
 }
+// device-to-device forms: the source of the one-off NCCL broadcast that replicates the keys to the other GPUs
+int tfhe_b200_export_bk_device(tfhe_b200_ctx* ctx, uint32_t* bk_dev, void* stream) {
+    if (!ctx || !bk_dev) return fail(ctx, TFHE_B200_ERR_PARAM, "export_bk_device: null argument");
+    if (!ctx->have_bk) return fail(ctx, TFHE_B200_ERR_STATE, "export_bk_device: bootstrapping key not loaded");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(bk_dev, ctx->bk_torus, BK_TORUS_BYTES, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_export_ksk_device(tfhe_b200_ctx* ctx, uint32_t* ksk_dev, void* stream) {
+    if (!ctx || !ksk_dev) return fail(ctx, TFHE_B200_ERR_PARAM, "export_ksk_device: null argument");
+    if (!ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "export_ksk_device: key-switching key not loaded");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ksk_dev, ctx->kskdev, KSK_BYTES, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
 int tfhe_b200_export_ksk(tfhe_b200_ctx* ctx, uint32_t* ksk_host) {
     if (!ctx || !ksk_host) return fail(ctx, TFHE_B200_ERR_PARAM, "export_ksk: null argument");
     if (!ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "export_ksk: key-switching key not loaded");

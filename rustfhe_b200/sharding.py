@@ -50,7 +50,9 @@ def evaluate_sharded(gate_fn, in0, in1, rank, world, gather=True):
     pad = np.zeros((per, width), np.uint32)
     pad[:e - s] = out_shard
     mine = torch.from_numpy(pad.view(np.int32))
+    if dist.get_backend() == "nccl":   # NCCL moves device memory only; gloo (CPU tests) takes the host tensor as is
+        mine = mine.cuda()
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine)
-    out = np.concatenate([p.numpy().view(np.uint32)[:b[1] - b[0]] for p, b in zip(parts, bounds)], axis=0)
+    out = np.concatenate([p.cpu().numpy().view(np.uint32)[:b[1] - b[0]] for p, b in zip(parts, bounds)], axis=0)
     return out

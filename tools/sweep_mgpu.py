@@ -1,0 +1,143 @@
+#!/usr/bin/env python3
+"""BASELINE.json configs 4 and 5 on N GPUs of one box (run under torchrun; N = 1 works without it).
+
+  config 5: 2^16 .. 2^20 random-bit NAND gates sharded across the ranks (contiguous shards, keys replicated once by
+            NCCL broadcast, no collective per gate); inputs are encrypted ON each device; a fixed random 4096-gate sample
+            per rank is decrypted on the device and checked.  Device time = max over ranks (CUDA events).
+  config 4: 32-bit ripple-carry adder (284 NAND gates, 64 levels) evaluated level by level with the level's gates sharded
+            across ranks and one all_gather per level -- reported honestly: it is latency bound and does not scale.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29577 \
+      tools/sweep_mgpu.py --out gpurun_out/sweep_mgpu_N.json
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SEED = 0x5EED0001
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--min-log2", type=int, default=16)
+    ap.add_argument("--max-log2", type=int, default=20)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import rustfhe_b200 as R
+    from rustfhe_b200 import _capi as K
+    from rustfhe_b200 import circuit as Cq
+    from rustfhe_b200.sharding import evaluate_sharded, shard_bounds
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    st = torch.cuda.current_stream()
+    sk = R.SecretKeys.generate(SEED)
+    s0 = sk.s_key_tlwelv0
+    eng = R.DeviceEngine(local)
+    t0 = time.time()
+    if world == 1:
+        eng.keygen_device(SEED, sk.s_key_tlwelv0, sk.s_key_tlwelv1)
+    else:
+        bk_d = torch.empty(K.BK_WORDS, dtype=torch.int32, device=dev)
+        ksk_d = torch.empty(K.KSK_WORDS, dtype=torch.int32, device=dev)
+        if rank == 0:
+            eng.keygen_device(SEED, sk.s_key_tlwelv0, sk.s_key_tlwelv1)
+            eng.export_bk_device(bk_d.data_ptr(), st.cuda_stream)
+            eng.export_ksk_device(ksk_d.data_ptr(), st.cuda_stream)
+        dist.broadcast(bk_d, 0)
+        dist.broadcast(ksk_d, 0)
+        if rank != 0:
+            eng.load_ksk_device(ksk_d.data_ptr(), st.cuda_stream)
+            eng.load_bk_device(bk_d.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize()
+        del bk_d, ksk_d
+    torch.cuda.synchronize()
+    res = {"gpu": torch.cuda.get_device_name(local), "n_gpus": world, "key_setup_s": time.time() - t0}
+
+    # ---- config 5 ----
+    sweep = []
+    rng = np.random.default_rng(SEED + 31 * rank)
+    for lb in range(args.min_log2, args.max_log2 + 1):
+        total = 1 << lb
+        s, e = shard_bounds(total, world)[rank]
+        B = e - s
+        eng.reserve(B)
+        bx, by = rng.integers(0, 2, B).astype(np.uint8), rng.integers(0, 2, B).astype(np.uint8)
+        dbx, dby = torch.from_numpy(bx).to(dev), torch.from_numpy(by).to(dev)
+        dx = torch.empty((B, K.n + 1), dtype=torch.int32, device=dev)
+        dy = torch.empty_like(dx)
+        do = torch.empty_like(dx)
+        eng.encrypt_bits_device(SEED + 1000 + rank, s, s0, dbx.data_ptr(), B, dx.data_ptr(), st.cuda_stream)
+        eng.encrypt_bits_device(SEED + 2000 + rank, s, s0, dby.data_ptr(), B, dy.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        eng.gate_batch_device(K.NAND, dx.data_ptr(), dy.data_ptr(), do.data_ptr(), B, st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        idx = np.sort(rng.choice(B, min(B, 4096), replace=False))
+        sel = do[torch.from_numpy(idx).to(dev)].contiguous()
+        dbits = torch.empty(len(idx), dtype=torch.uint8, device=dev)
+        eng.decrypt_bits_device(s0, sel.data_ptr(), len(idx), dbits.data_ptr(), None, st.cuda_stream)
+        torch.cuda.synchronize()
+        wrong = int((dbits.cpu().numpy() != (1 - (bx[idx] & by[idx]))).sum())
+        t = torch.tensor([ms, float(wrong)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sweep.append({"gates": total, "gates_per_gpu": B, "ms_max_over_ranks": float(t[0]), "gates_per_s": total / (float(t[0]) * 1e-3),
+                      "wrong_in_sample": int(t[1])})
+        del dx, dy, do, dbx, dby
+        if rank == 0:
+            print(sweep[-1], file=sys.stderr, flush=True)
+    res["config5_sweep"] = sweep
+
+    # ---- config 4 ----
+    r = np.random.default_rng(SEED + 2)
+    x, y = int(r.integers(0, 2 ** 32)), int(r.integers(0, 2 ** 32))
+    bits = np.array([(x >> i) & 1 for i in range(32)] + [(y >> i) & 1 for i in range(32)], np.uint8)
+    nl = Cq.ripple_carry_adder(32)
+    cts = R.Cryptor.encrypto(R.TLWE, s0, bits, seed=SEED + 2, ct_index0=0)
+
+    class Sharded:   # engine facade: every level's gates are split across the ranks, outputs all-gathered
+        def gate_batch(self, op, a, b=None):
+            return evaluate_sharded(lambda p, q: eng.gate_batch(op, p, q), a, b, rank, world, gather=True)
+
+    stt = {}
+    Cq.evaluate(Sharded(), nl, cts, stt)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    out = Cq.evaluate(Sharded(), nl, cts, stt)
+    wall = time.perf_counter() - t0
+    got = R.Cryptor.decrypto(R.TLWE, s0, out)
+    res["config4_adder32"] = {"gates": stt["gates"], "levels": stt["levels"], "wall_seconds": wall,
+                              "correct": bool(sum(int(b) << i for i, b in enumerate(got)) == x + y),
+                              "note": "latency bound: the carry chain gives ~2 levels per bit of width <= 3; sharding a level of <= 3 gates "
+                                      "across GPUs only adds the per-level all_gather"}
+    if rank == 0:
+        txt = json.dumps(res, indent=1)
+        if args.out:
+            open(args.out, "w").write(txt)
+        print(txt)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
