@@ -9,8 +9,9 @@ fn main() {
     let csrc = PathBuf::from(env::var("TFHE_B200_CSRC").unwrap_or_else(|_| "../../rustfhe_b200/csrc".into()));
     let obj = out.join("engine.o");
     let keys = out.join("hostkeys.o");
+    let wire = out.join("wire.o");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
-    for (src, dst) in [("engine.cu", &obj), ("hostkeys.cpp", &keys)] {
+    for (src, dst) in [("engine.cu", &obj), ("hostkeys.cpp", &keys), ("wire.cpp", &wire)] {
         let ok = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-c"])
             .arg(csrc.join(src))
@@ -22,7 +23,7 @@ fn main() {
         assert!(ok, "nvcc failed on {src}");
     }
     let lib = out.join("librustfhe_b200.a");
-    assert!(Command::new("ar").arg("crs").arg(&lib).arg(&obj).arg(&keys).status().unwrap().success());
+    assert!(Command::new("ar").arg("crs").arg(&lib).arg(&obj).arg(&keys).arg(&wire).status().unwrap().success());
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=static=rustfhe_b200");
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");

@@ -24,6 +24,15 @@ pub const OR: c_int = 2;
 pub const XOR: c_int = 3;
 pub const NOT: c_int = 4;
 pub const COPY: c_int = 5;
+pub const ANDNY: c_int = 6;
+// file kinds of tfhe_b200_file_{write,info,read}
+pub const FILE_SECRET: c_int = 1;
+pub const FILE_BK: c_int = 2;
+pub const FILE_KSK: c_int = 3;
+pub const FILE_TLWE0: c_int = 4;
+pub const FILE_TLWE1: c_int = 5;
+pub const FILE_TRLWE: c_int = 6;
+pub const FILE_TRGSW: c_int = 7;
 
 extern "C" {
     pub fn tfhe_b200_default_params(p: *mut Params) -> c_int;
@@ -39,4 +48,23 @@ extern "C" {
     pub fn tfhe_b200_keyswitch_batch(ctx: *mut Ctx, lwe1: *const u32, out: *mut u32, b: usize) -> c_int;
     pub fn tfhe_b200_external_product_batch(ctx: *mut Ctx, trgsw: *const u32, ntrgsw: usize, trlwe: *const u32, out: *mut u32, b: usize) -> c_int;
     pub fn tfhe_b200_negacyclic_mul_batch(ctx: *mut Ctx, a: *const u32, d: *const i32, out: *mut u32, b: usize) -> c_int;
+    // asynchronous host-pointer form + workspace reservation
+    pub fn tfhe_b200_gate_batch_async(ctx: *mut Ctx, op: c_int, in0: *const u32, in1: *const u32, out: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_sync(ctx: *mut Ctx) -> c_int;
+    pub fn tfhe_b200_reserve(ctx: *mut Ctx, max_batch: usize) -> c_int;
+    pub fn tfhe_b200_bootstrap_batch(ctx: *mut Ctx, input: *const u32, out: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_bootstrap_lv1_batch(ctx: *mut Ctx, input: *const u32, out_lwe1: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_cmux_batch(ctx: *mut Ctx, trgsw: *const u32, ntrgsw: usize, rep1: *const u32, rep0: *const u32, out: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_sample_extract_batch(ctx: *mut Ctx, trlwe: *const u32, index: c_int, out_lwe1: *mut u32, b: usize) -> c_int;
+    // device-side key generation (replaces the host loops of BootstrappingKey::new / KeySwitchingKey::new), export, encryption
+    pub fn tfhe_b200_keygen_device(ctx: *mut Ctx, seed: u64, s0: *const u8, s1: *const u8) -> c_int;
+    pub fn tfhe_b200_export_bk(ctx: *mut Ctx, bk: *mut u32) -> c_int;
+    pub fn tfhe_b200_export_ksk(ctx: *mut Ctx, ksk: *mut u32) -> c_int;
+    pub fn tfhe_b200_encrypt_bits_device(ctx: *mut Ctx, seed: u64, ct_index0: u64, s0: *const u8, bits_dev: *const u8, b: usize, out_dev: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn tfhe_b200_decrypt_bits_device(ctx: *mut Ctx, s0: *const u8, ct_dev: *const u32, b: usize, bits_dev: *mut u8, phase_dev: *mut u32, stream: *mut c_void) -> c_int;
+    // flat file format (the reference has no serialisation)
+    pub fn tfhe_b200_file_write(path: *const c_char, kind: c_int, payload: *const c_void, count: u64) -> c_int;
+    pub fn tfhe_b200_file_info(path: *const c_char, kind: *mut c_int, count: *mut u64, payload_bytes: *mut u64) -> c_int;
+    pub fn tfhe_b200_file_read(path: *const c_char, kind: c_int, payload: *mut c_void, payload_bytes: u64) -> c_int;
+    pub fn tfhe_b200_file_last_error() -> *const c_char;
 }
