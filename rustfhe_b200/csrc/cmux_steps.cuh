@@ -4,7 +4,8 @@
 // (TRGSWRepF::cross), utils/src/math.rs:85-113 (rotate), utils/src/math.rs:300-326 (decomposition_i32_).
 //
 // Work split of one gate: 6 warps.  Warp w = 3*poly + k.
-//   phase 1 (digit side)  : warp (poly,k) builds digit k of (X^abar * acc - acc)[poly], forward-NTTs it and leaves
+//   phase 1 (digit side)  : the three warps of a polynomial share the work of u = ((X^abar * acc - acc)[poly] + mask) ^ mask
+//                           (a third of the rows each); then warp (poly,k) takes digit k of u, forward-NTTs it and leaves
 //                           the spectrum in plane dh[3*poly+k]        (decomposition order = b-digits first, F10)
 //   phase 2 (key side)    : warp (poly,k) computes sum_j dh[j] * BKpart_k[poly][j] (11-bit key slice k), inverse-NTTs
 //                           it, lifts to the exact integer, shifts by 11k and leaves it in plane sp[3*poly+k]
@@ -40,17 +41,28 @@ TFHE_HD uint32_t rot_diff(const uint32_t* A, uint32_t k, uint32_t abar) {
     return (rv ^ m) - m - A[k];
 }
 
-// ---- phase 1a: lane = column c.  Build digit `dw` of the source polynomial, column NTT, scatter into tile S ----
-// ROTATE=true : source = X^abar * A - A   (blind rotation step);  ROTATE=false : source = A (plain external product)
+// ---- phase 1u: the masked source polynomial u = (src + mask) ^ mask is the same for the three digit warps of a
+// polynomial, so each of them computes the rows r = part, part+3, ... of it and leaves them in the plain tile U ----
+// ROTATE=true : src = X^abar * A - A   (blind rotation step);  ROTATE=false : src = A (plain external product)
 template <bool ROTATE>
-TFHE_HD void p1a(int lane, const uint32_t* A, uint32_t abar, uint32_t mask, int dw, uint32_t* S) {
+TFHE_HD void p1u(int lane, const uint32_t* A, uint32_t abar, uint32_t mask, int part, uint32_t* U) {
+#pragma unroll
+    for (int t = 0; t < 11; t++) {
+        const int r = part + 3 * t;
+        if (r < 32) {
+            const uint32_t k = 32u * r + lane;
+            const uint32_t src = ROTATE ? rot_diff(A, k, abar) : A[k];
+            U[k] = add_alu(src, mask) ^ mask;
+        }
+    }
+}
+// digit `dw` (0 = most significant) of an already masked word, sign-extended from 6 bits
+TFHE_HD int32_t masked_digit(uint32_t u, int dw) { return ((int32_t)(u << (6 * dw))) >> 26; }
+// ---- phase 1a: lane = column c.  Digit `dw` of column c from U, column NTT, scatter into tile S ----
+TFHE_HD void p1a(int lane, const uint32_t* U, int dw, uint32_t* S) {
     uint32_t x[32];
 #pragma unroll
-    for (int r = 0; r < 32; r++) {
-        const uint32_t k = 32u * r + lane;
-        const uint32_t src = ROTATE ? rot_diff(A, k, abar) : A[k];
-        x[r] = to_residue(gadget_digit(src, mask, dw));
-    }
+    for (int r = 0; r < 32; r++) x[r] = to_residue(masked_digit(U[32 * r + lane], dw));
     ct32(x, TwUniform<false>());
 #pragma unroll
     for (int r = 0; r < 32; r++) S[swz(r, lane)] = x[r];

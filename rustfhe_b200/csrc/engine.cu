@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(KT_WARPS * 32) bk_transform_kernel(const uint3
 // =====================================================================================================
 constexpr int WARPS_PER_GATE = 6;
 constexpr int THREADS_PER_GATE = WARPS_PER_GATE * 32;
-constexpr int GATE_SMEM_WORDS = 2 * 1024 /*acc*/ + 6 * 1024 /*dh: digit spectra / transpose scratch*/ + 320 /*abar u16[640]*/;
+constexpr int GATE_SMEM_WORDS = 2 * 1024 /*acc*/ + 2 * 1024 /*U: masked source polynomials*/ + 6 * 1024 /*dh: digit spectra / transpose scratch*/ +
+                                320 /*abar u16[640]*/;
 constexpr int TW_SMEM_WORDS = 2 * 32 * TWB_STRIDE;
 constexpr size_t br_smem_bytes(int G) { return (size_t)(TW_SMEM_WORDS + G * GATE_SMEM_WORDS) * 4; }
 
@@ -114,7 +115,8 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     const int pw = w6 / 3, kw = w6 % 3;
     const int tid6 = threadIdx.x - gl * THREADS_PER_GATE;
     uint32_t* acc = smem + TW_SMEM_WORDS + gl * GATE_SMEM_WORDS;
-    uint32_t* dh = acc + 2 * 1024;
+    uint32_t* U = acc + 2 * 1024;
+    uint32_t* dh = U + 2 * 1024;
     uint16_t* abar = reinterpret_cast<uint16_t*>(dh + 6 * 1024);
     uint64_t* macdone = reinterpret_cast<uint64_t*>(dh + 6 * 1024 + 318);  // abar uses 635 u16 = 317.5 words of its 320
 
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
 
     // ---- 635 x CMUX ----
     // Synchronisation per step (named barriers, so gates sharing a CTA and the two polynomials of a gate decouple):
+    //   poly barrier (96 threads)      : the masked source polynomial u[poly] (shared by its three digit warps) is complete
     //   B1 gate barrier (192 threads)  : the 6 digit spectra of this step are complete
     //   macdone (mbarrier, 6 arrivals) : every warp finished READING the digit spectra dh[] -> a warp may reuse its own
     //                                    plane dh[w6] as the transpose scratch of its inverse transform
@@ -190,8 +193,10 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)((blockIdx.x & 63) * 18 + tid6) * 128));
         }
 #endif
-        {   // phase 1: digit kw of poly pw -> spectrum plane dh[w6]
-            p1a<!EXTPROD>(lane, acc + pw * 1024, EXTPROD ? 0u : (uint32_t)abar[i], a.mask, kw, S);
+        {   // phase 1: a third of the rows of u[pw], then digit kw of u[pw] -> spectrum plane dh[w6]
+            p1u<!EXTPROD>(lane, acc + pw * 1024, EXTPROD ? 0u : (uint32_t)abar[i], a.mask, kw, U + pw * 1024);
+            bar_sync(bar_poly, 96);
+            p1a(lane, U + pw * 1024, kw, S);
             __syncwarp();
             p1b(lane, S, twF);
         }

@@ -25,14 +25,18 @@ void emul_key_transform(const uint32_t* trgsw, uint32_t* dev) {
 }
 
 static void cmux_core(const uint32_t* dev, const uint32_t* acc, bool rotate, uint32_t abar, uint32_t mask, uint32_t* sp) {
-    std::vector<uint32_t> dh(6 * 1024);
+    std::vector<uint32_t> dh(6 * 1024), U(2 * 1024);
+    for (int w = 0; w < 6; w++) {   // phase 1u: every warp contributes its rows of the masked source polynomial
+        const int poly = w / 3, k = w % 3;
+        for (int lane = 0; lane < 32; lane++) {
+            if (rotate) p1u<true>(lane, acc + poly * 1024, abar, mask, k, U.data() + poly * 1024);
+            else p1u<false>(lane, acc + poly * 1024, abar, mask, k, U.data() + poly * 1024);
+        }
+    }
     for (int w = 0; w < 6; w++) {
         const int poly = w / 3, k = w % 3;
         uint32_t* S = dh.data() + w * 1024;
-        for (int lane = 0; lane < 32; lane++) {
-            if (rotate) p1a<true>(lane, acc + poly * 1024, abar, mask, k, S);
-            else p1a<false>(lane, acc + poly * 1024, abar, mask, k, S);
-        }
+        for (int lane = 0; lane < 32; lane++) p1a(lane, U.data() + poly * 1024, k, S);
         for (int lane = 0; lane < 32; lane++) p1b(lane, S, h_fwdB);
     }
     for (int w = 0; w < 6; w++) {
