@@ -80,11 +80,9 @@ TFHE_HD void fwd_rows(int lane, uint32_t* S, const uint32_t* twF, uint32_t (&x)[
         const uint4 v = *reinterpret_cast<const uint4*>(S + swz_chunk(lane, q));
         x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
     }
+    ct32_wide(x, TwRow{twF + lane * TWB_STRIDE});   // column pass leaves < 8p: the row pass corrects inside stages 0, 2 and 4
 #pragma unroll
-    for (int c = 0; c < 32; c++) x[c] = csub(csub(x[c], 2u * P2), P2);  // column pass leaves < 8p; row pass wants < 2p
-    ct32(x, TwRow{twF + lane * TWB_STRIDE});
-#pragma unroll
-    for (int c = 0; c < 32; c++) x[c] = csub(csub(csub(x[c], 2u * P2), P2), P);  // < 8p -> [0,p)
+    for (int c = 0; c < 32; c++) x[c] = csub(csub(csub(x[c], 2u * P2), P2), P);  // < 6p -> [0,p)
 }
 TFHE_HD void p1b(int lane, uint32_t* S, const uint32_t* twF) {
     uint32_t x[32];
@@ -140,6 +138,7 @@ TFHE_HD void p2a(int lane, const uint32_t* slab, const uint32_t* dh, const uint3
     uint32_t x[32];
     p2a_mac_head(lane, slab, dh, twI, x);
     gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
+    gs_norm<2>(x);
 #pragma unroll
     for (int q = 0; q < 8; q++)
         *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
@@ -155,9 +154,10 @@ TFHE_HD void inv_rows(int lane, uint32_t (&x)[32], const uint32_t* twI, uint32_t
 TFHE_HD void p2b(int lane, const uint32_t* S, int part, uint32_t (&x)[32]) {
 #pragma unroll
     for (int r = 0; r < 32; r++) x[r] = S[swz(r, lane)];
-    gs32(x, TwUniform<true>());
+    gs32_lazy(x, TwUniform<true>());
+    gs_norm<1>(x);   // [0,p)
 #pragma unroll
-    for (int r = 0; r < 32; r++) x[r] = (uint32_t)lift(csub(x[r], P)) << (11 * part);
+    for (int r = 0; r < 32; r++) x[r] = (uint32_t)lift(x[r]) << (11 * part);
 }
 // ---- phase 2c: plain (unswizzled) store: coefficient k = 32 r + lane ----
 TFHE_HD void p2c(int lane, uint32_t* S, const uint32_t (&x)[32]) {

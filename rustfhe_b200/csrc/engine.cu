@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
             __syncwarp();
             if (lane == 0) mbar_arrive(macdone);
             gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
+            gs_norm<2>(x);
             mbar_wait(macdone, mac_parity);
             mac_parity ^= 1u;
 #pragma unroll

@@ -17,6 +17,7 @@
 // Everything here is __host__ __device__ so tests/host_emul can run the identical arithmetic on the CPU.
 #pragma once
 #include <stdint.h>
+#include <utility>
 #include "ntt_tables.h"
 
 #if defined(__CUDACC__)
@@ -135,77 +136,154 @@ TFHE_HD void ct_stage(uint32_t (&x)[32], const TW& tw) {  // stage S = 1..4: m =
         for (int j = 0; j < t; j++) ct_bfly<CORR>(x[2 * (i + 1) * t + j], x[2 * (i + 1) * t + j + t], w1, ws1);
     }
 }
-// Input bound: x < 2p.  Bounds after each stage (a butterfly outputs < X + 2p, csub(.,4p) maps [0,8p) to [0,4p)):
+// Input bound x < 2p (ct32): bounds after each stage (a butterfly outputs < X + 2p, csub(.,4p) maps [0,8p) to [0,4p)):
 //   s0: 4p   s1: 6p   s2: 8p   s3 (corrected to 4p): 6p   s4: 8p        -> output < 8p < 2^32
-template <class TW>
-TFHE_HD void ct32(uint32_t (&x)[32], const TW& tw) {
+// Input bound x < 8p (ct32_wide, the row pass fed straight from the column pass):
+//   s0 (corrected): 6p   s1: 8p   s2 (corrected): 6p   s3: 8p   s4 (corrected): 6p   -> output < 6p
+template <int C0, int C1, int C2, int C3, int C4, class TW>
+TFHE_HD void ct32_plan(uint32_t (&x)[32], const TW& tw) {
     {
         uint32_t w, ws;
         tw.get(1, w, ws);
 #pragma unroll
-        for (int j = 0; j < 16; j++) ct_bfly<0>(x[j], x[j + 16], w, ws);
+        for (int j = 0; j < 16; j++) ct_bfly<C0>(x[j], x[j + 16], w, ws);
     }
-    ct_stage<1, 0>(x, tw);
-    ct_stage<2, 0>(x, tw);
-    ct_stage<3, 4>(x, tw);
-    ct_stage<4, 0>(x, tw);
+    ct_stage<1, C1>(x, tw);
+    ct_stage<2, C2>(x, tw);
+    ct_stage<3, C3>(x, tw);
+    ct_stage<4, C4>(x, tw);
 }
-// ---- 32-point Gentleman-Sande network (exact mirror); values stay in [0,2p) ----
-TFHE_HD void gs_bfly(uint32_t& a, uint32_t& b, uint32_t w, uint32_t ws) {
-    const uint32_t U = a, V = b;
-    a = csub(add_alu(U, V), P2);
-    b = shoup_mul(U - V + P2, w, ws);
+template <class TW>
+TFHE_HD void ct32(uint32_t (&x)[32], const TW& tw) { ct32_plan<0, 0, 0, 4, 0>(x, tw); }
+template <class TW>
+TFHE_HD void ct32_wide(uint32_t (&x)[32], const TW& tw) { ct32_plan<4, 0, 4, 0, 4>(x, tw); }
+// ---- 32-point Gentleman-Sande network (exact mirror of ct32) with per-element lazy ranges ----
+// A GS butterfly maps (U, V) to (U + V, (U - V + K p) w): the product output is always < 2p (Shoup takes any 32-bit
+// input), the sum output has the SUM of the operand bounds.  Instead of one conditional subtraction per butterfly
+// (80 per network) the bound of every element is tracked at compile time and an operand is halved only where
+// bound(U) + bound(V) would pass 8p < 2^32: 24 conditional subtractions per network for inputs < 2p, none of them in
+// stages 0 and 1.  K = bound(V) keeps the difference non-negative and below 2^32.
+struct GsPlan {
+    unsigned char cu[5][16][2], cv[5][16][2];   // conditional subtractions on U / V before butterfly b of stage s (units of p, 0 = none)
+    unsigned char kv[5][16];                    // K of the difference
+    unsigned char out[32];                      // bound of every output, units of p
+};
+TFHE_HD constexpr GsPlan make_gs_plan(int in) {
+    GsPlan pl{};
+    int bnd[32] = {};
+    for (int i = 0; i < 32; i++) bnd[i] = in;
+    for (int S = 0; S < 5; S++) {
+        const int t = 1 << S, h = 16 >> S;
+        for (int i = 0; i < h; i++)
+            for (int j = 0; j < t; j++) {
+                const int u = 2 * i * t + j, v = u + t, bi = i * t + j;
+                int nu = 0, nv = 0;
+                while (bnd[u] + bnd[v] > 8) {
+                    if (bnd[u] >= bnd[v]) { const int m = (bnd[u] + 1) / 2; pl.cu[S][bi][nu++] = (unsigned char)m; bnd[u] = m; }
+                    else { const int m = (bnd[v] + 1) / 2; pl.cv[S][bi][nv++] = (unsigned char)m; bnd[v] = m; }
+                }
+                pl.kv[S][bi] = (unsigned char)bnd[v];
+                bnd[u] = bnd[u] + bnd[v];
+                bnd[v] = 2;
+            }
+    }
+    for (int i = 0; i < 32; i++) pl.out[i] = (unsigned char)bnd[i];
+    return pl;
 }
-template <int S, class TW>
-TFHE_HD void gs_stage(uint32_t (&x)[32], const TW& tw) {  // stage S = 0..3: h = 16 >> S blocks of half-width t = 2^S
+// butterfly BI (= block * t + j) of stage S of the plan for inputs < IN p
+template <int IN, int S, int BI>
+TFHE_HD void gs_bfly_p(uint32_t (&x)[32], uint32_t w, uint32_t ws) {
+    constexpr GsPlan pl = make_gs_plan(IN);
+    constexpr int t = 1 << S, i = BI / t, j = BI % t, u = 2 * i * t + j, v = u + t;
+    uint32_t U = x[u], V = x[v];
+    if constexpr (pl.cu[S][BI][0] != 0) U = csub(U, pl.cu[S][BI][0] * P);
+    if constexpr (pl.cu[S][BI][1] != 0) U = csub(U, pl.cu[S][BI][1] * P);
+    if constexpr (pl.cv[S][BI][0] != 0) V = csub(V, pl.cv[S][BI][0] * P);
+    if constexpr (pl.cv[S][BI][1] != 0) V = csub(V, pl.cv[S][BI][1] * P);
+    x[u] = add_alu(U, V);
+    x[v] = shoup_mul(U - V + pl.kv[S][BI] * P, w, ws);
+}
+template <int IN, int S, int I, class TW, int... J>   // blocks I and I+1 of stage S (16 >> S >= 2): one 16-byte twiddle load
+TFHE_HD void gs_blockpair_p(uint32_t (&x)[32], const TW& tw, std::integer_sequence<int, J...>) {
     constexpr int t = 1 << S, h = 16 >> S;
-#pragma unroll
-    for (int i = 0; i < h; i += 2) {
-        uint32_t w0, ws0, w1, ws1;
-        tw.get2(h + i, w0, ws0, w1, ws1);
-#pragma unroll
-        for (int j = 0; j < t; j++) gs_bfly(x[2 * i * t + j], x[2 * i * t + j + t], w0, ws0);
-#pragma unroll
-        for (int j = 0; j < t; j++) gs_bfly(x[2 * (i + 1) * t + j], x[2 * (i + 1) * t + j + t], w1, ws1);
+    uint32_t w0, ws0, w1, ws1;
+    tw.get2(h + I, w0, ws0, w1, ws1);
+    (gs_bfly_p<IN, S, I * t + J>(x, w0, ws0), ...);
+    (gs_bfly_p<IN, S, (I + 1) * t + J>(x, w1, ws1), ...);
+}
+template <int IN, int S, class TW, int... I2>
+TFHE_HD void gs_stage_p(uint32_t (&x)[32], const TW& tw, std::integer_sequence<int, I2...>) {
+    (gs_blockpair_p<IN, S, 2 * I2>(x, tw, std::make_integer_sequence<int, (1 << S)>{}), ...);
+}
+template <int IN, class TW, int... J>
+TFHE_HD void gs_last_p(uint32_t (&x)[32], const TW& tw, std::integer_sequence<int, J...>) {
+    uint32_t w, ws;
+    tw.get(1, w, ws);
+    (gs_bfly_p<IN, 4, J>(x, w, ws), ...);
+}
+template <int B, int T>
+TFHE_HD void gs_norm_one(uint32_t& v) {   // [0, B p) -> [0, T p)
+    if constexpr (B > T) {
+        v = csub(v, ((B + 1) / 2) * P);
+        gs_norm_one<(B + 1) / 2, T>(v);
     }
 }
+// brings every output of the IN-plan below T p (T = 2: input range of the next pass, 24 subtractions; T = 1: canonical, 56)
+template <int IN, int T, int... C>
+TFHE_HD void gs_norm_seq(uint32_t (&x)[32], std::integer_sequence<int, C...>) {
+    constexpr GsPlan pl = make_gs_plan(IN);
+    (gs_norm_one<pl.out[C], T>(x[C]), ...);
+}
+template <int T>
+TFHE_HD void gs_norm(uint32_t (&x)[32]) { gs_norm_seq<2, T>(x, std::make_integer_sequence<int, 32>{}); }
+
+// full network for inputs < 2p; outputs carry the plan's bounds (2p, 4p or 8p): follow with gs_norm<T>
 template <class TW>
-TFHE_HD void gs32(uint32_t (&x)[32], const TW& tw) {
-    gs_stage<0>(x, tw);
-    gs_stage<1>(x, tw);
-    gs_stage<2>(x, tw);
-    gs_stage<3>(x, tw);
-    {
-        uint32_t w, ws;
-        tw.get(1, w, ws);
-#pragma unroll
-        for (int j = 0; j < 16; j++) gs_bfly(x[j], x[j + 16], w, ws);
-    }
+TFHE_HD void gs32_lazy(uint32_t (&x)[32], const TW& tw) {
+    gs_stage_p<2, 0>(x, tw, std::make_integer_sequence<int, 8>{});
+    gs_stage_p<2, 1>(x, tw, std::make_integer_sequence<int, 4>{});
+    gs_stage_p<2, 2>(x, tw, std::make_integer_sequence<int, 2>{});
+    gs_stage_p<2, 3>(x, tw, std::make_integer_sequence<int, 1>{});
+    gs_last_p<2>(x, tw, std::make_integer_sequence<int, 16>{});
+}
+template <class TW>
+TFHE_HD void gs32(uint32_t (&x)[32], const TW& tw) {   // values in [0,2p) in, [0,2p) out
+    gs32_lazy(x, tw);
+    gs_norm<2>(x);
 }
 
-// Gentleman-Sande network split for software pipelining: stages 0 and 1 only touch the four values of one 16-byte chunk,
-// so the pointwise stage can run them chunk by chunk while it still waits for the next chunk's key and spectrum loads
-// (gs32_head4), and the transform proper starts at stage 2 (gs32_tail).  gs32 == 8 x gs32_head4 + gs32_tail.
+// The network split for software pipelining: stages 0 and 1 only touch the four values of one 16-byte chunk, so the
+// pointwise stage can run them chunk by chunk while it still waits for the next chunk's key and spectrum loads
+// (gs32_head4), and the transform proper starts at stage 2 (gs32_tail).  gs32_lazy == 8 x gs32_head4 + gs32_tail.
+TFHE_HD constexpr bool gs_head_is_uniform() {   // the plan for inputs < 2p has no subtraction in stages 0/1 and K = 2, (4,2)
+    const GsPlan pl = make_gs_plan(2);
+    for (int b = 0; b < 16; b++) {
+        if (pl.cu[0][b][0] || pl.cv[0][b][0] || pl.cu[1][b][0] || pl.cv[1][b][0]) return false;
+        if (pl.kv[0][b] != 2 || pl.kv[1][b] != ((b & 1) ? 2 : 4)) return false;
+    }
+    return true;
+}
+static_assert(gs_head_is_uniform(), "gs32_head4 hard-codes the lazy plan of stages 0 and 1");
+TFHE_HD void gs_bfly_k(uint32_t& a, uint32_t& b, uint32_t kp, uint32_t w, uint32_t ws) {
+    const uint32_t U = a, V = b;
+    a = add_alu(U, V);
+    b = shoup_mul(U - V + kp, w, ws);
+}
 template <class TW>
 TFHE_HD void gs32_head4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, int q, const TW& tw) {
     uint32_t w0, ws0, w1, ws1, w2, ws2;
     tw.get2(16 + 2 * q, w0, ws0, w1, ws1);
     tw.get(8 + q, w2, ws2);
-    gs_bfly(x0, x1, w0, ws0);
-    gs_bfly(x2, x3, w1, ws1);
-    gs_bfly(x0, x2, w2, ws2);
-    gs_bfly(x1, x3, w2, ws2);
+    gs_bfly_k(x0, x1, 2 * P, w0, ws0);
+    gs_bfly_k(x2, x3, 2 * P, w1, ws1);
+    gs_bfly_k(x0, x2, 4 * P, w2, ws2);
+    gs_bfly_k(x1, x3, 2 * P, w2, ws2);
 }
 template <class TW>
-TFHE_HD void gs32_tail(uint32_t (&x)[32], const TW& tw) {
-    gs_stage<2>(x, tw);
-    gs_stage<3>(x, tw);
-    {
-        uint32_t w, ws;
-        tw.get(1, w, ws);
-#pragma unroll
-        for (int j = 0; j < 16; j++) gs_bfly(x[j], x[j + 16], w, ws);
-    }
+TFHE_HD void gs32_tail(uint32_t (&x)[32], const TW& tw) {   // outputs carry the plan's bounds: follow with gs_norm<T>
+    gs_stage_p<2, 2>(x, tw, std::make_integer_sequence<int, 2>{});
+    gs_stage_p<2, 3>(x, tw, std::make_integer_sequence<int, 1>{});
+    gs_last_p<2>(x, tw, std::make_integer_sequence<int, 16>{});
 }
 
 // swizzled position of element (row r, column c) in a 32x32 word tile: 16-byte chunks are XOR-permuted with the
