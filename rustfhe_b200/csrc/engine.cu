@@ -8,6 +8,7 @@
 //   K6 keyswitch_kernel    : identity_key_switch as a tiled gather-accumulate (tlwe.rs:43-73)
 //   polymul_kernel         : exact negacyclic product micro-entry (math.rs:337-347)
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         bar_sync(bar_gate, THREADS_PER_GATE);
         uint32_t x[32];
         {   // phase 2: key slice kw of output poly pw
-            p2a_mac_head(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, dh, twI, x);
+            p2a_mac_head(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, dh, dh + 3 * 1024, twI, x);
             if (EXTPROD) {   // plain external product: the result replaces acc; every warp clears its share before it arrives
 #pragma unroll
                 for (int r = kw; r < 32; r += 3) acc[pw * 1024 + 32 * r + lane] = 0u;
@@ -248,6 +249,131 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         uint32_t* dst = a.out_init + (size_t)gate * (LWE_N + 1);
         for (int c = tid6; c <= LWE_N; c += THREADS_PER_GATE) dst[c] = (c == 0) ? acc[0] : 0u;
     }
+}
+
+// =====================================================================================================
+// K5L: latency shape of the blind rotation -- ONE gate on a cluster of TWO CTAs (two SMs), three warps each.
+// A warp instruction stream of one CMUX step needs ~3900 FMA-pipe cycles of its SM sub-partition; with six warps on one
+// SM two sub-partitions carry two warps and set the pace (measured 11.8 k cycles per step).  Here CTA `pw` of the pair
+// owns polynomial pw (0 = b, 1 = a): its three warps sit on three different sub-partitions, its accumulator and the
+// masked difference stay local, and the only exchange per step is the 12 KB of digit spectra, which every CTA also
+// stores into its peer's shared memory (distributed shared memory, double buffered) before ONE cluster barrier.
+// =====================================================================================================
+namespace cg = cooperative_groups;
+constexpr int PAIR_THREADS = 96;
+constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 3 * 1024 /*own spectra*/ + 2 * 3 * 1024 /*peer spectra x2*/ + 320;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) blind_rotate_pair_kernel(const BrArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int pw = (int)cluster.block_rank();
+    const long gate = blockIdx.x >> 1;
+    const int kw = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    uint32_t* twF = smem;
+    uint32_t* twI = smem + 32 * TWB_STRIDE;
+    uint32_t* acc = smem + TW_SMEM_WORDS;
+    uint32_t* U = acc + 1024;
+    uint32_t* own = U + 1024;            // [3][1024] spectra of this CTA's polynomial; plane kw doubles as transpose scratch
+    uint32_t* peer = own + 3 * 1024;     // [2][3][1024] spectra of the other polynomial, written by the other CTA
+    uint16_t* abar = reinterpret_cast<uint16_t*>(peer + 6 * 1024);
+    uint64_t* macdone = reinterpret_cast<uint64_t*>(peer + 6 * 1024 + 318);
+    uint32_t* remote = cluster.map_shared_rank(peer, pw ^ 1);   // where MY spectra go in the other CTA
+
+    for (int t = tid; t < 32 * TWB_STRIDE; t += PAIR_THREADS) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
+    if (tid == 0) mbar_init(macdone, 3);
+    {   // prologue (both CTAs read the inputs): gate pre-combination, rounding, acc_0 of the own polynomial
+        uint32_t* lin = own;
+        const bool second = gate >= a.split;
+        const long gsrc = second ? gate - a.split : gate;
+        const uint32_t* q0 = second ? a.in0b : a.in0;
+        const uint32_t* q1 = second ? a.in1b : a.in1;
+        const uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
+        const uint32_t* p0 = q0 + (size_t)gsrc * (LWE_N + 1);
+        const uint32_t* p1 = q1 ? q1 + (size_t)gsrc * (LWE_N + 1) : nullptr;
+        for (int c = tid; c <= LWE_N; c += PAIR_THREADS) {
+            uint32_t v = k0 * p0[c];
+            if (p1) v += k1 * p1[c];
+            if (c == 0) v += kb;
+            lin[c] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < LWE_N; i += PAIR_THREADS) abar[i] = (uint16_t)((lin[1 + i] + (1u << 20)) >> 21);
+        const uint32_t bbar = lin[0] >> 21;
+        const uint32_t nrot = (2048u - bbar) & 2047u;
+        for (int k = tid; k < 1024; k += PAIR_THREADS) {
+            const bool neg = ((uint32_t)k < (nrot & 1023u)) != (nrot >= 1024u);
+            acc[k] = pw == 0 ? (neg ? 0u - a.mu : a.mu) : 0u;
+        }
+    }
+    cluster.sync();   // both CTAs are set up (mbarriers, tables) before the first remote store
+    uint32_t mac_parity = 0;
+#pragma unroll 1
+    for (int i = 0; i < a.nsteps; i++) {
+        const uint32_t* step_bk = a.bkdev + (size_t)i * BK_STEP_WORDS;
+        uint32_t* S = own + kw * 1024;
+        uint32_t x[32];
+        p1u<true>(lane, acc, (uint32_t)abar[i], a.mask, kw, U);
+        bar_sync(1, PAIR_THREADS);
+        p1a(lane, U, kw, S);
+        __syncwarp();
+        fwd_rows(lane, S, twF, x);
+        {
+            uint32_t* R = remote + ((i & 1) * 3 + kw) * 1024;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint4 v = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = v;
+                *reinterpret_cast<uint4*>(R + swz_chunk(lane, q)) = v;
+            }
+        }
+        // split cluster barrier: arrive (release: my remote stores), fetch this step's whole key slab into registers while
+        // the barrier is pending (48 x 16 B per lane; the L2 round trips hide under the wait), then wait (acquire).
+        // (A point-to-point handshake on cluster-scope mbarriers was measured 10 % slower than this barrier.)
+        cluster.barrier_arrive();
+        {
+            uint4 bk[48];
+            p2a_slab_load(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, bk);
+            cluster.barrier_wait();   // all six spectra of this step are in both CTAs; the peer has finished the previous step's MAC
+            const uint32_t* P = peer + (i & 1) * 3 * 1024;
+            p2a_mac_head_regs(lane, bk, pw == 0 ? own : P, pw == 0 ? P : own, twI, x);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(macdone);
+            gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
+            gs_norm<2>(x);
+            mbar_wait(macdone, mac_parity);
+            mac_parity ^= 1u;
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            __syncwarp();
+            p2b(lane, S, kw, x);
+        }
+        {
+            const uint32_t A = smem_u32(acc + lane);
+#pragma unroll
+            for (int r = 0; r < 32; r++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(A + 128u * r), "r"(x[r]) : "memory");
+        }
+        bar_sync(1, PAIR_THREADS);
+    }
+    // ---- epilogue: CTA 0 owns b, CTA 1 owns a ----
+    if (a.trlwe_out) {
+        uint32_t* dst = a.trlwe_out + (size_t)gate * 2048 + pw * 1024;
+        for (int k = tid; k < 1024; k += PAIR_THREADS) dst[k] = acc[k];
+    }
+    if (pw == 1 && (a.ksdig || a.lwe1_out)) {
+        for (int i = tid; i < 1024; i += PAIR_THREADS) {
+            const uint32_t ai = (i == 0) ? acc[0] : 0u - acc[1024 - i];
+            if (a.ksdig) a.ksdig[(size_t)gate * 1024 + i] = (uint16_t)((ai + 0x8000u) >> 16);
+            if (a.lwe1_out) a.lwe1_out[(size_t)gate * 1025 + 1 + i] = ai;
+        }
+    }
+    if (pw == 0) {
+        if (a.lwe1_out && tid == 0) a.lwe1_out[(size_t)gate * 1025] = acc[0];
+        if (a.out_init) {
+            uint32_t* dst = a.out_init + (size_t)gate * (LWE_N + 1);
+            for (int c = tid; c <= LWE_N; c += PAIR_THREADS) dst[c] = (c == 0) ? acc[0] : 0u;
+        }
+    }
+    cluster.sync();   // no CTA leaves while its peer may still store into its shared memory
 }
 
 // =====================================================================================================
@@ -601,6 +727,8 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = set_smem(blind_rotate_kernel<2, false, 2>, 2)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<4, false, 1>, 4)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<2, true, 1>, 2)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_WORDS * 4)) != cudaSuccess)
+        return bail("smem attr (pair)", e);
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_STAGGER")) ctx->stagger_cycles = atoi(v);
     *out = ctx;
@@ -788,6 +916,10 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
     } else if (full) {   // default (variant 7)
         const unsigned grid = deal(4);
         blind_rotate_kernel<4, false, 1><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
+    } else if (2 * a.B <= (long)ctx->sm_count && ctx->variant != 9) {   // latency shape: one gate on a cluster of two SMs
+        a.cta_base = 1; a.cta_rem = 0;
+        ctx->gates_per_cta = 1;
+        blind_rotate_pair_kernel<<<(unsigned)(2 * a.B), PAIR_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
     } else {
         blind_rotate_kernel<1, false, 1><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
     }
