@@ -100,7 +100,7 @@ TFHE_HD void p2a_mac(int lane, const uint32_t* slab, const uint32_t* dh, uint32_
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
         for (int j = 0; j < BK_ROWS; j++) {
-            const uint4 d = *reinterpret_cast<const uint4*>(dh + j * NPOLY + swz_chunk(lane, q));
+            const uint4 d = *reinterpret_cast<const uint4*>(dh + j * TILE_WORDS + swz_chunk(lane, q));
 #if defined(TFHE_EXP_NOBK)   /* timing experiment only: no key traffic */
             const uint4 b = make_uint4(d.y, d.z, d.w, d.x);
 #elif defined(__CUDA_ARCH__)
@@ -123,7 +123,7 @@ TFHE_HD void p2a_mac_head(int lane, const uint32_t* slab, const uint32_t* dhb, c
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
         for (int j = 0; j < BK_ROWS; j++) {
-            const uint4 d = *reinterpret_cast<const uint4*>((j < 3 ? dhb + j * NPOLY : dha + (j - 3) * NPOLY) + swz_chunk(lane, q));
+            const uint4 d = *reinterpret_cast<const uint4*>((j < 3 ? dhb + j * TILE_WORDS : dha + (j - 3) * TILE_WORDS) + swz_chunk(lane, q));
 #if defined(__CUDA_ARCH__)
             const uint4 b = __ldg(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
 #else
@@ -153,7 +153,7 @@ TFHE_HD void p2a_mac_head_regs(int lane, const uint4 (&bk)[48], const uint32_t* 
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
         for (int j = 0; j < BK_ROWS; j++) {
-            const uint4 d = *reinterpret_cast<const uint4*>((j < 3 ? dhb + j * NPOLY : dha + (j - 3) * NPOLY) + swz_chunk(lane, q));
+            const uint4 d = *reinterpret_cast<const uint4*>((j < 3 ? dhb + j * TILE_WORDS : dha + (j - 3) * TILE_WORDS) + swz_chunk(lane, q));
             const uint4 b = bk[j * 8 + q];
             a0 += (uint64_t)d.x * b.x; a1 += (uint64_t)d.y * b.y; a2 += (uint64_t)d.z * b.z; a3 += (uint64_t)d.w * b.w;
         }
@@ -163,7 +163,7 @@ TFHE_HD void p2a_mac_head_regs(int lane, const uint4 (&bk)[48], const uint32_t* 
 }
 TFHE_HD void p2a(int lane, const uint32_t* slab, const uint32_t* dh, const uint32_t* twI, uint32_t* S) {
     uint32_t x[32];
-    p2a_mac_head(lane, slab, dh, dh + 3 * NPOLY, twI, x);
+    p2a_mac_head(lane, slab, dh, dh + 3 * TILE_WORDS, twI, x);
     gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
     gs_norm<2>(x);
 #pragma unroll

@@ -27,7 +27,7 @@ constexpr int KT_WARPS = 4;
 __global__ void __launch_bounds__(KT_WARPS * 32) bk_transform_kernel(const uint32_t* __restrict__ bk, uint32_t* __restrict__ dev,
                                                                     int npolys /* = nsteps*12 */) {
     __shared__ __align__(16) uint32_t twF[32 * TWB_STRIDE];
-    __shared__ __align__(16) uint32_t scratch[KT_WARPS][1024];
+    __shared__ __align__(16) uint32_t scratch[KT_WARPS][TILE_WORDS];
     for (int t = threadIdx.x; t < 32 * TWB_STRIDE; t += blockDim.x) twF[t] = g_fwdB[t];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) bk_transform_kernel(const uint3
 // =====================================================================================================
 constexpr int WARPS_PER_GATE = 6;
 constexpr int THREADS_PER_GATE = WARPS_PER_GATE * 32;
-constexpr int GATE_SMEM_WORDS = 2 * 1024 /*acc*/ + 2 * 1024 /*U: masked source polynomials*/ + 6 * 1024 /*dh: digit spectra / transpose scratch*/ +
+constexpr int GATE_SMEM_WORDS = 2 * 1024 /*acc*/ + 2 * 1024 /*U: masked source polynomials*/ + 6 * TILE_WORDS /*dh: digit spectra / transpose scratch*/ +
                                 320 /*abar u16[640]*/;
 constexpr int TW_SMEM_WORDS = 2 * 32 * TWB_STRIDE;
 constexpr size_t br_smem_bytes(int G) { return (size_t)(TW_SMEM_WORDS + G * GATE_SMEM_WORDS) * 4; }
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     uint32_t* acc = smem + TW_SMEM_WORDS + gl * GATE_SMEM_WORDS;
     uint32_t* U = acc + 2 * 1024;
     uint32_t* dh = U + 2 * 1024;
-    uint16_t* abar = reinterpret_cast<uint16_t*>(dh + 6 * 1024);
-    uint64_t* macdone = reinterpret_cast<uint64_t*>(dh + 6 * 1024 + 318);  // abar uses 635 u16 = 317.5 words of its 320
+    uint16_t* abar = reinterpret_cast<uint16_t*>(dh + 6 * TILE_WORDS);
+    uint64_t* macdone = reinterpret_cast<uint64_t*>(dh + 6 * TILE_WORDS + 318);  // abar uses 635 u16 = 317.5 words of its 320
 
     // gates are dealt out evenly: the first cta_rem CTAs own cta_base+1 consecutive gates, the others cta_base (<= G)
     const long cta = blockIdx.x;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
 #pragma unroll 1
     for (int i = 0; i < nsteps; i++) {
         const uint32_t* step_bk = a.bkdev + (EXTPROD ? (size_t)(gate % a.ntrgsw) : (size_t)i) * BK_STEP_WORDS;
-        uint32_t* S = dh + w6 * 1024;
+        uint32_t* S = dh + w6 * TILE_WORDS;
 #if defined(TFHE_EXP_PF)   /* experiment: sparse L2 prefetch of the next step's key, 1/64 of the slab per CTA */
         if (!EXTPROD && i + 1 < nsteps && tid6 < 18) {
             const char* nxt = reinterpret_cast<const char*>(step_bk + BK_STEP_WORDS);
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         bar_sync(bar_gate, THREADS_PER_GATE);
         uint32_t x[32];
         {   // phase 2: key slice kw of output poly pw
-            p2a_mac_head(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, dh, dh + 3 * 1024, twI, x);
+            p2a_mac_head(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, dh, dh + 3 * TILE_WORDS, twI, x);
             if (EXTPROD) {   // plain external product: the result replaces acc; every warp clears its share before it arrives
 #pragma unroll
                 for (int r = kw; r < 32; r += 3) acc[pw * 1024 + 32 * r + lane] = 0u;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
 // =====================================================================================================
 namespace cg = cooperative_groups;
 constexpr int PAIR_THREADS = 96;
-constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 3 * 1024 /*own spectra*/ + 2 * 3 * 1024 /*peer spectra x2*/ + 320;
+constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 3 * TILE_WORDS /*own spectra*/ + 2 * 3 * TILE_WORDS /*peer spectra x2*/ + 320;
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) blind_rotate_pair_kernel(const BrArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -272,10 +272,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
     uint32_t* twI = smem + 32 * TWB_STRIDE;
     uint32_t* acc = smem + TW_SMEM_WORDS;
     uint32_t* U = acc + 1024;
-    uint32_t* own = U + 1024;            // [3][1024] spectra of this CTA's polynomial; plane kw doubles as transpose scratch
-    uint32_t* peer = own + 3 * 1024;     // [2][3][1024] spectra of the other polynomial, written by the other CTA
-    uint16_t* abar = reinterpret_cast<uint16_t*>(peer + 6 * 1024);
-    uint64_t* macdone = reinterpret_cast<uint64_t*>(peer + 6 * 1024 + 318);
+    uint32_t* own = U + 1024;            // [3] tiles: spectra of this CTA's polynomial; plane kw doubles as transpose scratch
+    uint32_t* peer = own + 3 * TILE_WORDS;     // [2][3] tiles: spectra of the other polynomial, written by the other CTA
+    uint16_t* abar = reinterpret_cast<uint16_t*>(peer + 6 * TILE_WORDS);
+    uint64_t* macdone = reinterpret_cast<uint64_t*>(peer + 6 * TILE_WORDS + 318);
     uint32_t* remote = cluster.map_shared_rank(peer, pw ^ 1);   // where MY spectra go in the other CTA
 
     for (int t = tid; t < 32 * TWB_STRIDE; t += PAIR_THREADS) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
@@ -309,7 +309,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
 #pragma unroll 1
     for (int i = 0; i < a.nsteps; i++) {
         const uint32_t* step_bk = a.bkdev + (size_t)i * BK_STEP_WORDS;
-        uint32_t* S = own + kw * 1024;
+        uint32_t* S = own + kw * TILE_WORDS;
         uint32_t x[32];
         p1u<true>(lane, acc, (uint32_t)abar[i], a.mask, kw, U);
         bar_sync(1, PAIR_THREADS);
@@ -317,7 +317,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
         __syncwarp();
         fwd_rows(lane, S, twF, x);
         {
-            uint32_t* R = remote + ((i & 1) * 3 + kw) * 1024;
+            uint32_t* R = remote + ((i & 1) * 3 + kw) * TILE_WORDS;
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const uint4 v = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
@@ -333,7 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
             uint4 bk[48];
             p2a_slab_load(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, bk);
             cluster.barrier_wait();   // all six spectra of this step are in both CTAs; the peer has finished the previous step's MAC
-            const uint32_t* P = peer + (i & 1) * 3 * 1024;
+            const uint32_t* P = peer + (i & 1) * 3 * TILE_WORDS;
             p2a_mac_head_regs(lane, bk, pw == 0 ? own : P, pw == 0 ? P : own, twI, x);
             __syncwarp();
             if (lane == 0) mbar_arrive(macdone);
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(PM_WARPS * 32) polymul_kernel(const uint32_t* 
                                                                long o_stride, int accumulate) {
     __shared__ __align__(16) uint32_t twF[32 * TWB_STRIDE];
     __shared__ __align__(16) uint32_t twI[32 * TWB_STRIDE];
-    __shared__ __align__(16) uint32_t scratch[PM_WARPS][2][1024];
+    __shared__ __align__(16) uint32_t scratch[PM_WARPS][2][TILE_WORDS];
     for (int t = threadIdx.x; t < 32 * TWB_STRIDE; t += blockDim.x) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -14,7 +14,7 @@ extern "C" {
 
 // TRGSW torus polys [row j][poly][1024] (reference order: rows b-first, poly 0 = cipher, 1 = p_key) -> device layout
 void emul_key_transform(const uint32_t* trgsw, uint32_t* dev) {
-    std::vector<uint32_t> S(1024);
+    std::vector<uint32_t> S(TILE_WORDS);
     for (int j = 0; j < BK_ROWS; j++)
         for (int poly = 0; poly < 2; poly++)
             for (int part = 0; part < 3; part++) {
@@ -25,7 +25,7 @@ void emul_key_transform(const uint32_t* trgsw, uint32_t* dev) {
 }
 
 static void cmux_core(const uint32_t* dev, const uint32_t* acc, bool rotate, uint32_t abar, uint32_t mask, uint32_t* sp) {
-    std::vector<uint32_t> dh(6 * 1024), U(2 * 1024);
+    std::vector<uint32_t> dh(6 * TILE_WORDS), U(2 * 1024);
     for (int w = 0; w < 6; w++) {   // phase 1u: every warp contributes its rows of the masked source polynomial
         const int poly = w / 3, k = w % 3;
         for (int lane = 0; lane < 32; lane++) {
@@ -35,13 +35,13 @@ static void cmux_core(const uint32_t* dev, const uint32_t* acc, bool rotate, uin
     }
     for (int w = 0; w < 6; w++) {
         const int poly = w / 3, k = w % 3;
-        uint32_t* S = dh.data() + w * 1024;
+        uint32_t* S = dh.data() + w * TILE_WORDS;
         for (int lane = 0; lane < 32; lane++) p1a(lane, U.data() + poly * 1024, k, S);
         for (int lane = 0; lane < 32; lane++) p1b(lane, S, h_fwdB);
     }
     for (int w = 0; w < 6; w++) {
         const int poly = w / 3, k = w % 3;
-        uint32_t* S = sp + w * 1024;
+        uint32_t* S = sp + w * TILE_WORDS;
         uint32_t x[32][32];
         for (int lane = 0; lane < 32; lane++) p2a(lane, dev + bk_off(0, poly, k, 0, 0, 0), dh.data(), h_invB, S);
         for (int lane = 0; lane < 32; lane++) p2b(lane, S, k, x[lane]);
@@ -50,19 +50,19 @@ static void cmux_core(const uint32_t* dev, const uint32_t* acc, bool rotate, uin
 }
 // plain external product: out = TRGSW (x) trlwe  (hom_nand/src/trgsw.rs:264-306)
 void emul_external_product(const uint32_t* dev, const uint32_t* trlwe, uint32_t mask, uint32_t* out) {
-    std::vector<uint32_t> sp(6 * 1024);
+    std::vector<uint32_t> sp(6 * TILE_WORDS);
     cmux_core(dev, trlwe, false, 0, mask, sp.data());
     for (int poly = 0; poly < 2; poly++)
         for (int k = 0; k < 1024; k++)
-            out[poly * 1024 + k] = sp[(3 * poly) * 1024 + k] + sp[(3 * poly + 1) * 1024 + k] + sp[(3 * poly + 2) * 1024 + k];
+            out[poly * 1024 + k] = sp[(3 * poly) * TILE_WORDS + k] + sp[(3 * poly + 1) * TILE_WORDS + k] + sp[(3 * poly + 2) * TILE_WORDS + k];
 }
 // one blind-rotation step: acc <- BK (x) (X^abar acc - acc) + acc   (hom_nand/src/tfhe.rs:103-110)
 void emul_cmux_rotate(const uint32_t* dev, uint32_t* acc, uint32_t abar, uint32_t mask) {
-    std::vector<uint32_t> sp(6 * 1024);
+    std::vector<uint32_t> sp(6 * TILE_WORDS);
     cmux_core(dev, acc, true, abar, mask, sp.data());
     for (int poly = 0; poly < 2; poly++)
         for (int k = 0; k < 1024; k++)
-            acc[poly * 1024 + k] += sp[(3 * poly) * 1024 + k] + sp[(3 * poly + 1) * 1024 + k] + sp[(3 * poly + 2) * 1024 + k];
+            acc[poly * 1024 + k] += sp[(3 * poly) * TILE_WORDS + k] + sp[(3 * poly + 1) * TILE_WORDS + k] + sp[(3 * poly + 2) * TILE_WORDS + k];
 }
 uint32_t emul_prime(void) { return P; }
 int32_t emul_key_slice(uint32_t c, int part) { return key_slice(c, part); }

@@ -286,11 +286,14 @@ TFHE_HD void gs32_tail(uint32_t (&x)[32], const TW& tw) {   // outputs carry the
     gs_last_p<2>(x, tw, std::make_integer_sequence<int, 16>{});
 }
 
-// swizzled position of element (row r, column c) in a 32x32 word tile: 16-byte chunks are XOR-permuted with the
-// row so that both "lane = column, loop over rows" word accesses and "lane = row" 128-bit accesses are
-// bank-conflict free.
-TFHE_HD int swz(int r, int c) { return r * 32 + ((((c >> 2) ^ (r & 7)) << 2) | (c & 3)); }
-TFHE_HD int swz_chunk(int r, int q) { return r * 32 + ((q ^ (r & 7)) << 2); }
+// position of element (row r, column c) of a 32x32 word tile in shared memory.  Rows are PADDED to 36 words: the scalar
+// "lane = column, loop over rows" accesses stay consecutive, and the 128-bit "lane = row" accesses of a quarter warp
+// land on banks 4(r+q) mod 32 -- all 32 banks, conflict free -- while every address is one base register plus an
+// immediate (an XOR swizzle needs eight base registers, which the 80-register kernel kept recomputing on the FMA pipe).
+constexpr int TILE_STRIDE = 36;
+constexpr int TILE_WORDS = 32 * TILE_STRIDE;
+TFHE_HD int swz(int r, int c) { return r * TILE_STRIDE + c; }
+TFHE_HD int swz_chunk(int r, int q) { return r * TILE_STRIDE + 4 * q; }
 
 // ---- decomposition pieces (reference: utils/src/math.rs:300-326 with the mask of math.rs:542-560) ----
 // digit `dw` (0 = most significant) of x after the mask trick, sign-extended from 6 bits
