@@ -49,6 +49,23 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one blind_rotate_kernel launch (1024 gates) from the committed
+    `ncu --set full` summary (profiles/r01_ncu_blind_rotate_latest.txt); None when the summary is missing."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_blind_rotate_latest.txt")
+    try:
+        tot = 0.0
+        for line in open(p):
+            for key in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
+                if line.startswith(key):
+                    unit = line[line.index("[") + 1:line.index("]")].lower()
+                    val = float(line.split("=")[1])
+                    tot += val * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+        return tot or None
+    except Exception:
+        return None
+
+
 def int_peak():
     """IMAD issue-slot peak measured on this pool's B200 by tools/microbench/intpipe.cu (profiles/intpipe_r01.json)."""
     p = os.path.join(ROOT, "profiles", "intpipe_r01.json")
@@ -355,7 +372,7 @@ def run_gpu(args):
                                 "this same run; in the timed region consecutive batches overlap on two streams"},
             "roofline": {"bound": "hbm", "kernel": "blind_rotate_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                         "algorithmic_bytes_per_launch": algo_bytes, "traffic": None,
+                         "algorithmic_bytes_per_launch": algo_bytes, "traffic": ncu_traffic(),
                          "note": "HBM is NOT the binding roof of this kernel (key bytes are read once per 1024-gate launch); "
                                  "the binding roof is the integer FMA pipe, see int_roofline"},
             "int_roofline": {"bound": "integer FMA pipe (IMAD issue slots)", "kernel": "blind_rotate_kernel",
@@ -372,7 +389,7 @@ def run_gpu(args):
             try:
                 nthreads = os.cpu_count() or 1
                 gps1, secs1, B1, ok1, Kc = cpu_reference_run(1, 16)
-                gpsN, secsN, BN, okN, _ = cpu_reference_run(nthreads, 16, Kc)
+                gpsN, secsN, BN, okN, _ = cpu_reference_run(nthreads, max(1, BATCH // nthreads), Kc)   # the whole 1024-gate batch
                 line["cpu_baseline"] = {"value": gpsN, "unit": "gates/s", "cores": nthreads, "kind": "port",
                                         "value_1core": gps1, "ms_per_gate_1core": 1e3 / gps1, "decrypt_ok": bool(ok1 and okN),
                                         "sample": f"{BN} NAND gates on {nthreads} threads ({secsN:.1f} s) and {B1} gates on 1 thread "
