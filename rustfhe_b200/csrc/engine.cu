@@ -437,6 +437,91 @@ __global__ void __launch_bounds__(KS_THREADS* KS_GROUPS) keyswitch_kernel(const 
         atomicAdd(o + 3, 0u - acc[g].w);
     }
 }
+// ---- K6b: key switch with the key rows staged through shared memory, one WARP per gate ----
+// The register-tile kernel above is ALU bound on its digit select (12 instructions per gate, digit and 16-byte chunk:
+// the digit is CTA-uniform but every thread tests it).  Here a warp owns one gate and all 159 chunks of its output row
+// (5 per lane): the digit picks the ROW ADDRESS in shared memory, so per (gate, digit) there are two instructions of
+// select and five (LDS.128 + 4 adds) instead of 5 warps x 12.  The rows of a stage (4 levels x 3 multiples of one key
+// index = 30 KB) are copied once per CTA with cp.async into a 3-deep ring (one __syncthreads per stage) and consumed by
+// the 16 gates of the tile.
+#if !defined(KS2_NG)
+#define KS2_NG 16
+#endif
+constexpr int KS2_GATES = KS2_NG;                  // warps per CTA
+constexpr int KS2_THREADS = KS2_GATES * 32;
+constexpr int KS2_LV = 4;                          // levels per stage
+constexpr int KS2_ROWS = KS2_LV * 3;               // rows per stage
+constexpr int KS2_ROW_WORDS = 640;                 // 636 words padded to a multiple of 16 bytes x 32 lanes x 5
+constexpr int KS2_RING = 3;
+constexpr int KS2_STAGE_WORDS = KS2_ROWS * KS2_ROW_WORDS;
+constexpr size_t KS2_SMEM_BYTES = (size_t)KS2_RING * KS2_STAGE_WORDS * 4 + (size_t)KS_ICHUNK * KS2_GATES * 2;
+__global__ void __launch_bounds__(KS2_THREADS) keyswitch2_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
+                                                                uint32_t* __restrict__ out, long B) {
+    extern __shared__ __align__(16) uint32_t ks_smem[];
+    uint32_t* ring = ks_smem;
+    uint16_t* dg = reinterpret_cast<uint16_t*>(ks_smem + KS2_RING * KS2_STAGE_WORDS);   // [ichunk][16]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long g0 = (long)blockIdx.x * KS2_GATES;
+    const int ichunk = 1024 / (int)gridDim.y;
+    const int i0 = blockIdx.y * ichunk;
+    const int nstages = ichunk * (8 / KS2_LV);
+    for (int t = threadIdx.x; t < ichunk * KS2_GATES; t += KS2_THREADS) {
+        const int g = t / ichunk, ii = t % ichunk;
+        dg[ii * KS2_GATES + g] = (g0 + g < B) ? dig[(size_t)(g0 + g) * 1024 + i0 + ii] : (uint16_t)0;
+    }
+    auto stage_in = [&](int k) {   // rows (i0 + k/2, levels 4*(k&1) .. +3, all three multiples) -> ring slot k % 3
+        const uint4* src = ksk + ((size_t)(i0 + (k >> 1)) * 8 + (size_t)(k & 1) * KS2_LV) * 3 * KS_CHUNKS;
+        const uint32_t dst = smem_u32(ring + (k % KS2_RING) * KS2_STAGE_WORDS);
+        for (int t = threadIdx.x; t < KS2_ROWS * KS_CHUNKS; t += KS2_THREADS) {
+            const int row = t / KS_CHUNKS, c = t - row * KS_CHUNKS;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(row * KS2_ROW_WORDS + 4 * c) * 4u), "l"(src + t)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_in(0);
+    if (nstages > 1) stage_in(1); else asm volatile("cp.async.commit_group;" ::: "memory");
+    uint4 acc[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) acc[q] = make_uint4(0, 0, 0, 0);
+    const bool live = g0 + warp < B;
+#pragma unroll 1
+    for (int k = 0; k < nstages; k++) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // stage k has landed (at most the newest group is still in flight)
+        __syncthreads();                                          // ... for every thread; and everybody is done with stage k-1
+        if (k + 2 < nstages) stage_in(k + 2); else asm volatile("cp.async.commit_group;" ::: "memory");
+        if (live) {
+            const uint32_t d16 = dg[(k >> 1) * KS2_GATES + warp];
+            const uint32_t* rows = ring + (k % KS2_RING) * KS2_STAGE_WORDS;
+#pragma unroll
+            for (int l = 0; l < KS2_LV; l++) {
+                const uint32_t d = (d16 >> (14 - 2 * ((k & 1) * KS2_LV + l))) & 3u;   // level 0 in bits 15:14
+                if (d != 0) {
+                    const uint4* r = reinterpret_cast<const uint4*>(rows + (l * 3 + (int)d - 1) * KS2_ROW_WORDS) + lane;
+#pragma unroll
+                    for (int q = 0; q < 5; q++) {
+                        if (q < 4 || lane < KS_CHUNKS - 128) {
+                            const uint4 v = r[32 * q];
+                            acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!live) return;
+    uint32_t* o = out + (size_t)(g0 + warp) * (LWE_N + 1);
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        const int c = lane + 32 * q;
+        if (c < KS_CHUNKS) {
+            atomicAdd(o + 4 * c + 0, 0u - acc[q].x);
+            atomicAdd(o + 4 * c + 1, 0u - acc[q].y);
+            atomicAdd(o + 4 * c + 2, 0u - acc[q].z);
+            atomicAdd(o + 4 * c + 3, 0u - acc[q].w);
+        }
+    }
+}
 // prepares the key-switch inputs from explicit level-1 samples (step-level entry tfhe_b200_keyswitch_batch)
 __global__ void lwe1_prepare_kernel(const uint32_t* __restrict__ lwe1, uint16_t* __restrict__ dig, uint32_t* __restrict__ out, long B) {
     const long g = blockIdx.x;
@@ -624,6 +709,7 @@ struct tfhe_b200_ctx {
     uint64_t last_batch = 0;
     int gates_per_cta = 1;
     int variant = 7;  // blind-rotate launch shape, see launch_blind_rotate
+    int ks_variant = 2;  // key-switch kernel: 2 = rows staged in shared memory, one warp per gate; 1 = register tiles
     std::string err;
 };
 static thread_local std::string g_create_err;
@@ -731,6 +817,9 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
         return bail("smem attr (pair)", e);
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_STAGGER")) ctx->stagger_cycles = atoi(v);
+    if (const char* v = getenv("TFHE_B200_KS_VARIANT")) ctx->ks_variant = atoi(v);
+    if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
+        return bail("smem attr (keyswitch2)", e);
     *out = ctx;
     return TFHE_B200_OK;
 }
@@ -931,12 +1020,20 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
 static int launch_keyswitch(tfhe_b200_ctx* ctx, const uint16_t* dig, uint32_t* out, long B, cudaStream_t st, bool timed) {
     const int slot = (int)(ctx->timed % tfhe_b200_ctx::RING);
     if (timed) CK(cudaEventRecord(ctx->ev[slot][2], st));
-    const long tile = (long)KS_GT * KS_GROUPS;
-    const long tiles = (B + tile - 1) / tile;
-    int isplit = KS_ISPLIT_MIN;   // small batches (latency path, narrow circuit levels): split the key indices further to fill the SMs
-    while (isplit < 128 && tiles * isplit < 2L * ctx->sm_count) isplit *= 2;
-    dim3 grid((unsigned)tiles, isplit);
-    keyswitch_kernel<<<grid, dim3(KS_THREADS, KS_GROUPS), 0, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B);
+    if (ctx->ks_variant == 1) {   // register-tile kernel (TFHE_B200_KS_VARIANT=1)
+        const long tile = (long)KS_GT * KS_GROUPS;
+        const long tiles = (B + tile - 1) / tile;
+        int isplit = KS_ISPLIT_MIN;   // small batches (latency path, narrow circuit levels): split the key indices further to fill the SMs
+        while (isplit < 128 && tiles * isplit < 2L * ctx->sm_count) isplit *= 2;
+        dim3 grid((unsigned)tiles, isplit);
+        keyswitch_kernel<<<grid, dim3(KS_THREADS, KS_GROUPS), 0, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B);
+    } else {                      // shared-memory staged kernel, one warp per gate (default)
+        const long tiles = (B + KS2_GATES - 1) / KS2_GATES;
+        int isplit = KS_ISPLIT_MIN;
+        while (isplit < 128 && tiles * isplit < 2L * ctx->sm_count) isplit *= 2;
+        dim3 grid((unsigned)tiles, isplit);
+        keyswitch2_kernel<<<grid, KS2_THREADS, KS2_SMEM_BYTES, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     if (timed) { CK(cudaEventRecord(ctx->ev[slot][3], st)); ctx->timed++; }
