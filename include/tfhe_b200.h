@@ -129,6 +129,12 @@ int tfhe_b200_external_product_batch(tfhe_b200_ctx* ctx, const uint32_t* trgsw /
 int tfhe_b200_negacyclic_mul_batch(tfhe_b200_ctx* ctx, const uint32_t* a /*[B][N]*/, const int32_t* d /*[B][N]*/,
                                    uint32_t* out /*[B][N]*/, size_t B);
 
+/* device-pointer forms of the two micro-benchmark entries (enqueue on `stream`, no synchronisation) */
+int tfhe_b200_external_product_batch_device(tfhe_b200_ctx* ctx, const uint32_t* trgsw_dev, size_t ntrgsw,
+                                            const uint32_t* trlwe_dev, uint32_t* out_dev, size_t B, void* stream);
+int tfhe_b200_negacyclic_mul_batch_device(tfhe_b200_ctx* ctx, const uint32_t* a_dev, const int32_t* d_dev, uint32_t* out_dev,
+                                          size_t B, void* stream);
+
 /* ---- host-side key generation / encryption (TFHE::new, Cryptor::{encrypto,decrypto}; tfhe.rs:21-25,
  * tlwe.rs:197-241,247-277, trgsw.rs:117-139,213-229, trlwe.rs:127-137, digest.rs:14-33).  Seeded counter-based
  * generator (the reference uses thread_rng and cannot be seeded, math.rs:421-476). */

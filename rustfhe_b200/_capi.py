@@ -23,7 +23,7 @@ SYMBOLS = [
     "tfhe_b200_gate_batch_async", "tfhe_b200_sync", "tfhe_b200_reserve",
     "tfhe_b200_bootstrap_batch", "tfhe_b200_mux_batch", "tfhe_b200_mux_batch_device", "tfhe_b200_blind_rotate_batch",
     "tfhe_b200_bootstrap_lv1_batch", "tfhe_b200_keyswitch_batch", "tfhe_b200_external_product_batch",
-    "tfhe_b200_negacyclic_mul_batch", "tfhe_b200_keygen_secret", "tfhe_b200_keygen_bk", "tfhe_b200_keygen_ksk",
+    "tfhe_b200_negacyclic_mul_batch", "tfhe_b200_external_product_batch_device", "tfhe_b200_negacyclic_mul_batch_device", "tfhe_b200_keygen_secret", "tfhe_b200_keygen_bk", "tfhe_b200_keygen_ksk",
     "tfhe_b200_encrypt_bits", "tfhe_b200_phase", "tfhe_b200_decrypt_bits", "tfhe_b200_version",
     "tfhe_b200_keygen_device", "tfhe_b200_export_bk", "tfhe_b200_export_ksk", "tfhe_b200_export_bk_device",
     "tfhe_b200_export_ksk_device", "tfhe_b200_encrypt_bits_device",
@@ -83,6 +83,8 @@ def lib():
         "tfhe_b200_keyswitch_batch": (i32, [vp, vp, vp, sz]),
         "tfhe_b200_external_product_batch": (i32, [vp, vp, sz, vp, vp, sz]),
         "tfhe_b200_negacyclic_mul_batch": (i32, [vp, vp, vp, vp, sz]),
+        "tfhe_b200_external_product_batch_device": (i32, [vp, vp, sz, vp, vp, sz, vp]),
+        "tfhe_b200_negacyclic_mul_batch_device": (i32, [vp, vp, vp, vp, sz, vp]),
         "tfhe_b200_keygen_secret": (i32, [u64, vp, vp]),
         "tfhe_b200_keygen_bk": (i32, [u64, vp, vp, vp]),
         "tfhe_b200_keygen_ksk": (i32, [u64, vp, vp, vp]),

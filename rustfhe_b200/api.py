@@ -390,6 +390,14 @@ class DeviceEngine:
         self._ck(self._l.tfhe_b200_external_product_batch(self._ctx, ptr(trgsw), len(trgsw), ptr(trlwe), ptr(out), len(trlwe)))
         return out
 
+    def external_product_batch_device(self, trgsw_ptr, ntrgsw, trlwe_ptr, out_ptr, B, stream=0):
+        self._ck(self._l.tfhe_b200_external_product_batch_device(self._ctx, C.c_void_p(trgsw_ptr), ntrgsw, C.c_void_p(trlwe_ptr),
+                                                                 C.c_void_p(out_ptr), B, C.c_void_p(stream)))
+
+    def negacyclic_mul_batch_device(self, a_ptr, d_ptr, out_ptr, B, stream=0):
+        self._ck(self._l.tfhe_b200_negacyclic_mul_batch_device(self._ctx, C.c_void_p(a_ptr), C.c_void_p(d_ptr), C.c_void_p(out_ptr), B,
+                                                               C.c_void_p(stream)))
+
     def cmux_batch(self, trgsw, rep_1, rep_0):
         trgsw = np.ascontiguousarray(trgsw, np.uint32).reshape(-1, 2 * K.L, 2, K.N)
         rep_1 = np.ascontiguousarray(rep_1, np.uint32).reshape(-1, 2, K.N)

@@ -813,6 +813,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = set_smem(blind_rotate_kernel<2, false, 2>, 2)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<4, false, 1>, 4)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<2, true, 1>, 2)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<4, true, 1>, 4)) != cudaSuccess) return bail("smem attr", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_WORDS * 4)) != cudaSuccess)
         return bail("smem attr (pair)", e);
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
@@ -1257,6 +1258,28 @@ int tfhe_b200_decrypt_bits_device(tfhe_b200_ctx* ctx, const uint8_t* s0, const u
 
 }  // extern "C"
 
+// external product / cmux on device pointers: transform the TRGSW samples into slot scratch, then one CMUX step per product
+static int run_extprod(tfhe_b200_ctx* ctx, Slot* s, const uint32_t* trgsw_dev, size_t ntrgsw, const uint32_t* rep1, const uint32_t* rep0,
+                       uint32_t* out, size_t B, cudaStream_t st) {
+    RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, ntrgsw * BK_STEP_WORDS * 4));
+    RC(transform_keys(ctx, trgsw_dev, s->scratch, (int)ntrgsw, st));
+    BrArgs a{};
+    a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
+    a.trlwe_in = rep1; a.trlwe_in0 = rep0; a.trlwe_out = out; a.ntrgsw = (long)ntrgsw;
+    if (B > (size_t)ctx->sm_count) {   // throughput shape: 4 products per CTA
+        const unsigned grid = (unsigned)((B + 3) / 4);
+        a.cta_base = (int)(B / grid); a.cta_rem = (int)(B % grid);
+        blind_rotate_kernel<4, true, 1><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
+    } else {
+        const unsigned grid = (unsigned)((B + 1) / 2);
+        a.cta_base = (int)(B / grid); a.cta_rem = (int)(B % grid);
+        blind_rotate_kernel<2, true, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TFHE_B200_OK;
+}
+
 // ---- step-level entries: host pointers, synchronous.  `fn` enqueues the device work on (slot, stream). ----
 struct HostIo {
     const void* in[3] = {nullptr, nullptr, nullptr};
@@ -1328,18 +1351,31 @@ int tfhe_b200_external_product_batch(tfhe_b200_ctx* ctx, const uint32_t* trgsw, 
     HostIo io; io.in[0] = trlwe; io.in_bytes[0] = B * 2048 * 4; io.in[1] = trgsw; io.in_bytes[1] = ntrgsw * 12 * 1024 * 4;
     io.out = out; io.out_bytes = B * 2048 * 4;
     return with_host_io(ctx, io, [&](Slot* s, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
-        RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, ntrgsw * BK_STEP_WORDS * 4));
-        RC(transform_keys(ctx, di[1], s->scratch, (int)ntrgsw, st));
-        BrArgs a{};
-        a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
-        a.trlwe_in = di[0]; a.trlwe_out = dout; a.ntrgsw = (long)ntrgsw;
-        const unsigned grid = (unsigned)((B + 1) / 2);
-        a.cta_base = (int)(B / grid); a.cta_rem = (int)(B % grid);
-        blind_rotate_kernel<2, true, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
-        ctx->launches++;
-        CK(cudaGetLastError());
-        return TFHE_B200_OK;
+        return run_extprod(ctx, s, di[1], ntrgsw, di[0], nullptr, dout, B, st);
     });
+}
+// device-pointer forms of the two micro-benchmark entries (BASELINE config 3 measured device resident)
+int tfhe_b200_external_product_batch_device(tfhe_b200_ctx* ctx, const uint32_t* trgsw_dev, size_t ntrgsw, const uint32_t* trlwe_dev,
+                                            uint32_t* out_dev, size_t B, void* stream) {
+    if (!ctx || !trgsw_dev || !trlwe_dev || !out_dev || ntrgsw == 0) return fail(ctx, TFHE_B200_ERR_PARAM, "external_product_batch_device: bad argument");
+    if (B == 0) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, false, &s));
+    RC(run_extprod(ctx, s, trgsw_dev, ntrgsw, trlwe_dev, nullptr, out_dev, B, st));
+    return slot_release(ctx, s, st);
+}
+int tfhe_b200_negacyclic_mul_batch_device(tfhe_b200_ctx* ctx, const uint32_t* a_dev, const int32_t* d_dev, uint32_t* out_dev, size_t B,
+                                          void* stream) {
+    if (!ctx || !a_dev || !d_dev || !out_dev) return fail(ctx, TFHE_B200_ERR_PARAM, "negacyclic_mul_batch_device: null argument");
+    if (B == 0) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    polymul_kernel<<<(unsigned)((B + PM_WARPS - 1) / PM_WARPS), PM_WARPS * 32, 0, (cudaStream_t)stream>>>(a_dev, d_dev, out_dev, (long)B, 1024, 1024,
+                                                                                                           1024, 0);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TFHE_B200_OK;
 }
 int tfhe_b200_negacyclic_mul_batch(tfhe_b200_ctx* ctx, const uint32_t* a, const int32_t* d, uint32_t* out, size_t B) {
     if (!ctx || !a || !d || !out) return fail(ctx, TFHE_B200_ERR_PARAM, "negacyclic_mul_batch: null argument");
@@ -1362,17 +1398,7 @@ int tfhe_b200_cmux_batch(tfhe_b200_ctx* ctx, const uint32_t* trgsw, size_t ntrgs
     HostIo io; io.in[0] = rep1; io.in_bytes[0] = B * 2048 * 4; io.in[1] = trgsw; io.in_bytes[1] = ntrgsw * 12 * 1024 * 4;
     io.in[2] = rep0; io.in_bytes[2] = B * 2048 * 4; io.out = out; io.out_bytes = B * 2048 * 4;
     return with_host_io(ctx, io, [&](Slot* s, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
-        RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, ntrgsw * BK_STEP_WORDS * 4));
-        RC(transform_keys(ctx, di[1], s->scratch, (int)ntrgsw, st));
-        BrArgs a{};
-        a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
-        a.trlwe_in = di[0]; a.trlwe_in0 = di[2]; a.trlwe_out = dout; a.ntrgsw = (long)ntrgsw;
-        const unsigned grid = (unsigned)((B + 1) / 2);
-        a.cta_base = (int)(B / grid); a.cta_rem = (int)(B % grid);
-        blind_rotate_kernel<2, true, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
-        ctx->launches++;
-        CK(cudaGetLastError());
-        return TFHE_B200_OK;
+        return run_extprod(ctx, s, di[1], ntrgsw, di[0], di[2], dout, B, st);
     });
 }
 // TRLWERep::sample_extract_index(index) (trlwe.rs:110-121): [B][2][N] -> [B][N+1]
