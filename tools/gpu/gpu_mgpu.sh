@@ -1,5 +1,5 @@
 #!/bin/bash
-# N-GPU run: bench (both arms) + configs 4/5 sweep.  usage: tests/gpu_mgpu.sh N
+# N-GPU run: bench (both arms) + configs 4/5 sweep.  usage: tools/gpu/gpu_mgpu.sh N
 N=${1:-2}
 mkdir -p gpurun_out
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 10 --warmup 3 \

@@ -1,7 +1,7 @@
 """Small end-to-end run for compute-sanitizer: latency shape (cluster pair), throughput shape, mux, external product."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import rustfhe_b200 as R
 seed = 0x5EED0001
