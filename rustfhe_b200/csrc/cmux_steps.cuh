@@ -115,7 +115,9 @@ TFHE_HD void p2a_mac(int lane, const uint32_t* slab, const uint32_t* dh, uint32_
 }
 // same, with the first two inverse row stages of each chunk folded into the MAC loop (see gs32_head4): butterfly work
 // fills the wait for the next chunk's loads.  Finish with gs32_tail.
-// dhb / dha: the three digit spectra of the b polynomial (key rows 0..2) and of the a polynomial (rows 3..5)
+// dhb / dha: the three digit spectra of the b polynomial (key rows 0..2) and of the a polynomial (rows 3..5).
+// SLAB_IN_SMEM: the slab was staged in shared memory (latency shape) instead of being streamed from global memory.
+template <bool SLAB_IN_SMEM = false>
 TFHE_HD void p2a_mac_head(int lane, const uint32_t* slab, const uint32_t* dhb, const uint32_t* dha, const uint32_t* twI, uint32_t (&x)[32]) {
     const TwRow tw{twI + lane * TWB_STRIDE};
 #pragma unroll
@@ -125,7 +127,8 @@ TFHE_HD void p2a_mac_head(int lane, const uint32_t* slab, const uint32_t* dhb, c
         for (int j = 0; j < BK_ROWS; j++) {
             const uint4 d = *reinterpret_cast<const uint4*>((j < 3 ? dhb + j * TILE_WORDS : dha + (j - 3) * TILE_WORDS) + swz_chunk(lane, q));
 #if defined(__CUDA_ARCH__)
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
+            const uint4 b = SLAB_IN_SMEM ? *(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane)
+                                         : __ldg(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
 #else
             const uint4 b = *(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
 #endif

@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
 // =====================================================================================================
 namespace cg = cooperative_groups;
 constexpr int PAIR_THREADS = 96;
-constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 3 * TILE_WORDS /*own spectra*/ + 2 * 3 * TILE_WORDS /*peer spectra x2*/ + 320;
+constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 3 * TILE_WORDS /*own spectra*/ + 2 * 3 * TILE_WORDS /*peer spectra x2*/ + 320 +
+                                2 * 3 * (int)BK_SLAB_WORDS /*key slabs of this and the next step, one per warp*/;
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) blind_rotate_pair_kernel(const BrArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -276,7 +277,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
     uint32_t* peer = own + 3 * TILE_WORDS;     // [2][3] tiles: spectra of the other polynomial, written by the other CTA
     uint16_t* abar = reinterpret_cast<uint16_t*>(peer + 6 * TILE_WORDS);
     uint64_t* macdone = reinterpret_cast<uint64_t*>(peer + 6 * TILE_WORDS + 318);
+    uint32_t* slabs = peer + 6 * TILE_WORDS + 320;              // [2][3][BK_SLAB_WORDS]: warp-private, filled one step ahead by cp.async
     uint32_t* remote = cluster.map_shared_rank(peer, pw ^ 1);   // where MY spectra go in the other CTA
+    // the key slab of step i for this warp: 48 x 512 B, copied asynchronously a whole step ahead so that no L2 round trip is
+    // left on the critical path of a lone warp
+    auto slab_fetch = [&](int step) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.bkdev + (size_t)step * BK_STEP_WORDS + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS) + lane;
+        const uint32_t dst = smem_u32(slabs + ((step & 1) * 3 + kw) * BK_SLAB_WORDS) + 16u * lane;
+#pragma unroll
+        for (int t = 0; t < 48; t++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u * t), "l"(src + 32 * t) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
     for (int t = tid; t < 32 * TWB_STRIDE; t += PAIR_THREADS) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
     if (tid == 0) mbar_init(macdone, 3);
@@ -305,6 +316,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
         }
     }
     cluster.sync();   // both CTAs are set up (mbarriers, tables) before the first remote store
+    if (a.nsteps > 0) slab_fetch(0);
     uint32_t mac_parity = 0;
 #pragma unroll 1
     for (int i = 0; i < a.nsteps; i++) {
@@ -325,16 +337,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
                 *reinterpret_cast<uint4*>(R + swz_chunk(lane, q)) = v;
             }
         }
-        // split cluster barrier: arrive (release: my remote stores), fetch this step's whole key slab into registers while
-        // the barrier is pending (48 x 16 B per lane; the L2 round trips hide under the wait), then wait (acquire).
-        // (A point-to-point handshake on cluster-scope mbarriers was measured 10 % slower than this barrier.)
+        // split cluster barrier: arrive (release: my remote stores), start the copy of the NEXT step's key slab, then wait
+        // (acquire).  (A point-to-point handshake on cluster-scope mbarriers was measured 10 % slower than this barrier.)
         cluster.barrier_arrive();
+        if (i + 1 < a.nsteps) slab_fetch(i + 1); else asm volatile("cp.async.commit_group;" ::: "memory");
         {
-            uint4 bk[48];
-            p2a_slab_load(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, bk);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // this step's slab (committed one step ago) has landed
+            __syncwarp();
             cluster.barrier_wait();   // all six spectra of this step are in both CTAs; the peer has finished the previous step's MAC
+            const uint32_t* slab = slabs + ((i & 1) * 3 + kw) * BK_SLAB_WORDS;
             const uint32_t* P = peer + (i & 1) * 3 * TILE_WORDS;
-            p2a_mac_head_regs(lane, bk, pw == 0 ? own : P, pw == 0 ? P : own, twI, x);
+            p2a_mac_head<true>(lane, slab, pw == 0 ? own : P, pw == 0 ? P : own, twI, x);
             __syncwarp();
             if (lane == 0) mbar_arrive(macdone);
             gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
