@@ -358,7 +358,8 @@ def run_gpu(args):
                        "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world} (independent gate shards, keys replicated)",
                        "l2": f"inputs rotate over {NROT} batches ({NROT * BATCH * 2 * CT_WORDS * 4 / 1e6:.0f} MB) > L2; keys "
                              f"{(BK_BYTES_DEVICE + KSK_BYTES) / 1e6:.0f} MB > L2; no explicit flush",
-                       "gates_per_cta": st["gates_per_cta"], "streams": 2},
+                       "gates_per_cta": st["gates_per_cta"], "streams": 2,
+                       "key_slices": int(os.environ.get("TFHE_B200_KEY_SLICES", "3")) if os.environ.get("TFHE_B200_KEY_SLICES") in ("2", "3") else 3},
             "value_serial": gates / (serial_ms * 1e-3),
             "latency_us_per_gate_amortised": 1e3 * ms / args.steps / BATCH,
             "latency_us_single_gate": latency_us,

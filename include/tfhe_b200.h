@@ -82,6 +82,9 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p /* NULL = defaults */, int de
 int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx);
 const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx /* NULL = last error of a failed ctx_create */);
 int tfhe_b200_set_decomp_mask(tfhe_b200_ctx* ctx, uint32_t mask);
+/* Key slices per bootstrapping-key polynomial: 3 (default) = exact external product in the worst case; 2 = opt-in fast mode
+ * (one third less work per CMUX; exact with probability 1 - 3e-16 per gate over the key's masks) */
+int tfhe_b200_set_key_slices(tfhe_b200_ctx* ctx, int slices);
 int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out); /* waits for the recorded events */
 int tfhe_b200_reset_stats(tfhe_b200_ctx* ctx);
 

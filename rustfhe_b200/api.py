@@ -318,6 +318,10 @@ class DeviceEngine:
     def set_decomp_mask(self, mask):
         self._ck(self._l.tfhe_b200_set_decomp_mask(self._ctx, mask))
 
+    def set_key_slices(self, slices):
+        """3 = exact in the worst case (default); 2 = opt-in fast mode."""
+        self._ck(self._l.tfhe_b200_set_key_slices(self._ctx, slices))
+
     def reset_stats(self):
         self._ck(self._l.tfhe_b200_reset_stats(self._ctx))
 

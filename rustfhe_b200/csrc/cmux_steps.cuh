@@ -23,11 +23,12 @@ constexpr int GADGET_L = 3;
 constexpr int BK_ROWS = 6;                               // 2 * L
 constexpr size_t BK_POLY_WORDS = 1024;                   // one transformed key-slice polynomial
 constexpr size_t BK_SLAB_WORDS = BK_ROWS * 1024;         // [j][q][lane][4] : what one phase-2 warp streams per step
-constexpr size_t BK_STEP_WORDS = 2 * 3 * BK_SLAB_WORDS;  // [poly][part] slabs of one TRGSW = 36 polys = 147,456 B
+constexpr size_t BK_STEP_WORDS = 2 * 3 * BK_SLAB_WORDS;  // [poly][part] slabs of one TRGSW = 36 polys = 147,456 B (three key slices)
+TFHE_HD size_t bk_step_words(int ns) { return (size_t)2 * ns * BK_SLAB_WORDS; }   // ns key slices
 
 // device BK layout: word offset of (step i, output poly, key slice part, row j, chunk q, lane, e)
-TFHE_HD size_t bk_off(int i, int poly, int part, int j, int q, int lane) {
-    return ((((((size_t)i * 2 + poly) * 3 + part) * BK_ROWS + j) * 8 + q) * 32 + lane) * 4;
+TFHE_HD size_t bk_off(int i, int poly, int part, int j, int q, int lane, int ns = 3) {
+    return ((((((size_t)i * 2 + poly) * ns + part) * BK_ROWS + j) * 8 + q) * 32 + lane) * 4;
 }
 
 // value of (X^abar * A - A)[k], abar in [0, 2048).  Written with explicit sign masks (no predicated negate) so that every
@@ -181,13 +182,14 @@ TFHE_HD void inv_rows(int lane, uint32_t (&x)[32], const uint32_t* twI, uint32_t
         *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
 }
 // ---- phase 2b: lane = column c.  Column INTT -> exact signed integers, shifted by 11*part (kept in registers) ----
-TFHE_HD void p2b(int lane, const uint32_t* S, int part, uint32_t (&x)[32]) {
+TFHE_HD void p2b(int lane, const uint32_t* S, int part, uint32_t (&x)[32], int ns = 3) {
 #pragma unroll
     for (int r = 0; r < 32; r++) x[r] = S[swz(r, lane)];
     gs32_lazy(x, TwUniform<true>());
     gs_norm<1>(x);   // [0,p)
+    const int sh = slice_shift(ns) * part;
 #pragma unroll
-    for (int r = 0; r < 32; r++) x[r] = (uint32_t)lift(x[r]) << (11 * part);
+    for (int r = 0; r < 32; r++) x[r] = (uint32_t)lift(x[r]) << sh;
 }
 // ---- phase 2c: plain (unswizzled) store: coefficient k = 32 r + lane ----
 TFHE_HD void p2c(int lane, uint32_t* S, const uint32_t (&x)[32]) {
@@ -196,10 +198,10 @@ TFHE_HD void p2c(int lane, uint32_t* S, const uint32_t (&x)[32]) {
 }
 
 // ---- key transform: column `lane` of key slice `part` of a torus polynomial ----
-TFHE_HD void key_cols(int lane, const uint32_t* src, int part, uint32_t* S) {
+TFHE_HD void key_cols(int lane, const uint32_t* src, int part, uint32_t* S, int ns = 3) {
     uint32_t x[32];
 #pragma unroll
-    for (int r = 0; r < 32; r++) x[r] = to_residue(key_slice(src[32 * r + lane], part));
+    for (int r = 0; r < 32; r++) x[r] = to_residue(key_slice(src[32 * r + lane], part, ns));
     fwd_cols(lane, x, S);
 }
 // row pass + fold 2^32/N (Montgomery factor and the inverse transform's 1/N), store in the device BK layout

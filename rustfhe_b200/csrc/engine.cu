@@ -25,7 +25,7 @@ using namespace tfhe;
 // =====================================================================================================
 constexpr int KT_WARPS = 4;
 __global__ void __launch_bounds__(KT_WARPS * 32) bk_transform_kernel(const uint32_t* __restrict__ bk, uint32_t* __restrict__ dev,
-                                                                    int npolys /* = nsteps*12 */) {
+                                                                    int npolys /* = nsteps*12 */, int ns /* key slices: 3 or 2 */) {
     __shared__ __align__(16) uint32_t twF[32 * TWB_STRIDE];
     __shared__ __align__(16) uint32_t scratch[KT_WARPS][TILE_WORDS];
     for (int t = threadIdx.x; t < 32 * TWB_STRIDE; t += blockDim.x) twF[t] = g_fwdB[t];
@@ -36,10 +36,10 @@ __global__ void __launch_bounds__(KT_WARPS * 32) bk_transform_kernel(const uint3
     const int poly = pid & 1, j = (pid >> 1) % BK_ROWS, i = pid / (2 * BK_ROWS);
     const uint32_t* src = bk + (size_t)pid * 1024;
     uint32_t* S = scratch[warp];
-    for (int part = 0; part < 3; part++) {
-        key_cols(lane, src, part, S);
+    for (int part = 0; part < ns; part++) {
+        key_cols(lane, src, part, S, ns);
         __syncwarp();
-        key_rows(lane, S, twF, dev + bk_off(i, poly, part, j, 0, 0));
+        key_rows(lane, S, twF, dev + bk_off(i, poly, part, j, 0, 0, ns));
         __syncwarp();
     }
 }
@@ -81,6 +81,7 @@ struct BrArgs {
     int stagger_cycles;
     // gate -> CTA distribution (see the kernel prologue)
     int cta_base, cta_rem;
+    int ns;                  // key slices per polynomial: 3 (exact in the worst case) or 2 (opt-in fast mode)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,7 +107,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
 
-template <int G, bool EXTPROD, int MINB>
+template <int G, bool EXTPROD, int MINB, int NS = 3>
 __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel(const BrArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* twF = smem;
@@ -186,11 +187,11 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     uint32_t mac_parity = 0;
 #pragma unroll 1
     for (int i = 0; i < nsteps; i++) {
-        const uint32_t* step_bk = a.bkdev + (EXTPROD ? (size_t)(gate % a.ntrgsw) : (size_t)i) * BK_STEP_WORDS;
+        const uint32_t* step_bk = a.bkdev + (EXTPROD ? (size_t)(gate % a.ntrgsw) : (size_t)i) * bk_step_words(NS);
         uint32_t* S = dh + w6 * TILE_WORDS;
 #if defined(TFHE_EXP_PF)   /* experiment: sparse L2 prefetch of the next step's key, 1/64 of the slab per CTA */
         if (!EXTPROD && i + 1 < nsteps && tid6 < 18) {
-            const char* nxt = reinterpret_cast<const char*>(step_bk + BK_STEP_WORDS);
+            const char* nxt = reinterpret_cast<const char*>(step_bk + bk_step_words(NS));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)((blockIdx.x & 63) * 18 + tid6) * 128));
         }
 #endif
@@ -203,8 +204,8 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         }
         bar_sync(bar_gate, THREADS_PER_GATE);
         uint32_t x[32];
-        {   // phase 2: key slice kw of output poly pw
-            p2a_mac_head(lane, step_bk + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS, dh, dh + 3 * TILE_WORDS, twI, x);
+        if (kw < NS) {   // phase 2: key slice kw of output poly pw (with two key slices the third warp of a polynomial only signals)
+            p2a_mac_head(lane, step_bk + (size_t)(pw * NS + kw) * BK_SLAB_WORDS, dh, dh + 3 * TILE_WORDS, twI, x);
             if (EXTPROD) {   // plain external product: the result replaces acc; every warp clears its share before it arrives
 #pragma unroll
                 for (int r = kw; r < 32; r += 3) acc[pw * 1024 + 32 * r + lane] = 0u;
@@ -214,19 +215,24 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
             gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
             gs_norm<2>(x);
             mbar_wait(macdone, mac_parity);
-            mac_parity ^= 1u;
 #pragma unroll
             for (int q = 0; q < 8; q++)
                 *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
             __syncwarp();
-            p2b(lane, S, kw, x);   // x[r] = exact slice value (already shifted) of coefficient 32 r + lane
-        }
-        // phase 3: acc[pw] += x by shared-memory reductions (the three slice warps of a polynomial add concurrently)
-        {
+            p2b(lane, S, kw, x, NS);   // x[r] = exact slice value (already shifted) of coefficient 32 r + lane
+            // phase 3: acc[pw] += x by shared-memory reductions (the slice warps of a polynomial add concurrently)
             const uint32_t A = smem_u32(acc + pw * 1024 + lane);
 #pragma unroll
             for (int r = 0; r < 32; r++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(A + 128u * r), "r"(x[r]) : "memory");
+        } else {
+            if (EXTPROD) {
+#pragma unroll
+                for (int r = kw; r < 32; r += 3) acc[pw * 1024 + 32 * r + lane] = 0u;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(macdone);
         }
+        mac_parity ^= 1u;
         bar_sync(bar_poly, 96);   // acc[pw] is complete before the next step decomposes it
     }
     bar_sync(bar_gate, THREADS_PER_GATE);
@@ -263,6 +269,7 @@ namespace cg = cooperative_groups;
 constexpr int PAIR_THREADS = 96;
 constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 3 * TILE_WORDS /*own spectra*/ + 2 * 3 * TILE_WORDS /*peer spectra x2*/ + 320 +
                                 2 * 3 * (int)BK_SLAB_WORDS /*key slabs of this and the next step, one per warp*/;
+template <int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) blind_rotate_pair_kernel(const BrArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -282,7 +289,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
     // the key slab of step i for this warp: 48 x 512 B, copied asynchronously a whole step ahead so that no L2 round trip is
     // left on the critical path of a lone warp
     auto slab_fetch = [&](int step) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.bkdev + (size_t)step * BK_STEP_WORDS + (size_t)(pw * 3 + kw) * BK_SLAB_WORDS) + lane;
+        if (kw >= NS) { asm volatile("cp.async.commit_group;" ::: "memory"); return; }
+        const uint4* src = reinterpret_cast<const uint4*>(a.bkdev + (size_t)step * bk_step_words(NS) + (size_t)(pw * NS + kw) * BK_SLAB_WORDS) + lane;
         const uint32_t dst = smem_u32(slabs + ((step & 1) * 3 + kw) * BK_SLAB_WORDS) + 16u * lane;
 #pragma unroll
         for (int t = 0; t < 48; t++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u * t), "l"(src + 32 * t) : "memory");
@@ -320,7 +328,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
     uint32_t mac_parity = 0;
 #pragma unroll 1
     for (int i = 0; i < a.nsteps; i++) {
-        const uint32_t* step_bk = a.bkdev + (size_t)i * BK_STEP_WORDS;
         uint32_t* S = own + kw * TILE_WORDS;
         uint32_t x[32];
         p1u<true>(lane, acc, (uint32_t)abar[i], a.mask, kw, U);
@@ -347,23 +354,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
             cluster.barrier_wait();   // all six spectra of this step are in both CTAs; the peer has finished the previous step's MAC
             const uint32_t* slab = slabs + ((i & 1) * 3 + kw) * BK_SLAB_WORDS;
             const uint32_t* P = peer + (i & 1) * 3 * TILE_WORDS;
-            p2a_mac_head<true>(lane, slab, pw == 0 ? own : P, pw == 0 ? P : own, twI, x);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(macdone);
-            gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
-            gs_norm<2>(x);
-            mbar_wait(macdone, mac_parity);
+            if (kw < NS) {
+                p2a_mac_head<true>(lane, slab, pw == 0 ? own : P, pw == 0 ? P : own, twI, x);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(macdone);
+                gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
+                gs_norm<2>(x);
+                mbar_wait(macdone, mac_parity);
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                __syncwarp();
+                p2b(lane, S, kw, x, NS);
+                const uint32_t A = smem_u32(acc + lane);
+#pragma unroll
+                for (int r = 0; r < 32; r++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(A + 128u * r), "r"(x[r]) : "memory");
+            } else if (lane == 0) {
+                mbar_arrive(macdone);
+            }
             mac_parity ^= 1u;
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-                *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-            __syncwarp();
-            p2b(lane, S, kw, x);
-        }
-        {
-            const uint32_t A = smem_u32(acc + lane);
-#pragma unroll
-            for (int r = 0; r < 32; r++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(A + 128u * r), "r"(x[r]) : "memory");
         }
         bar_sync(1, PAIR_THREADS);
     }
@@ -722,6 +731,7 @@ struct tfhe_b200_ctx {
     uint64_t last_batch = 0;
     int gates_per_cta = 1;
     int variant = 7;  // blind-rotate launch shape, see launch_blind_rotate
+    int key_slices = 3;  // 3 = exact in the worst case (default); 2 = opt-in fast mode (tfhe_b200_set_key_slices)
     int ks_variant = 2;  // key-switch kernel: 2 = rows staged in shared memory, one warp per gate; 1 = register tiles
     std::string err;
 };
@@ -767,6 +777,9 @@ static int slot_release(tfhe_b200_ctx* ctx, Slot* s, cudaStream_t st) {
     return TFHE_B200_OK;
 }
 
+extern "C" {
+static int transform_keys(tfhe_b200_ctx* ctx, const uint32_t* src_dev, uint32_t* dst_dev, int nsteps, cudaStream_t st);
+}
 template <class Kern>
 static cudaError_t set_smem(Kern k, int G) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(G)); }
 
@@ -827,11 +840,18 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = set_smem(blind_rotate_kernel<4, false, 1>, 4)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<2, true, 1>, 2)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<4, true, 1>, 4)) != cudaSuccess) return bail("smem attr", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_WORDS * 4)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(blind_rotate_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_WORDS * 4)) != cudaSuccess)
         return bail("smem attr (pair)", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_WORDS * 4)) != cudaSuccess)
+        return bail("smem attr (pair)", e);
+    if ((e = set_smem(blind_rotate_kernel<4, false, 1, 2>, 4)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<1, false, 1, 2>, 1)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<2, true, 1, 2>, 2)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = set_smem(blind_rotate_kernel<4, true, 1, 2>, 4)) != cudaSuccess) return bail("smem attr", e);
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_STAGGER")) ctx->stagger_cycles = atoi(v);
     if (const char* v = getenv("TFHE_B200_KS_VARIANT")) ctx->ks_variant = atoi(v);
+    if (const char* v = getenv("TFHE_B200_KEY_SLICES")) ctx->key_slices = (atoi(v) == 2) ? 2 : 3;
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (keyswitch2)", e);
     *out = ctx;
@@ -877,6 +897,25 @@ int tfhe_b200_reserve(tfhe_b200_ctx* ctx, size_t max_batch) {
     return TFHE_B200_OK;
 }
 
+// Key slices per bootstrapping-key polynomial.  3 (default): 11/11/10-bit slices, every slice product is below p/2 in the WORST
+// case, the result is the exact external product unconditionally.  2 (opt-in fast mode): 16/16-bit slices, two inverse
+// transforms and a third of the pointwise work less per CMUX; a slice product then stays below p/2 only with overwhelming
+// probability over the key's masks (9.8 sigma: about 1e-22 per coefficient, 3e-16 per gate), not in the worst case.
+// Re-transforms the loaded bootstrapping key.
+int tfhe_b200_set_key_slices(tfhe_b200_ctx* ctx, int slices) {
+    if (!ctx || (slices != 2 && slices != 3)) return fail(ctx, TFHE_B200_ERR_PARAM, "set_key_slices: 2 or 3");
+    if (slices == ctx->key_slices) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    ctx->key_slices = slices;
+    if (ctx->have_bk) {
+        cudaStream_t st = ctx->slots[0].stream;
+        RC(transform_keys(ctx, ctx->bk_torus, ctx->bkdev, LWE_N, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return TFHE_B200_OK;
+}
+
 int tfhe_b200_sync(tfhe_b200_ctx* ctx) {
     if (!ctx) return TFHE_B200_ERR_PARAM;
     CK(cudaSetDevice(ctx->device));
@@ -897,7 +936,7 @@ int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out) {
     out->last_batch = ctx->last_batch;
     out->gates_per_cta = ctx->gates_per_cta;
     out->sm_count = ctx->sm_count;
-    out->device_key_bytes = (uint64_t)LWE_N * BK_STEP_WORDS * 4 + (uint64_t)1024 * 8 * 3 * (LWE_N + 1) * 4;
+    out->device_key_bytes = (uint64_t)LWE_N * bk_step_words(ctx->key_slices) * 4 + (uint64_t)1024 * 8 * 3 * (LWE_N + 1) * 4;
     const uint64_t cnt = ctx->timed < (uint64_t)tfhe_b200_ctx::RING ? ctx->timed : (uint64_t)tfhe_b200_ctx::RING;
     double sb = 0, sk = 0;
     for (uint64_t k = 0; k < cnt; k++) {
@@ -917,7 +956,7 @@ int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out) {
 // ---- keys ----
 static int transform_keys(tfhe_b200_ctx* ctx, const uint32_t* src_dev, uint32_t* dst_dev, int nsteps, cudaStream_t st) {
     const int npolys = nsteps * 12;
-    bk_transform_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(src_dev, dst_dev, npolys);
+    bk_transform_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(src_dev, dst_dev, npolys, ctx->key_slices);
     ctx->launches++;
     CK(cudaGetLastError());
     return TFHE_B200_OK;
@@ -972,7 +1011,7 @@ static void op_coeffs(int op, uint32_t mu, int32_t* c0, int32_t* c1, uint32_t* c
     }
 }
 static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, bool timed) {
-    a.bkdev = ctx->bkdev; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu;
+    a.bkdev = ctx->bkdev; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.ns = ctx->key_slices;
     if (a.split <= 0) a.split = a.B;
     const int slot = (int)(ctx->timed % tfhe_b200_ctx::RING);
     if (timed) CK(cudaEventRecord(ctx->ev[slot][0], st));
@@ -983,6 +1022,7 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
     // a half-empty last wave.
     const bool full = a.B > (long)ctx->sm_count;
     a.stagger_cycles = full ? ctx->stagger_cycles : 0;
+    const int variant = (a.ns == 2 && ctx->variant != 9) ? 7 : ctx->variant;   // the measured alternatives exist for three slices only
     auto deal = [&](int G) {
         const long cap = (long)G * ctx->sm_count;
         const long rounds = (a.B + cap - 1) / cap;
@@ -998,33 +1038,36 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         ctx->gates_per_cta = G;
         return (unsigned)nctas;
     };
-    if (full && ctx->variant == 0) {
+    if (full && variant == 0) {
         const unsigned grid = fixed(2);
         blind_rotate_kernel<2, false, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
-    } else if (full && ctx->variant == 2) {
+    } else if (full && variant == 2) {
         blind_rotate_kernel<1, false, 2><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-    } else if (full && ctx->variant == 3) {
+    } else if (full && variant == 3) {
         blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-    } else if (full && ctx->variant == 4) {
+    } else if (full && variant == 4) {
         const unsigned grid = fixed(3);
         blind_rotate_kernel<3, false, 1><<<grid, 3 * THREADS_PER_GATE, br_smem_bytes(3), st>>>(a);
-    } else if (full && ctx->variant == 5) {
+    } else if (full && variant == 5) {
         blind_rotate_kernel<1, false, 4><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-    } else if (full && ctx->variant == 6) {
+    } else if (full && variant == 6) {
         const unsigned grid = fixed(2);
         blind_rotate_kernel<2, false, 2><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
-    } else if (full && ctx->variant == 8) {
+    } else if (full && variant == 8) {
         const unsigned grid = fixed(4);
         blind_rotate_kernel<4, false, 1><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
     } else if (full) {   // default (variant 7)
         const unsigned grid = deal(4);
-        blind_rotate_kernel<4, false, 1><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
-    } else if (2 * a.B <= (long)ctx->sm_count && ctx->variant != 9) {   // latency shape: one gate on a cluster of two SMs
+        if (a.ns == 2) blind_rotate_kernel<4, false, 1, 2><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
+        else blind_rotate_kernel<4, false, 1, 3><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
+    } else if (2 * a.B <= (long)ctx->sm_count && variant != 9) {   // latency shape: one gate on a cluster of two SMs
         a.cta_base = 1; a.cta_rem = 0;
         ctx->gates_per_cta = 1;
-        blind_rotate_pair_kernel<<<(unsigned)(2 * a.B), PAIR_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
+        if (a.ns == 2) blind_rotate_pair_kernel<2><<<(unsigned)(2 * a.B), PAIR_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
+        else blind_rotate_pair_kernel<3><<<(unsigned)(2 * a.B), PAIR_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
     } else {
-        blind_rotate_kernel<1, false, 1><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
+        if (a.ns == 2) blind_rotate_kernel<1, false, 1, 2><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
+        else blind_rotate_kernel<1, false, 1><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1278,15 +1321,17 @@ static int run_extprod(tfhe_b200_ctx* ctx, Slot* s, const uint32_t* trgsw_dev, s
     RC(transform_keys(ctx, trgsw_dev, s->scratch, (int)ntrgsw, st));
     BrArgs a{};
     a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
-    a.trlwe_in = rep1; a.trlwe_in0 = rep0; a.trlwe_out = out; a.ntrgsw = (long)ntrgsw;
+    a.trlwe_in = rep1; a.trlwe_in0 = rep0; a.trlwe_out = out; a.ntrgsw = (long)ntrgsw; a.ns = ctx->key_slices;
     if (B > (size_t)ctx->sm_count) {   // throughput shape: 4 products per CTA
         const unsigned grid = (unsigned)((B + 3) / 4);
         a.cta_base = (int)(B / grid); a.cta_rem = (int)(B % grid);
-        blind_rotate_kernel<4, true, 1><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
+        if (a.ns == 2) blind_rotate_kernel<4, true, 1, 2><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
+        else blind_rotate_kernel<4, true, 1><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
     } else {
         const unsigned grid = (unsigned)((B + 1) / 2);
         a.cta_base = (int)(B / grid); a.cta_rem = (int)(B % grid);
-        blind_rotate_kernel<2, true, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
+        if (a.ns == 2) blind_rotate_kernel<2, true, 1, 2><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
+        else blind_rotate_kernel<2, true, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
     }
     ctx->launches++;
     CK(cudaGetLastError());

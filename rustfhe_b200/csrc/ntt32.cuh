@@ -305,8 +305,17 @@ TFHE_HD int32_t gadget_digit(uint32_t x, uint32_t mask, int dw) {
 // min(v, v + p) in unsigned arithmetic -- one VIADDMNMX
 TFHE_HD uint32_t to_residue(int32_t v) { return csub((uint32_t)v, 0u - P); }
 
-// centred 11/11/10-bit slices of a torus word: c0 + 2^11 c1 + 2^22 c2 == C (mod 2^32), |c0|,|c1| <= 1024, |c2| <= 512
-TFHE_HD int32_t key_slice(uint32_t C, int part) {
+// centred slices of a torus word.
+//   ns = 3 (default, exact in the worst case): 11/11/10 bits, c0 + 2^11 c1 + 2^22 c2 == C (mod 2^32), |c0|,|c1| <= 1024, |c2| <= 512
+//   ns = 2 (opt-in fast mode):  16/16 bits,    c0 + 2^16 c1 == C (mod 2^32),           |c0|,|c1| <= 32768
+TFHE_HD int slice_shift(int ns) { return ns == 3 ? 11 : 16; }
+TFHE_HD int32_t key_slice(uint32_t C, int part, int ns = 3) {
+    if (ns == 2) {
+        const int32_t c0 = (int32_t)((C & 0xFFFFu) ^ 0x8000u) - 0x8000;
+        if (part == 0) return c0;
+        const uint32_t C1 = ((C - (uint32_t)c0) >> 16) & 0xFFFFu;
+        return (int32_t)(C1 ^ 0x8000u) - 0x8000;
+    }
     const int32_t c0 = (int32_t)((C & 0x7FFu) ^ 0x400u) - 0x400;
     if (part == 0) return c0;
     const uint32_t C1 = (C - (uint32_t)c0) >> 11;

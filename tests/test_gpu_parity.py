@@ -346,3 +346,33 @@ def test_async_batches_overlap_and_match(engine, oracle, keys, rng):
         assert np.array_equal(keys.decrypt(got), want[k]), k
     ref = engine.gate_batch(0, ins[2][0].numpy().view(np.uint32), ins[2][1].numpy().view(np.uint32))
     assert np.array_equal(ref, outs[2].numpy().view(np.uint32))
+
+
+def test_fast_mode_two_key_slices(oracle, keys, rng):
+    """Opt-in fast mode (tfhe_b200_set_key_slices(ctx, 2)): 16/16-bit key slices, exact with overwhelming probability instead of
+    in the worst case.  On real keys and real accumulators the output ciphertexts are the same bits as
+    the exact oracle's (and hence as the default mode's); switching back to 3 slices re-transforms the key."""
+    import rustfhe_b200 as R
+    if int(__import__("os").environ.get("TFHE_B200_KEY_SLICES", "3")) == 2:
+        pytest.skip("suite already runs in fast mode")
+    eng = R.DeviceEngine(0)
+    try:
+        eng.load_ksk(keys.ksk)
+        eng.load_bk(keys.bk)
+        B = 300
+        x = rng.integers(0, 2, B).astype(np.uint8)
+        y = rng.integers(0, 2, B).astype(np.uint8)
+        c0, c1 = keys.encrypt(x, 61000), keys.encrypt(y, 62000)
+        exact = eng.gate_batch(R.NAND, c0, c1)
+        eng.set_key_slices(2)
+        fast = eng.gate_batch(R.NAND, c0, c1)
+        assert np.array_equal(keys.decrypt(fast), 1 - (x & y))
+        assert np.array_equal(fast, exact)
+        idx = rng.choice(B, 8, replace=False)
+        assert np.array_equal(fast[idx], oracle.gate_exact(keys, oracle.NAND, c0[idx], c1[idx]))
+        few = eng.gate_batch(R.XOR, c0[:3], c1[:3])          # latency shape (cluster pair) in fast mode
+        assert np.array_equal(few, oracle.gate_exact(keys, oracle.XOR, c0[:3], c1[:3]))
+        eng.set_key_slices(3)
+        assert np.array_equal(eng.gate_batch(R.NAND, c0[:40], c1[:40]), exact[:40])
+    finally:
+        eng.close()
