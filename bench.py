@@ -177,6 +177,9 @@ def run_reference(args):
 
 
 def run_gpu(args):
+    # keep stdout for the ONE JSON line: libraries that print to fd 1 (NCCL's "NCCL version ..." banner) go to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -398,7 +401,7 @@ def run_gpu(args):
                                                   f"Rust glue (no Rust toolchain in the image)"}
             except Exception as ex:  # the GPU numbers stand on their own
                 line["cpu_baseline"] = {"value": None, "unit": "gates/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
