@@ -60,11 +60,18 @@ TFHE_HD void p1u(int lane, const uint32_t* A, uint32_t abar, uint32_t mask, int 
 // digit `dw` (0 = most significant) of an already masked word, sign-extended from 6 bits
 TFHE_HD int32_t masked_digit(uint32_t u, int dw) { return ((int32_t)(u << (6 * dw))) >> 26; }
 // ---- phase 1a: lane = column c.  Digit `dw` of column c from U, column NTT, scatter into tile S ----
-TFHE_HD void p1a(int lane, const uint32_t* U, int dw, uint32_t* S) {
+// Stage 0 pairs rows r and r+16 with the single twiddle psi^512; the digit of row r+16 goes through the table
+// digit_tab[d + 32] = d * psi^512 mod p instead of a Shoup multiplication: a = X + T, b = X - T + p, both < 2p.
+TFHE_HD void p1a(int lane, const uint32_t* U, int dw, uint32_t* S, const uint32_t* digit_tab) {
     uint32_t x[32];
 #pragma unroll
-    for (int r = 0; r < 32; r++) x[r] = to_residue(masked_digit(U[32 * r + lane], dw));
-    ct32(x, TwUniform<false>());
+    for (int r = 0; r < 16; r++) {
+        const uint32_t X = to_residue(masked_digit(U[32 * r + lane], dw));
+        const uint32_t T = digit_tab[masked_digit(U[32 * (r + 16) + lane], dw) + 32];
+        x[r] = add_alu(X, T);
+        x[r + 16] = X - T + P;
+    }
+    ct32_after_stage0(x, TwUniform<false>());
 #pragma unroll
     for (int r = 0; r < 32; r++) S[swz(r, lane)] = x[r];
 }

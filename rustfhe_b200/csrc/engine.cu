@@ -51,7 +51,7 @@ constexpr int WARPS_PER_GATE = 6;
 constexpr int THREADS_PER_GATE = WARPS_PER_GATE * 32;
 constexpr int GATE_SMEM_WORDS = 2 * 1024 /*acc*/ + 2 * 1024 /*U: masked source polynomials*/ + 6 * TILE_WORDS /*dh: digit spectra / transpose scratch*/ +
                                 320 /*abar u16[640]*/;
-constexpr int TW_SMEM_WORDS = 2 * 32 * TWB_STRIDE;
+constexpr int TW_SMEM_WORDS = 2 * 32 * TWB_STRIDE + DIGIT_TAB_WORDS;   // forward + inverse twiddle rows, digit table
 constexpr size_t br_smem_bytes(int G) { return (size_t)(TW_SMEM_WORDS + G * GATE_SMEM_WORDS) * 4; }
 
 struct BrArgs {
@@ -129,10 +129,12 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     const bool active = gl < cnt;
     const long gate = active ? first + gl : a.B - 1;
 
+    uint32_t* dtab = smem + 2 * 32 * TWB_STRIDE;
     for (int t = threadIdx.x; t < 32 * TWB_STRIDE; t += blockDim.x) {
         twF[t] = g_fwdB[t];
         twI[t] = g_invB[t];
     }
+    for (int t = threadIdx.x; t < DIGIT_TAB_WORDS; t += blockDim.x) dtab[t] = g_digit_tab.v[t];
     if (tid6 == 0) mbar_init(macdone, WARPS_PER_GATE);
     // ---- prologue: gate pre-combination (tfhe.rs:27-71), rounding of (b, a) (tfhe.rs:97,107-108), acc_0 ----
     int nsteps = a.nsteps;
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         {   // phase 1: a third of the rows of u[pw], then digit kw of u[pw] -> spectrum plane dh[w6]
             p1u<!EXTPROD>(lane, acc + pw * 1024, EXTPROD ? 0u : (uint32_t)abar[i], a.mask, kw, U + pw * 1024);
             bar_sync(bar_poly, 96);
-            p1a(lane, U + pw * 1024, kw, S);
+            p1a(lane, U + pw * 1024, kw, S, dtab);
             __syncwarp();
             p1b(lane, S, twF);
         }
@@ -297,7 +299,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    uint32_t* dtab = smem + 2 * 32 * TWB_STRIDE;
     for (int t = tid; t < 32 * TWB_STRIDE; t += PAIR_THREADS) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
+    if (tid < DIGIT_TAB_WORDS) dtab[tid] = g_digit_tab.v[tid];
     if (tid == 0) mbar_init(macdone, 3);
     {   // prologue (both CTAs read the inputs): gate pre-combination, rounding, acc_0 of the own polynomial
         uint32_t* lin = own;
@@ -332,7 +336,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
         uint32_t x[32];
         p1u<true>(lane, acc, (uint32_t)abar[i], a.mask, kw, U);
         bar_sync(1, PAIR_THREADS);
-        p1a(lane, U, kw, S);
+        p1a(lane, U, kw, S, dtab);
         __syncwarp();
         fwd_rows(lane, S, twF, x);
         {

@@ -36,7 +36,7 @@ static void cmux_core(const uint32_t* dev, const uint32_t* acc, bool rotate, uin
     for (int w = 0; w < 6; w++) {
         const int poly = w / 3, k = w % 3;
         uint32_t* S = dh.data() + w * TILE_WORDS;
-        for (int lane = 0; lane < 32; lane++) p1a(lane, U.data() + poly * 1024, k, S);
+        for (int lane = 0; lane < 32; lane++) p1a(lane, U.data() + poly * 1024, k, S, h_digit_tab.v);
         for (int lane = 0; lane < 32; lane++) p1b(lane, S, h_fwdB);
     }
     for (int w = 0; w < 6; w++) {

@@ -44,6 +44,26 @@ static __device__ const uint32_t g_invB[32 * NTT_TWB_STRIDE] = {NTT_INV_B_LIST};
 static __constant__ uint32_t c_zero = 0;  // opaque to ptxas (a __constant__ may be rewritten by the host)
 #endif
 
+// Stage 0 of the forward COLUMN pass multiplies gadget digits d in [-32, 32) by the single twiddle psi^512: a 64-entry table
+// IOTA[d + 32] = d * psi^512 mod p in [0, p) replaces those 16 Shoup multiplications per transform (DIGIT_TAB_WORDS words
+// of shared memory behind the twiddle rows).
+constexpr int DIGIT_TAB_WORDS = 64;
+struct DigitTab { uint32_t v[DIGIT_TAB_WORDS]; };
+TFHE_HD constexpr DigitTab make_digit_tab() {
+    constexpr uint32_t fwdA[64] = {NTT_FWD_A_LIST};
+    DigitTab t{};
+    for (int k = 0; k < DIGIT_TAB_WORDS; k++) {
+        const int d = k - 32;
+        const uint64_t r = (uint64_t)(d < 0 ? (int64_t)NTT_P + d : d);
+        t.v[k] = (uint32_t)(r * fwdA[2] % NTT_P);
+    }
+    return t;
+}
+static const DigitTab h_digit_tab = make_digit_tab();
+#if defined(__CUDACC__)
+static __device__ const DigitTab g_digit_tab = make_digit_tab();
+#endif
+
 // a + b as a THREE-input add with an opaque zero: keeps ptxas from emitting IMAD.IADD, i.e. keeps plain additions on
 // the ALU pipe and off the FMA-heavy pipe that bounds the transforms (profiles/r01_ncu_blind_rotate_v1.txt).
 TFHE_HD uint32_t add_alu(uint32_t a, uint32_t b) {
@@ -155,6 +175,14 @@ TFHE_HD void ct32_plan(uint32_t (&x)[32], const TW& tw) {
 }
 template <class TW>
 TFHE_HD void ct32(uint32_t (&x)[32], const TW& tw) { ct32_plan<0, 0, 0, 4, 0>(x, tw); }
+// stages 1..4 only, for inputs < 2p whose stage 0 was done by table lookup (bounds 4p, 6p, corrected 6p, 8p)
+template <class TW>
+TFHE_HD void ct32_after_stage0(uint32_t (&x)[32], const TW& tw) {
+    ct_stage<1, 0>(x, tw);
+    ct_stage<2, 0>(x, tw);
+    ct_stage<3, 4>(x, tw);
+    ct_stage<4, 0>(x, tw);
+}
 template <class TW>
 TFHE_HD void ct32_wide(uint32_t (&x)[32], const TW& tw) { ct32_plan<4, 0, 4, 0, 4>(x, tw); }
 // ---- 32-point Gentleman-Sande network (exact mirror of ct32) with per-element lazy ranges ----
