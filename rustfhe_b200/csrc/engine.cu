@@ -475,7 +475,10 @@ __global__ void __launch_bounds__(KS_THREADS* KS_GROUPS) keyswitch_kernel(const 
 #endif
 constexpr int KS2_GATES = KS2_NG;                  // warps per CTA
 constexpr int KS2_THREADS = KS2_GATES * 32;
-constexpr int KS2_LV = 4;                          // levels per stage
+#if !defined(KS2_LVDEF)
+#define KS2_LVDEF 4
+#endif
+constexpr int KS2_LV = KS2_LVDEF;                  // levels per stage
 constexpr int KS2_ROWS = KS2_LV * 3;               // rows per stage
 constexpr int KS2_ROW_WORDS = 640;                 // 636 words padded to a multiple of 16 bytes x 32 lanes x 5
 constexpr int KS2_RING = 3;
@@ -495,8 +498,9 @@ __global__ void __launch_bounds__(KS2_THREADS) keyswitch2_kernel(const uint4* __
         const int g = t / ichunk, ii = t % ichunk;
         dg[ii * KS2_GATES + g] = (g0 + g < B) ? dig[(size_t)(g0 + g) * 1024 + i0 + ii] : (uint16_t)0;
     }
-    auto stage_in = [&](int k) {   // rows (i0 + k/2, levels 4*(k&1) .. +3, all three multiples) -> ring slot k % 3
-        const uint4* src = ksk + ((size_t)(i0 + (k >> 1)) * 8 + (size_t)(k & 1) * KS2_LV) * 3 * KS_CHUNKS;
+    auto stage_in = [&](int k) {   // rows (key index i0 + k / SPI, KS2_LV levels, all three multiples) -> ring slot k % 3
+        constexpr int SPI = 8 / KS2_LV;   // stages per key index
+        const uint4* src = ksk + ((size_t)(i0 + k / SPI) * 8 + (size_t)(k % SPI) * KS2_LV) * 3 * KS_CHUNKS;
         const uint32_t dst = smem_u32(ring + (k % KS2_RING) * KS2_STAGE_WORDS);
         for (int t = threadIdx.x; t < KS2_ROWS * KS_CHUNKS; t += KS2_THREADS) {
             const int row = t / KS_CHUNKS, c = t - row * KS_CHUNKS;
@@ -517,11 +521,12 @@ __global__ void __launch_bounds__(KS2_THREADS) keyswitch2_kernel(const uint4* __
         __syncthreads();                                          // ... for every thread; and everybody is done with stage k-1
         if (k + 2 < nstages) stage_in(k + 2); else asm volatile("cp.async.commit_group;" ::: "memory");
         if (live) {
-            const uint32_t d16 = dg[(k >> 1) * KS2_GATES + warp];
+            constexpr int SPI = 8 / KS2_LV;
+            const uint32_t d16 = dg[(k / SPI) * KS2_GATES + warp];
             const uint32_t* rows = ring + (k % KS2_RING) * KS2_STAGE_WORDS;
 #pragma unroll
             for (int l = 0; l < KS2_LV; l++) {
-                const uint32_t d = (d16 >> (14 - 2 * ((k & 1) * KS2_LV + l))) & 3u;   // level 0 in bits 15:14
+                const uint32_t d = (d16 >> (14 - 2 * ((k % SPI) * KS2_LV + l))) & 3u;   // level 0 in bits 15:14
                 if (d != 0) {
                     const uint4* r = reinterpret_cast<const uint4*>(rows + (l * 3 + (int)d - 1) * KS2_ROW_WORDS) + lane;
 #pragma unroll
