@@ -146,6 +146,30 @@ TFHE_HD void p2a_mac_head(int lane, const uint32_t* slab, const uint32_t* dhb, c
         gs32_head4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3], q, tw);
     }
 }
+// latency shape, split MAC: the three key rows that meet this CTA's OWN digit spectra are accumulated first (64-bit partial
+// sums for all 32 positions stay in registers) while the cluster barrier that delivers the peer's spectra is still pending;
+// p2a_mac_finish adds the other three rows, reduces and runs the first two inverse stages.  j0: first key row of the part.
+TFHE_HD void p2a_mac_part(int lane, const uint32_t* slab, const uint32_t* dh3, int j0, uint64_t (&acc)[32], bool first) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        uint64_t a0 = first ? 0 : acc[4 * q], a1 = first ? 0 : acc[4 * q + 1], a2 = first ? 0 : acc[4 * q + 2], a3 = first ? 0 : acc[4 * q + 3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const uint4 d = *reinterpret_cast<const uint4*>(dh3 + j * TILE_WORDS + swz_chunk(lane, q));
+            const uint4 b = *(reinterpret_cast<const uint4*>(slab) + ((j0 + j) * 8 + q) * 32 + lane);
+            a0 += (uint64_t)d.x * b.x; a1 += (uint64_t)d.y * b.y; a2 += (uint64_t)d.z * b.z; a3 += (uint64_t)d.w * b.w;
+        }
+        acc[4 * q] = a0; acc[4 * q + 1] = a1; acc[4 * q + 2] = a2; acc[4 * q + 3] = a3;
+    }
+}
+TFHE_HD void p2a_mac_finish(int lane, const uint64_t (&acc)[32], const uint32_t* twI, uint32_t (&x)[32]) {
+    const TwRow tw{twI + lane * TWB_STRIDE};
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        x[4 * q] = redc64(acc[4 * q]); x[4 * q + 1] = redc64(acc[4 * q + 1]); x[4 * q + 2] = redc64(acc[4 * q + 2]); x[4 * q + 3] = redc64(acc[4 * q + 3]);
+        gs32_head4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3], q, tw);
+    }
+}
 // latency shape: the whole key slab of the step is already in registers (loaded while the cluster barrier was pending)
 TFHE_HD void p2a_slab_load(int lane, const uint32_t* slab, uint4 (&bk)[48]) {
 #pragma unroll

@@ -355,11 +355,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
         {
             asm volatile("cp.async.wait_group 1;" ::: "memory");   // this step's slab (committed one step ago) has landed
             __syncwarp();
-            cluster.barrier_wait();   // all six spectra of this step are in both CTAs; the peer has finished the previous step's MAC
             const uint32_t* slab = slabs + ((i & 1) * 3 + kw) * BK_SLAB_WORDS;
             const uint32_t* P = peer + (i & 1) * 3 * TILE_WORDS;
+            bar_sync(2, PAIR_THREADS);   // this CTA's own three spectra are complete (local barrier; the cluster one is still pending)
             if (kw < NS) {
-                p2a_mac_head<true>(lane, slab, pw == 0 ? own : P, pw == 0 ? P : own, twI, x);
+                // the key rows that meet this CTA's own spectra need nothing from the peer: accumulate them while the cluster
+                // barrier is pending, then wait and add the rows of the peer's spectra
+                uint64_t mac[32];
+                p2a_mac_part(lane, slab, own, pw == 0 ? 0 : 3, mac, true);
+                cluster.barrier_wait();   // the peer's spectra are here; the peer has finished the previous step's MAC
+                p2a_mac_part(lane, slab, P, pw == 0 ? 3 : 0, mac, false);
+                p2a_mac_finish(lane, mac, twI, x);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(macdone);
                 gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
@@ -373,8 +379,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
                 const uint32_t A = smem_u32(acc + lane);
 #pragma unroll
                 for (int r = 0; r < 32; r++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(A + 128u * r), "r"(x[r]) : "memory");
-            } else if (lane == 0) {
-                mbar_arrive(macdone);
+            } else {
+                cluster.barrier_wait();
+                if (lane == 0) mbar_arrive(macdone);
             }
             mac_parity ^= 1u;
         }
@@ -1069,7 +1076,8 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         const unsigned grid = deal(4);
         if (a.ns == 2) blind_rotate_kernel<4, false, 1, 2><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
         else blind_rotate_kernel<4, false, 1, 3><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
-    } else if (2 * a.B <= (long)ctx->sm_count && variant != 9) {   // latency shape: one gate on a cluster of two SMs
+    } else if (3 * a.B <= (long)ctx->sm_count && variant != 9) {   // latency shape: one gate on a cluster of two SMs (measured
+                                                                   // better than one CTA per gate up to about #SMs/3 gates)
         a.cta_base = 1; a.cta_rem = 0;
         ctx->gates_per_cta = 1;
         if (a.ns == 2) blind_rotate_pair_kernel<2><<<(unsigned)(2 * a.B), PAIR_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
