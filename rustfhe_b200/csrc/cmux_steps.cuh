@@ -109,9 +109,7 @@ TFHE_HD void p2a_mac(int lane, const uint32_t* slab, const uint32_t* dh, uint32_
 #pragma unroll
         for (int j = 0; j < BK_ROWS; j++) {
             const uint4 d = *reinterpret_cast<const uint4*>(dh + j * TILE_WORDS + swz_chunk(lane, q));
-#if defined(TFHE_EXP_NOBK)   /* timing experiment only: no key traffic */
-            const uint4 b = make_uint4(d.y, d.z, d.w, d.x);
-#elif defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__)
             const uint4 b = __ldg(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);
 #else
             const uint4 b = *(reinterpret_cast<const uint4*>(slab) + (j * 8 + q) * 32 + lane);

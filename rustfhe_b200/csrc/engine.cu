@@ -78,18 +78,13 @@ struct BrArgs {
     const uint32_t* trlwe_in;  // [B][2][N]
     const uint32_t* trlwe_in0; // [B][2][N] or null: cmux, the product is taken of (trlwe_in - trlwe_in0) and trlwe_in0 is added back
     long ntrgsw;
-    int stagger_cycles;
     // gate -> CTA distribution (see the kernel prologue)
     int cta_base, cta_rem;
     int ns;                  // key slices per polynomial: 3 (exact in the worst case) or 2 (opt-in fast mode)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bar_sync(int id, int nthreads) {
-#if !defined(TFHE_EXP_NOBAR)   /* timing experiment only */
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-#endif
-}
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
@@ -97,9 +92,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-#if defined(TFHE_EXP_NOBAR)
-    return;
-#endif
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -170,13 +162,6 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     }
     __syncthreads();
     if (!active) return;   // gate slots without a gate leave here: every barrier below is private to one gate
-    // optional start offset between the gates of a CTA (TFHE_B200_STAGGER, cycles per step; measured: no effect, default 0)
-    if (!EXTPROD && a.stagger_cycles > 0) {
-        const long long wait = (long long)gl * a.stagger_cycles / G;
-        const long long t0 = clock64();
-        while (clock64() - t0 < wait) __nanosleep(200);
-    }
-
     // ---- 635 x CMUX ----
     // Synchronisation per step (named barriers, so gates sharing a CTA and the two polynomials of a gate decouple):
     //   poly barrier (96 threads)      : the masked source polynomial u[poly] (shared by its three digit warps) is complete
@@ -191,12 +176,6 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     for (int i = 0; i < nsteps; i++) {
         const uint32_t* step_bk = a.bkdev + (EXTPROD ? (size_t)(gate % a.ntrgsw) : (size_t)i) * bk_step_words(NS);
         uint32_t* S = dh + w6 * TILE_WORDS;
-#if defined(TFHE_EXP_PF)   /* experiment: sparse L2 prefetch of the next step's key, 1/64 of the slab per CTA */
-        if (!EXTPROD && i + 1 < nsteps && tid6 < 18) {
-            const char* nxt = reinterpret_cast<const char*>(step_bk + bk_step_words(NS));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)((blockIdx.x & 63) * 18 + tid6) * 128));
-        }
-#endif
         {   // phase 1: a third of the rows of u[pw], then digit kw of u[pw] -> spectrum plane dh[w6]
             p1u<!EXTPROD>(lane, acc + pw * 1024, EXTPROD ? 0u : (uint32_t)abar[i], a.mask, kw, U + pw * 1024);
             bar_sync(bar_poly, 96);
@@ -735,7 +714,6 @@ struct tfhe_b200_ctx {
     uint32_t* bk_torus = nullptr;  // [n][2l][2][N] torus-domain key as loaded / generated (kept for export: 31 MB)
     uint8_t* keybits = nullptr;    // device copy of (s0[n] | pad to 1024 | s1[N]) during device keygen
     int32_t* s1poly = nullptr;     // s1 as a polynomial of small integers, the multiplier of the a*s products
-    int stagger_cycles = 0;
     bool have_bk = false, have_ksk = false;
     static constexpr int NSLOT = 4;
     Slot slots[NSLOT];
@@ -846,13 +824,8 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = cudaMalloc(&ctx->keybits, 2048)) != cudaSuccess) return bail("cudaMalloc(keybits)", e);
     if ((e = cudaMalloc(&ctx->s1poly, 1024 * 4)) != cudaSuccess) return bail("cudaMalloc(s1poly)", e);
     for (auto& s : ctx->slots) if ((e = cudaMalloc(&s.s0buf, 1024)) != cudaSuccess) return bail("cudaMalloc(s0buf)", e);
-    if ((e = set_smem(blind_rotate_kernel<2, false, 1>, 2)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<1, false, 1>, 1)) != cudaSuccess) return bail("smem attr", e);
-    if ((e = set_smem(blind_rotate_kernel<1, false, 2>, 1)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<1, false, 3>, 1)) != cudaSuccess) return bail("smem attr", e);
-    if ((e = set_smem(blind_rotate_kernel<1, false, 4>, 1)) != cudaSuccess) return bail("smem attr", e);
-    if ((e = set_smem(blind_rotate_kernel<3, false, 1>, 3)) != cudaSuccess) return bail("smem attr", e);
-    if ((e = set_smem(blind_rotate_kernel<2, false, 2>, 2)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<4, false, 1>, 4)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<2, true, 1>, 2)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<4, true, 1>, 4)) != cudaSuccess) return bail("smem attr", e);
@@ -865,7 +838,6 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = set_smem(blind_rotate_kernel<2, true, 1, 2>, 2)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<4, true, 1, 2>, 4)) != cudaSuccess) return bail("smem attr", e);
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
-    if (const char* v = getenv("TFHE_B200_STAGGER")) ctx->stagger_cycles = atoi(v);
     if (const char* v = getenv("TFHE_B200_KS_VARIANT")) ctx->ks_variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_KEY_SLICES")) ctx->key_slices = (atoi(v) == 2) ? 2 : 3;
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
@@ -1037,7 +1009,6 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
     // evenly over rounds * #SMs CTAs so that a batch that is not a multiple of G * #SMs ends with 3-gate CTAs instead of
     // a half-empty last wave.
     const bool full = a.B > (long)ctx->sm_count;
-    a.stagger_cycles = full ? ctx->stagger_cycles : 0;
     const int variant = (a.ns == 2 && ctx->variant != 9) ? 7 : ctx->variant;   // the measured alternatives exist for three slices only
     auto deal = [&](int G) {
         const long cap = (long)G * ctx->sm_count;
@@ -1054,24 +1025,8 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         ctx->gates_per_cta = G;
         return (unsigned)nctas;
     };
-    if (full && variant == 0) {
-        const unsigned grid = fixed(2);
-        blind_rotate_kernel<2, false, 1><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
-    } else if (full && variant == 2) {
-        blind_rotate_kernel<1, false, 2><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-    } else if (full && variant == 3) {
+    if (full && variant == 3) {   // the earlier default, kept selectable for A/B runs: three 1-gate CTAs per SM (96 registers)
         blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-    } else if (full && variant == 4) {
-        const unsigned grid = fixed(3);
-        blind_rotate_kernel<3, false, 1><<<grid, 3 * THREADS_PER_GATE, br_smem_bytes(3), st>>>(a);
-    } else if (full && variant == 5) {
-        blind_rotate_kernel<1, false, 4><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-    } else if (full && variant == 6) {
-        const unsigned grid = fixed(2);
-        blind_rotate_kernel<2, false, 2><<<grid, 2 * THREADS_PER_GATE, br_smem_bytes(2), st>>>(a);
-    } else if (full && variant == 8) {
-        const unsigned grid = fixed(4);
-        blind_rotate_kernel<4, false, 1><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
     } else if (full) {   // default (variant 7)
         const unsigned grid = deal(4);
         if (a.ns == 2) blind_rotate_kernel<4, false, 1, 2><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);

@@ -82,9 +82,6 @@ TFHE_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 }
 // min(x, x - m) for unsigned x: conditional subtraction without a branch (VIADDMNMX.U32 on sm_100a)
 TFHE_HD uint32_t csub(uint32_t x, uint32_t m) {
-#if defined(TFHE_EXP_NOCORR)   /* timing experiment only */
-    return x;
-#endif
     uint32_t y = x - m;
 #if defined(__CUDA_ARCH__)
     return min(x, y);
