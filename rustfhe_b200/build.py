@@ -23,8 +23,8 @@ def _newer(target, sources):
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("engine.cu", "hostkeys.cpp", "wire.cpp", "ntt32.cuh", "cmux_steps.cuh", "ntt_tables.h",
-                                            "tfhe_rng.cuh")] + [
+    return [os.path.join(CSRC, f) for f in ("engine.cu", "blind_rotate.cuh", "keyswitch.cuh", "aux_kernels.cuh", "hostkeys.cpp", "wire.cpp",
+                                            "ntt32.cuh", "cmux_steps.cuh", "ntt_tables.h", "tfhe_rng.cuh")] + [
         os.path.join(HERE, "..", "include", "tfhe_b200.h")]
 
 

@@ -1,12 +1,9 @@
-// engine.cu -- CUDA kernels (sm_100a) and C-ABI of the B200 TFHE gate-bootstrapping engine.
-//
-// Kernels (DESIGN.md has the roofline of each):
-//   K8 bk_transform_kernel : torus-domain bootstrapping key -> NTT domain, 3 centred 11-bit slices per polynomial
-//                            (replaces TRGSWRepF::from, hom_nand/src/trgsw.rs:68-76)
-//   K5 blind_rotate_kernel : gate pre-combination + 635 x CMUX + sample extract (tfhe.rs:27-113, trgsw.rs:264-322,
-//                            trlwe.rs:110-121), persistent per gate, state resident in shared memory
-//   K6 keyswitch_kernel    : identity_key_switch as a tiled gather-accumulate (tlwe.rs:43-73)
-//   polymul_kernel         : exact negacyclic product micro-entry (math.rs:337-347)
+// engine.cu -- host side and C ABI (include/tfhe_b200.h) of the B200 TFHE gate-bootstrapping engine; the one translation unit
+// that is compiled with nvcc for sm_100a.  Device code (DESIGN.md has the roofline of each kernel):
+//   blind_rotate.cuh : K8 bk_transform_kernel, K5 blind_rotate_kernel, K5L blind_rotate_pair_kernel
+//   keyswitch.cuh    : K6 keyswitch2_kernel (default), keyswitch_kernel, lwe1_prepare_kernel
+//   aux_kernels.cuh  : polymul_kernel, device keygen / encryption / decryption / sample-extract kernels
+//   cmux_steps.cuh, ntt32.cuh, tfhe_rng.cuh : per-lane arithmetic shared with the CPU emulation and the host keygen
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <cstdio>
@@ -15,676 +12,11 @@
 #include <string>
 #include <vector>
 #include "../../include/tfhe_b200.h"
-#include "cmux_steps.cuh"
-#include "tfhe_rng.cuh"
+#include "blind_rotate.cuh"
+#include "keyswitch.cuh"
+#include "aux_kernels.cuh"
 
 using namespace tfhe;
-
-// =====================================================================================================
-// K8: key transform.  One warp per (step i, row j, poly); loops over the three slices.
-// =====================================================================================================
-constexpr int KT_WARPS = 4;
-__global__ void __launch_bounds__(KT_WARPS * 32) bk_transform_kernel(const uint32_t* __restrict__ bk, uint32_t* __restrict__ dev,
-                                                                    int npolys /* = nsteps*12 */, int ns /* key slices: 3 or 2 */) {
-    __shared__ __align__(16) uint32_t twF[32 * TWB_STRIDE];
-    __shared__ __align__(16) uint32_t scratch[KT_WARPS][TILE_WORDS];
-    for (int t = threadIdx.x; t < 32 * TWB_STRIDE; t += blockDim.x) twF[t] = g_fwdB[t];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pid = blockIdx.x * KT_WARPS + warp;
-    if (pid >= npolys) return;
-    const int poly = pid & 1, j = (pid >> 1) % BK_ROWS, i = pid / (2 * BK_ROWS);
-    const uint32_t* src = bk + (size_t)pid * 1024;
-    uint32_t* S = scratch[warp];
-    for (int part = 0; part < ns; part++) {
-        key_cols(lane, src, part, S, ns);
-        __syncwarp();
-        key_rows(lane, S, twF, dev + bk_off(i, poly, part, j, 0, 0, ns));
-        __syncwarp();
-    }
-}
-
-// =====================================================================================================
-// K5: blind rotation.  G gates per CTA, 6 warps per gate.
-// =====================================================================================================
-constexpr int WARPS_PER_GATE = 6;
-constexpr int THREADS_PER_GATE = WARPS_PER_GATE * 32;
-constexpr int GATE_SMEM_WORDS = 2 * 1024 /*acc*/ + 2 * 1024 /*U: masked source polynomials*/ + 6 * TILE_WORDS /*dh: digit spectra / transpose scratch*/ +
-                                320 /*abar u16[640]*/;
-constexpr int TW_SMEM_WORDS = 2 * 32 * TWB_STRIDE + DIGIT_TAB_WORDS;   // forward + inverse twiddle rows, digit table
-constexpr size_t br_smem_bytes(int G) { return (size_t)(TW_SMEM_WORDS + G * GATE_SMEM_WORDS) * 4; }
-
-struct BrArgs {
-    const uint32_t* bkdev;   // NTT-domain key, BK_STEP_WORDS per step
-    const uint32_t* in0;     // [B][n+1]
-    const uint32_t* in1;     // [B][n+1] or null
-    int32_t c0, c1;          // lin = c0*in0 + c1*in1 + (cb, 0, ...)
-    uint32_t cb;
-    // second operand set for gates >= split (fused hom_mux first stage: two different gates in one launch); split = B when unused
-    long split;
-    const uint32_t* in0b;
-    const uint32_t* in1b;
-    int32_t c0b, c1b;
-    uint32_t cbb;
-    uint32_t mu, mask;
-    int nsteps;
-    long B;
-    // outputs (any may be null)
-    uint32_t* out_init;      // [B][n+1]  <- (b', 0, ..., 0)  : accumulator the key-switch kernel subtracts from
-    uint16_t* ksdig;         // [B][N]    <- packed key-switch digits of the extracted sample
-    uint32_t* trlwe_out;     // [B][2][N]
-    uint32_t* lwe1_out;      // [B][N+1]
-    // external-product mode
-    const uint32_t* trlwe_in;  // [B][2][N]
-    const uint32_t* trlwe_in0; // [B][2][N] or null: cmux, the product is taken of (trlwe_in - trlwe_in0) and trlwe_in0 is added back
-    long ntrgsw;
-    // gate -> CTA distribution (see the kernel prologue)
-    int cta_base, cta_rem;
-    int ns;                  // key slices per polynomial: 3 (exact in the worst case) or 2 (opt-in fast mode)
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
-}
-
-template <int G, bool EXTPROD, int MINB, int NS = 3>
-__global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel(const BrArgs a) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t* twF = smem;
-    uint32_t* twI = smem + 32 * TWB_STRIDE;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gl = warp / WARPS_PER_GATE, w6 = warp % WARPS_PER_GATE;
-    const int pw = w6 / 3, kw = w6 % 3;
-    const int tid6 = threadIdx.x - gl * THREADS_PER_GATE;
-    uint32_t* acc = smem + TW_SMEM_WORDS + gl * GATE_SMEM_WORDS;
-    uint32_t* U = acc + 2 * 1024;
-    uint32_t* dh = U + 2 * 1024;
-    uint16_t* abar = reinterpret_cast<uint16_t*>(dh + 6 * TILE_WORDS);
-    uint64_t* macdone = reinterpret_cast<uint64_t*>(dh + 6 * TILE_WORDS + 318);  // abar uses 635 u16 = 317.5 words of its 320
-
-    // gates are dealt out evenly: the first cta_rem CTAs own cta_base+1 consecutive gates, the others cta_base (<= G)
-    const long cta = blockIdx.x;
-    const long first = cta * a.cta_base + (cta < a.cta_rem ? cta : a.cta_rem);
-    const int cnt = a.cta_base + (cta < a.cta_rem ? 1 : 0);
-    const bool active = gl < cnt;
-    const long gate = active ? first + gl : a.B - 1;
-
-    uint32_t* dtab = smem + 2 * 32 * TWB_STRIDE;
-    for (int t = threadIdx.x; t < 32 * TWB_STRIDE; t += blockDim.x) {
-        twF[t] = g_fwdB[t];
-        twI[t] = g_invB[t];
-    }
-    for (int t = threadIdx.x; t < DIGIT_TAB_WORDS; t += blockDim.x) dtab[t] = g_digit_tab.v[t];
-    if (tid6 == 0) mbar_init(macdone, WARPS_PER_GATE);
-    // ---- prologue: gate pre-combination (tfhe.rs:27-71), rounding of (b, a) (tfhe.rs:97,107-108), acc_0 ----
-    int nsteps = a.nsteps;
-    if (EXTPROD) {
-        nsteps = 1;
-        const uint32_t* src = a.trlwe_in + (size_t)gate * 2048;
-        const uint32_t* sub = a.trlwe_in0 ? a.trlwe_in0 + (size_t)gate * 2048 : nullptr;   // cmux: rep_1 - rep_0 (trgsw.rs:315-322)
-        for (int k = tid6; k < 2048; k += THREADS_PER_GATE) acc[k] = sub ? src[k] - sub[k] : src[k];
-    } else {
-        uint32_t* lin = dh;
-        const bool second = gate >= a.split;
-        const long gsrc = second ? gate - a.split : gate;
-        const uint32_t* q0 = second ? a.in0b : a.in0;
-        const uint32_t* q1 = second ? a.in1b : a.in1;
-        const uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
-        const uint32_t* p0 = q0 + (size_t)gsrc * (LWE_N + 1);
-        const uint32_t* p1 = q1 ? q1 + (size_t)gsrc * (LWE_N + 1) : nullptr;
-        for (int c = tid6; c <= LWE_N; c += THREADS_PER_GATE) {
-            uint32_t v = k0 * p0[c];
-            if (p1) v += k1 * p1[c];
-            if (c == 0) v += kb;
-            lin[c] = v;
-        }
-        __syncthreads();
-        for (int i = tid6; i < LWE_N; i += THREADS_PER_GATE) abar[i] = (uint16_t)((lin[1 + i] + (1u << 20)) >> 21);  // round
-        const uint32_t bbar = lin[0] >> 21;                                                                         // floor
-        const uint32_t nrot = (2048u - bbar) & 2047u;  // acc_0 = X^{-bbar} * (mu, ..., mu ; 0)
-        for (int k = tid6; k < 1024; k += THREADS_PER_GATE) {
-            const bool neg = ((uint32_t)k < (nrot & 1023u)) != (nrot >= 1024u);
-            acc[k] = neg ? 0u - a.mu : a.mu;
-            acc[1024 + k] = 0;
-        }
-    }
-    __syncthreads();
-    if (!active) return;   // gate slots without a gate leave here: every barrier below is private to one gate
-    // ---- 635 x CMUX ----
-    // Synchronisation per step (named barriers, so gates sharing a CTA and the two polynomials of a gate decouple):
-    //   poly barrier (96 threads)      : the masked source polynomial u[poly] (shared by its three digit warps) is complete
-    //   B1 gate barrier (192 threads)  : the 6 digit spectra of this step are complete
-    //   macdone (mbarrier, 6 arrivals) : every warp finished READING the digit spectra dh[] -> a warp may reuse its own
-    //                                    plane dh[w6] as the transpose scratch of its inverse transform
-    //   poly barrier (96 threads)      : the three key-slice warps of a polynomial have added their exact slices into
-    //                                    acc[poly] (red.shared, no output planes: 24 KB less shared memory per gate)
-    const int bar_gate = 1 + gl, bar_poly = 1 + G + 2 * gl + pw;
-    uint32_t mac_parity = 0;
-#pragma unroll 1
-    for (int i = 0; i < nsteps; i++) {
-        const uint32_t* step_bk = a.bkdev + (EXTPROD ? (size_t)(gate % a.ntrgsw) : (size_t)i) * bk_step_words(NS);
-        uint32_t* S = dh + w6 * TILE_WORDS;
-        {   // phase 1: a third of the rows of u[pw], then digit kw of u[pw] -> spectrum plane dh[w6]
-            p1u<!EXTPROD>(lane, acc + pw * 1024, EXTPROD ? 0u : (uint32_t)abar[i], a.mask, kw, U + pw * 1024);
-            bar_sync(bar_poly, 96);
-            p1a(lane, U + pw * 1024, kw, S, dtab);
-            __syncwarp();
-            p1b(lane, S, twF);
-        }
-        bar_sync(bar_gate, THREADS_PER_GATE);
-        uint32_t x[32];
-        if (kw < NS) {   // phase 2: key slice kw of output poly pw (with two key slices the third warp of a polynomial only signals)
-            p2a_mac_head(lane, step_bk + (size_t)(pw * NS + kw) * BK_SLAB_WORDS, dh, dh + 3 * TILE_WORDS, twI, x);
-            if (EXTPROD) {   // plain external product: the result replaces acc; every warp clears its share before it arrives
-#pragma unroll
-                for (int r = kw; r < 32; r += 3) acc[pw * 1024 + 32 * r + lane] = 0u;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(macdone);
-            gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
-            gs_norm<2>(x);
-            mbar_wait(macdone, mac_parity);
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-                *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-            __syncwarp();
-            p2b(lane, S, kw, x, NS);   // x[r] = exact slice value (already shifted) of coefficient 32 r + lane
-            // phase 3: acc[pw] += x by shared-memory reductions (the slice warps of a polynomial add concurrently)
-            const uint32_t A = smem_u32(acc + pw * 1024 + lane);
-#pragma unroll
-            for (int r = 0; r < 32; r++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(A + 128u * r), "r"(x[r]) : "memory");
-        } else {
-            if (EXTPROD) {
-#pragma unroll
-                for (int r = kw; r < 32; r += 3) acc[pw * 1024 + 32 * r + lane] = 0u;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(macdone);
-        }
-        mac_parity ^= 1u;
-        bar_sync(bar_poly, 96);   // acc[pw] is complete before the next step decomposes it
-    }
-    bar_sync(bar_gate, THREADS_PER_GATE);
-
-    // ---- epilogue: sample_extract_index(0) (trlwe.rs:110-121) + key-switch digits (tlwe.rs:47-64) ----
-    if (a.trlwe_out) {
-        uint32_t* dst = a.trlwe_out + (size_t)gate * 2048;
-        const uint32_t* add = (EXTPROD && a.trlwe_in0) ? a.trlwe_in0 + (size_t)gate * 2048 : nullptr;   // cmux: ... + rep_0
-        for (int k = tid6; k < 2048; k += THREADS_PER_GATE) dst[k] = add ? acc[k] + add[k] : acc[k];
-    }
-    if (a.ksdig || a.lwe1_out) {
-        for (int i = tid6; i < 1024; i += THREADS_PER_GATE) {
-            const uint32_t ai = (i == 0) ? acc[1024] : 0u - acc[1024 + 1024 - i];
-            if (a.ksdig) a.ksdig[(size_t)gate * 1024 + i] = (uint16_t)((ai + 0x8000u) >> 16);
-            if (a.lwe1_out) a.lwe1_out[(size_t)gate * 1025 + 1 + i] = ai;
-        }
-        if (a.lwe1_out && tid6 == 0) a.lwe1_out[(size_t)gate * 1025] = acc[0];
-    }
-    if (a.out_init) {
-        uint32_t* dst = a.out_init + (size_t)gate * (LWE_N + 1);
-        for (int c = tid6; c <= LWE_N; c += THREADS_PER_GATE) dst[c] = (c == 0) ? acc[0] : 0u;
-    }
-}
-
-// =====================================================================================================
-// K5L: latency shape of the blind rotation -- ONE gate on a cluster of TWO CTAs (two SMs), three warps each.
-// A warp instruction stream of one CMUX step needs ~3900 FMA-pipe cycles of its SM sub-partition; with six warps on one
-// SM two sub-partitions carry two warps and set the pace (measured 11.8 k cycles per step).  Here CTA `pw` of the pair
-// owns polynomial pw (0 = b, 1 = a): its three warps sit on three different sub-partitions, its accumulator and the
-// masked difference stay local, and the only exchange per step is the 12 KB of digit spectra, which every CTA also
-// stores into its peer's shared memory (distributed shared memory, double buffered) before ONE cluster barrier.
-// =====================================================================================================
-namespace cg = cooperative_groups;
-constexpr int PAIR_THREADS = 96;
-constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 3 * TILE_WORDS /*own spectra*/ + 2 * 3 * TILE_WORDS /*peer spectra x2*/ + 320 +
-                                2 * 3 * (int)BK_SLAB_WORDS /*key slabs of this and the next step, one per warp*/;
-template <int NS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) blind_rotate_pair_kernel(const BrArgs a) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int pw = (int)cluster.block_rank();
-    const long gate = blockIdx.x >> 1;
-    const int kw = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-    uint32_t* twF = smem;
-    uint32_t* twI = smem + 32 * TWB_STRIDE;
-    uint32_t* acc = smem + TW_SMEM_WORDS;
-    uint32_t* U = acc + 1024;
-    uint32_t* own = U + 1024;            // [3] tiles: spectra of this CTA's polynomial; plane kw doubles as transpose scratch
-    uint32_t* peer = own + 3 * TILE_WORDS;     // [2][3] tiles: spectra of the other polynomial, written by the other CTA
-    uint16_t* abar = reinterpret_cast<uint16_t*>(peer + 6 * TILE_WORDS);
-    uint64_t* macdone = reinterpret_cast<uint64_t*>(peer + 6 * TILE_WORDS + 318);
-    uint32_t* slabs = peer + 6 * TILE_WORDS + 320;              // [2][3][BK_SLAB_WORDS]: warp-private, filled one step ahead by cp.async
-    uint32_t* remote = cluster.map_shared_rank(peer, pw ^ 1);   // where MY spectra go in the other CTA
-    // the key slab of step i for this warp: 48 x 512 B, copied asynchronously a whole step ahead so that no L2 round trip is
-    // left on the critical path of a lone warp
-    auto slab_fetch = [&](int step) {
-        if (kw >= NS) { asm volatile("cp.async.commit_group;" ::: "memory"); return; }
-        const uint4* src = reinterpret_cast<const uint4*>(a.bkdev + (size_t)step * bk_step_words(NS) + (size_t)(pw * NS + kw) * BK_SLAB_WORDS) + lane;
-        const uint32_t dst = smem_u32(slabs + ((step & 1) * 3 + kw) * BK_SLAB_WORDS) + 16u * lane;
-#pragma unroll
-        for (int t = 0; t < 48; t++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u * t), "l"(src + 32 * t) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    uint32_t* dtab = smem + 2 * 32 * TWB_STRIDE;
-    for (int t = tid; t < 32 * TWB_STRIDE; t += PAIR_THREADS) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
-    if (tid < DIGIT_TAB_WORDS) dtab[tid] = g_digit_tab.v[tid];
-    if (tid == 0) mbar_init(macdone, 3);
-    {   // prologue (both CTAs read the inputs): gate pre-combination, rounding, acc_0 of the own polynomial
-        uint32_t* lin = own;
-        const bool second = gate >= a.split;
-        const long gsrc = second ? gate - a.split : gate;
-        const uint32_t* q0 = second ? a.in0b : a.in0;
-        const uint32_t* q1 = second ? a.in1b : a.in1;
-        const uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
-        const uint32_t* p0 = q0 + (size_t)gsrc * (LWE_N + 1);
-        const uint32_t* p1 = q1 ? q1 + (size_t)gsrc * (LWE_N + 1) : nullptr;
-        for (int c = tid; c <= LWE_N; c += PAIR_THREADS) {
-            uint32_t v = k0 * p0[c];
-            if (p1) v += k1 * p1[c];
-            if (c == 0) v += kb;
-            lin[c] = v;
-        }
-        __syncthreads();
-        for (int i = tid; i < LWE_N; i += PAIR_THREADS) abar[i] = (uint16_t)((lin[1 + i] + (1u << 20)) >> 21);
-        const uint32_t bbar = lin[0] >> 21;
-        const uint32_t nrot = (2048u - bbar) & 2047u;
-        for (int k = tid; k < 1024; k += PAIR_THREADS) {
-            const bool neg = ((uint32_t)k < (nrot & 1023u)) != (nrot >= 1024u);
-            acc[k] = pw == 0 ? (neg ? 0u - a.mu : a.mu) : 0u;
-        }
-    }
-    cluster.sync();   // both CTAs are set up (mbarriers, tables) before the first remote store
-    if (a.nsteps > 0) slab_fetch(0);
-    uint32_t mac_parity = 0;
-#pragma unroll 1
-    for (int i = 0; i < a.nsteps; i++) {
-        uint32_t* S = own + kw * TILE_WORDS;
-        uint32_t x[32];
-        p1u<true>(lane, acc, (uint32_t)abar[i], a.mask, kw, U);
-        bar_sync(1, PAIR_THREADS);
-        p1a(lane, U, kw, S, dtab);
-        __syncwarp();
-        fwd_rows(lane, S, twF, x);
-        {
-            uint32_t* R = remote + ((i & 1) * 3 + kw) * TILE_WORDS;
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const uint4 v = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-                *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = v;
-                *reinterpret_cast<uint4*>(R + swz_chunk(lane, q)) = v;
-            }
-        }
-        // split cluster barrier: arrive (release: my remote stores), start the copy of the NEXT step's key slab, then wait
-        // (acquire).  (A point-to-point handshake on cluster-scope mbarriers was measured 10 % slower than this barrier.)
-        cluster.barrier_arrive();
-        if (i + 1 < a.nsteps) slab_fetch(i + 1); else asm volatile("cp.async.commit_group;" ::: "memory");
-        {
-            asm volatile("cp.async.wait_group 1;" ::: "memory");   // this step's slab (committed one step ago) has landed
-            __syncwarp();
-            const uint32_t* slab = slabs + ((i & 1) * 3 + kw) * BK_SLAB_WORDS;
-            const uint32_t* P = peer + (i & 1) * 3 * TILE_WORDS;
-            bar_sync(2, PAIR_THREADS);   // this CTA's own three spectra are complete (local barrier; the cluster one is still pending)
-            if (kw < NS) {
-                // the key rows that meet this CTA's own spectra need nothing from the peer: accumulate them while the cluster
-                // barrier is pending, then wait and add the rows of the peer's spectra
-                uint64_t mac[32];
-                p2a_mac_part(lane, slab, own, pw == 0 ? 0 : 3, mac, true);
-                cluster.barrier_wait();   // the peer's spectra are here; the peer has finished the previous step's MAC
-                p2a_mac_part(lane, slab, P, pw == 0 ? 3 : 0, mac, false);
-                p2a_mac_finish(lane, mac, twI, x);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(macdone);
-                gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
-                gs_norm<2>(x);
-                mbar_wait(macdone, mac_parity);
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-                __syncwarp();
-                p2b(lane, S, kw, x, NS);
-                const uint32_t A = smem_u32(acc + lane);
-#pragma unroll
-                for (int r = 0; r < 32; r++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(A + 128u * r), "r"(x[r]) : "memory");
-            } else {
-                cluster.barrier_wait();
-                if (lane == 0) mbar_arrive(macdone);
-            }
-            mac_parity ^= 1u;
-        }
-        bar_sync(1, PAIR_THREADS);
-    }
-    // ---- epilogue: CTA 0 owns b, CTA 1 owns a ----
-    if (a.trlwe_out) {
-        uint32_t* dst = a.trlwe_out + (size_t)gate * 2048 + pw * 1024;
-        for (int k = tid; k < 1024; k += PAIR_THREADS) dst[k] = acc[k];
-    }
-    if (pw == 1 && (a.ksdig || a.lwe1_out)) {
-        for (int i = tid; i < 1024; i += PAIR_THREADS) {
-            const uint32_t ai = (i == 0) ? acc[0] : 0u - acc[1024 - i];
-            if (a.ksdig) a.ksdig[(size_t)gate * 1024 + i] = (uint16_t)((ai + 0x8000u) >> 16);
-            if (a.lwe1_out) a.lwe1_out[(size_t)gate * 1025 + 1 + i] = ai;
-        }
-    }
-    if (pw == 0) {
-        if (a.lwe1_out && tid == 0) a.lwe1_out[(size_t)gate * 1025] = acc[0];
-        if (a.out_init) {
-            uint32_t* dst = a.out_init + (size_t)gate * (LWE_N + 1);
-            for (int c = tid; c <= LWE_N; c += PAIR_THREADS) dst[c] = (c == 0) ? acc[0] : 0u;
-        }
-    }
-    cluster.sync();   // no CTA leaves while its peer may still store into its shared memory
-}
-
-// =====================================================================================================
-// K6: key switch.  out[g] -= sum_{i,l : d != 0} KSK[i][l][d-1]  with d = 2-bit digit (i,l) of gate g.
-// CTA = (tile of KS_GT gates) x (slice of 1024/KS_ISPLIT key indices); thread = one 16-byte column chunk of the
-// 636-word rows (159 chunks).  Every KSK row is read once per CTA and applied to all gates of the tile; the digit
-// is CTA-uniform so the select is a uniform branch.  Partial sums are merged with red.global.add.u32.
-// =====================================================================================================
-constexpr int KS_GT = 16;           // gates per thread group (accumulators live in registers: 16 x uint4)
-#if !defined(KS_NG)
-#define KS_NG 2
-#endif
-constexpr int KS_GROUPS = KS_NG;    // thread groups per CTA: they walk the same key rows, the second one hits L1
-constexpr int KS_ISPLIT_MIN = 8;    // key indices are split over gridDim.y CTAs: 8 for large batches, up to 128 for small ones
-constexpr int KS_ICHUNK = 1024 / KS_ISPLIT_MIN;   // largest slice of key indices one CTA walks
-constexpr int KS_CHUNKS = (LWE_N + 1) / 4;  // 159
-constexpr int KS_THREADS = 160;
-__global__ void __launch_bounds__(KS_THREADS* KS_GROUPS) keyswitch_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
-                                                                         uint32_t* __restrict__ out, long B) {
-    __shared__ __align__(16) uint16_t dg[KS_GROUPS][KS_ICHUNK][KS_GT];
-    const int grp = threadIdx.y;
-    const long g0 = ((long)blockIdx.x * KS_GROUPS + grp) * KS_GT;
-    const int ichunk = 1024 / (int)gridDim.y;
-    const int i0 = blockIdx.y * ichunk;
-    for (int t = threadIdx.x; t < ichunk * KS_GT; t += KS_THREADS) {
-        const int g = t / ichunk, ii = t % ichunk;
-        dg[grp][ii][g] = (g0 + g < B) ? dig[(size_t)(g0 + g) * 1024 + i0 + ii] : (uint16_t)0;
-    }
-    __syncthreads();
-    const int t = threadIdx.x;
-    if (t >= KS_CHUNKS || g0 >= B) return;
-    uint4 acc[KS_GT];
-#pragma unroll
-    for (int g = 0; g < KS_GT; g++) acc[g] = make_uint4(0, 0, 0, 0);
-    const uint4* base = ksk + (size_t)i0 * 8 * 3 * KS_CHUNKS + t;
-#pragma unroll 1
-    for (int ii = 0; ii < ichunk; ii++) {
-        uint32_t dw[KS_GT / 2];
-#pragma unroll
-        for (int g = 0; g < KS_GT / 2; g++) dw[g] = reinterpret_cast<const uint32_t*>(dg[grp][ii])[g];  // two gates per word
-#pragma unroll
-        for (int l = 0; l < 8; l++) {
-            const uint4* row = base + (size_t)(ii * 8 + l) * 3 * KS_CHUNKS;
-            const uint4 r0 = __ldg(row), r1 = __ldg(row + KS_CHUNKS), r2 = __ldg(row + 2 * KS_CHUNKS);
-#pragma unroll
-            for (int g = 0; g < KS_GT; g++) {
-                const uint32_t d = (dw[g >> 1] >> ((g & 1) * 16 + 14 - 2 * l)) & 3u;
-                if (d == 1) { acc[g].x += r0.x; acc[g].y += r0.y; acc[g].z += r0.z; acc[g].w += r0.w; }
-                else if (d == 2) { acc[g].x += r1.x; acc[g].y += r1.y; acc[g].z += r1.z; acc[g].w += r1.w; }
-                else if (d == 3) { acc[g].x += r2.x; acc[g].y += r2.y; acc[g].z += r2.z; acc[g].w += r2.w; }
-            }
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < KS_GT; g++) {
-        if (g0 + g >= B) break;
-        uint32_t* o = out + (size_t)(g0 + g) * (LWE_N + 1) + 4 * t;
-        atomicAdd(o + 0, 0u - acc[g].x);
-        atomicAdd(o + 1, 0u - acc[g].y);
-        atomicAdd(o + 2, 0u - acc[g].z);
-        atomicAdd(o + 3, 0u - acc[g].w);
-    }
-}
-// ---- K6b: key switch with the key rows staged through shared memory, one WARP per gate ----
-// The register-tile kernel above is ALU bound on its digit select (12 instructions per gate, digit and 16-byte chunk:
-// the digit is CTA-uniform but every thread tests it).  Here a warp owns one gate and all 159 chunks of its output row
-// (5 per lane): the digit picks the ROW ADDRESS in shared memory, so per (gate, digit) there are two instructions of
-// select and five (LDS.128 + 4 adds) instead of 5 warps x 12.  The rows of a stage (4 levels x 3 multiples of one key
-// index = 30 KB) are copied once per CTA with cp.async into a 3-deep ring (one __syncthreads per stage) and consumed by
-// the 16 gates of the tile.
-#if !defined(KS2_NG)
-#define KS2_NG 16
-#endif
-constexpr int KS2_GATES = KS2_NG;                  // warps per CTA
-constexpr int KS2_THREADS = KS2_GATES * 32;
-#if !defined(KS2_LVDEF)
-#define KS2_LVDEF 4
-#endif
-constexpr int KS2_LV = KS2_LVDEF;                  // levels per stage
-constexpr int KS2_ROWS = KS2_LV * 3;               // rows per stage
-constexpr int KS2_ROW_WORDS = 640;                 // 636 words padded to a multiple of 16 bytes x 32 lanes x 5
-constexpr int KS2_RING = 3;
-constexpr int KS2_STAGE_WORDS = KS2_ROWS * KS2_ROW_WORDS;
-constexpr size_t KS2_SMEM_BYTES = (size_t)KS2_RING * KS2_STAGE_WORDS * 4 + (size_t)KS_ICHUNK * KS2_GATES * 2;
-__global__ void __launch_bounds__(KS2_THREADS) keyswitch2_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
-                                                                uint32_t* __restrict__ out, long B) {
-    extern __shared__ __align__(16) uint32_t ks_smem[];
-    uint32_t* ring = ks_smem;
-    uint16_t* dg = reinterpret_cast<uint16_t*>(ks_smem + KS2_RING * KS2_STAGE_WORDS);   // [ichunk][16]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long g0 = (long)blockIdx.x * KS2_GATES;
-    const int ichunk = 1024 / (int)gridDim.y;
-    const int i0 = blockIdx.y * ichunk;
-    const int nstages = ichunk * (8 / KS2_LV);
-    for (int t = threadIdx.x; t < ichunk * KS2_GATES; t += KS2_THREADS) {
-        const int g = t / ichunk, ii = t % ichunk;
-        dg[ii * KS2_GATES + g] = (g0 + g < B) ? dig[(size_t)(g0 + g) * 1024 + i0 + ii] : (uint16_t)0;
-    }
-    auto stage_in = [&](int k) {   // rows (key index i0 + k / SPI, KS2_LV levels, all three multiples) -> ring slot k % 3
-        constexpr int SPI = 8 / KS2_LV;   // stages per key index
-        const uint4* src = ksk + ((size_t)(i0 + k / SPI) * 8 + (size_t)(k % SPI) * KS2_LV) * 3 * KS_CHUNKS;
-        const uint32_t dst = smem_u32(ring + (k % KS2_RING) * KS2_STAGE_WORDS);
-        for (int t = threadIdx.x; t < KS2_ROWS * KS_CHUNKS; t += KS2_THREADS) {
-            const int row = t / KS_CHUNKS, c = t - row * KS_CHUNKS;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(row * KS2_ROW_WORDS + 4 * c) * 4u), "l"(src + t)
-                         : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    stage_in(0);
-    if (nstages > 1) stage_in(1); else asm volatile("cp.async.commit_group;" ::: "memory");
-    uint4 acc[5];
-#pragma unroll
-    for (int q = 0; q < 5; q++) acc[q] = make_uint4(0, 0, 0, 0);
-    const bool live = g0 + warp < B;
-#pragma unroll 1
-    for (int k = 0; k < nstages; k++) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // stage k has landed (at most the newest group is still in flight)
-        __syncthreads();                                          // ... for every thread; and everybody is done with stage k-1
-        if (k + 2 < nstages) stage_in(k + 2); else asm volatile("cp.async.commit_group;" ::: "memory");
-        if (live) {
-            constexpr int SPI = 8 / KS2_LV;
-            const uint32_t d16 = dg[(k / SPI) * KS2_GATES + warp];
-            const uint32_t* rows = ring + (k % KS2_RING) * KS2_STAGE_WORDS;
-#pragma unroll
-            for (int l = 0; l < KS2_LV; l++) {
-                const uint32_t d = (d16 >> (14 - 2 * ((k % SPI) * KS2_LV + l))) & 3u;   // level 0 in bits 15:14
-                if (d != 0) {
-                    const uint4* r = reinterpret_cast<const uint4*>(rows + (l * 3 + (int)d - 1) * KS2_ROW_WORDS) + lane;
-#pragma unroll
-                    for (int q = 0; q < 5; q++) {
-                        if (q < 4 || lane < KS_CHUNKS - 128) {
-                            const uint4 v = r[32 * q];
-                            acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    if (!live) return;
-    uint32_t* o = out + (size_t)(g0 + warp) * (LWE_N + 1);
-#pragma unroll
-    for (int q = 0; q < 5; q++) {
-        const int c = lane + 32 * q;
-        if (c < KS_CHUNKS) {
-            atomicAdd(o + 4 * c + 0, 0u - acc[q].x);
-            atomicAdd(o + 4 * c + 1, 0u - acc[q].y);
-            atomicAdd(o + 4 * c + 2, 0u - acc[q].z);
-            atomicAdd(o + 4 * c + 3, 0u - acc[q].w);
-        }
-    }
-}
-// prepares the key-switch inputs from explicit level-1 samples (step-level entry tfhe_b200_keyswitch_batch)
-__global__ void lwe1_prepare_kernel(const uint32_t* __restrict__ lwe1, uint16_t* __restrict__ dig, uint32_t* __restrict__ out, long B) {
-    const long g = blockIdx.x;
-    if (g >= B) return;
-    const uint32_t* src = lwe1 + (size_t)g * 1025;
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) dig[(size_t)g * 1024 + i] = (uint16_t)((src[1 + i] + 0x8000u) >> 16);
-    for (int c = threadIdx.x; c <= LWE_N; c += blockDim.x) out[(size_t)g * (LWE_N + 1) + c] = (c == 0) ? src[0] : 0u;
-}
-
-// =====================================================================================================
-// exact negacyclic product a (torus) * d (small ints): one warp per product, 7 transforms
-// =====================================================================================================
-constexpr int PM_WARPS = 2;
-// product g reads a = A + g*a_stride, d = D + g*d_stride (d_stride 0: one multiplier shared by the batch) and writes
-// out + g*o_stride (accumulate: += instead of =)
-__global__ void __launch_bounds__(PM_WARPS * 32) polymul_kernel(const uint32_t* __restrict__ A, const int32_t* __restrict__ D,
-                                                               uint32_t* __restrict__ out, long B, long a_stride, long d_stride,
-                                                               long o_stride, int accumulate) {
-    __shared__ __align__(16) uint32_t twF[32 * TWB_STRIDE];
-    __shared__ __align__(16) uint32_t twI[32 * TWB_STRIDE];
-    __shared__ __align__(16) uint32_t scratch[PM_WARPS][2][TILE_WORDS];
-    for (int t = threadIdx.x; t < 32 * TWB_STRIDE; t += blockDim.x) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long g = (long)blockIdx.x * PM_WARPS + warp;
-    if (g >= B) return;
-    const uint32_t* a = A + (size_t)g * a_stride;
-    const int32_t* d = D + (size_t)g * d_stride;
-    uint32_t* S = scratch[warp][0];
-    uint32_t* T = scratch[warp][1];
-    uint32_t dh[32], x[32], res[32];
-#pragma unroll
-    for (int r = 0; r < 32; r++) x[r] = to_residue(d[32 * r + lane]);
-    fwd_cols(lane, x, S);
-    __syncwarp();
-    fwd_rows(lane, S, twF, dh);  // spectrum of d, row layout, in [0,p)
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; r++) res[r] = 0;
-    for (int part = 0; part < 3; part++) {
-        key_cols(lane, a, part, S);
-        __syncwarp();
-        key_rows(lane, S, twF, T);  // [q][lane][4], scaled by 2^32/N
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const uint4 b = *reinterpret_cast<const uint4*>(T + (q * 32 + lane) * 4);
-            x[4 * q] = redc64((uint64_t)dh[4 * q] * b.x);
-            x[4 * q + 1] = redc64((uint64_t)dh[4 * q + 1] * b.y);
-            x[4 * q + 2] = redc64((uint64_t)dh[4 * q + 2] * b.z);
-            x[4 * q + 3] = redc64((uint64_t)dh[4 * q + 3] * b.w);
-        }
-        inv_rows(lane, x, twI, S);
-        __syncwarp();
-        p2b(lane, S, part, x);
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 32; r++) res[r] += x[r];
-    }
-    uint32_t* o = out + (size_t)g * o_stride;
-#pragma unroll
-    for (int r = 0; r < 32; r++) o[32 * r + lane] = accumulate ? o[32 * r + lane] + res[r] : res[r];
-}
-
-// =====================================================================================================
-// Device-side key generation and encryption.  Same seeded counter generator and the same operation
-// order as the host keygen (hostkeys.cpp, tfhe_rng.cuh): the device keys are bit-identical to the host keys.
-// Reference: BootstrappingKey::new (tfhe.rs:119-126), TRGSW/TRLWE encrypt (trgsw.rs:117-139,213-229; trlwe.rs:127-137),
-// KeySwitchingKey::new (tlwe.rs:247-277), TLWE encrypt / decrypt (tlwe.rs:213-240).
-// =====================================================================================================
-using tfhe_rng::Rng;
-// rows of the bootstrapping key before the a*s product: A = uniform, B = noise      bk: [n][2l][2][N], poly 0 = B, poly 1 = A
-__global__ void bk_fill_kernel(uint32_t* __restrict__ bk, uint64_t seed, long nwords /* = rows * N */) {
-    const Rng ra(seed, tfhe_rng::BK_A), re(seed, tfhe_rng::BK_E);
-    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < nwords; t += (long)gridDim.x * blockDim.x) {
-        const long row = t >> 10;
-        const int k = (int)(t & 1023);
-        bk[(size_t)(row * 2 + 1) * 1024 + k] = ra.u32((uint64_t)t);
-        bk[(size_t)(row * 2 + 0) * 1024 + k] = re.gauss((uint64_t)t, tfhe_rng::SCALE_BK);
-    }
-}
-// gadget term of TRGSW_{s1}(s0_i): s0_i / Bg^(j+1) on B[0] of rows j < l and on A[0] of rows l + j (trgsw.rs:213-229)
-__global__ void bk_gadget_kernel(uint32_t* __restrict__ bk, const uint8_t* __restrict__ s0, int rows) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows) return;
-    const int i = row / 6, j = row % 6;
-    const uint32_t mu = (uint32_t)s0[i] << (32 - 6 * ((j % 3) + 1));
-    bk[(size_t)(row * 2 + (j < 3 ? 0 : 1)) * 1024] += mu;
-}
-// one warp per LWE row under s0: a = uniform, b = <a, s0> + noise + message.
-//   mode 0: key-switching key, row id = (i, l, d-1), message = d * s1_i / 2^(2(l+1))      (tlwe.rs:247-283)
-//   mode 1: encryption of bits[g], row id = ct_index0 + g, message = +-1/8                  (tlwe.rs:181-186,213-228)
-__global__ void lwe_rows_kernel(uint32_t* __restrict__ out, long rows, uint64_t seed, uint64_t index0, const uint8_t* __restrict__ s0,
-                                const uint8_t* __restrict__ s1, const uint8_t* __restrict__ bits, int mode) {
-    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const Rng ra(seed, mode == 0 ? tfhe_rng::KSK_A : tfhe_rng::ENC_A), re(seed, mode == 0 ? tfhe_rng::KSK_E : tfhe_rng::ENC_E);
-    const uint64_t id = index0 + (uint64_t)row;
-    uint32_t* ct = out + (size_t)row * (LWE_N + 1);
-    uint32_t part = 0;
-    for (int c = lane; c < LWE_N; c += 32) {
-        const uint32_t av = ra.u32(id * LWE_N + c);
-        ct[1 + c] = av;
-        if (s0[c]) part += av;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-    if (lane == 0) {
-        uint32_t msg;
-        if (mode == 0) {
-            const int i = (int)(row / 24), l = (int)((row / 3) % 8), d = (int)(row % 3) + 1;
-            msg = (uint32_t)(d * s1[i]) << (32 - 2 * (l + 1));
-        } else {
-            msg = bits[row] ? 0x20000000u : 0xE0000000u;
-        }
-        ct[0] = msg + re.gauss(id, tfhe_rng::SCALE_LV0) + part;
-    }
-}
-// phase = b - <a, s0> and the decoded bit (tlwe.rs:187-194,230-240); one warp per ciphertext
-__global__ void lwe_phase_kernel(const uint32_t* __restrict__ ct, long rows, const uint8_t* __restrict__ s0, uint32_t* __restrict__ phase,
-                                 uint8_t* __restrict__ bits) {
-    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const uint32_t* c = ct + (size_t)row * (LWE_N + 1);
-    uint32_t part = 0;
-    for (int k = lane; k < LWE_N; k += 32) if (s0[k]) part += c[1 + k];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-    if (lane == 0) {
-        const uint32_t ph = c[0] - part;
-        if (phase) phase[row] = ph;
-        if (bits) bits[row] = ((float)ph * (1.0f / 4294967296.0f)) < 0.5f ? 1 : 0;   // torus2binary, math.rs:684-690
-    }
-}
-// TRLWERep::sample_extract_index(index) (trlwe.rs:110-121): b' = b[index]; a'_i = a[index-i] (i <= index), -a[N+index-i] otherwise
-__global__ void sample_extract_kernel(const uint32_t* __restrict__ trlwe, uint32_t* __restrict__ out, long B, int index) {
-    const long g = blockIdx.x;
-    if (g >= B) return;
-    const uint32_t* b = trlwe + (size_t)g * 2048;
-    const uint32_t* a = b + 1024;
-    uint32_t* o = out + (size_t)g * 1025;
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) o[1 + i] = (i <= index) ? a[index - i] : 0u - a[1024 + index - i];
-    if (threadIdx.x == 0) o[0] = b[index];
-}
 
 // =====================================================================================================
 // host side: context + C ABI
@@ -1446,3 +778,4 @@ int tfhe_b200_sample_extract_batch(tfhe_b200_ctx* ctx, const uint32_t* trlwe, in
 }
 
 }  // extern "C"
+

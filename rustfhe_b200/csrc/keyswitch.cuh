@@ -1,0 +1,164 @@
+// keyswitch.cuh -- TLWERep::identity_key_switch (tlwe.rs:43-73) as device kernels (included by engine.cu only).
+#pragma once
+#include "blind_rotate.cuh"   // smem_u32, LWE_N
+
+// =====================================================================================================
+// K6: key switch.  out[g] -= sum_{i,l : d != 0} KSK[i][l][d-1]  with d = 2-bit digit (i,l) of gate g.
+// CTA = (tile of KS_GT gates) x (slice of 1024/KS_ISPLIT key indices); thread = one 16-byte column chunk of the
+// 636-word rows (159 chunks).  Every KSK row is read once per CTA and applied to all gates of the tile; the digit
+// is CTA-uniform so the select is a uniform branch.  Partial sums are merged with red.global.add.u32.
+// =====================================================================================================
+constexpr int KS_GT = 16;           // gates per thread group (accumulators live in registers: 16 x uint4)
+#if !defined(KS_NG)
+#define KS_NG 2
+#endif
+constexpr int KS_GROUPS = KS_NG;    // thread groups per CTA: they walk the same key rows, the second one hits L1
+constexpr int KS_ISPLIT_MIN = 8;    // key indices are split over gridDim.y CTAs: 8 for large batches, up to 128 for small ones
+constexpr int KS_ICHUNK = 1024 / KS_ISPLIT_MIN;   // largest slice of key indices one CTA walks
+constexpr int KS_CHUNKS = (LWE_N + 1) / 4;  // 159
+constexpr int KS_THREADS = 160;
+__global__ void __launch_bounds__(KS_THREADS* KS_GROUPS) keyswitch_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
+                                                                         uint32_t* __restrict__ out, long B) {
+    __shared__ __align__(16) uint16_t dg[KS_GROUPS][KS_ICHUNK][KS_GT];
+    const int grp = threadIdx.y;
+    const long g0 = ((long)blockIdx.x * KS_GROUPS + grp) * KS_GT;
+    const int ichunk = 1024 / (int)gridDim.y;
+    const int i0 = blockIdx.y * ichunk;
+    for (int t = threadIdx.x; t < ichunk * KS_GT; t += KS_THREADS) {
+        const int g = t / ichunk, ii = t % ichunk;
+        dg[grp][ii][g] = (g0 + g < B) ? dig[(size_t)(g0 + g) * 1024 + i0 + ii] : (uint16_t)0;
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= KS_CHUNKS || g0 >= B) return;
+    uint4 acc[KS_GT];
+#pragma unroll
+    for (int g = 0; g < KS_GT; g++) acc[g] = make_uint4(0, 0, 0, 0);
+    const uint4* base = ksk + (size_t)i0 * 8 * 3 * KS_CHUNKS + t;
+#pragma unroll 1
+    for (int ii = 0; ii < ichunk; ii++) {
+        uint32_t dw[KS_GT / 2];
+#pragma unroll
+        for (int g = 0; g < KS_GT / 2; g++) dw[g] = reinterpret_cast<const uint32_t*>(dg[grp][ii])[g];  // two gates per word
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            const uint4* row = base + (size_t)(ii * 8 + l) * 3 * KS_CHUNKS;
+            const uint4 r0 = __ldg(row), r1 = __ldg(row + KS_CHUNKS), r2 = __ldg(row + 2 * KS_CHUNKS);
+#pragma unroll
+            for (int g = 0; g < KS_GT; g++) {
+                const uint32_t d = (dw[g >> 1] >> ((g & 1) * 16 + 14 - 2 * l)) & 3u;
+                if (d == 1) { acc[g].x += r0.x; acc[g].y += r0.y; acc[g].z += r0.z; acc[g].w += r0.w; }
+                else if (d == 2) { acc[g].x += r1.x; acc[g].y += r1.y; acc[g].z += r1.z; acc[g].w += r1.w; }
+                else if (d == 3) { acc[g].x += r2.x; acc[g].y += r2.y; acc[g].z += r2.z; acc[g].w += r2.w; }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < KS_GT; g++) {
+        if (g0 + g >= B) break;
+        uint32_t* o = out + (size_t)(g0 + g) * (LWE_N + 1) + 4 * t;
+        atomicAdd(o + 0, 0u - acc[g].x);
+        atomicAdd(o + 1, 0u - acc[g].y);
+        atomicAdd(o + 2, 0u - acc[g].z);
+        atomicAdd(o + 3, 0u - acc[g].w);
+    }
+}
+// ---- K6b: key switch with the key rows staged through shared memory, one WARP per gate ----
+// The register-tile kernel above is ALU bound on its digit select (12 instructions per gate, digit and 16-byte chunk:
+// the digit is CTA-uniform but every thread tests it).  Here a warp owns one gate and all 159 chunks of its output row
+// (5 per lane): the digit picks the ROW ADDRESS in shared memory, so per (gate, digit) there are two instructions of
+// select and five (LDS.128 + 4 adds) instead of 5 warps x 12.  The rows of a stage (4 levels x 3 multiples of one key
+// index = 30 KB) are copied once per CTA with cp.async into a 3-deep ring (one __syncthreads per stage) and consumed by
+// the 16 gates of the tile.
+#if !defined(KS2_NG)
+#define KS2_NG 16
+#endif
+constexpr int KS2_GATES = KS2_NG;                  // warps per CTA
+constexpr int KS2_THREADS = KS2_GATES * 32;
+#if !defined(KS2_LVDEF)
+#define KS2_LVDEF 4
+#endif
+constexpr int KS2_LV = KS2_LVDEF;                  // levels per stage
+constexpr int KS2_ROWS = KS2_LV * 3;               // rows per stage
+constexpr int KS2_ROW_WORDS = 640;                 // 636 words padded to a multiple of 16 bytes x 32 lanes x 5
+constexpr int KS2_RING = 3;
+constexpr int KS2_STAGE_WORDS = KS2_ROWS * KS2_ROW_WORDS;
+constexpr size_t KS2_SMEM_BYTES = (size_t)KS2_RING * KS2_STAGE_WORDS * 4 + (size_t)KS_ICHUNK * KS2_GATES * 2;
+__global__ void __launch_bounds__(KS2_THREADS) keyswitch2_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
+                                                                uint32_t* __restrict__ out, long B) {
+    extern __shared__ __align__(16) uint32_t ks_smem[];
+    uint32_t* ring = ks_smem;
+    uint16_t* dg = reinterpret_cast<uint16_t*>(ks_smem + KS2_RING * KS2_STAGE_WORDS);   // [ichunk][16]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long g0 = (long)blockIdx.x * KS2_GATES;
+    const int ichunk = 1024 / (int)gridDim.y;
+    const int i0 = blockIdx.y * ichunk;
+    const int nstages = ichunk * (8 / KS2_LV);
+    for (int t = threadIdx.x; t < ichunk * KS2_GATES; t += KS2_THREADS) {
+        const int g = t / ichunk, ii = t % ichunk;
+        dg[ii * KS2_GATES + g] = (g0 + g < B) ? dig[(size_t)(g0 + g) * 1024 + i0 + ii] : (uint16_t)0;
+    }
+    auto stage_in = [&](int k) {   // rows (key index i0 + k / SPI, KS2_LV levels, all three multiples) -> ring slot k % 3
+        constexpr int SPI = 8 / KS2_LV;   // stages per key index
+        const uint4* src = ksk + ((size_t)(i0 + k / SPI) * 8 + (size_t)(k % SPI) * KS2_LV) * 3 * KS_CHUNKS;
+        const uint32_t dst = smem_u32(ring + (k % KS2_RING) * KS2_STAGE_WORDS);
+        for (int t = threadIdx.x; t < KS2_ROWS * KS_CHUNKS; t += KS2_THREADS) {
+            const int row = t / KS_CHUNKS, c = t - row * KS_CHUNKS;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(row * KS2_ROW_WORDS + 4 * c) * 4u), "l"(src + t)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_in(0);
+    if (nstages > 1) stage_in(1); else asm volatile("cp.async.commit_group;" ::: "memory");
+    uint4 acc[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) acc[q] = make_uint4(0, 0, 0, 0);
+    const bool live = g0 + warp < B;
+#pragma unroll 1
+    for (int k = 0; k < nstages; k++) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // stage k has landed (at most the newest group is still in flight)
+        __syncthreads();                                          // ... for every thread; and everybody is done with stage k-1
+        if (k + 2 < nstages) stage_in(k + 2); else asm volatile("cp.async.commit_group;" ::: "memory");
+        if (live) {
+            constexpr int SPI = 8 / KS2_LV;
+            const uint32_t d16 = dg[(k / SPI) * KS2_GATES + warp];
+            const uint32_t* rows = ring + (k % KS2_RING) * KS2_STAGE_WORDS;
+#pragma unroll
+            for (int l = 0; l < KS2_LV; l++) {
+                const uint32_t d = (d16 >> (14 - 2 * ((k % SPI) * KS2_LV + l))) & 3u;   // level 0 in bits 15:14
+                if (d != 0) {
+                    const uint4* r = reinterpret_cast<const uint4*>(rows + (l * 3 + (int)d - 1) * KS2_ROW_WORDS) + lane;
+#pragma unroll
+                    for (int q = 0; q < 5; q++) {
+                        if (q < 4 || lane < KS_CHUNKS - 128) {
+                            const uint4 v = r[32 * q];
+                            acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!live) return;
+    uint32_t* o = out + (size_t)(g0 + warp) * (LWE_N + 1);
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        const int c = lane + 32 * q;
+        if (c < KS_CHUNKS) {
+            atomicAdd(o + 4 * c + 0, 0u - acc[q].x);
+            atomicAdd(o + 4 * c + 1, 0u - acc[q].y);
+            atomicAdd(o + 4 * c + 2, 0u - acc[q].z);
+            atomicAdd(o + 4 * c + 3, 0u - acc[q].w);
+        }
+    }
+}
+// prepares the key-switch inputs from explicit level-1 samples (step-level entry tfhe_b200_keyswitch_batch)
+__global__ void lwe1_prepare_kernel(const uint32_t* __restrict__ lwe1, uint16_t* __restrict__ dig, uint32_t* __restrict__ out, long B) {
+    const long g = blockIdx.x;
+    if (g >= B) return;
+    const uint32_t* src = lwe1 + (size_t)g * 1025;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) dig[(size_t)g * 1024 + i] = (uint16_t)((src[1 + i] + 0x8000u) >> 16);
+    for (int c = threadIdx.x; c <= LWE_N; c += blockDim.x) out[(size_t)g * (LWE_N + 1) + c] = (c == 0) ? src[0] : 0u;
+}
+
