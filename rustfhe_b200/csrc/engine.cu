@@ -357,7 +357,10 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         ctx->gates_per_cta = G;
         return (unsigned)nctas;
     };
-    if (full && variant == 3) {   // the earlier default, kept selectable for A/B runs: three 1-gate CTAs per SM (96 registers)
+    if (full && (variant == 3 || a.B <= 2L * ctx->sm_count) && a.ns == 3) {
+        // 1-gate CTAs, up to three per SM (96 registers): the earlier default (TFHE_B200_BR_VARIANT=3 for A/B runs) and still the
+        // best shape between one and two gates per SM (296 gates: 5.7 ms against 6.3 ms for 2-gate CTAs of the 80-register
+        // kernel and 5.8 ms for 1-gate CTAs compiled for 168 registers)
         blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
     } else if (full) {   // default (variant 7)
         const unsigned grid = deal(4);
