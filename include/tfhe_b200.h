@@ -109,6 +109,13 @@ int tfhe_b200_sync(tfhe_b200_ctx* ctx); /* waits for every batch this context ha
 /* optional: pre-allocate all internal workspaces for batches of up to max_batch gates (otherwise they grow on demand,
  * and cudaMalloc blocks while earlier batches are still running) */
 int tfhe_b200_reserve(tfhe_b200_ctx* ctx, size_t max_batch);
+/* One launch for a batch of gates with DIFFERENT opcodes -- one level of a levelised circuit (the reference evaluates
+ * nander expressions one gate at a time, nander/src/lib.rs:72-89).  ops[g] is one of the opcodes above; in1[g] is ignored
+ * for NOT / COPY gates. */
+int tfhe_b200_gate_batch_mixed(tfhe_b200_ctx* ctx, const uint8_t* ops /*[B]*/, const uint32_t* in0, const uint32_t* in1,
+                               uint32_t* out, size_t B);
+int tfhe_b200_gate_batch_mixed_device(tfhe_b200_ctx* ctx, const uint8_t* ops_dev, const uint32_t* in0, const uint32_t* in1,
+                                      uint32_t* out, size_t B, void* stream);
 int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t B); /* TFHE::bootstrap */
 /* hom_mux(control, input_0, input_1) = (input_1 & control) | (input_0 & !control): three bootstraps, tfhe.rs:27-40 */
 int tfhe_b200_mux_batch(tfhe_b200_ctx* ctx, const uint32_t* control, const uint32_t* in0, const uint32_t* in1,

@@ -20,7 +20,8 @@ SYMBOLS = [
     "tfhe_b200_default_params", "tfhe_b200_ctx_create", "tfhe_b200_ctx_destroy", "tfhe_b200_last_error",
     "tfhe_b200_set_decomp_mask", "tfhe_b200_set_key_slices", "tfhe_b200_get_stats", "tfhe_b200_reset_stats", "tfhe_b200_load_bk", "tfhe_b200_load_bk_device",
     "tfhe_b200_load_ksk", "tfhe_b200_load_ksk_device", "tfhe_b200_gate_batch", "tfhe_b200_gate_batch_device",
-    "tfhe_b200_gate_batch_async", "tfhe_b200_sync", "tfhe_b200_reserve",
+    "tfhe_b200_gate_batch_async", "tfhe_b200_sync", "tfhe_b200_reserve", "tfhe_b200_gate_batch_mixed",
+    "tfhe_b200_gate_batch_mixed_device",
     "tfhe_b200_bootstrap_batch", "tfhe_b200_mux_batch", "tfhe_b200_mux_batch_device", "tfhe_b200_blind_rotate_batch",
     "tfhe_b200_bootstrap_lv1_batch", "tfhe_b200_keyswitch_batch", "tfhe_b200_external_product_batch",
     "tfhe_b200_negacyclic_mul_batch", "tfhe_b200_external_product_batch_device", "tfhe_b200_negacyclic_mul_batch_device", "tfhe_b200_keygen_secret", "tfhe_b200_keygen_bk", "tfhe_b200_keygen_ksk",
@@ -76,6 +77,8 @@ def lib():
         "tfhe_b200_gate_batch_async": (i32, [vp, i32, vp, vp, vp, sz]),
         "tfhe_b200_sync": (i32, [vp]),
         "tfhe_b200_reserve": (i32, [vp, sz]),
+        "tfhe_b200_gate_batch_mixed": (i32, [vp, vp, vp, vp, vp, sz]),
+        "tfhe_b200_gate_batch_mixed_device": (i32, [vp, vp, vp, vp, vp, sz, vp]),
         "tfhe_b200_bootstrap_batch": (i32, [vp, vp, vp, sz]),
         "tfhe_b200_mux_batch": (i32, [vp, vp, vp, vp, vp, sz]),
         "tfhe_b200_mux_batch_device": (i32, [vp, vp, vp, vp, vp, sz, vp]),

@@ -340,6 +340,16 @@ class DeviceEngine:
         self._ck(self._l.tfhe_b200_gate_batch(self._ctx, op, ptr(in0), ptr(in1), ptr(out), len(in0)))
         return out
 
+    def gate_batch_mixed(self, ops, in0, in1):
+        """One launch for gates with different opcodes (`ops`: uint8 [B]); in1 rows of NOT / COPY gates are ignored."""
+        ops = np.ascontiguousarray(ops, np.uint8)
+        in0 = _u32_batch(in0, K.n + 1)
+        in1 = _u32_batch(in1, K.n + 1)
+        assert len(ops) == len(in0) == len(in1)
+        out = np.empty_like(in0)
+        self._ck(self._l.tfhe_b200_gate_batch_mixed(self._ctx, ptr(ops), ptr(in0), ptr(in1), ptr(out), len(in0)))
+        return out
+
     def gate_batch_async(self, op, in0, in1, out):
         """Asynchronous form: `in0`, `in1`, `out` are caller-owned (pinned) uint32 arrays [B][n+1] that must stay
         alive until `sync()`; consecutive calls overlap on the device."""

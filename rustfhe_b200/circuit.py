@@ -175,6 +175,33 @@ def ripple_carry_adder(nbits=32):
     return nl
 
 
+def prefix_adder(nbits=32):
+    """Kogge-Stone parallel-prefix adder over the TFHE engine's native gates (hom_and / hom_or / hom_xor, the Logip mapping of
+    nander/src/lib.rs:40-62): 2 + 2 log2(nbits) levels of width ~nbits..3 nbits instead of the ripple-carry chain's 2 nbits
+    levels of width <= 3 -- the shape on which level-synchronous batching turns gate THROUGHPUT into circuit latency.
+    Same interface as ripple_carry_adder: inputs x[0..nbits), y[0..nbits) little endian; outputs nbits sum bits + carry out."""
+    nl = Netlist()
+    x = nl.add_inputs(nbits)
+    y = nl.add_inputs(nbits)
+    g = [nl.gate(AND, x[i], y[i]) for i in range(nbits)]      # generate
+    p = [nl.gate(XOR, x[i], y[i]) for i in range(nbits)]      # propagate (also the half sum)
+    G, P = list(g), list(p)
+    d = 1
+    while d < nbits:
+        G2, P2 = list(G), list(P)
+        for i in range(d, nbits):
+            t = nl.gate(AND, P[i], G[i - d])
+            G2[i] = nl.gate(OR, G[i], t)                      # G[i] | (P[i] & G[i-d])
+            if i >= 2 * d:                                    # P of a span that already reaches bit 0 is never used again
+                P2[i] = nl.gate(AND, P[i], P[i - d])
+        G, P = G2, P2
+        d *= 2
+    outs = [p[0]] + [nl.gate(XOR, p[i], G[i - 1]) for i in range(1, nbits)]   # carry into bit i = G[i-1] (span i-1..0)
+    outs.append(G[nbits - 1])
+    nl.outputs = outs
+    return nl
+
+
 def expr_to_netlist(expr):
     """Compile a LogicExpr with the TFHE Logip mapping (native and/or/xor/not gates, nander/src/lib.rs:40-62)."""
     nl = Netlist()
@@ -197,7 +224,8 @@ def expr_to_netlist(expr):
 # ------------------------------------------------------------------------------------------------------------
 def evaluate(engine, netlist, inputs=None, stats=None):
     """Level-synchronous evaluation on one device context.  `inputs`: uint32 [n_inputs][n+1] ciphertexts.
-    Host-side wire table + one engine.gate_batch call per (level, opcode).  Returns the output ciphertexts."""
+    Host-side wire table + ONE engine call per level (tfhe_b200_gate_batch_mixed when the level mixes opcodes).
+    Returns the output ciphertexts."""
     W = K.n + 1
     wires = np.zeros((netlist.n_wires, W), np.uint32)
     if netlist.n_inputs:
@@ -206,12 +234,18 @@ def evaluate(engine, netlist, inputs=None, stats=None):
         wires[w, 0] = 0x20000000 if bit else 0xE0000000
     levels = netlist.levels()
     hist = []
+    mixed = getattr(engine, "gate_batch_mixed", None)
     for lev in levels:
-        width = 0
-        for op, (i0, i1, o) in lev.items():
-            out = engine.gate_batch(op, wires[i0], None if op == NOT else wires[i1])
-            wires[o] = out
-            width += len(o)
+        width = sum(len(o) for (_, _, o) in lev.values())
+        if mixed is not None and len(lev) > 1:   # gates of different kinds: still ONE launch for the level
+            ops = np.concatenate([np.full(len(o), op, np.uint8) for op, (_, _, o) in lev.items()])
+            i0 = np.concatenate([a for (a, _, _) in lev.values()])
+            i1 = np.concatenate([b for (_, b, _) in lev.values()])
+            o = np.concatenate([c for (_, _, c) in lev.values()])
+            wires[o] = mixed(ops, wires[i0], wires[i1])
+        else:
+            for op, (i0, i1, o) in lev.items():
+                wires[o] = engine.gate_batch(op, wires[i0], None if op == NOT else wires[i1])
         hist.append(width)
     if stats is not None:
         stats["levels"] = len(levels)

@@ -5,6 +5,7 @@
 //   K5L blind_rotate_pair_kernel  : latency shape, one gate on a cluster of two CTAs
 #pragma once
 #include <cooperative_groups.h>
+#include "../../include/tfhe_b200.h"
 #include "cmux_steps.cuh"
 
 using namespace tfhe;
@@ -49,6 +50,7 @@ struct BrArgs {
     const uint32_t* in1;     // [B][n+1] or null
     int32_t c0, c1;          // lin = c0*in0 + c1*in1 + (cb, 0, ...)
     uint32_t cb;
+    const uint8_t* ops;      // [B] or null: per-gate opcode (a circuit level with mixed gates in ONE launch); overrides c0/c1/cb
     // second operand set for gates >= split (fused hom_mux first stage: two different gates in one launch); split = B when unused
     long split;
     const uint32_t* in0b;
@@ -86,6 +88,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         "WAIT_%=:\n\t"
         "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
         "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
+// linear pre-combination of a gate opcode (tfhe.rs:27-71; same table as op_coeffs on the host): lin = k0*in0 + k1*in1 + (kb, 0)
+__device__ __forceinline__ void gate_coeffs(int op, uint32_t mu, uint32_t& k0, uint32_t& k1, uint32_t& kb) {
+    switch (op) {
+    case TFHE_B200_NAND: k0 = 0u - 1u; k1 = 0u - 1u; kb = mu; break;
+    case TFHE_B200_AND: k0 = 1; k1 = 1; kb = 0u - mu; break;
+    case TFHE_B200_OR: k0 = 1; k1 = 1; kb = mu; break;
+    case TFHE_B200_XOR: k0 = 2; k1 = 2; kb = 2u * mu; break;
+    case TFHE_B200_NOT: k0 = 0u - 1u; k1 = 0; kb = 0; break;
+    case TFHE_B200_ANDNY: k0 = 0u - 1u; k1 = 1; kb = 0u - mu; break;
+    default: k0 = 1; k1 = 0; kb = 0; break;   // COPY
+    }
 }
 
 template <int G, bool EXTPROD, int MINB, int NS = 3>
@@ -130,9 +145,10 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         const long gsrc = second ? gate - a.split : gate;
         const uint32_t* q0 = second ? a.in0b : a.in0;
         const uint32_t* q1 = second ? a.in1b : a.in1;
-        const uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
+        uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
+        if (a.ops) gate_coeffs(a.ops[gate], a.mu, k0, k1, kb);
         const uint32_t* p0 = q0 + (size_t)gsrc * (LWE_N + 1);
-        const uint32_t* p1 = q1 ? q1 + (size_t)gsrc * (LWE_N + 1) : nullptr;
+        const uint32_t* p1 = (q1 && k1 != 0) ? q1 + (size_t)gsrc * (LWE_N + 1) : nullptr;
         for (int c = tid6; c <= LWE_N; c += THREADS_PER_GATE) {
             uint32_t v = k0 * p0[c];
             if (p1) v += k1 * p1[c];
@@ -277,9 +293,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
         const long gsrc = second ? gate - a.split : gate;
         const uint32_t* q0 = second ? a.in0b : a.in0;
         const uint32_t* q1 = second ? a.in1b : a.in1;
-        const uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
+        uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
+        if (a.ops) gate_coeffs(a.ops[gate], a.mu, k0, k1, kb);
         const uint32_t* p0 = q0 + (size_t)gsrc * (LWE_N + 1);
-        const uint32_t* p1 = q1 ? q1 + (size_t)gsrc * (LWE_N + 1) : nullptr;
+        const uint32_t* p1 = (q1 && k1 != 0) ? q1 + (size_t)gsrc * (LWE_N + 1) : nullptr;
         for (int c = tid; c <= LWE_N; c += PAIR_THREADS) {
             uint32_t v = k0 * p0[c];
             if (p1) v += k1 * p1[c];

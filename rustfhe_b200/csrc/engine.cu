@@ -33,6 +33,7 @@ struct Slot {
     uint32_t* tmp[4] = {nullptr, nullptr, nullptr, nullptr}; size_t tmp_cap[4] = {0, 0, 0, 0};
     uint32_t* scratch = nullptr; size_t scratch_cap = 0;   // hom_mux intermediates / transformed TRGSWs of step-level calls
     uint8_t* s0buf = nullptr;                               // [1024] device copy of a caller's lv0 secret key (encrypt / decrypt)
+    uint8_t* opsbuf = nullptr; size_t opsbuf_cap = 0;       // per-gate opcodes of a mixed batch (host-pointer entry)
 };
 
 static const size_t BK_TORUS_BYTES = (size_t)LWE_N * 12 * 1024 * 4;
@@ -184,7 +185,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->bkdev); cudaFree(ctx->kskdev); cudaFree(ctx->bk_torus); cudaFree(ctx->keybits); cudaFree(ctx->s1poly);
     for (auto& s : ctx->slots) {
-        cudaFree(s.ksdig); cudaFree(s.scratch); cudaFree(s.s0buf);
+        cudaFree(s.ksdig); cudaFree(s.scratch); cudaFree(s.s0buf); cudaFree(s.opsbuf);
         for (auto p : s.tmp) cudaFree(p);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -486,6 +487,52 @@ int tfhe_b200_gate_batch_async(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, 
 }
 int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B) {
     RC(tfhe_b200_gate_batch_async(ctx, op, in0, in1, out, B));
+    return tfhe_b200_sync(ctx);
+}
+// One launch for a batch whose gates have DIFFERENT opcodes (one level of a circuit): ops[g] in TFHE_B200_NAND..ANDNY;
+// in1[g] is ignored for NOT / COPY gates (in1 may be NULL only if every gate is one of those).
+int tfhe_b200_gate_batch_mixed_device(tfhe_b200_ctx* ctx, const uint8_t* ops_dev, const uint32_t* in0, const uint32_t* in1, uint32_t* out,
+                                      size_t B, void* stream) {
+    if (!ctx || !ops_dev || !in0 || !out) return fail(ctx, TFHE_B200_ERR_PARAM, "gate_batch_mixed: null argument");
+    if (!ctx->have_bk || !ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "gate_batch_mixed: keys not loaded");
+    if (B == 0) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, false, &s));
+    BrArgs a{};
+    a.ops = ops_dev; a.in0 = in0; a.in1 = in1; a.B = (long)B;
+    RC(run_gates(ctx, s, a, out, st));
+    return slot_release(ctx, s, st);
+}
+int tfhe_b200_gate_batch_mixed(tfhe_b200_ctx* ctx, const uint8_t* ops, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B) {
+    if (!ctx || !ops || !in0 || !out) return fail(ctx, TFHE_B200_ERR_PARAM, "gate_batch_mixed: null argument");
+    if (!ctx->have_bk || !ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "gate_batch_mixed: keys not loaded");
+    for (size_t g = 0; g < B; g++) {
+        if (ops[g] > TFHE_B200_ANDNY) return fail(ctx, TFHE_B200_ERR_PARAM, "gate_batch_mixed: bad opcode");
+        if (!in1 && ops[g] != TFHE_B200_NOT && ops[g] != TFHE_B200_COPY) return fail(ctx, TFHE_B200_ERR_PARAM, "gate_batch_mixed: in1 required");
+    }
+    if (B == 0) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = nullptr;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, true, &s));
+    const size_t bytes = B * CT_BYTES;
+    RC(grow(ctx, (void**)&s->tmp[0], &s->tmp_cap[0], bytes));
+    RC(grow(ctx, (void**)&s->tmp[3], &s->tmp_cap[3], bytes));
+    RC(grow(ctx, (void**)&s->opsbuf, &s->opsbuf_cap, B));
+    CK(cudaMemcpyAsync(s->tmp[0], in0, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->opsbuf, ops, B, cudaMemcpyHostToDevice, st));
+    BrArgs a{};
+    a.ops = s->opsbuf; a.in0 = s->tmp[0]; a.B = (long)B;
+    if (in1) {
+        RC(grow(ctx, (void**)&s->tmp[1], &s->tmp_cap[1], bytes));
+        CK(cudaMemcpyAsync(s->tmp[1], in1, bytes, cudaMemcpyHostToDevice, st));
+        a.in1 = s->tmp[1];
+    }
+    RC(run_gates(ctx, s, a, s->tmp[3], st));
+    CK(cudaMemcpyAsync(out, s->tmp[3], bytes, cudaMemcpyDeviceToHost, st));
+    RC(slot_release(ctx, s, st));
     return tfhe_b200_sync(ctx);
 }
 int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t B) {

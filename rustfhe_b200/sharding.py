@@ -33,7 +33,7 @@ def replicate_keys(bk_words, ksk_words, rank, world, device=None):
     return bk, ksk
 
 
-def evaluate_sharded(gate_fn, in0, in1, rank, world, gather=True):
+def evaluate_sharded(gate_fn, in0, in1, rank, world, gather=True, ops=None):
     """Evaluate one batch of gates split across ranks.  `gate_fn(in0_shard, in1_shard) -> out_shard` is the per-rank
     engine call (tfhe_b200_gate_batch).  With gather=True every rank returns the whole output batch (one all_gather of
     2544 B per ciphertext -- the per-LEVEL exchange of a levelised circuit, never per gate)."""
@@ -43,7 +43,11 @@ def evaluate_sharded(gate_fn, in0, in1, rank, world, gather=True):
     bounds = shard_bounds(B, world)
     s, e = bounds[rank]
     width = in0.shape[1]
-    out_shard = gate_fn(in0[s:e], None if in1 is None else in1[s:e]) if e > s else np.zeros((0, width), np.uint32)
+    if e > s:
+        args = (in0[s:e], None if in1 is None else in1[s:e])
+        out_shard = gate_fn(*args) if ops is None else gate_fn(ops[s:e], *args)   # ops: per-gate opcodes of a mixed level
+    else:
+        out_shard = np.zeros((0, width), np.uint32)
     if not gather or world == 1:
         return out_shard
     per = bounds[0][1] - bounds[0][0]

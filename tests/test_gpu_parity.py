@@ -376,3 +376,24 @@ def test_fast_mode_two_key_slices(oracle, keys, rng):
         assert np.array_equal(eng.gate_batch(R.NAND, c0[:40], c1[:40]), exact[:40])
     finally:
         eng.close()
+
+
+def test_mixed_opcode_batch(engine, oracle, keys, rng):
+    """tfhe_b200_gate_batch_mixed: one launch for gates of different kinds (a circuit level) == the per-opcode launches, bit for
+    bit; in1 of NOT / COPY gates is ignored."""
+    import rustfhe_b200 as R
+    B = 210
+    ops = rng.integers(0, 7, B).astype(np.uint8)
+    x = rng.integers(0, 2, B).astype(np.uint8)
+    y = rng.integers(0, 2, B).astype(np.uint8)
+    c0, c1 = keys.encrypt(x, 71000), keys.encrypt(y, 72000)
+    out = engine.gate_batch_mixed(ops, c0, c1)
+    want_bits = {R.NAND: 1 - (x & y), R.AND: x & y, R.OR: x | y, R.XOR: x ^ y, R.NOT: 1 - x, R.COPY: x, R.ANDNY: (1 - x) & y}
+    for op in range(7):
+        idx = np.flatnonzero(ops == op)
+        assert len(idx) > 0
+        ref = engine.gate_batch(op, c0[idx], None if op in (R.NOT, R.COPY) else c1[idx])
+        assert np.array_equal(out[idx], ref), op
+        assert np.array_equal(keys.decrypt(out[idx]), want_bits[op][idx]), op
+    with pytest.raises(R.TfheError):
+        engine.gate_batch_mixed(np.full(B, 9, np.uint8), c0, c1)

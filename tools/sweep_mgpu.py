@@ -117,6 +117,9 @@ def main():
         def gate_batch(self, op, a, b=None):
             return evaluate_sharded(lambda p, q: eng.gate_batch(op, p, q), a, b, rank, world, gather=True)
 
+        def gate_batch_mixed(self, ops, a, b):
+            return evaluate_sharded(lambda o, p, q: eng.gate_batch_mixed(o, p, q), a, b, rank, world, gather=True, ops=ops)
+
     stt = {}
     Cq.evaluate(Sharded(), nl, cts, stt)
     if world > 1:
@@ -129,6 +132,20 @@ def main():
                               "correct": bool(sum(int(b) << i for i, b in enumerate(got)) == x + y),
                               "note": "latency bound: the carry chain gives ~2 levels per bit of width <= 3; sharding a level of <= 3 gates "
                                       "across GPUs only adds the per-level all_gather"}
+    # the same addition as a Kogge-Stone prefix adder on native and/or/xor gates: 11 levels of width 16..64
+    nlp = Cq.prefix_adder(32)
+    stp = {}
+    Cq.evaluate(Sharded(), nlp, cts, stp)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    outp = Cq.evaluate(Sharded(), nlp, cts, stp)
+    wallp = time.perf_counter() - t0
+    gotp = R.Cryptor.decrypto(R.TLWE, s0, outp)
+    res["adder32_prefix_native_gates"] = {"gates": stp["gates"], "levels": stp["levels"], "width_histogram": stp["width_histogram"],
+                                          "wall_seconds": wallp, "correct": bool(sum(int(b) << i for i, b in enumerate(gotp)) == x + y),
+                                          "note": "not a BASELINE config: shows the level-synchronous evaluator turning batch throughput into circuit "
+                                                  "latency (the ripple-carry netlist of config 4 is a chain of 66 narrow levels)"}
     if rank == 0:
         txt = json.dumps(res, indent=1)
         if args.out:
