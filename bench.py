@@ -164,7 +164,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "bootstrapped HomNAND gates/sec", "value": v, "unit": "gates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_secs / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64 FFT + u32 torus", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "batched independent HomNAND gates, default TFHE parameters (n=635,N=1024,l=3,Bg=64,t=8)",
                    "batch_per_step": nthreads * gpt, "note": "bounded sample of the 1024-gate batch; CPU time per gate is batch independent"},
         "cpu_baseline": {"value": v, "unit": "gates/s", "cores": nthreads, "kind": "port",
@@ -355,9 +355,10 @@ def run_gpu(args):
         line = {
             "metric": "bootstrapped HomNAND gates/sec", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32 (torus mod 2^32; NTT over a 29-bit prime)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "batched 1024 independent HomNAND gates per GPU (BASELINE configs[1]), default TFHE parameters "
                                    "n=635 N=1024 l=3 Bg=64 t=8 basebit=2, decomposition mask 0x02084000 (reference-faithful)",
+                       "arithmetic": "torus words mod 2^32; exact negacyclic NTT over the 29-bit prime 536856577, three 11-bit key slices",
                        "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world} (independent gate shards, keys replicated)",
                        "l2": f"inputs rotate over {NROT} batches ({NROT * BATCH * 2 * CT_WORDS * 4 / 1e6:.0f} MB) > L2; keys "
                              f"{(BK_BYTES_DEVICE + KSK_BYTES) / 1e6:.0f} MB > L2; no explicit flush",
