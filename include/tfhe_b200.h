@@ -116,6 +116,17 @@ int tfhe_b200_gate_batch_mixed(tfhe_b200_ctx* ctx, const uint8_t* ops /*[B]*/, c
                                uint32_t* out, size_t B);
 int tfhe_b200_gate_batch_mixed_device(tfhe_b200_ctx* ctx, const uint8_t* ops_dev, const uint32_t* in0, const uint32_t* in1,
                                       uint32_t* out, size_t B, void* stream);
+/* Device-resident circuits: a levelised gate netlist (wire indices into one table of ciphertexts) uploaded once; a run
+ * enqueues one blind-rotate + one key-switch launch per level on `stream` and never returns to the host in between.
+ * Arrays are the levels concatenated: ops[g], in0[g], in1[g] (ignored for NOT / COPY), out[g] are wire indices < n_wires;
+ * a gate may only read wires written by earlier levels (or inputs / constants). */
+typedef struct tfhe_b200_circuit tfhe_b200_circuit;
+int tfhe_b200_circuit_create(tfhe_b200_ctx* ctx, size_t n_levels, const size_t* level_gates, const uint8_t* ops,
+                             const int32_t* in0, const int32_t* in1, const int32_t* out, size_t n_wires,
+                             tfhe_b200_circuit** circuit);
+int tfhe_b200_circuit_run_device(tfhe_b200_ctx* ctx, const tfhe_b200_circuit* circuit, uint32_t* wires_dev /*[n_wires][n+1]*/,
+                                 void* stream);
+int tfhe_b200_circuit_destroy(tfhe_b200_ctx* ctx, tfhe_b200_circuit* circuit);
 int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t B); /* TFHE::bootstrap */
 /* hom_mux(control, input_0, input_1) = (input_1 & control) | (input_0 & !control): three bootstraps, tfhe.rs:27-40 */
 int tfhe_b200_mux_batch(tfhe_b200_ctx* ctx, const uint32_t* control, const uint32_t* in0, const uint32_t* in1,

@@ -21,7 +21,7 @@ SYMBOLS = [
     "tfhe_b200_set_decomp_mask", "tfhe_b200_set_key_slices", "tfhe_b200_get_stats", "tfhe_b200_reset_stats", "tfhe_b200_load_bk", "tfhe_b200_load_bk_device",
     "tfhe_b200_load_ksk", "tfhe_b200_load_ksk_device", "tfhe_b200_gate_batch", "tfhe_b200_gate_batch_device",
     "tfhe_b200_gate_batch_async", "tfhe_b200_sync", "tfhe_b200_reserve", "tfhe_b200_gate_batch_mixed",
-    "tfhe_b200_gate_batch_mixed_device",
+    "tfhe_b200_gate_batch_mixed_device", "tfhe_b200_circuit_create", "tfhe_b200_circuit_run_device", "tfhe_b200_circuit_destroy",
     "tfhe_b200_bootstrap_batch", "tfhe_b200_mux_batch", "tfhe_b200_mux_batch_device", "tfhe_b200_blind_rotate_batch",
     "tfhe_b200_bootstrap_lv1_batch", "tfhe_b200_keyswitch_batch", "tfhe_b200_external_product_batch",
     "tfhe_b200_negacyclic_mul_batch", "tfhe_b200_external_product_batch_device", "tfhe_b200_negacyclic_mul_batch_device", "tfhe_b200_keygen_secret", "tfhe_b200_keygen_bk", "tfhe_b200_keygen_ksk",
@@ -79,6 +79,9 @@ def lib():
         "tfhe_b200_reserve": (i32, [vp, sz]),
         "tfhe_b200_gate_batch_mixed": (i32, [vp, vp, vp, vp, vp, sz]),
         "tfhe_b200_gate_batch_mixed_device": (i32, [vp, vp, vp, vp, vp, sz, vp]),
+        "tfhe_b200_circuit_create": (i32, [vp, sz, vp, vp, vp, vp, vp, sz, C.POINTER(vp)]),
+        "tfhe_b200_circuit_run_device": (i32, [vp, vp, vp, vp]),
+        "tfhe_b200_circuit_destroy": (i32, [vp, vp]),
         "tfhe_b200_bootstrap_batch": (i32, [vp, vp, vp, sz]),
         "tfhe_b200_mux_batch": (i32, [vp, vp, vp, vp, vp, sz]),
         "tfhe_b200_mux_batch_device": (i32, [vp, vp, vp, vp, vp, sz, vp]),

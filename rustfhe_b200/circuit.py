@@ -254,6 +254,50 @@ def evaluate(engine, netlist, inputs=None, stats=None):
     return wires[netlist.outputs] if netlist.outputs else wires
 
 
+class DeviceCircuit:
+    """A levelised netlist resident on the device (tfhe_b200_circuit_*): `run(inputs)` uploads the input ciphertexts into the
+    wire table, enqueues one launch pair per level with no host round trip in between, and downloads the outputs."""
+
+    def __init__(self, engine, netlist):
+        import ctypes as C
+        self.engine, self.netlist = engine, netlist
+        levels = netlist.levels()
+        sizes, ops, i0, i1, o = [], [], [], [], []
+        for lev in levels:
+            n = 0
+            for op, (a, b, c) in lev.items():
+                ops.append(np.full(len(c), op, np.uint8)); i0.append(a); i1.append(b); o.append(c); n += len(c)
+            sizes.append(n)
+        cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0), dt)
+        self._sizes = (C.c_size_t * max(1, len(sizes)))(*sizes)
+        self._h = C.c_void_p()
+        self.levels, self.gates = len(levels), int(sum(sizes))
+        rc = engine._l.tfhe_b200_circuit_create(engine._ctx, len(sizes), self._sizes, K.ptr(cat(ops, np.uint8)), K.ptr(cat(i0, np.int32)),
+                                                K.ptr(cat(i1, np.int32)), K.ptr(cat(o, np.int32)), netlist.n_wires, C.byref(self._h))
+        engine._ck(rc)
+
+    def run(self, inputs=None):
+        import ctypes as C
+        import torch
+        nl, W = self.netlist, K.n + 1
+        wires = np.zeros((nl.n_wires, W), np.uint32)
+        if nl.n_inputs:
+            wires[:nl.n_inputs] = np.ascontiguousarray(inputs, np.uint32).reshape(nl.n_inputs, W)
+        for w, bit in nl.consts.items():
+            wires[w, 0] = 0x20000000 if bit else 0xE0000000
+        dev = torch.device("cuda", self.engine.device)
+        d = torch.from_numpy(wires.view(np.int32)).to(dev)
+        st = torch.cuda.current_stream(dev)
+        self.engine._ck(self.engine._l.tfhe_b200_circuit_run_device(self.engine._ctx, self._h, C.c_void_p(d.data_ptr()), C.c_void_p(st.cuda_stream)))
+        out = d[torch.as_tensor(nl.outputs, device=dev)] if nl.outputs else d
+        return out.cpu().numpy().view(np.uint32)
+
+    def close(self):
+        if self._h:
+            self.engine._l.tfhe_b200_circuit_destroy(self.engine._ctx, self._h)
+            self._h = None
+
+
 def eval_logic_expr(pros, expr):
     """eval_logic_expr(&pros, exp) (nander/src/lib.rs:72-89) for pros = TFHE, evaluated level by level in batches."""
     return evaluate(pros.engine, expr_to_netlist(expr))

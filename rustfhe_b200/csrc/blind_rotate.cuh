@@ -50,6 +50,9 @@ struct BrArgs {
     const uint32_t* in1;     // [B][n+1] or null
     int32_t c0, c1;          // lin = c0*in0 + c1*in1 + (cb, 0, ...)
     uint32_t cb;
+    const int32_t* idx0;     // [B] or null: ROW INDICES into in0 / in1 / out_init instead of row = gate (device-resident circuit
+    const int32_t* idx1;     //               evaluation: all three then point at the same wire table)
+    const int32_t* idxo;
     const uint8_t* ops;      // [B] or null: per-gate opcode (a circuit level with mixed gates in ONE launch); overrides c0/c1/cb
     // second operand set for gates >= split (fused hom_mux first stage: two different gates in one launch); split = B when unused
     long split;
@@ -147,8 +150,8 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         const uint32_t* q1 = second ? a.in1b : a.in1;
         uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
         if (a.ops) gate_coeffs(a.ops[gate], a.mu, k0, k1, kb);
-        const uint32_t* p0 = q0 + (size_t)gsrc * (LWE_N + 1);
-        const uint32_t* p1 = (q1 && k1 != 0) ? q1 + (size_t)gsrc * (LWE_N + 1) : nullptr;
+        const uint32_t* p0 = q0 + (size_t)(a.idx0 ? (long)a.idx0[gate] : gsrc) * (LWE_N + 1);
+        const uint32_t* p1 = (q1 && k1 != 0) ? q1 + (size_t)(a.idx1 ? (long)a.idx1[gate] : gsrc) * (LWE_N + 1) : nullptr;
         for (int c = tid6; c <= LWE_N; c += THREADS_PER_GATE) {
             uint32_t v = k0 * p0[c];
             if (p1) v += k1 * p1[c];
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         if (a.lwe1_out && tid6 == 0) a.lwe1_out[(size_t)gate * 1025] = acc[0];
     }
     if (a.out_init) {
-        uint32_t* dst = a.out_init + (size_t)gate * (LWE_N + 1);
+        uint32_t* dst = a.out_init + (size_t)(a.idxo ? (long)a.idxo[gate] : gate) * (LWE_N + 1);
         for (int c = tid6; c <= LWE_N; c += THREADS_PER_GATE) dst[c] = (c == 0) ? acc[0] : 0u;
     }
 }
@@ -295,8 +298,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
         const uint32_t* q1 = second ? a.in1b : a.in1;
         uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
         if (a.ops) gate_coeffs(a.ops[gate], a.mu, k0, k1, kb);
-        const uint32_t* p0 = q0 + (size_t)gsrc * (LWE_N + 1);
-        const uint32_t* p1 = (q1 && k1 != 0) ? q1 + (size_t)gsrc * (LWE_N + 1) : nullptr;
+        const uint32_t* p0 = q0 + (size_t)(a.idx0 ? (long)a.idx0[gate] : gsrc) * (LWE_N + 1);
+        const uint32_t* p1 = (q1 && k1 != 0) ? q1 + (size_t)(a.idx1 ? (long)a.idx1[gate] : gsrc) * (LWE_N + 1) : nullptr;
         for (int c = tid; c <= LWE_N; c += PAIR_THREADS) {
             uint32_t v = k0 * p0[c];
             if (p1) v += k1 * p1[c];
@@ -387,7 +390,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) bli
     if (pw == 0) {
         if (a.lwe1_out && tid == 0) a.lwe1_out[(size_t)gate * 1025] = acc[0];
         if (a.out_init) {
-            uint32_t* dst = a.out_init + (size_t)gate * (LWE_N + 1);
+            uint32_t* dst = a.out_init + (size_t)(a.idxo ? (long)a.idxo[gate] : gate) * (LWE_N + 1);
             for (int c = tid; c <= LWE_N; c += PAIR_THREADS) dst[c] = (c == 0) ? acc[0] : 0u;
         }
     }

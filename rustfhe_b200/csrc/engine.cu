@@ -382,7 +382,8 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
     if (timed) CK(cudaEventRecord(ctx->ev[slot][1], st));
     return TFHE_B200_OK;
 }
-static int launch_keyswitch(tfhe_b200_ctx* ctx, const uint16_t* dig, uint32_t* out, long B, cudaStream_t st, bool timed) {
+static int launch_keyswitch(tfhe_b200_ctx* ctx, const uint16_t* dig, uint32_t* out, long B, cudaStream_t st, bool timed,
+                            const int32_t* idxo = nullptr) {
     const int slot = (int)(ctx->timed % tfhe_b200_ctx::RING);
     if (timed) CK(cudaEventRecord(ctx->ev[slot][2], st));
     if (ctx->ks_variant == 1) {   // register-tile kernel (TFHE_B200_KS_VARIANT=1)
@@ -391,13 +392,13 @@ static int launch_keyswitch(tfhe_b200_ctx* ctx, const uint16_t* dig, uint32_t* o
         int isplit = KS_ISPLIT_MIN;   // small batches (latency path, narrow circuit levels): split the key indices further to fill the SMs
         while (isplit < 128 && tiles * isplit < 2L * ctx->sm_count) isplit *= 2;
         dim3 grid((unsigned)tiles, isplit);
-        keyswitch_kernel<<<grid, dim3(KS_THREADS, KS_GROUPS), 0, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B);
+        keyswitch_kernel<<<grid, dim3(KS_THREADS, KS_GROUPS), 0, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B, idxo);
     } else {                      // shared-memory staged kernel, one warp per gate (default)
         const long tiles = (B + KS2_GATES - 1) / KS2_GATES;
         int isplit = KS_ISPLIT_MIN;
         while (isplit < 128 && tiles * isplit < 2L * ctx->sm_count) isplit *= 2;
         dim3 grid((unsigned)tiles, isplit);
-        keyswitch2_kernel<<<grid, KS2_THREADS, KS2_SMEM_BYTES, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B);
+        keyswitch2_kernel<<<grid, KS2_THREADS, KS2_SMEM_BYTES, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B, idxo);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -412,7 +413,7 @@ static int run_gates(tfhe_b200_ctx* ctx, Slot* s, BrArgs& a, uint32_t* out, cuda
     RC(grow(ctx, (void**)&s->ksdig, &s->ksdig_cap, (size_t)a.B * 1024 * sizeof(uint16_t)));
     a.nsteps = LWE_N; a.out_init = out; a.ksdig = s->ksdig;
     RC(launch_blind_rotate(ctx, a, st, true));
-    RC(launch_keyswitch(ctx, s->ksdig, out, a.B, st, true));
+    RC(launch_keyswitch(ctx, s->ksdig, out, a.B, st, true, a.idxo));
     ctx->last_batch = (uint64_t)a.B;
     return TFHE_B200_OK;
 }
@@ -570,6 +571,87 @@ int tfhe_b200_mux_batch(tfhe_b200_ctx* ctx, const uint32_t* control, const uint3
     return tfhe_b200_sync(ctx);
 }
 
+}  // extern "C"
+
+// ---- device-resident circuits: a levelised netlist uploaded once, evaluated with one launch pair per level and no host
+// round trip (the reference walks the expression tree one gate at a time, nander/src/lib.rs:72-89) ----
+struct tfhe_b200_circuit {
+    std::vector<size_t> level_first, level_gates;
+    uint8_t* ops = nullptr;       // device, all levels concatenated
+    int32_t* idx = nullptr;       // device: [3][total] = in0 | in1 | out wire indices
+    size_t total = 0, max_level = 0, n_wires = 0;
+};
+extern "C" {
+int tfhe_b200_circuit_create(tfhe_b200_ctx* ctx, size_t n_levels, const size_t* level_gates, const uint8_t* ops, const int32_t* in0,
+                             const int32_t* in1, const int32_t* out, size_t n_wires, tfhe_b200_circuit** circuit) {
+    if (!ctx || !circuit || (n_levels && (!level_gates || !ops || !in0 || !in1 || !out)))
+        return fail(ctx, TFHE_B200_ERR_PARAM, "circuit_create: null argument");
+    *circuit = nullptr;
+    tfhe_b200_circuit* c = new tfhe_b200_circuit();
+    c->n_wires = n_wires;
+    for (size_t l = 0; l < n_levels; l++) {
+        c->level_first.push_back(c->total);
+        c->level_gates.push_back(level_gates[l]);
+        c->total += level_gates[l];
+        if (level_gates[l] > c->max_level) c->max_level = level_gates[l];
+    }
+    for (size_t g = 0; g < c->total; g++) {
+        const bool one = ops[g] == TFHE_B200_NOT || ops[g] == TFHE_B200_COPY;
+        if (ops[g] > TFHE_B200_ANDNY || in0[g] < 0 || (size_t)in0[g] >= n_wires || out[g] < 0 || (size_t)out[g] >= n_wires ||
+            (!one && (in1[g] < 0 || (size_t)in1[g] >= n_wires))) {
+            delete c;
+            return fail(ctx, TFHE_B200_ERR_PARAM, "circuit_create: opcode or wire index out of range");
+        }
+    }
+    if (c->total) {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e == cudaSuccess) e = cudaMalloc(&c->ops, c->total);
+        if (e == cudaSuccess) e = cudaMalloc(&c->idx, 3 * c->total * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMemcpy(c->ops, ops, c->total, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(c->idx, in0, c->total * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(c->idx + c->total, in1, c->total * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(c->idx + 2 * c->total, out, c->total * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("circuit_create: ") + cudaGetErrorString(e);
+            cudaFree(c->ops); cudaFree(c->idx);
+            delete c;
+            return TFHE_B200_ERR_CUDA;
+        }
+    }
+    *circuit = c;
+    return TFHE_B200_OK;
+}
+int tfhe_b200_circuit_destroy(tfhe_b200_ctx* ctx, tfhe_b200_circuit* c) {
+    if (!ctx || !c) return TFHE_B200_ERR_PARAM;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->ops); cudaFree(c->idx);
+    delete c;
+    return TFHE_B200_OK;
+}
+// wires_dev: [n_wires][n+1] on the device; inputs and constants filled in by the caller, gate outputs written in place.
+// Everything is enqueued on `stream`; levels are ordered by the stream, the gates of a level are one blind-rotate + one
+// key-switch launch.
+int tfhe_b200_circuit_run_device(tfhe_b200_ctx* ctx, const tfhe_b200_circuit* c, uint32_t* wires_dev, void* stream) {
+    if (!ctx || !c || !wires_dev) return fail(ctx, TFHE_B200_ERR_PARAM, "circuit_run: null argument");
+    if (!ctx->have_bk || !ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "circuit_run: keys not loaded");
+    if (c->total == 0) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, false, &s));
+    RC(grow(ctx, (void**)&s->ksdig, &s->ksdig_cap, c->max_level * 1024 * sizeof(uint16_t)));
+    for (size_t l = 0; l < c->level_gates.size(); l++) {
+        const size_t f = c->level_first[l], n = c->level_gates[l];
+        if (n == 0) continue;
+        BrArgs a{};
+        a.ops = c->ops + f;
+        a.idx0 = c->idx + f; a.idx1 = c->idx + c->total + f; a.idxo = c->idx + 2 * c->total + f;
+        a.in0 = wires_dev; a.in1 = wires_dev; a.B = (long)n;
+        RC(run_gates(ctx, s, a, wires_dev, st));
+    }
+    return slot_release(ctx, s, st);
+}
 }  // extern "C"
 
 // ---- device-side key generation, encryption, decryption ----

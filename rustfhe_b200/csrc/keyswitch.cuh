@@ -18,7 +18,7 @@ constexpr int KS_ICHUNK = 1024 / KS_ISPLIT_MIN;   // largest slice of key indice
 constexpr int KS_CHUNKS = (LWE_N + 1) / 4;  // 159
 constexpr int KS_THREADS = 160;
 __global__ void __launch_bounds__(KS_THREADS* KS_GROUPS) keyswitch_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
-                                                                         uint32_t* __restrict__ out, long B) {
+                                                                         uint32_t* __restrict__ out, long B, const int32_t* __restrict__ idxo) {
     __shared__ __align__(16) uint16_t dg[KS_GROUPS][KS_ICHUNK][KS_GT];
     const int grp = threadIdx.y;
     const long g0 = ((long)blockIdx.x * KS_GROUPS + grp) * KS_GT;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(KS_THREADS* KS_GROUPS) keyswitch_kernel(const 
 #pragma unroll
     for (int g = 0; g < KS_GT; g++) {
         if (g0 + g >= B) break;
-        uint32_t* o = out + (size_t)(g0 + g) * (LWE_N + 1) + 4 * t;
+        uint32_t* o = out + (size_t)(idxo ? (long)idxo[g0 + g] : g0 + g) * (LWE_N + 1) + 4 * t;
         atomicAdd(o + 0, 0u - acc[g].x);
         atomicAdd(o + 1, 0u - acc[g].y);
         atomicAdd(o + 2, 0u - acc[g].z);
@@ -85,7 +85,7 @@ constexpr int KS2_RING = 3;
 constexpr int KS2_STAGE_WORDS = KS2_ROWS * KS2_ROW_WORDS;
 constexpr size_t KS2_SMEM_BYTES = (size_t)KS2_RING * KS2_STAGE_WORDS * 4 + (size_t)KS_ICHUNK * KS2_GATES * 2;
 __global__ void __launch_bounds__(KS2_THREADS) keyswitch2_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
-                                                                uint32_t* __restrict__ out, long B) {
+                                                                uint32_t* __restrict__ out, long B, const int32_t* __restrict__ idxo) {
     extern __shared__ __align__(16) uint32_t ks_smem[];
     uint32_t* ring = ks_smem;
     uint16_t* dg = reinterpret_cast<uint16_t*>(ks_smem + KS2_RING * KS2_STAGE_WORDS);   // [ichunk][16]
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(KS2_THREADS) keyswitch2_kernel(const uint4* __
         }
     }
     if (!live) return;
-    uint32_t* o = out + (size_t)(g0 + warp) * (LWE_N + 1);
+    uint32_t* o = out + (size_t)(idxo ? (long)idxo[g0 + warp] : g0 + warp) * (LWE_N + 1);
 #pragma unroll
     for (int q = 0; q < 5; q++) {
         const int c = lane + 32 * q;

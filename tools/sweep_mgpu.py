@@ -146,6 +146,18 @@ def main():
                                           "wall_seconds": wallp, "correct": bool(sum(int(b) << i for i, b in enumerate(gotp)) == x + y),
                                           "note": "not a BASELINE config: shows the level-synchronous evaluator turning batch throughput into circuit "
                                                   "latency (the ripple-carry netlist of config 4 is a chain of 66 narrow levels)"}
+    # device-resident evaluation (tfhe_b200_circuit_*): no host round trip between levels; rank 0's GPU only
+    if rank == 0:
+        for name, net in (("config4_adder32_device_resident", nl), ("adder32_prefix_device_resident", nlp)):
+            dc = Cq.DeviceCircuit(eng, net)
+            dc.run(cts)
+            t0 = time.perf_counter()
+            outd = dc.run(cts)
+            walld = time.perf_counter() - t0
+            dc.close()
+            gotd = R.Cryptor.decrypto(R.TLWE, s0, outd)
+            res[name] = {"gates": dc.gates, "levels": dc.levels, "wall_seconds": walld,
+                         "correct": bool(sum(int(b) << i for i, b in enumerate(gotd)) == x + y)}
     if rank == 0:
         txt = json.dumps(res, indent=1)
         if args.out:
