@@ -239,8 +239,9 @@ def run_gpu(args):
     hx.copy_(dx); hy.copy_(dy)
     dout = torch.empty((BATCH, CT_WORDS), dtype=torch.int32, device=dev)
 
-    streams = [stream, torch.cuda.Stream(device=dev)]   # consecutive steps alternate streams: independent batches overlap
-    douts = [dout, torch.empty_like(dout)]
+    NSTREAMS = max(1, int(os.environ.get("BENCH_STREAMS", "2")))
+    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(NSTREAMS - 1)]   # consecutive steps rotate over the streams:
+    douts = [dout] + [torch.empty_like(dout) for _ in range(NSTREAMS - 1)]               # independent batches overlap on the device
 
     def step_device(it, st=None, o_buf=None):
         o = (it % NROT) * BATCH
@@ -282,17 +283,20 @@ def run_gpu(args):
     join = torch.cuda.Event()
     barrier(); torch.cuda.synchronize()
     e0.record(stream)
-    streams[1].wait_event(e0)
+    for s_ in streams[1:]:
+        s_.wait_event(e0)
     for it in range(args.steps):
-        step_device(args.warmup + it, streams[it % 2], douts[it % 2])
-    join.record(streams[1])
-    stream.wait_event(join)
+        step_device(args.warmup + it, streams[it % NSTREAMS], douts[it % NSTREAMS])
+    for s_ in streams[1:]:
+        join = torch.cuda.Event()
+        join.record(s_)
+        stream.wait_event(join)
     e1.record(stream)
     torch.cuda.synchronize(); barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.stats()["kernel_launches"] - launches0
     o = ((args.warmup + args.steps - 1) % NROT) * BATCH
-    got = R.Cryptor.decrypto(R.TLWE, s0, douts[(args.steps - 1) % 2].cpu().numpy().view(np.uint32))
+    got = R.Cryptor.decrypto(R.TLWE, s0, douts[(args.steps - 1) % NSTREAMS].cpu().numpy().view(np.uint32))
     wrong += int((got != (1 - (bx[o:o + BATCH] & by[o:o + BATCH]))).sum())
 
     # ---- B = 1 latency (SURVEY 8d "latency metric"): one gate per call, median of 30 after 3 warm-ups, CUDA events ----
@@ -362,7 +366,7 @@ def run_gpu(args):
                        "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world} (independent gate shards, keys replicated)",
                        "l2": f"inputs rotate over {NROT} batches ({NROT * BATCH * 2 * CT_WORDS * 4 / 1e6:.0f} MB) > L2; keys "
                              f"{(BK_BYTES_DEVICE + KSK_BYTES) / 1e6:.0f} MB > L2; no explicit flush",
-                       "gates_per_cta": st["gates_per_cta"], "streams": 2,
+                       "gates_per_cta": st["gates_per_cta"], "streams": NSTREAMS,
                        "key_slices": int(os.environ.get("TFHE_B200_KEY_SLICES", "3")) if os.environ.get("TFHE_B200_KEY_SLICES") in ("2", "3") else 3},
             "value_serial": gates / (serial_ms * 1e-3),
             "latency_us_per_gate_amortised": 1e3 * ms / args.steps / BATCH,
