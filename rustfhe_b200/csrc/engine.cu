@@ -29,6 +29,7 @@ struct Slot {
     cudaStream_t stream = nullptr;   // internal stream, used by the host-pointer entry points
     cudaEvent_t done = nullptr;
     bool pending = false;
+    cudaStream_t last = nullptr;     // the stream `done` was last recorded on
     uint16_t* ksdig = nullptr; size_t ksdig_cap = 0;
     uint32_t* tmp[4] = {nullptr, nullptr, nullptr, nullptr}; size_t tmp_cap[4] = {0, 0, 0, 0};
     uint32_t* scratch = nullptr; size_t scratch_cap = 0;   // hom_mux intermediates / transformed TRGSWs of step-level calls
@@ -59,6 +60,8 @@ struct tfhe_b200_ctx {
     int gates_per_cta = 1;
     int variant = 7;  // blind-rotate launch shape, see launch_blind_rotate
     int key_slices = 3;  // 3 = exact in the worst case (default); 2 = opt-in fast mode (tfhe_b200_set_key_slices)
+    int deal_fixed = -1;  // how a full batch is cut into CTAs: 0 = dealt evenly over whole waves (best for a batch running alone),
+                          // 1 = 4-gate CTAs only (best when batches on other streams back-fill the last wave), -1 = decide per call
     int ks_variant = 2;  // key-switch kernel: 2 = rows staged in shared memory, one warp per gate; 1 = register tiles
     std::string err;
 };
@@ -101,6 +104,7 @@ static int slot_acquire(tfhe_b200_ctx* ctx, cudaStream_t* st, bool own_stream, S
 static int slot_release(tfhe_b200_ctx* ctx, Slot* s, cudaStream_t st) {
     CK(cudaEventRecord(s->done, st));
     s->pending = true;
+    s->last = st;
     return TFHE_B200_OK;
 }
 
@@ -172,6 +176,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = set_smem(blind_rotate_kernel<4, true, 1, 2>, 4)) != cudaSuccess) return bail("smem attr", e);
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_KS_VARIANT")) ctx->ks_variant = atoi(v);
+    if (const char* v = getenv("TFHE_B200_DEAL_FIXED")) ctx->deal_fixed = atoi(v);
     if (const char* v = getenv("TFHE_B200_KEY_SLICES")) ctx->key_slices = (atoi(v) == 2) ? 2 : 3;
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (keyswitch2)", e);
@@ -331,6 +336,19 @@ static void op_coeffs(int op, uint32_t mu, int32_t* c0, int32_t* c1, uint32_t* c
     default: *c0 = 1; *c1 = 0; *cb = 0; *two = false; break;
     }
 }
+// Is a batch issued earlier on ANOTHER stream still running?  Then the device is shared between batches and whatever a
+// batch leaves idle in its last wave is taken by the next one: cut the batch into full 4-gate CTAs (measured at 1024 gates,
+// two streams: 60.2 k gates/s against 57.3 k dealt evenly; alone it is the other way round, 52.3 k against 56.4 k).
+static bool batches_overlap(tfhe_b200_ctx* ctx, cudaStream_t st) {
+    if (ctx->deal_fixed >= 0) return ctx->deal_fixed != 0;
+    for (Slot& s : ctx->slots)
+        if (s.pending && s.last != st) {
+            const cudaError_t q = cudaEventQuery(s.done);
+            if (q == cudaErrorNotReady) return true;
+            if (q == cudaSuccess) s.pending = false;   // complete: nothing to wait for any more
+        }
+    return false;
+}
 static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, bool timed) {
     a.bkdev = ctx->bkdev; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.ns = ctx->key_slices;
     if (a.split <= 0) a.split = a.B;
@@ -364,7 +382,7 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         // kernel and 5.8 ms for 1-gate CTAs compiled for 168 registers)
         blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
     } else if (full) {   // default (variant 7)
-        const unsigned grid = deal(4);
+        const unsigned grid = batches_overlap(ctx, st) ? fixed(4) : deal(4);
         if (a.ns == 2) blind_rotate_kernel<4, false, 1, 2><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
         else blind_rotate_kernel<4, false, 1, 3><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
     } else if (3 * a.B <= (long)ctx->sm_count && variant != 9) {   // latency shape: one gate on a cluster of two SMs (measured
