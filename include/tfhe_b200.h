@@ -90,7 +90,9 @@ int tfhe_b200_reset_stats(tfhe_b200_ctx* ctx);
 
 /* ---- keys: BootstrappingKey::new / KeySwitchingKey::new products (tfhe.rs:119-126, tlwe.rs:247-277) ----
  * load_bk transforms the torus-domain key on the device into the NTT domain (replaces TRGSWRepF::from,
- * trgsw.rs:68-76).  The *_device variants read device memory (e.g. the destination of an NCCL broadcast). */
+ * trgsw.rs:68-76).  The *_device variants read device memory (e.g. the destination of an NCCL broadcast) and are
+ * asynchronous on the caller's stream; batches issued afterwards wait for the load, whatever stream they run on.  Loading
+ * keys while batches are still in flight is the caller's race: tfhe_b200_sync first. */
 int tfhe_b200_load_bk(tfhe_b200_ctx* ctx, const uint32_t* bk_host);
 int tfhe_b200_load_bk_device(tfhe_b200_ctx* ctx, const uint32_t* bk_dev, void* stream);
 int tfhe_b200_load_ksk(tfhe_b200_ctx* ctx, const uint32_t* ksk_host);

@@ -52,6 +52,8 @@ struct tfhe_b200_ctx {
     static constexpr int NSLOT = 4;
     Slot slots[NSLOT];
     unsigned next_slot = 0;
+    cudaEvent_t keys_ev = nullptr;           // recorded behind the last asynchronous key load (load_*_device on a caller's stream);
+    bool keys_pending = false;               // every later batch waits for it, whatever stream it is issued on
     static constexpr int RING = 64;          // event ring: per-launch device times of the last RING timed gate batches
     cudaEvent_t ev[RING][4] = {};
     uint64_t timed = 0;
@@ -98,7 +100,17 @@ static int slot_acquire(tfhe_b200_ctx* ctx, cudaStream_t* st, bool own_stream, S
     Slot& s = ctx->slots[ctx->next_slot++ % tfhe_b200_ctx::NSLOT];
     if (own_stream) *st = s.stream;
     if (s.pending) CK(cudaStreamWaitEvent(*st, s.done, 0));
+    if (ctx->keys_pending) {
+        if (cudaEventQuery(ctx->keys_ev) == cudaSuccess) ctx->keys_pending = false;
+        else CK(cudaStreamWaitEvent(*st, ctx->keys_ev, 0));
+    }
     *out = &s;
+    return TFHE_B200_OK;
+}
+static int keys_loaded_on(tfhe_b200_ctx* ctx, cudaStream_t st) {
+    if (ctx->keys_pending) CK(cudaStreamWaitEvent(st, ctx->keys_ev, 0));   // chain: the new record also covers an earlier load
+    CK(cudaEventRecord(ctx->keys_ev, st));
+    ctx->keys_pending = true;
     return TFHE_B200_OK;
 }
 static int slot_release(tfhe_b200_ctx* ctx, Slot* s, cudaStream_t st) {
@@ -155,6 +167,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
         if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
     for (auto& slot : ctx->ev) for (auto& ev : slot) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->keys_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->bkdev, (size_t)LWE_N * BK_STEP_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc(bk)", e);
     if ((e = cudaMalloc(&ctx->kskdev, (size_t)1024 * 8 * 3 * (LWE_N + 1) * 4)) != cudaSuccess) return bail("cudaMalloc(ksk)", e);
     if ((e = cudaMalloc(&ctx->bk_torus, BK_TORUS_BYTES)) != cudaSuccess) return bail("cudaMalloc(bk_torus)", e);
@@ -196,6 +209,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (auto& slot : ctx->ev) for (auto ev : slot) if (ev) cudaEventDestroy(ev);
+    if (ctx->keys_ev) cudaEventDestroy(ctx->keys_ev);
     delete ctx;
     return TFHE_B200_OK;
 }
@@ -293,7 +307,7 @@ int tfhe_b200_load_bk_device(tfhe_b200_ctx* ctx, const uint32_t* bk_dev, void* s
     if (bk_dev != ctx->bk_torus) CK(cudaMemcpyAsync(ctx->bk_torus, bk_dev, BK_TORUS_BYTES, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     RC(transform_keys(ctx, ctx->bk_torus, ctx->bkdev, LWE_N, (cudaStream_t)stream));
     ctx->have_bk = true;
-    return TFHE_B200_OK;
+    return keys_loaded_on(ctx, (cudaStream_t)stream);
 }
 int tfhe_b200_load_bk(tfhe_b200_ctx* ctx, const uint32_t* bk_host) {
     if (!ctx || !bk_host) return fail(ctx, TFHE_B200_ERR_PARAM, "load_bk: null argument");
@@ -309,7 +323,7 @@ int tfhe_b200_load_ksk_device(tfhe_b200_ctx* ctx, const uint32_t* ksk_dev, void*
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->kskdev, ksk_dev, (size_t)1024 * 8 * 3 * (LWE_N + 1) * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     ctx->have_ksk = true;
-    return TFHE_B200_OK;
+    return keys_loaded_on(ctx, (cudaStream_t)stream);
 }
 int tfhe_b200_load_ksk(tfhe_b200_ctx* ctx, const uint32_t* ksk_host) {
     if (!ctx || !ksk_host) return fail(ctx, TFHE_B200_ERR_PARAM, "load_ksk: null argument");
