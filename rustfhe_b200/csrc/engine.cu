@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../../include/tfhe_b200.h"
@@ -62,6 +63,7 @@ struct tfhe_b200_ctx {
     int gates_per_cta = 1;
     int variant = 7;  // blind-rotate launch shape, see launch_blind_rotate
     int key_slices = 3;  // 3 = exact in the worst case (default); 2 = opt-in fast mode (tfhe_b200_set_key_slices)
+    int pair_max = 0;     // largest batch that runs on 2-SM clusters (set at create: #SMs / 2)
     int deal_fixed = -1;  // how a full batch is cut into CTAs: 0 = dealt evenly over whole waves (best for a batch running alone),
                           // 1 = 4-gate CTAs only (best when batches on other streams back-fill the last wave), -1 = decide per call
     int ks_variant = 2;  // key-switch kernel: 2 = rows staged in shared memory, one warp per gate; 1 = register tiles
@@ -190,6 +192,8 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_KS_VARIANT")) ctx->ks_variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_DEAL_FIXED")) ctx->deal_fixed = atoi(v);
+    ctx->pair_max = ctx->sm_count / 2;
+    if (const char* v = getenv("TFHE_B200_PAIR_MAX")) ctx->pair_max = std::min(atoi(v), ctx->sm_count / 2);
     if (const char* v = getenv("TFHE_B200_KEY_SLICES")) ctx->key_slices = (atoi(v) == 2) ? 2 : 3;
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (keyswitch2)", e);
@@ -399,12 +403,13 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         const unsigned grid = batches_overlap(ctx, st) ? fixed(4) : deal(4);
         if (a.ns == 2) blind_rotate_kernel<4, false, 1, 2><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
         else blind_rotate_kernel<4, false, 1, 3><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
-    } else if (3 * a.B <= (long)ctx->sm_count && variant != 9) {   // latency shape: one gate on a cluster of two SMs (measured
-                                                                   // better than one CTA per gate up to about #SMs/3 gates)
+    } else if (a.B <= (long)ctx->pair_max && variant != 9) {   // latency shape: one gate on a cluster of two SMs, as long as
+                                                                // the clusters fit in one wave (74 gates: 3.66 ms against 3.92 ms
+                                                                // with one CTA per gate; TFHE_B200_PAIR_MAX moves the limit)
         a.cta_base = 1; a.cta_rem = 0;
         ctx->gates_per_cta = 1;
-        if (a.ns == 2) blind_rotate_pair_kernel<2><<<(unsigned)(2 * a.B), PAIR_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
-        else blind_rotate_pair_kernel<3><<<(unsigned)(2 * a.B), PAIR_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
+        if (a.ns == 2) blind_rotate_pair_kernel<2><<<(unsigned)(2 * a.B), PAIR_LAUNCH_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
+        else blind_rotate_pair_kernel<3><<<(unsigned)(2 * a.B), PAIR_LAUNCH_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
     } else {
         if (a.ns == 2) blind_rotate_kernel<1, false, 1, 2><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
         else blind_rotate_kernel<1, false, 1><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
