@@ -89,6 +89,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+// one elected lane: expect `bytes` on the mbarrier and start a bulk (TMA) copy global -> shared that completes on it
+__device__ __forceinline__ void bulk_fetch(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -261,8 +268,9 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
 namespace cg = cooperative_groups;
 constexpr int PAIR_THREADS = 96;                         // the three working warps
 constexpr int PAIR_LAUNCH_THREADS = PAIR_THREADS + 32;   // + the fence warp
-constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 3 * TILE_WORDS /*own spectra*/ + 2 * 3 * TILE_WORDS /*peer spectra x2*/ + 320 +
+constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 3 * TILE_WORDS /*own spectra*/ + 2 * 3 * TILE_WORDS /*peer spectra x2*/ + 336 +
                                 2 * 3 * (int)BK_SLAB_WORDS /*key slabs of this and the next step, one per warp*/;
+static_assert((TW_SMEM_WORDS + 2048 + 9 * TILE_WORDS + 336) % 4 == 0 && (BK_SLAB_WORDS * 4) % 16 == 0, "bulk copies need 16-byte alignment");
 template <int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS, 1) blind_rotate_pair_kernel(const BrArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -278,23 +286,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS,
     uint32_t* peer = own + 3 * TILE_WORDS;     // [2][3] tiles: spectra of the other polynomial, written by the other CTA
     uint16_t* abar = reinterpret_cast<uint16_t*>(peer + 6 * TILE_WORDS);
     uint64_t* macdone = reinterpret_cast<uint64_t*>(peer + 6 * TILE_WORDS + 318);
-    uint32_t* slabs = peer + 6 * TILE_WORDS + 320;              // [2][3][BK_SLAB_WORDS]: warp-private, filled one step ahead by cp.async
+    uint64_t* slabbar = reinterpret_cast<uint64_t*>(peer + 6 * TILE_WORDS + 320);   // [2][3]: one per slab buffer
+    uint32_t* slabs = peer + 6 * TILE_WORDS + 336;              // [2][3][BK_SLAB_WORDS]: warp-private, filled one step ahead
     uint32_t* remote = cluster.map_shared_rank(peer, pw ^ 1);   // where MY spectra go in the other CTA
-    // the key slab of step i for this warp: 48 x 512 B, copied asynchronously a whole step ahead so that no L2 round trip is
-    // left on the critical path of a lone warp
+    // the key slab of step i for this warp (24 KB, contiguous): ONE bulk (TMA) copy issued by one lane a whole step ahead,
+    // completing on the buffer's mbarrier, so that no L2 round trip is left on the critical path of a lone warp (48 cp.async
+    // per lane were measured 4-5 % slower from 2 gates up: their issue alone took 4 % of a step)
     auto slab_fetch = [&](int step) {
-        if (kw >= NS) { asm volatile("cp.async.commit_group;" ::: "memory"); return; }
-        const uint4* src = reinterpret_cast<const uint4*>(a.bkdev + (size_t)step * bk_step_words(NS) + (size_t)(pw * NS + kw) * BK_SLAB_WORDS) + lane;
-        const uint32_t dst = smem_u32(slabs + ((step & 1) * 3 + kw) * BK_SLAB_WORDS) + 16u * lane;
-#pragma unroll
-        for (int t = 0; t < 48; t++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u * t), "l"(src + 32 * t) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (kw >= NS || lane != 0) return;
+        bulk_fetch(slabs + ((step & 1) * 3 + kw) * BK_SLAB_WORDS, a.bkdev + (size_t)step * bk_step_words(NS) + (size_t)(pw * NS + kw) * BK_SLAB_WORDS,
+                   (uint32_t)BK_SLAB_WORDS * 4u, slabbar + (step & 1) * 3 + kw);
+    };
+    auto slab_wait = [&](int step) {
+        if (kw < NS) mbar_wait(slabbar + (step & 1) * 3 + kw, (uint32_t)(step >> 1) & 1u);
     };
 
     uint32_t* dtab = smem + 2 * 32 * TWB_STRIDE;
     for (int t = tid; t < 32 * TWB_STRIDE; t += PAIR_LAUNCH_THREADS) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
     if (tid < DIGIT_TAB_WORDS) dtab[tid] = g_digit_tab.v[tid];
-    if (tid == 0) mbar_init(macdone, 3);
+    if (tid == 0) {
+        mbar_init(macdone, 3);
+        for (int k = 0; k < 6; k++) mbar_init(slabbar + k, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     {   // prologue (both CTAs read the inputs): gate pre-combination, rounding, acc_0 of the own polynomial
         uint32_t* lin = own;
         const bool second = gate >= a.split;
@@ -361,8 +375,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS,
         asm volatile("fence.acq_rel.cta;" ::: "memory");
         bar_arrive(3, PAIR_LAUNCH_THREADS);
         cluster_arrive_relaxed();
-        if (i + 1 < a.nsteps) slab_fetch(i + 1); else asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this step's slab (committed one step ago) has landed
+        if (i + 1 < a.nsteps) slab_fetch(i + 1);
+        slab_wait(i);   // this step's slab (requested one step ago) has landed
         {
             __syncwarp();
             const uint32_t* slab = slabs + ((i & 1) * 3 + kw) * BK_SLAB_WORDS;
