@@ -96,6 +96,20 @@ __device__ __forceinline__ void bulk_fetch(void* dst, const void* src, uint32_t 
                  "r"(bytes), "r"(smem_u32(b))
                  : "memory");
 }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {   // shared::cluster address of `saddr` in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// one elected lane: bulk copy shared (this CTA) -> shared of another CTA of the cluster, counting its bytes on THAT CTA's mbarrier
+__device__ __forceinline__ void bulk_send(uint32_t dst_cluster, const void* src, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+                 "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -266,11 +280,12 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
 // stores into its peer's shared memory (distributed shared memory, double buffered) before ONE cluster barrier.
 // =====================================================================================================
 namespace cg = cooperative_groups;
-constexpr int PAIR_THREADS = 96;                         // the three working warps
-constexpr int PAIR_LAUNCH_THREADS = PAIR_THREADS + 32;   // + the fence warp
-constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 3 * TILE_WORDS /*own spectra*/ + 2 * 3 * TILE_WORDS /*peer spectra x2*/ + 336 +
-                                2 * 3 * (int)BK_SLAB_WORDS /*key slabs of this and the next step, one per warp*/;
-static_assert((TW_SMEM_WORDS + 2048 + 9 * TILE_WORDS + 336) % 4 == 0 && (BK_SLAB_WORDS * 4) % 16 == 0, "bulk copies need 16-byte alignment");
+constexpr int PAIR_THREADS = 96;
+constexpr int PAIR_LAUNCH_THREADS = PAIR_THREADS;
+constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 2 * 3 * TILE_WORDS /*own spectra x2*/ + 2 * 3 * TILE_WORDS /*peer spectra x2*/ +
+                                336 + 2 * 3 * (int)BK_SLAB_WORDS /*key slabs of this and the next step, one per warp*/;
+static_assert((TW_SMEM_WORDS + 2048) % 4 == 0 && TILE_WORDS % 4 == 0 && (BK_SLAB_WORDS * 4) % 16 == 0, "bulk copies need 16-byte alignment");
+static_assert(PAIR_SMEM_WORDS * 4 + 1024 <= 227 * 1024, "cluster kernel exceeds the shared memory of an SM");
 template <int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS, 1) blind_rotate_pair_kernel(const BrArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -282,13 +297,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS,
     uint32_t* twI = smem + 32 * TWB_STRIDE;
     uint32_t* acc = smem + TW_SMEM_WORDS;
     uint32_t* U = acc + 1024;
-    uint32_t* own = U + 1024;            // [3] tiles: spectra of this CTA's polynomial; plane kw doubles as transpose scratch
-    uint32_t* peer = own + 3 * TILE_WORDS;     // [2][3] tiles: spectra of the other polynomial, written by the other CTA
+    uint32_t* own2 = U + 1024;           // [2][3] tiles: spectra of this CTA's polynomial, by step parity (the tile of the other
+                                         // parity is the transpose scratch of the inverse transform)
+    uint32_t* peer = own2 + 6 * TILE_WORDS;    // [2][3] tiles: spectra of the other polynomial, copied in by the other CTA
     uint16_t* abar = reinterpret_cast<uint16_t*>(peer + 6 * TILE_WORDS);
-    uint64_t* macdone = reinterpret_cast<uint64_t*>(peer + 6 * TILE_WORDS + 318);
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(peer + 6 * TILE_WORDS + 332);      // [2]: the peer's spectra of a step have landed
     uint64_t* slabbar = reinterpret_cast<uint64_t*>(peer + 6 * TILE_WORDS + 320);   // [2][3]: one per slab buffer
     uint32_t* slabs = peer + 6 * TILE_WORDS + 336;              // [2][3][BK_SLAB_WORDS]: warp-private, filled one step ahead
-    uint32_t* remote = cluster.map_shared_rank(peer, pw ^ 1);   // where MY spectra go in the other CTA
+    const uint32_t remote = map_to_cta(smem_u32(peer), (uint32_t)(pw ^ 1));    // where MY spectra go in the other CTA
+    const uint32_t remote_bar = map_to_cta(smem_u32(xbar), (uint32_t)(pw ^ 1));
     // the key slab of step i for this warp (24 KB, contiguous): ONE bulk (TMA) copy issued by one lane a whole step ahead,
     // completing on the buffer's mbarrier, so that no L2 round trip is left on the critical path of a lone warp (48 cp.async
     // per lane were measured 4-5 % slower from 2 gates up: their issue alone took 4 % of a step)
@@ -305,12 +322,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS,
     for (int t = tid; t < 32 * TWB_STRIDE; t += PAIR_LAUNCH_THREADS) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
     if (tid < DIGIT_TAB_WORDS) dtab[tid] = g_digit_tab.v[tid];
     if (tid == 0) {
-        mbar_init(macdone, 3);
         for (int k = 0; k < 6; k++) mbar_init(slabbar + k, 1);
+        mbar_init(xbar, 1);
+        mbar_init(xbar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // prologue (both CTAs read the inputs): gate pre-combination, rounding, acc_0 of the own polynomial
-        uint32_t* lin = own;
+        uint32_t* lin = own2;
         const bool second = gate >= a.split;
         const long gsrc = second ? gate - a.split : gate;
         const uint32_t* q0 = second ? a.in0b : a.in0;
@@ -336,83 +354,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS,
     }
     cluster.sync();   // both CTAs are set up (mbarriers, tables) before the first remote store
     if (a.nsteps > 0) slab_fetch(0);
-    uint32_t mac_parity = 0;
-    // The release side of the cluster barrier (SASS: MEMBAR.ALL.GPU + ERRBAR, measured 18 % of a step when every working
-    // warp pays it) is delegated to a fourth warp on the otherwise idle sub-partition: a working warp waits for the
-    // acknowledgement of its own remote stores (fence at CTA scope), signals a named barrier and arrives relaxed; the
-    // fence warp joins that barrier and arrives with release semantics at cluster scope (cumulative: it covers the stores
-    // it synchronised with).  Measured 3.22 ms against 3.52 ms per gate on the same box.
-    if (kw == 3) {
+    // Exchange of the digit spectra, one step: every working warp copies its finished 4.5 KB tile into the peer's shared
+    // memory with ONE bulk copy (shared::cta -> shared::cluster) that counts its bytes on the PEER's mbarrier; the peer waits
+    // on that mbarrier only.  No remote stores, no acknowledgements, no fence and no cluster barrier (SASS of
+    // barrier.cluster.arrive.release: MEMBAR.ALL.GPU + ERRBAR, 18 % of a step when every warp paid it, 9 % of waiting left
+    // when a fourth warp paid it).  Buffers are reused every other step; that is safe without a reverse signal: the peer
+    // sends the spectra of step i only after it has received mine of step i-1, i.e. after my step i-2 is consumed.
 #pragma unroll 1
-        for (int i = 0; i < a.nsteps; i++) {
-            bar_sync(3, PAIR_LAUNCH_THREADS);
-            cluster_arrive_release();
-            cluster_wait_acquire();
-        }
-    }
-    const int nsteps_work = kw == 3 ? 0 : a.nsteps;
-#pragma unroll 1
-    for (int i = 0; i < nsteps_work; i++) {
+    for (int i = 0; i < a.nsteps; i++) {
+        uint32_t* own = own2 + (i & 1) * 3 * TILE_WORDS;
         uint32_t* S = own + kw * TILE_WORDS;
+        uint32_t* T = own2 + ((i + 1) & 1) * 3 * TILE_WORDS + kw * TILE_WORDS;   // scratch: last step's tile, long since consumed
         uint32_t x[32];
         p1u<true>(lane, acc, (uint32_t)abar[i], a.mask, kw, U);
         bar_sync(1, PAIR_THREADS);
+        if (tid == 0) mbar_expect_tx(xbar + (i & 1), 3u * TILE_WORDS * 4u);   // arm this step's arrival of the peer's three tiles
         p1a(lane, U, kw, S, dtab);
         __syncwarp();
         fwd_rows(lane, S, twF, x);
-        {
-            uint32_t* R = remote + ((i & 1) * 3 + kw) * TILE_WORDS;
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const uint4 v = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-                *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = v;
-                *reinterpret_cast<uint4*>(R + swz_chunk(lane, q)) = v;
-            }
-        }
-        // split cluster barrier: arrive (my remote stores are acknowledged; the fence warp releases them), start the copy of
-        // the NEXT step's key slab, then wait (acquire).  (A point-to-point handshake on cluster-scope mbarriers was
-        // measured 10 % slower than this barrier.)
-        asm volatile("fence.acq_rel.cta;" ::: "memory");
-        bar_arrive(3, PAIR_LAUNCH_THREADS);
-        cluster_arrive_relaxed();
+        for (int q = 0; q < 8; q++) *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my tile rows are visible to the copy engine
+        __syncwarp();
+        if (lane == 0) bulk_send(remote + (uint32_t)(((i & 1) * 3 + kw) * TILE_WORDS) * 4u, S, (uint32_t)TILE_WORDS * 4u, remote_bar + 8u * (i & 1));
         if (i + 1 < a.nsteps) slab_fetch(i + 1);
         slab_wait(i);   // this step's slab (requested one step ago) has landed
         {
-            __syncwarp();
             const uint32_t* slab = slabs + ((i & 1) * 3 + kw) * BK_SLAB_WORDS;
             const uint32_t* P = peer + (i & 1) * 3 * TILE_WORDS;
-            bar_sync(2, PAIR_THREADS);   // this CTA's own three spectra are complete (local barrier; the cluster one is still pending)
+            bar_sync(2, PAIR_THREADS);   // this CTA's own three spectra are complete
             if (kw < NS) {
-                // the key rows that meet this CTA's own spectra need nothing from the peer: accumulate them while the cluster
-                // barrier is pending, then wait and add the rows of the peer's spectra
+                // the key rows that meet this CTA's own spectra need nothing from the peer: accumulate them while the peer's
+                // tiles are in flight, then wait and add the rows of the peer's spectra
                 uint64_t mac[32];
                 p2a_mac_part(lane, slab, own, pw == 0 ? 0 : 3, mac, true);
-                cluster_wait_acquire();   // the peer's spectra are here; the peer has finished the previous step's MAC
+                mbar_wait(xbar + (i & 1), (uint32_t)(i >> 1) & 1u);
                 p2a_mac_part(lane, slab, P, pw == 0 ? 3 : 0, mac, false);
                 p2a_mac_finish(lane, mac, twI, x);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(macdone);
                 gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
                 gs_norm<2>(x);
-                mbar_wait(macdone, mac_parity);
 #pragma unroll
                 for (int q = 0; q < 8; q++)
-                    *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                    *reinterpret_cast<uint4*>(T + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
                 __syncwarp();
-                p2b(lane, S, kw, x, NS);
+                p2b(lane, T, kw, x, NS);
                 const uint32_t A = smem_u32(acc + lane);
 #pragma unroll
                 for (int r = 0; r < 32; r++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(A + 128u * r), "r"(x[r]) : "memory");
-            } else {
-                cluster_wait_acquire();
-                if (lane == 0) mbar_arrive(macdone);
             }
-            mac_parity ^= 1u;
         }
         bar_sync(1, PAIR_THREADS);
     }
     // ---- epilogue: CTA 0 owns b, CTA 1 owns a ----
-    if (PAIR_LAUNCH_THREADS > PAIR_THREADS) __syncthreads();   // the fence warp left its loop before the last accumulation
     if (a.trlwe_out) {
         uint32_t* dst = a.trlwe_out + (size_t)gate * 2048 + pw * 1024;
         for (int k = tid; k < 1024; k += PAIR_LAUNCH_THREADS) dst[k] = acc[k];
