@@ -282,6 +282,8 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     join = torch.cuda.Event()
     barrier(); torch.cuda.synchronize()
+    if NSTREAMS > 1:
+        eng.set_batch_overlap(1)   # batches are kept in flight on several streams: cut every one of them into full CTAs
     e0.record(stream)
     for s_ in streams[1:]:
         s_.wait_event(e0)
@@ -295,6 +297,7 @@ def run_gpu(args):
     torch.cuda.synchronize(); barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.stats()["kernel_launches"] - launches0
+    eng.set_batch_overlap(-1)
     o = ((args.warmup + args.steps - 1) % NROT) * BATCH
     got = R.Cryptor.decrypto(R.TLWE, s0, douts[(args.steps - 1) % NSTREAMS].cpu().numpy().view(np.uint32))
     wrong += int((got != (1 - (bx[o:o + BATCH] & by[o:o + BATCH]))).sum())
@@ -327,6 +330,7 @@ def run_gpu(args):
             raise RuntimeError(lib.tfhe_b200_last_error(eng._ctx))
 
     step_host(0); eng.sync()
+    eng.set_batch_overlap(1)       # the asynchronous calls below keep up to four batches in flight
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for it in range(args.steps):

@@ -85,6 +85,14 @@ int tfhe_b200_set_decomp_mask(tfhe_b200_ctx* ctx, uint32_t mask);
 /* Key slices per bootstrapping-key polynomial: 3 (default) = exact external product in the worst case; 2 = opt-in fast mode
  * (one third less work per CMUX; exact with probability 1 - 3e-16 per gate over the key's masks) */
 int tfhe_b200_set_key_slices(tfhe_b200_ctx* ctx, int slices);
+/* How a full batch (more than two gates per SM) is cut into CTAs.  AUTO (default): decided per call -- if an earlier batch is
+ * still running on another stream the batch is cut into 4-gate CTAs only (the next batch back-fills the last wave), otherwise
+ * it is dealt evenly over whole waves (best for a batch that has the device to itself).  STREAMED / LONE force either; a
+ * caller that keeps several batches in flight sets STREAMED so that the first batch of a burst is cut the same way. */
+#define TFHE_B200_OVERLAP_AUTO (-1)
+#define TFHE_B200_OVERLAP_LONE 0
+#define TFHE_B200_OVERLAP_STREAMED 1
+int tfhe_b200_set_batch_overlap(tfhe_b200_ctx* ctx, int mode);
 int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out); /* waits for the recorded events */
 int tfhe_b200_reset_stats(tfhe_b200_ctx* ctx);
 

@@ -53,6 +53,7 @@ extern "C" {
     pub fn tfhe_b200_sync(ctx: *mut Ctx) -> c_int;
     pub fn tfhe_b200_gate_batch_mixed(ctx: *mut Ctx, ops: *const u8, in0: *const u32, in1: *const u32, out: *mut u32, b: usize) -> c_int;
     pub fn tfhe_b200_set_key_slices(ctx: *mut Ctx, slices: c_int) -> c_int;
+    pub fn tfhe_b200_set_batch_overlap(ctx: *mut Ctx, mode: c_int) -> c_int;
     pub fn tfhe_b200_reserve(ctx: *mut Ctx, max_batch: usize) -> c_int;
     pub fn tfhe_b200_bootstrap_batch(ctx: *mut Ctx, input: *const u32, out: *mut u32, b: usize) -> c_int;
     pub fn tfhe_b200_bootstrap_lv1_batch(ctx: *mut Ctx, input: *const u32, out_lwe1: *mut u32, b: usize) -> c_int;

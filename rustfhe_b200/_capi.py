@@ -18,7 +18,7 @@ KSK_WORDS = N * KS_T * 3 * (n + 1)
 # every symbol include/tfhe_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "tfhe_b200_default_params", "tfhe_b200_ctx_create", "tfhe_b200_ctx_destroy", "tfhe_b200_last_error",
-    "tfhe_b200_set_decomp_mask", "tfhe_b200_set_key_slices", "tfhe_b200_get_stats", "tfhe_b200_reset_stats", "tfhe_b200_load_bk", "tfhe_b200_load_bk_device",
+    "tfhe_b200_set_decomp_mask", "tfhe_b200_set_key_slices", "tfhe_b200_set_batch_overlap", "tfhe_b200_get_stats", "tfhe_b200_reset_stats", "tfhe_b200_load_bk", "tfhe_b200_load_bk_device",
     "tfhe_b200_load_ksk", "tfhe_b200_load_ksk_device", "tfhe_b200_gate_batch", "tfhe_b200_gate_batch_device",
     "tfhe_b200_gate_batch_async", "tfhe_b200_sync", "tfhe_b200_reserve", "tfhe_b200_gate_batch_mixed",
     "tfhe_b200_gate_batch_mixed_device", "tfhe_b200_circuit_create", "tfhe_b200_circuit_run_device", "tfhe_b200_circuit_destroy",
@@ -66,6 +66,7 @@ def lib():
         "tfhe_b200_last_error": (C.c_char_p, [vp]),
         "tfhe_b200_set_decomp_mask": (i32, [vp, u32]),
         "tfhe_b200_set_key_slices": (i32, [vp, i32]),
+        "tfhe_b200_set_batch_overlap": (i32, [vp, i32]),
         "tfhe_b200_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "tfhe_b200_reset_stats": (i32, [vp]),
         "tfhe_b200_load_bk": (i32, [vp, vp]),

@@ -322,6 +322,10 @@ class DeviceEngine:
         """3 = exact in the worst case (default); 2 = opt-in fast mode."""
         self._ck(self._l.tfhe_b200_set_key_slices(self._ctx, slices))
 
+    def set_batch_overlap(self, mode):
+        """-1 = decide per call (default), 0 = batches run alone, 1 = several batches are kept in flight (include/tfhe_b200.h)."""
+        self._ck(self._l.tfhe_b200_set_batch_overlap(self._ctx, mode))
+
     def reset_stats(self):
         self._ck(self._l.tfhe_b200_reset_stats(self._ctx))
 

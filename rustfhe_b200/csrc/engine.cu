@@ -260,6 +260,12 @@ int tfhe_b200_set_key_slices(tfhe_b200_ctx* ctx, int slices) {
     return TFHE_B200_OK;
 }
 
+int tfhe_b200_set_batch_overlap(tfhe_b200_ctx* ctx, int mode) {
+    if (!ctx || mode < TFHE_B200_OVERLAP_AUTO || mode > TFHE_B200_OVERLAP_STREAMED) return fail(ctx, TFHE_B200_ERR_PARAM, "set_batch_overlap: -1, 0 or 1");
+    ctx->deal_fixed = mode;
+    return TFHE_B200_OK;
+}
+
 int tfhe_b200_sync(tfhe_b200_ctx* ctx) {
     if (!ctx) return TFHE_B200_ERR_PARAM;
     CK(cudaSetDevice(ctx->device));

@@ -352,6 +352,27 @@ def test_async_batches_overlap_and_match(engine, oracle, keys, rng):
     assert np.array_equal(ref, outs[2].numpy().view(np.uint32))
 
 
+def test_batch_overlap_modes_same_bits(engine, keys, rng):
+    """tfhe_b200_set_batch_overlap: the two ways a full batch is cut into CTAs (dealt evenly / 4-gate CTAs only) and the
+    per-call default give the same ciphertext bits; bad modes are rejected."""
+    from rustfhe_b200 import TfheError
+    B = 601
+    x = rng.integers(0, 2, B).astype(np.uint8)
+    y = rng.integers(0, 2, B).astype(np.uint8)
+    c0, c1 = keys.encrypt(x, 71000), keys.encrypt(y, 72000)
+    try:
+        outs = []
+        for mode in (-1, 0, 1):
+            engine.set_batch_overlap(mode)
+            outs.append(engine.gate_batch(3, c0, c1))   # XOR
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+        assert np.array_equal(keys.decrypt(outs[0]), x ^ y)
+        with pytest.raises(TfheError):
+            engine.set_batch_overlap(2)
+    finally:
+        engine.set_batch_overlap(-1)
+
+
 def test_fast_mode_two_key_slices(oracle, keys, rng):
     """Opt-in fast mode (tfhe_b200_set_key_slices(ctx, 2)): 16/16-bit key slices, exact with overwhelming probability instead of
     in the worst case.  On real keys and real accumulators the output ciphertexts are the same bits as
