@@ -131,8 +131,13 @@ __device__ __forceinline__ void gate_coeffs(int op, uint32_t mu, uint32_t& k0, u
     }
 }
 
-template <int G, bool EXTPROD, int MINB, int NS = 3>
+// SLAB_TMA (one gate per CTA only): every phase-2 warp keeps a private 24 KB buffer for its key slab; the slab of the NEXT
+// step is requested with one bulk (TMA) copy as soon as the warp has consumed the current one, so that with few warps per
+// sub-partition no L2 round trip is left inside the multiply-accumulate.
+constexpr size_t br_smem_bytes_tma() { return br_smem_bytes(1) + (size_t)WARPS_PER_GATE * BK_SLAB_WORDS * 4 + 64; }
+template <int G, bool EXTPROD, int MINB, int NS = 3, bool SLAB_TMA = false>
 __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel(const BrArgs a) {
+    static_assert(!SLAB_TMA || (G == 1 && !EXTPROD), "the slab buffers fit beside one gate only");
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* twF = smem;
     uint32_t* twI = smem + 32 * TWB_STRIDE;
@@ -160,6 +165,12 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     }
     for (int t = threadIdx.x; t < DIGIT_TAB_WORDS; t += blockDim.x) dtab[t] = g_digit_tab.v[t];
     if (tid6 == 0) mbar_init(macdone, WARPS_PER_GATE);
+    uint64_t* slabbar = reinterpret_cast<uint64_t*>(smem + TW_SMEM_WORDS + G * GATE_SMEM_WORDS) + w6;   // SLAB_TMA: [6] + slabs [6][BK_SLAB_WORDS]
+    uint32_t* myslab = smem + TW_SMEM_WORDS + G * GATE_SMEM_WORDS + 16 + w6 * BK_SLAB_WORDS;
+    if (SLAB_TMA && lane == 0) {
+        mbar_init(slabbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     // ---- prologue: gate pre-combination (tfhe.rs:27-71), rounding of (b, a) (tfhe.rs:97,107-108), acc_0 ----
     int nsteps = a.nsteps;
     if (EXTPROD) {
@@ -205,6 +216,8 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
     //                                    acc[poly] (red.shared, no output planes: 24 KB less shared memory per gate)
     const int bar_gate = 1 + gl, bar_poly = 1 + G + 2 * gl + pw;
     uint32_t mac_parity = 0;
+    if (SLAB_TMA && kw < NS && lane == 0 && nsteps > 0)
+        bulk_fetch(myslab, a.bkdev + (size_t)(pw * NS + kw) * BK_SLAB_WORDS, (uint32_t)BK_SLAB_WORDS * 4u, slabbar);
 #pragma unroll 1
     for (int i = 0; i < nsteps; i++) {
         const uint32_t* step_bk = a.bkdev + (EXTPROD ? (size_t)(gate % a.ntrgsw) : (size_t)i) * bk_step_words(NS);
@@ -219,7 +232,15 @@ __global__ void __launch_bounds__(G* THREADS_PER_GATE, MINB) blind_rotate_kernel
         bar_sync(bar_gate, THREADS_PER_GATE);
         uint32_t x[32];
         if (kw < NS) {   // phase 2: key slice kw of output poly pw (with two key slices the third warp of a polynomial only signals)
-            p2a_mac_head(lane, step_bk + (size_t)(pw * NS + kw) * BK_SLAB_WORDS, dh, dh + 3 * TILE_WORDS, twI, x);
+            if (SLAB_TMA) {
+                mbar_wait(slabbar, (uint32_t)i & 1u);   // this step's slab (requested a step ago) has landed
+                p2a_mac_head<true>(lane, myslab, dh, dh + 3 * TILE_WORDS, twI, x);
+                __syncwarp();                           // every lane has consumed the slab: request the next one into the same buffer
+                if (lane == 0 && i + 1 < nsteps)
+                    bulk_fetch(myslab, step_bk + bk_step_words(NS) + (size_t)(pw * NS + kw) * BK_SLAB_WORDS, (uint32_t)BK_SLAB_WORDS * 4u, slabbar);
+            } else {
+                p2a_mac_head(lane, step_bk + (size_t)(pw * NS + kw) * BK_SLAB_WORDS, dh, dh + 3 * TILE_WORDS, twI, x);
+            }
             if (EXTPROD) {   // plain external product: the result replaces acc; every warp clears its share before it arrives
 #pragma unroll
                 for (int r = kw; r < 32; r += 3) acc[pw * 1024 + 32 * r + lane] = 0u;

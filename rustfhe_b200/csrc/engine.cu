@@ -63,6 +63,7 @@ struct tfhe_b200_ctx {
     int gates_per_cta = 1;
     int variant = 7;  // blind-rotate launch shape, see launch_blind_rotate
     int key_slices = 3;  // 3 = exact in the worst case (default); 2 = opt-in fast mode (tfhe_b200_set_key_slices)
+    int slab_tma = 1;     // one gate per CTA: key slabs staged by bulk copies (TFHE_B200_SLAB_TMA=0: streamed from L2 by the warps)
     int pair_max = 0;     // largest batch that runs on 2-SM clusters (set at create: #SMs / 2)
     int deal_fixed = -1;  // how a full batch is cut into CTAs: 0 = dealt evenly over whole waves (best for a batch running alone),
                           // 1 = 4-gate CTAs only (best when batches on other streams back-fill the last wave), -1 = decide per call
@@ -186,6 +187,10 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = cudaFuncSetAttribute(blind_rotate_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_WORDS * 4)) != cudaSuccess)
         return bail("smem attr (pair)", e);
     if ((e = set_smem(blind_rotate_kernel<4, false, 1, 2>, 4)) != cudaSuccess) return bail("smem attr", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes_tma())) != cudaSuccess)
+        return bail("smem attr (slab tma)", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_kernel<1, false, 1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes_tma())) != cudaSuccess)
+        return bail("smem attr (slab tma)", e);
     if ((e = set_smem(blind_rotate_kernel<1, false, 1, 2>, 1)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<2, true, 1, 2>, 2)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<4, true, 1, 2>, 4)) != cudaSuccess) return bail("smem attr", e);
@@ -193,6 +198,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if (const char* v = getenv("TFHE_B200_KS_VARIANT")) ctx->ks_variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_DEAL_FIXED")) ctx->deal_fixed = atoi(v);
     ctx->pair_max = ctx->sm_count / 2;
+    if (const char* v = getenv("TFHE_B200_SLAB_TMA")) ctx->slab_tma = atoi(v);
     if (const char* v = getenv("TFHE_B200_PAIR_MAX")) ctx->pair_max = std::min(atoi(v), ctx->sm_count / 2);
     if (const char* v = getenv("TFHE_B200_KEY_SLICES")) ctx->key_slices = (atoi(v) == 2) ? 2 : 3;
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
@@ -416,6 +422,9 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         ctx->gates_per_cta = 1;
         if (a.ns == 2) blind_rotate_pair_kernel<2><<<(unsigned)(2 * a.B), PAIR_LAUNCH_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
         else blind_rotate_pair_kernel<3><<<(unsigned)(2 * a.B), PAIR_LAUNCH_THREADS, (size_t)PAIR_SMEM_WORDS * 4, st>>>(a);
+    } else if (ctx->slab_tma) {   // one gate per CTA, 254 registers, key slabs staged by bulk copies
+        if (a.ns == 2) blind_rotate_kernel<1, false, 1, 2, true><<<fixed(1), THREADS_PER_GATE, br_smem_bytes_tma(), st>>>(a);
+        else blind_rotate_kernel<1, false, 1, 3, true><<<fixed(1), THREADS_PER_GATE, br_smem_bytes_tma(), st>>>(a);
     } else {
         if (a.ns == 2) blind_rotate_kernel<1, false, 1, 2><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
         else blind_rotate_kernel<1, false, 1><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);

@@ -312,10 +312,10 @@ def test_cmux_exact_and_selects(engine, oracle, keys, rng):
         assert np.abs(err).max() < 2 ** 32 / 64, idx
 
 
-@pytest.mark.parametrize("B", [5, 49, 50, 149, 601])
+@pytest.mark.parametrize("B", [5, 49, 74, 75, 148, 149, 601])
 def test_launch_shapes_deterministic_and_exact(engine, oracle, keys, rng, B):
-    """Every launch shape (2-SM cluster per gate for B <= #SMs/3, one gate per CTA up to #SMs, 4-gate CTAs with uneven
-    dealing above) gives the same bits run after run (a shared-memory race would not) and matches the exact oracle on a
+    """Every launch shape (2-SM cluster per gate for B <= #SMs/2, one gate per CTA with bulk-copied key slabs up to #SMs, 1-gate
+    CTAs up to 2 #SMs, 4-gate CTAs with uneven dealing above) gives the same bits run after run (a shared-memory race would not) and matches the exact oracle on a
     sample; all decrypts are right."""
     x = rng.integers(0, 2, B).astype(np.uint8)
     y = rng.integers(0, 2, B).astype(np.uint8)

@@ -18,8 +18,10 @@ def main():
     seed = 0x5EED0001
     sk = R.SecretKeys.generate(seed)
     os.environ.pop("TFHE_B200_BR_VARIANT", None)
+    os.environ.pop("TFHE_B200_SLAB_TMA", None)
     pair = R.TFHE.new_on_device(sk.s_key_tlwelv0, sk.s_key_tlwelv1, seed).engine
     os.environ["TFHE_B200_BR_VARIANT"] = "9"
+    os.environ["TFHE_B200_SLAB_TMA"] = "0"     # the plain one-CTA-per-gate kernel (keys streamed from L2) is the reference shape
     solo = R.TFHE.new_on_device(sk.s_key_tlwelv0, sk.s_key_tlwelv1, seed).engine
     rng = np.random.default_rng(7)
     bad = 0
