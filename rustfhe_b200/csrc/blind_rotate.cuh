@@ -304,7 +304,7 @@ namespace cg = cooperative_groups;
 constexpr int PAIR_THREADS = 96;
 constexpr int PAIR_LAUNCH_THREADS = PAIR_THREADS;
 constexpr int PAIR_SMEM_WORDS = TW_SMEM_WORDS + 1024 /*acc*/ + 1024 /*U*/ + 2 * 3 * TILE_WORDS /*own spectra x2*/ + 2 * 3 * TILE_WORDS /*peer spectra x2*/ +
-                                336 + 2 * 3 * (int)BK_SLAB_WORDS /*key slabs of this and the next step, one per warp*/;
+                                464 + 2 * 3 * (int)BK_SLAB_WORDS /*key slabs of this and the next step, one per warp*/;
 static_assert((TW_SMEM_WORDS + 2048) % 4 == 0 && TILE_WORDS % 4 == 0 && (BK_SLAB_WORDS * 4) % 16 == 0, "bulk copies need 16-byte alignment");
 static_assert(PAIR_SMEM_WORDS * 4 + 1024 <= 227 * 1024, "cluster kernel exceeds the shared memory of an SM");
 template <int NS>
@@ -324,7 +324,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS,
     uint16_t* abar = reinterpret_cast<uint16_t*>(peer + 6 * TILE_WORDS);
     uint64_t* xbar = reinterpret_cast<uint64_t*>(peer + 6 * TILE_WORDS + 332);      // [2]: the peer's spectra of a step have landed
     uint64_t* slabbar = reinterpret_cast<uint64_t*>(peer + 6 * TILE_WORDS + 320);   // [2][3]: one per slab buffer
-    uint32_t* slabs = peer + 6 * TILE_WORDS + 336;              // [2][3][BK_SLAB_WORDS]: warp-private, filled one step ahead
+    uint32_t* twcF = peer + 6 * TILE_WORDS + 336;               // [64] + [64]: the warp-uniform column twiddles of the forward and
+    uint32_t* twcI = twcF + 64;                                 // inverse transforms in the layout of a twiddle row
+    uint32_t* slabs = peer + 6 * TILE_WORDS + 464;              // [2][3][BK_SLAB_WORDS]: warp-private, filled one step ahead
     const uint32_t remote = map_to_cta(smem_u32(peer), (uint32_t)(pw ^ 1));    // where MY spectra go in the other CTA
     const uint32_t remote_bar = map_to_cta(smem_u32(xbar), (uint32_t)(pw ^ 1));
     // the key slab of step i for this warp (24 KB, contiguous): ONE bulk (TMA) copy issued by one lane a whole step ahead,
@@ -342,6 +344,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS,
     uint32_t* dtab = smem + 2 * 32 * TWB_STRIDE;
     for (int t = tid; t < 32 * TWB_STRIDE; t += PAIR_LAUNCH_THREADS) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
     if (tid < DIGIT_TAB_WORDS) dtab[tid] = g_digit_tab.v[tid];
+    if (tid < 64) { twcF[tid] = c_fwdA[tid]; twcI[tid] = c_invA[tid]; }
     if (tid == 0) {
         for (int k = 0; k < 6; k++) mbar_init(slabbar + k, 1);
         mbar_init(xbar, 1);
@@ -390,9 +393,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS,
         p1u<true>(lane, acc, (uint32_t)abar[i], a.mask, kw, U);
         bar_sync(1, PAIR_THREADS);
         if (tid == 0) mbar_expect_tx(xbar + (i & 1), 3u * TILE_WORDS * 4u);   // arm this step's arrival of the peer's three tiles
-        p1a(lane, U, kw, S, dtab);
-        __syncwarp();
-        fwd_rows(lane, S, twF, x);
+        fwd_shared(lane, U, kw, S, twcF, twF, x);   // both passes through one code body: the step fits the instruction cache
 #pragma unroll
         for (int q = 0; q < 8; q++) *reinterpret_cast<uint4*>(S + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my tile rows are visible to the copy engine
@@ -411,14 +412,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS,
                 p2a_mac_part(lane, slab, own, pw == 0 ? 0 : 3, mac, true);
                 mbar_wait(xbar + (i & 1), (uint32_t)(i >> 1) & 1u);
                 p2a_mac_part(lane, slab, P, pw == 0 ? 3 : 0, mac, false);
-                p2a_mac_finish(lane, mac, twI, x);
-                gs32_tail(x, TwRow{twI + lane * TWB_STRIDE});
-                gs_norm<2>(x);
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    *reinterpret_cast<uint4*>(T + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-                __syncwarp();
-                p2b(lane, T, kw, x, NS);
+                p2a_mac_redc(mac, x);
+                inv_shared(lane, x, T, twI, twcI, kw, NS);
                 const uint32_t A = smem_u32(acc + lane);
 #pragma unroll
                 for (int r = 0; r < 32; r++) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(A + 128u * r), "r"(x[r]) : "memory");

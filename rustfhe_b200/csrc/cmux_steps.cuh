@@ -146,7 +146,7 @@ TFHE_HD void p2a_mac_head(int lane, const uint32_t* slab, const uint32_t* dhb, c
 }
 // latency shape, split MAC: the three key rows that meet this CTA's OWN digit spectra are accumulated first (64-bit partial
 // sums for all 32 positions stay in registers) while the cluster barrier that delivers the peer's spectra is still pending;
-// p2a_mac_finish adds the other three rows, reduces and runs the first two inverse stages.  j0: first key row of the part.
+// a second call adds the other three rows; p2a_mac_redc reduces.  j0: first key row of the part.
 TFHE_HD void p2a_mac_part(int lane, const uint32_t* slab, const uint32_t* dh3, int j0, uint64_t (&acc)[32], bool first) {
 #pragma unroll
     for (int q = 0; q < 8; q++) {
@@ -158,14 +158,6 @@ TFHE_HD void p2a_mac_part(int lane, const uint32_t* slab, const uint32_t* dh3, i
             a0 += (uint64_t)d.x * b.x; a1 += (uint64_t)d.y * b.y; a2 += (uint64_t)d.z * b.z; a3 += (uint64_t)d.w * b.w;
         }
         acc[4 * q] = a0; acc[4 * q + 1] = a1; acc[4 * q + 2] = a2; acc[4 * q + 3] = a3;
-    }
-}
-TFHE_HD void p2a_mac_finish(int lane, const uint64_t (&acc)[32], const uint32_t* twI, uint32_t (&x)[32]) {
-    const TwRow tw{twI + lane * TWB_STRIDE};
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        x[4 * q] = redc64(acc[4 * q]); x[4 * q + 1] = redc64(acc[4 * q + 1]); x[4 * q + 2] = redc64(acc[4 * q + 2]); x[4 * q + 3] = redc64(acc[4 * q + 3]);
-        gs32_head4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3], q, tw);
     }
 }
 // latency shape: the whole key slab of the step is already in registers (loaded while the cluster barrier was pending)
@@ -219,6 +211,67 @@ TFHE_HD void p2b(int lane, const uint32_t* S, int part, uint32_t (&x)[32], int n
     const int sh = slice_shift(ns) * part;
 #pragma unroll
     for (int r = 0; r < 32; r++) x[r] = (uint32_t)lift(x[r]) << sh;
+}
+// ---- latency shape: both passes of a transform through ONE code body ----
+// The cluster kernel runs one warp per sub-partition, so its unrolled step is fetched once per step and warp: at 47 KB it
+// does not fit the SM's 32 KB instruction cache and every step streams its code from L2 (7-13 % of the cycles by ncu, and the
+// slower boxes of the pool pay more).  Here the column pass and the row pass of a transform share one 32-point network (a
+// loop of two trips that must not be unrolled): the twiddles of either pass come from shared memory (tw_col: the
+// warp-uniform column twiddles, 64 words; tw_rows: the per-lane rows), the column pass gives up the digit table and the
+// constant-bank operands (about 2 % more work) and the step shrinks by a third.
+// Forward: digit `dw` of column `lane` of U -> spectrum row `lane` in [0, p), in x; S is the transpose scratch.
+TFHE_HD void fwd_shared(int lane, const uint32_t* U, int dw, uint32_t* S, const uint32_t* tw_col, const uint32_t* tw_rows, uint32_t (&x)[32]) {
+#pragma unroll
+    for (int r = 0; r < 32; r++) x[r] = to_residue(masked_digit(U[32 * r + lane], dw));
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        ct32_wide(x, TwRow{pass ? tw_rows + lane * TWB_STRIDE : tw_col});   // inputs < 8p (digits < p, column outputs < 6p) -> < 6p
+        if (pass == 0) {
+#pragma unroll
+            for (int r = 0; r < 32; r++) S[swz(r, lane)] = x[r];
+#if defined(__CUDA_ARCH__)
+            __syncwarp();
+#endif
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint4 v = *reinterpret_cast<const uint4*>(S + swz_chunk(lane, q));
+                x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+            }
+#if defined(__CUDA_ARCH__)
+            __syncwarp();   // every lane has its row before the caller overwrites S with the spectrum
+#endif
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; c++) x[c] = csub(csub(csub(x[c], 2u * P2), P2), P);  // < 6p -> [0,p)
+}
+// Inverse: x = row `lane` of the pointwise products, values < 2p -> exact signed slice values of column `lane`, shifted by
+// the slice position (what p2a's row pass + p2b produce); T is the transpose scratch.
+TFHE_HD void inv_shared(int lane, uint32_t (&x)[32], uint32_t* T, const uint32_t* tw_rows, const uint32_t* tw_col, int part, int ns) {
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        gs32_lazy(x, TwRow{pass ? tw_col : tw_rows + lane * TWB_STRIDE});
+        if (pass == 0) {
+            gs_norm<2>(x);
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                *reinterpret_cast<uint4*>(T + swz_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+#if defined(__CUDA_ARCH__)
+            __syncwarp();
+#endif
+#pragma unroll
+            for (int r = 0; r < 32; r++) x[r] = T[swz(r, lane)];
+        }
+    }
+    gs_norm<1>(x);   // [0,p)
+    const int sh = slice_shift(ns) * part;
+#pragma unroll
+    for (int r = 0; r < 32; r++) x[r] = (uint32_t)lift(x[r]) << sh;
+}
+// reduction of the 64-bit pointwise sums of the split MAC (p2a_mac_part x 2) without the fused inverse stages
+TFHE_HD void p2a_mac_redc(const uint64_t (&acc)[32], uint32_t (&x)[32]) {
+#pragma unroll
+    for (int c = 0; c < 32; c++) x[c] = redc64(acc[c]);
 }
 // ---- phase 2c: plain (unswizzled) store: coefficient k = 32 r + lane ----
 TFHE_HD void p2c(int lane, uint32_t* S, const uint32_t (&x)[32]) {
