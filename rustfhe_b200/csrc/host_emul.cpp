@@ -64,6 +64,40 @@ void emul_cmux_rotate(const uint32_t* dev, uint32_t* acc, uint32_t abar, uint32_
         for (int k = 0; k < 1024; k++)
             acc[poly * 1024 + k] += sp[(3 * poly) * TILE_WORDS + k] + sp[(3 * poly + 1) * TILE_WORDS + k] + sp[(3 * poly + 2) * TILE_WORDS + k];
 }
+// The same external product through the step functions of the LATENCY kernel (blind_rotate_pair_kernel): both passes of a
+// transform in one code body (fwd_shared / inv_shared), the multiply-accumulate split in two halves of the key rows.
+// These functions contain a warp-level synchronisation (the transpose through a shared tile), so the 32 lanes of a warp
+// are run twice: the first round fills the tile (its own results are discarded), the second reads complete rows / columns;
+// what a lane writes does not depend on the round.
+void emul_external_product_shared(const uint32_t* dev, const uint32_t* trlwe, uint32_t mask, uint32_t* out) {
+    std::vector<uint32_t> dh(6 * TILE_WORDS), U(2 * 1024), S(TILE_WORDS), T(TILE_WORDS);
+    for (int w = 0; w < 6; w++)
+        for (int lane = 0; lane < 32; lane++) p1u<false>(lane, trlwe + (w / 3) * 1024, 0, mask, w % 3, U.data() + (w / 3) * 1024);
+    for (int w = 0; w < 6; w++) {
+        uint32_t x[32][32];
+        for (int round = 0; round < 2; round++)
+            for (int lane = 0; lane < 32; lane++) fwd_shared(lane, U.data() + (w / 3) * 1024, w % 3, S.data(), h_fwdA, h_fwdB, x[lane]);
+        for (int lane = 0; lane < 32; lane++)
+            for (int q = 0; q < 8; q++)
+                *reinterpret_cast<uint4*>(dh.data() + w * TILE_WORDS + swz_chunk(lane, q)) = make_uint4(x[lane][4 * q], x[lane][4 * q + 1], x[lane][4 * q + 2], x[lane][4 * q + 3]);
+    }
+    memset(out, 0, 2 * 1024 * sizeof(uint32_t));
+    for (int w = 0; w < 6; w++) {
+        const int poly = w / 3, k = w % 3;
+        const uint32_t* slab = dev + bk_off(0, poly, k, 0, 0, 0);
+        uint32_t x[32][32];
+        for (int round = 0; round < 2; round++)
+            for (int lane = 0; lane < 32; lane++) {
+                uint64_t mac[32];
+                p2a_mac_part(lane, slab, dh.data(), 0, mac, true);
+                p2a_mac_part(lane, slab, dh.data() + 3 * TILE_WORDS, 3, mac, false);
+                p2a_mac_redc(mac, x[lane]);
+                inv_shared(lane, x[lane], T.data(), h_invB, h_invA, k, 3);
+            }
+        for (int lane = 0; lane < 32; lane++)
+            for (int r = 0; r < 32; r++) out[poly * 1024 + 32 * r + lane] += x[lane][r];
+    }
+}
 uint32_t emul_prime(void) { return P; }
 int32_t emul_key_slice(uint32_t c, int part) { return key_slice(c, part); }
 }

@@ -85,6 +85,7 @@ def emul():
     e.emul_key_transform.argtypes = [u32p, u32p]
     e.emul_external_product.argtypes = [u32p, u32p, C.c_uint32, u32p]
     e.emul_cmux_rotate.argtypes = [u32p, u32p, C.c_uint32, C.c_uint32]
+    e.emul_external_product_shared.argtypes = [u32p, u32p, C.c_uint32, u32p]
     e.emul_key_slice.restype = C.c_int32
     e.emul_key_slice.argtypes = [C.c_uint32, C.c_int]
     e.emul_prime.restype = C.c_uint32
@@ -118,6 +119,9 @@ def test_kernel_arithmetic_on_cpu_matches_oracle(emul, oracle, rng):
             emul.emul_external_product(dev, trlwe, mask, out)
             oracle.lib().orc_external_product_exact(trgsw, trlwe, mask, ref)
             assert np.array_equal(out, ref)
+            out2 = np.zeros(2 * N, np.uint32)   # the step functions of the latency kernel (one code body per transform)
+            emul.emul_external_product_shared(dev, trlwe, mask, out2)
+            assert np.array_equal(out2, ref)
         acc = u32(2 * N)
         acc2 = acc.copy()
         for abar in (0, 1, 777, 1024, 1500, 2047):
