@@ -341,9 +341,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_LAUNCH_THREADS,
         if (kw < NS) mbar_wait(slabbar + (step & 1) * 3 + kw, (uint32_t)(step >> 1) & 1u);
     };
 
-    uint32_t* dtab = smem + 2 * 32 * TWB_STRIDE;
     for (int t = tid; t < 32 * TWB_STRIDE; t += PAIR_LAUNCH_THREADS) { twF[t] = g_fwdB[t]; twI[t] = g_invB[t]; }
-    if (tid < DIGIT_TAB_WORDS) dtab[tid] = g_digit_tab.v[tid];
     if (tid < 64) { twcF[tid] = c_fwdA[tid]; twcI[tid] = c_invA[tid]; }
     if (tid == 0) {
         for (int k = 0; k < 6; k++) mbar_init(slabbar + k, 1);

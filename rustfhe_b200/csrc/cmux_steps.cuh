@@ -160,32 +160,6 @@ TFHE_HD void p2a_mac_part(int lane, const uint32_t* slab, const uint32_t* dh3, i
         acc[4 * q] = a0; acc[4 * q + 1] = a1; acc[4 * q + 2] = a2; acc[4 * q + 3] = a3;
     }
 }
-// latency shape: the whole key slab of the step is already in registers (loaded while the cluster barrier was pending)
-TFHE_HD void p2a_slab_load(int lane, const uint32_t* slab, uint4 (&bk)[48]) {
-#pragma unroll
-    for (int t = 0; t < 48; t++) {
-#if defined(__CUDA_ARCH__)
-        bk[t] = __ldg(reinterpret_cast<const uint4*>(slab) + t * 32 + lane);
-#else
-        bk[t] = *(reinterpret_cast<const uint4*>(slab) + t * 32 + lane);
-#endif
-    }
-}
-TFHE_HD void p2a_mac_head_regs(int lane, const uint4 (&bk)[48], const uint32_t* dhb, const uint32_t* dha, const uint32_t* twI, uint32_t (&x)[32]) {
-    const TwRow tw{twI + lane * TWB_STRIDE};
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-        for (int j = 0; j < BK_ROWS; j++) {
-            const uint4 d = *reinterpret_cast<const uint4*>((j < 3 ? dhb + j * TILE_WORDS : dha + (j - 3) * TILE_WORDS) + swz_chunk(lane, q));
-            const uint4 b = bk[j * 8 + q];
-            a0 += (uint64_t)d.x * b.x; a1 += (uint64_t)d.y * b.y; a2 += (uint64_t)d.z * b.z; a3 += (uint64_t)d.w * b.w;
-        }
-        x[4 * q] = redc64(a0); x[4 * q + 1] = redc64(a1); x[4 * q + 2] = redc64(a2); x[4 * q + 3] = redc64(a3);
-        gs32_head4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3], q, tw);
-    }
-}
 TFHE_HD void p2a(int lane, const uint32_t* slab, const uint32_t* dh, const uint32_t* twI, uint32_t* S) {
     uint32_t x[32];
     p2a_mac_head(lane, slab, dh, dh + 3 * TILE_WORDS, twI, x);
