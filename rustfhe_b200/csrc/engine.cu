@@ -198,6 +198,19 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if (const char* v = getenv("TFHE_B200_KS_VARIANT")) ctx->ks_variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_DEAL_FIXED")) ctx->deal_fixed = atoi(v);
     ctx->pair_max = ctx->sm_count / 2;
+    {   // clusters of two that the device can keep resident at once (GPCs with an odd number of SMs leave one unpaired): beyond
+        // that a batch of clusters would need a second wave
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (unsigned)ctx->pair_max); cfg.blockDim = dim3(PAIR_LAUNCH_THREADS); cfg.dynamicSmemBytes = (size_t)PAIR_SMEM_WORDS * 4;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, blind_rotate_pair_kernel<3>, &cfg) == cudaSuccess && nclusters > 0)
+            ctx->pair_max = std::min(ctx->pair_max, nclusters);
+        else
+            cudaGetLastError();
+    }
     if (const char* v = getenv("TFHE_B200_SLAB_TMA")) ctx->slab_tma = atoi(v);
     if (const char* v = getenv("TFHE_B200_PAIR_MAX")) ctx->pair_max = std::min(atoi(v), ctx->sm_count / 2);
     if (const char* v = getenv("TFHE_B200_KEY_SLICES")) ctx->key_slices = (atoi(v) == 2) ? 2 : 3;
