@@ -2,6 +2,7 @@
 
   librustfhe_b200.so : CUDA kernels (sm_100a) + C ABI (include/tfhe_b200.h) + host keygen   -- the product
   libhostemul.so     : CPU execution of the kernels' per-lane arithmetic -- CPU tests only, never a fallback
+  examples/homnand_bench : the reference's homnand-bench example through the C++ host side (include/tfhe_b200.hpp)
 """
 import os
 import shutil
@@ -11,6 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librustfhe_b200.so")
 EMUL = os.path.join(CSRC, "libhostemul.so")
+ROOT = os.path.dirname(HERE)
+EXAMPLE = os.path.join(ROOT, "examples", "homnand_bench")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O3,-pthread",
               "-shared", "-cudart", "static"]
 
@@ -43,6 +46,11 @@ def build(force=False, verbose=False):
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include",
                                os.path.join(CSRC, "host_emul.cpp"), "-o", EMUL])
+    ex_src = [EXAMPLE + ".cpp", os.path.join(ROOT, "include", "tfhe_b200.hpp"), os.path.join(ROOT, "include", "tfhe_b200.h"), LIB]
+    if force or not _newer(EXAMPLE, ex_src):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([gxx, "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), EXAMPLE + ".cpp", "-L" + HERE,
+                               "-lrustfhe_b200", "-Wl,-rpath,$ORIGIN/../rustfhe_b200", "-o", EXAMPLE])
     return LIB
 
 

@@ -422,3 +422,14 @@ def test_mixed_opcode_batch(engine, oracle, keys, rng):
         assert np.array_equal(keys.decrypt(out[idx]), want_bits[op][idx]), op
     with pytest.raises(R.TfheError):
         engine.gate_batch_mixed(np.full(B, 9, np.uint8), c0, c1)
+
+
+def test_cpp_host_side_homnand_bench():
+    """examples/homnand_bench (the reference's examples/homnand-bench.rs on include/tfhe_b200.hpp: truth tables of
+    nand/and/or/xor/not/mux on fresh encryptions, then 1024 gates as one batch) decrypts everything right."""
+    import subprocess
+    from rustfhe_b200 import build as B
+    B.build()
+    r = subprocess.run([B.EXAMPLE], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    assert "all decryptions right" in r.stdout and "hom_nand_batch: 1024 gates" in r.stdout

@@ -34,6 +34,21 @@ def test_no_cpu_fallback_without_gpu():
     assert ei.value.code == 2 and "no CPU fallback" in str(ei.value)
 
 
+def test_cpp_host_side_builds_and_fails_loudly_without_gpu():
+    """include/tfhe_b200.hpp (the C++ mirror of the hom_nand crate's gate API) compiles against the C ABI; the reference's
+    homnand-bench example built on it exits with code 3 and the engine's message when there is no B200 -- no fallback."""
+    import subprocess
+    import torch
+    from rustfhe_b200 import build as B
+    B.build()
+    assert os.path.exists(B.EXAMPLE)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the example is run by the GPU suite")
+    r = subprocess.run([B.EXAMPLE], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3, (r.returncode, r.stdout, r.stderr)
+    assert "no CPU fallback" in r.stderr
+
+
 def test_default_params_and_bad_params():
     from rustfhe_b200 import _capi as K
     lib = K.lib()
