@@ -111,6 +111,14 @@ public:
     std::vector<TLWERep> hom_or_batch(const std::vector<TLWERep>& a, const std::vector<TLWERep>& b) const { return gates(TFHE_B200_OR, a, &b); }
     std::vector<TLWERep> hom_xor_batch(const std::vector<TLWERep>& a, const std::vector<TLWERep>& b) const { return gates(TFHE_B200_XOR, a, &b); }
     std::vector<TLWERep> hom_not_batch(const std::vector<TLWERep>& a) const { return gates(TFHE_B200_NOT, a, nullptr); }
+    std::vector<TLWERep> hom_mux_batch(const std::vector<TLWERep>& control, const std::vector<TLWERep>& input_0, const std::vector<TLWERep>& input_1) const {
+        if (control.size() != input_0.size() || control.size() != input_1.size()) throw Error(TFHE_B200_ERR_PARAM, "hom_mux_batch: operand batches differ in length");
+        std::vector<TLWERep> out(control.size());
+        if (control.empty()) return out;
+        if (2 * control.size() > reserved_) reserve(2 * control.size());   // the first stage runs both AND batches in one launch
+        check(tfhe_b200_mux_batch(ctx_, control[0].w.data(), input_0[0].w.data(), input_1[0].w.data(), out[0].w.data(), control.size()), ctx_, "mux_batch");
+        return out;
+    }
 
     // pre-allocates every work slot of the engine for batches of up to max_batch gates (done automatically by the batch forms
     // the first time a larger batch arrives: no cudaMalloc in later calls)
