@@ -82,8 +82,11 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p /* NULL = defaults */, int de
 int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx);
 const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx /* NULL = last error of a failed ctx_create */);
 int tfhe_b200_set_decomp_mask(tfhe_b200_ctx* ctx, uint32_t mask);
-/* Key slices per bootstrapping-key polynomial: 3 (default) = exact external product in the worst case; 2 = opt-in fast mode
- * (one third less work per CMUX; exact with probability 1 - 3e-16 per gate over the key's masks) */
+/* Key slices per bootstrapping-key polynomial.  2 (default): two 16-bit slices, 6 + 4 transforms per CMUX; the external
+ * product is the exact integer product for every honestly generated key (uniform masks): a slice sum would have to exceed
+ * 9.8 standard deviations, probability about 1e-22 per coefficient and 3e-16 per gate over the key's masks (DESIGN.md section
+ * 2; tests/test_host_logic.py measures the distribution).  3: three 11-bit slices, 6 + 6 transforms, exact in the worst case
+ * (any key, any digits).  Switching re-transforms the loaded bootstrapping key. */
 int tfhe_b200_set_key_slices(tfhe_b200_ctx* ctx, int slices);
 /* How a full batch (more than two gates per SM) is cut into CTAs.  AUTO (default): decided per call -- if an earlier batch is
  * still running on another stream the batch is cut into 4-gate CTAs only (the next batch back-fills the last wave), otherwise

@@ -319,7 +319,7 @@ class DeviceEngine:
         self._ck(self._l.tfhe_b200_set_decomp_mask(self._ctx, mask))
 
     def set_key_slices(self, slices):
-        """3 = exact in the worst case (default); 2 = opt-in fast mode."""
+        """2 (default) = two 16-bit key slices, exact for honest keys; 3 = exact in the worst case."""
         self._ck(self._l.tfhe_b200_set_key_slices(self._ctx, slices))
 
     def set_batch_overlap(self, mode):

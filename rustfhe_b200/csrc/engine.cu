@@ -14,6 +14,7 @@
 #include <vector>
 #include "../../include/tfhe_b200.h"
 #include "blind_rotate.cuh"
+#include "blind_rotate_t2.cuh"
 #include "keyswitch.cuh"
 #include "aux_kernels.cuh"
 
@@ -45,6 +46,7 @@ struct tfhe_b200_ctx {
     int device = 0;
     int sm_count = 0;
     uint32_t* bkdev = nullptr;   // n * BK_STEP_WORDS
+    uint32_t* bkdev_t2 = nullptr;   // n * T2_STEP_WORDS: the two-slice key in the throughput kernel's layout (blind_rotate_t2.cuh)
     uint32_t* kskdev = nullptr;  // [N][t][3][n+1]
     uint32_t* bk_torus = nullptr;  // [n][2l][2][N] torus-domain key as loaded / generated (kept for export: 31 MB)
     uint8_t* keybits = nullptr;    // device copy of (s0[n] | pad to 1024 | s1[N]) during device keygen
@@ -62,7 +64,10 @@ struct tfhe_b200_ctx {
     uint64_t last_batch = 0;
     int gates_per_cta = 1;
     int variant = 7;  // blind-rotate launch shape, see launch_blind_rotate
-    int key_slices = 3;  // 3 = exact in the worst case (default); 2 = opt-in fast mode (tfhe_b200_set_key_slices)
+    int key_slices = 2;  // 2 (default) = two 16-bit slices, exact for honestly generated keys (DESIGN.md section 2 has the bound);
+                         // 3 = three 11-bit slices, exact in the worst case (tfhe_b200_set_key_slices)
+    int t2_gates = 6;    // gates per CTA of the throughput kernel (TFHE_B200_T2_G: 4 or 6)
+    int t2_twreg = 1;    // which row twiddles the throughput kernel keeps in registers (TFHE_B200_T2_TWREG: bit 0 forward, bit 1 inverse)
     int slab_tma = 1;     // one gate per CTA: key slabs staged by bulk copies (TFHE_B200_SLAB_TMA=0: streamed from L2 by the warps)
     int pair_max = 0;     // largest batch that runs on 2-SM clusters (set at create: #SMs / 2)
     int deal_fixed = -1;  // how a full batch is cut into CTAs: 0 = dealt evenly over whole waves (best for a batch running alone),
@@ -131,7 +136,7 @@ static cudaError_t set_smem(Kern k, int G) { return cudaFuncSetAttribute(k, cuda
 
 extern "C" {
 
-const char* tfhe_b200_version(void) { return "rustfhe_b200 0.2 (sm_100a, p=536856577, 3x11-bit key slices)"; }
+const char* tfhe_b200_version(void) { return "rustfhe_b200 0.3 (sm_100a, p=536856577, 2x16-bit key slices; 3x11-bit selectable)"; }
 
 int tfhe_b200_default_params(tfhe_b200_params* p) {
     if (!p) return TFHE_B200_ERR_PARAM;
@@ -172,6 +177,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     for (auto& slot : ctx->ev) for (auto& ev : slot) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->keys_ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->bkdev, (size_t)LWE_N * BK_STEP_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc(bk)", e);
+    if ((e = cudaMalloc(&ctx->bkdev_t2, (size_t)LWE_N * T2_STEP_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc(bk t2)", e);
     if ((e = cudaMalloc(&ctx->kskdev, (size_t)1024 * 8 * 3 * (LWE_N + 1) * 4)) != cudaSuccess) return bail("cudaMalloc(ksk)", e);
     if ((e = cudaMalloc(&ctx->bk_torus, BK_TORUS_BYTES)) != cudaSuccess) return bail("cudaMalloc(bk_torus)", e);
     if ((e = cudaMalloc(&ctx->keybits, 2048)) != cudaSuccess) return bail("cudaMalloc(keybits)", e);
@@ -194,6 +200,15 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = set_smem(blind_rotate_kernel<1, false, 1, 2>, 1)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<2, true, 1, 2>, 2)) != cudaSuccess) return bail("smem attr", e);
     if ((e = set_smem(blind_rotate_kernel<4, true, 1, 2>, 4)) != cudaSuccess) return bail("smem attr", e);
+    {
+        auto t2attr = [&](auto kern, int G) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_smem_bytes(G)); };
+        if ((e = t2attr(blind_rotate_t2_kernel<6, 0>, 6)) != cudaSuccess || (e = t2attr(blind_rotate_t2_kernel<6, 1>, 6)) != cudaSuccess ||
+            (e = t2attr(blind_rotate_t2_kernel<6, 3>, 6)) != cudaSuccess || (e = t2attr(blind_rotate_t2_kernel<4, 0>, 4)) != cudaSuccess ||
+            (e = t2attr(blind_rotate_t2_kernel<4, 1>, 4)) != cudaSuccess || (e = t2attr(blind_rotate_t2_kernel<4, 3>, 4)) != cudaSuccess)
+            return bail("smem attr (t2)", e);
+    }
+    if (const char* v = getenv("TFHE_B200_T2_G")) ctx->t2_gates = (atoi(v) == 4) ? 4 : 6;
+    if (const char* v = getenv("TFHE_B200_T2_TWREG")) ctx->t2_twreg = atoi(v) & 3;
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_KS_VARIANT")) ctx->ks_variant = atoi(v);
     if (const char* v = getenv("TFHE_B200_DEAL_FIXED")) ctx->deal_fixed = atoi(v);
@@ -213,7 +228,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     }
     if (const char* v = getenv("TFHE_B200_SLAB_TMA")) ctx->slab_tma = atoi(v);
     if (const char* v = getenv("TFHE_B200_PAIR_MAX")) ctx->pair_max = std::min(atoi(v), ctx->sm_count / 2);
-    if (const char* v = getenv("TFHE_B200_KEY_SLICES")) ctx->key_slices = (atoi(v) == 2) ? 2 : 3;
+    if (const char* v = getenv("TFHE_B200_KEY_SLICES")) ctx->key_slices = (atoi(v) == 3) ? 3 : 2;
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (keyswitch2)", e);
     *out = ctx;
@@ -224,7 +239,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     if (!ctx) return TFHE_B200_ERR_PARAM;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->bkdev); cudaFree(ctx->kskdev); cudaFree(ctx->bk_torus); cudaFree(ctx->keybits); cudaFree(ctx->s1poly);
+    cudaFree(ctx->bkdev); cudaFree(ctx->bkdev_t2); cudaFree(ctx->kskdev); cudaFree(ctx->bk_torus); cudaFree(ctx->keybits); cudaFree(ctx->s1poly);
     for (auto& s : ctx->slots) {
         cudaFree(s.ksdig); cudaFree(s.scratch); cudaFree(s.s0buf); cudaFree(s.opsbuf);
         for (auto p : s.tmp) cudaFree(p);
@@ -328,6 +343,11 @@ static int transform_keys(tfhe_b200_ctx* ctx, const uint32_t* src_dev, uint32_t*
     bk_transform_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(src_dev, dst_dev, npolys, ctx->key_slices);
     ctx->launches++;
     CK(cudaGetLastError());
+    if (ctx->key_slices == 2 && dst_dev == ctx->bkdev) {   // the whole key: also in the throughput kernel's layout
+        bk_transform_t2_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(src_dev, ctx->bkdev_t2, npolys);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
     return TFHE_B200_OK;
 }
 int tfhe_b200_load_bk_device(tfhe_b200_ctx* ctx, const uint32_t* bk_dev, void* stream) {
@@ -403,7 +423,7 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
     // evenly over rounds * #SMs CTAs so that a batch that is not a multiple of G * #SMs ends with 3-gate CTAs instead of
     // a half-empty last wave.
     const bool full = a.B > (long)ctx->sm_count;
-    const int variant = (a.ns == 2 && ctx->variant != 9) ? 7 : ctx->variant;   // the measured alternatives exist for three slices only
+    const int variant = (a.ns == 2 && ctx->variant != 9 && ctx->variant != 8) ? 7 : ctx->variant;   // the other measured alternatives exist for three slices only
     auto deal = [&](int G) {
         const long cap = (long)G * ctx->sm_count;
         const long rounds = (a.B + cap - 1) / cap;
@@ -424,7 +444,22 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         // best shape between one and two gates per SM (296 gates: 5.7 ms against 6.3 ms for 2-gate CTAs of the 80-register
         // kernel and 5.8 ms for 1-gate CTAs compiled for 168 registers)
         blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-    } else if (full) {   // default (variant 7)
+    } else if (full && a.ns == 2 && variant != 8) {   // default: the two-warps-per-gate throughput kernel (blind_rotate_t2.cuh)
+        const int G = ctx->t2_gates;
+        const unsigned grid = batches_overlap(ctx, st) ? fixed(G) : deal(G);
+        a.bkdev = ctx->bkdev_t2;
+        const size_t sm = t2_smem_bytes(G);
+        const int tw = ctx->t2_twreg;
+        if (G == 6) {
+            if (tw == 0) blind_rotate_t2_kernel<6, 0><<<grid, 6 * T2_THREADS_PER_GATE, sm, st>>>(a);
+            else if (tw == 3) blind_rotate_t2_kernel<6, 3><<<grid, 6 * T2_THREADS_PER_GATE, sm, st>>>(a);
+            else blind_rotate_t2_kernel<6, 1><<<grid, 6 * T2_THREADS_PER_GATE, sm, st>>>(a);
+        } else {
+            if (tw == 0) blind_rotate_t2_kernel<4, 0><<<grid, 4 * T2_THREADS_PER_GATE, sm, st>>>(a);
+            else if (tw == 3) blind_rotate_t2_kernel<4, 3><<<grid, 4 * T2_THREADS_PER_GATE, sm, st>>>(a);
+            else blind_rotate_t2_kernel<4, 1><<<grid, 4 * T2_THREADS_PER_GATE, sm, st>>>(a);
+        }
+    } else if (full) {   // three slices (variant 7), or two slices on the six-warps-per-gate kernel (variant 8, for A/B runs)
         const unsigned grid = batches_overlap(ctx, st) ? fixed(4) : deal(4);
         if (a.ns == 2) blind_rotate_kernel<4, false, 1, 2><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
         else blind_rotate_kernel<4, false, 1, 3><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);

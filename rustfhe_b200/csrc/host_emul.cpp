@@ -6,7 +6,7 @@
 #include <vector_functions.h>
 #include <cstring>
 #include <vector>
-#include "cmux_steps.cuh"
+#include "t2_steps.cuh"
 
 using namespace tfhe;
 
@@ -98,6 +98,57 @@ void emul_external_product_shared(const uint32_t* dev, const uint32_t* trlwe, ui
             for (int r = 0; r < 32; r++) out[poly * 1024 + 32 * r + lane] += x[lane][r];
     }
 }
+
+// ---- throughput kernel (blind_rotate_t2.cuh, t2_steps.cuh): one gate on two warps, two 16-bit key slices ----
+// TRGSW torus polys [row j][poly][1024] -> throughput layout [poly][q][j][slice][lane][4] of one step
+void emul_key_transform_t2(const uint32_t* trgsw, uint32_t* dev) {
+    std::vector<uint32_t> S(TILE_WORDS);
+    for (int j = 0; j < BK_ROWS; j++)
+        for (int poly = 0; poly < 2; poly++)
+            for (int part = 0; part < 2; part++) {
+                const uint32_t* src = trgsw + (size_t)(j * 2 + poly) * 1024;
+                for (int lane = 0; lane < 32; lane++) key_cols(lane, src, part, S.data(), 2);
+                for (int lane = 0; lane < 32; lane++) key_rows_t2(lane, S.data(), h_fwdB, dev + t2_bk_off(0, poly, 0, j, part, 0));
+            }
+}
+// one step: acc <- BK (x) src + acc with src = X^abar acc - acc (rotate) or acc <- BK (x) acc (plain external product)
+static void t2_step(const uint32_t* dev, uint32_t* acc, bool rotate, uint32_t abar, uint32_t mask) {
+    std::vector<uint32_t> dh(6 * T2_TILE_WORDS);
+    for (int pw = 0; pw < 2; pw++) {
+        uint32_t u[32][32];
+        for (int lane = 0; lane < 32; lane++) {
+            if (rotate) t2_u<true>(lane, acc + pw * 1024, abar, mask, u[lane]);
+            else t2_u<false>(lane, acc + pw * 1024, abar, mask, u[lane]);
+        }
+        for (int dw = 0; dw < 3; dw++) {
+            uint32_t* S = dh.data() + (3 * pw + dw) * T2_TILE_WORDS;
+            for (int lane = 0; lane < 32; lane++) t2_fwd_cols(lane, u[lane], 6 * dw, S, h_digit_tab.v);
+            for (int lane = 0; lane < 32; lane++) t2_fwd_rows(lane, S, TwRow{h_fwdB + lane * TWB_STRIDE});
+        }
+    }
+    std::vector<uint32_t> T(2 * 2 * T2_TILE_WORDS);
+    for (int pw = 0; pw < 2; pw++) {
+        for (int lane = 0; lane < 32; lane++) {
+            uint32_t y0[32], y1[32];
+            t2_mac(lane, dev + (size_t)pw * (T2_STEP_WORDS / 2), dh.data(), TwRow{h_invB + lane * TWB_STRIDE}, y0, y1);
+            t2_inv_store(lane, y0, T.data() + (2 * pw) * T2_TILE_WORDS);
+            t2_inv_store(lane, y1, T.data() + (2 * pw + 1) * T2_TILE_WORDS);
+        }
+    }
+    for (int pw = 0; pw < 2; pw++)
+        for (int lane = 0; lane < 32; lane++) {
+            uint32_t z[32];
+            for (int r = 0; r < 32; r++) z[r] = rotate ? acc[pw * 1024 + 32 * r + lane] : 0u;
+            for (int s = 0; s < 2; s++) t2_inv_cols(lane, T.data() + (2 * pw + s) * T2_TILE_WORDS, 16 * s, z);
+            for (int r = 0; r < 32; r++) acc[pw * 1024 + 32 * r + lane] = z[r];
+        }
+}
+void emul_external_product_t2(const uint32_t* dev, const uint32_t* trlwe, uint32_t mask, uint32_t* out) {
+    memcpy(out, trlwe, 2 * 1024 * sizeof(uint32_t));
+    t2_step(dev, out, false, 0, mask);
+}
+void emul_cmux_rotate_t2(const uint32_t* dev, uint32_t* acc, uint32_t abar, uint32_t mask) { t2_step(dev, acc, true, abar, mask); }
 uint32_t emul_prime(void) { return P; }
 int32_t emul_key_slice(uint32_t c, int part) { return key_slice(c, part); }
+int32_t emul_key_slice2(uint32_t c, int part) { return key_slice(c, part, 2); }
 }

@@ -14,9 +14,10 @@ from conftest import phase_err
 pytestmark = pytest.mark.gpu
 
 N, n = 1024, 635
-# the suite can be run in the opt-in fast mode (TFHE_B200_KEY_SLICES=2): exact on random and real keys, but by design not on
-# the adversarial worst-case vectors below, which are then left out
-FAST_MODE = __import__("os").environ.get("TFHE_B200_KEY_SLICES") == "2"
+# Default arithmetic: two 16-bit key slices -- exact on random and real keys (every slice sum stays 9.8 sigma below p/2), but by
+# design not on the adversarial worst-case KEY below; that vector runs in the worst-case-exact three-slice
+# mode (test_exact_mode_three_key_slices, or the whole suite with TFHE_B200_KEY_SLICES=3).
+FAST_MODE = __import__("os").environ.get("TFHE_B200_KEY_SLICES") != "3"
 
 
 def u32(rng, *shape):
@@ -312,10 +313,10 @@ def test_cmux_exact_and_selects(engine, oracle, keys, rng):
         assert np.abs(err).max() < 2 ** 32 / 64, idx
 
 
-@pytest.mark.parametrize("B", [5, 49, 74, 75, 148, 149, 601])
+@pytest.mark.parametrize("B", [5, 49, 74, 75, 148, 149, 601, 889])
 def test_launch_shapes_deterministic_and_exact(engine, oracle, keys, rng, B):
     """Every launch shape (2-SM cluster per gate for B <= #SMs/2, one gate per CTA with bulk-copied key slabs up to #SMs, 1-gate
-    CTAs up to 2 #SMs, 4-gate CTAs with uneven dealing above) gives the same bits run after run (a shared-memory race would not) and matches the exact oracle on a
+    CTAs up to 2 #SMs, the two-warps-per-gate throughput kernel with uneven dealing above) gives the same bits run after run (a shared-memory race would not) and matches the exact oracle on a
     sample; all decrypts are right."""
     x = rng.integers(0, 2, B).astype(np.uint8)
     y = rng.integers(0, 2, B).astype(np.uint8)
@@ -373,13 +374,11 @@ def test_batch_overlap_modes_same_bits(engine, keys, rng):
         engine.set_batch_overlap(-1)
 
 
-def test_fast_mode_two_key_slices(oracle, keys, rng):
-    """Opt-in fast mode (tfhe_b200_set_key_slices(ctx, 2)): 16/16-bit key slices, exact with overwhelming probability instead of
-    in the worst case.  On real keys and real accumulators the output ciphertexts are the same bits as
-    the exact oracle's (and hence as the default mode's); switching back to 3 slices re-transforms the key."""
+def test_exact_mode_three_key_slices(oracle, keys, rng):
+    """tfhe_b200_set_key_slices(ctx, 3): three 11-bit key slices, exact in the WORST case (every slice sum < p/2 for any key and
+    any digits).  On real keys the default two-slice mode gives the same ciphertext bits; the adversarial
+    key (all words 0x7FFFFFFF) against all digits -32 is exact in this mode only.  Switching re-transforms the loaded key."""
     import rustfhe_b200 as R
-    if int(__import__("os").environ.get("TFHE_B200_KEY_SLICES", "3")) == 2:
-        pytest.skip("suite already runs in fast mode")
     eng = R.DeviceEngine(0)
     try:
         eng.load_ksk(keys.ksk)
@@ -388,16 +387,26 @@ def test_fast_mode_two_key_slices(oracle, keys, rng):
         x = rng.integers(0, 2, B).astype(np.uint8)
         y = rng.integers(0, 2, B).astype(np.uint8)
         c0, c1 = keys.encrypt(x, 61000), keys.encrypt(y, 62000)
-        exact = eng.gate_batch(R.NAND, c0, c1)
         eng.set_key_slices(2)
         fast = eng.gate_batch(R.NAND, c0, c1)
-        assert np.array_equal(keys.decrypt(fast), 1 - (x & y))
+        eng.set_key_slices(3)
+        exact = eng.gate_batch(R.NAND, c0, c1)
+        assert np.array_equal(keys.decrypt(exact), 1 - (x & y))
         assert np.array_equal(fast, exact)
         idx = rng.choice(B, 8, replace=False)
-        assert np.array_equal(fast[idx], oracle.gate_exact(keys, oracle.NAND, c0[idx], c1[idx]))
-        few = eng.gate_batch(R.XOR, c0[:3], c1[:3])          # latency shape (cluster pair) in fast mode
+        assert np.array_equal(exact[idx], oracle.gate_exact(keys, oracle.NAND, c0[idx], c1[idx]))
+        few = eng.gate_batch(R.XOR, c0[:3], c1[:3])          # latency shape (cluster pair), three slices
         assert np.array_equal(few, oracle.gate_exact(keys, oracle.XOR, c0[:3], c1[:3]))
-        eng.set_key_slices(3)
+        trlwe = u32(rng, 3, 2, N)
+        trlwe[1] = 0x7DF7C000                                 # all digits -32
+        trgsw = u32(rng, 3, 6, 2, N)
+        trgsw[1] = 0x7FFFFFFF                                 # every key slice at its extreme
+        out = eng.external_product_batch(trgsw, trlwe)
+        for g in range(3):
+            ref = np.zeros(2 * N, np.uint32)
+            oracle.lib().orc_external_product_exact(trgsw[g].reshape(-1), trlwe[g].reshape(-1), 0x02084000, ref)
+            assert np.array_equal(out[g].reshape(-1), ref), g
+        eng.set_key_slices(2)
         assert np.array_equal(eng.gate_batch(R.NAND, c0[:40], c1[:40]), exact[:40])
     finally:
         eng.close()
@@ -429,7 +438,7 @@ def test_cpp_host_side_homnand_bench():
     nand/and/or/xor/not/mux on fresh encryptions, then 1024 gates as one batch) decrypts everything right."""
     import subprocess
     from rustfhe_b200 import build as B
-    B.build()
+    B.build_example()
     r = subprocess.run([B.EXAMPLE], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
     assert "all decryptions right" in r.stdout and "hom_nand_batch: 1024 gates" in r.stdout

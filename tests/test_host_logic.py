@@ -40,7 +40,7 @@ def test_cpp_host_side_builds_and_fails_loudly_without_gpu():
     import subprocess
     import torch
     from rustfhe_b200 import build as B
-    B.build()
+    B.build_example()
     assert os.path.exists(B.EXAMPLE)
     if torch.cuda.is_available():
         pytest.skip("GPU present: the example is run by the GPU suite")
@@ -94,8 +94,7 @@ def test_encrypt_decrypt_roundtrip_and_parity(oracle, keys, rng):
 @pytest.fixture(scope="module")
 def emul():
     from rustfhe_b200 import build
-    build.build()
-    e = C.CDLL(build.EMUL)
+    e = C.CDLL(build.build_emul())
     u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
     e.emul_key_transform.argtypes = [u32p, u32p]
     e.emul_external_product.argtypes = [u32p, u32p, C.c_uint32, u32p]
@@ -104,6 +103,11 @@ def emul():
     e.emul_key_slice.restype = C.c_int32
     e.emul_key_slice.argtypes = [C.c_uint32, C.c_int]
     e.emul_prime.restype = C.c_uint32
+    e.emul_key_transform_t2.argtypes = [u32p, u32p]
+    e.emul_external_product_t2.argtypes = [u32p, u32p, C.c_uint32, u32p]
+    e.emul_cmux_rotate_t2.argtypes = [u32p, u32p, C.c_uint32, C.c_uint32]
+    e.emul_key_slice2.restype = C.c_int32
+    e.emul_key_slice2.argtypes = [C.c_uint32, C.c_int]
     return e
 
 
@@ -141,6 +145,38 @@ def test_kernel_arithmetic_on_cpu_matches_oracle(emul, oracle, rng):
         acc2 = acc.copy()
         for abar in (0, 1, 777, 1024, 1500, 2047):
             emul.emul_cmux_rotate(dev, acc, abar, oracle.MASK_FAITHFUL)
+            r = np.zeros(2 * N, np.uint32)
+            oracle.lib().orc_rotate(acc2[:N].copy(), N, abar, r[:N])
+            oracle.lib().orc_rotate(acc2[N:].copy(), N, abar, r[N:])
+            pr = np.zeros(2 * N, np.uint32)
+            oracle.lib().orc_external_product_exact(trgsw, (r - acc2).astype(np.uint32), oracle.MASK_FAITHFUL, pr)
+            acc2 = (acc2 + pr).astype(np.uint32)
+            assert np.array_equal(acc, acc2), abar
+
+
+def test_throughput_kernel_arithmetic_on_cpu_matches_oracle(emul, oracle, rng):
+    """the per-lane code of the throughput kernel (t2_steps.cuh: one gate on two warps, two 16-bit key slices, unnormalised
+    spectra, XOR-swizzled tiles, [poly][chunk][row][slice] key layout) executed on the CPU against the exact-integer oracle.
+    With two slices a slice sum stays below p/2 for honest (uniform) keys, not for the adversarial all-extreme vector."""
+    def u32(k):
+        return rng.integers(0, 2 ** 32, k, dtype=np.uint64).astype(np.uint32)
+    for c in [0, 1, 0x7FFF, 0x8000, 0xFFFF, 0x10000, 0xFFFFFFFF, 0x80000000, 0x7FFFFFFF] + [int(v) for v in rng.integers(0, 2 ** 32, 2000)]:
+        s = [emul.emul_key_slice2(c, k) for k in range(2)]
+        assert (s[0] + (s[1] << 16)) % 2 ** 32 == c and -32768 <= s[0] < 32768 and -32768 <= s[1] < 32768
+    for trial in range(3):
+        trgsw, trlwe = u32(12 * N), u32(2 * N)
+        dev = np.zeros(24 * N, np.uint32)
+        emul.emul_key_transform_t2(trgsw, dev)
+        assert dev.max() < emul.emul_prime()
+        for mask in (oracle.MASK_FAITHFUL, oracle.MASK_TESTED):
+            out, ref = np.zeros(2 * N, np.uint32), np.zeros(2 * N, np.uint32)
+            emul.emul_external_product_t2(dev, trlwe, mask, out)
+            oracle.lib().orc_external_product_exact(trgsw, trlwe, mask, ref)
+            assert np.array_equal(out, ref)
+        acc = u32(2 * N)
+        acc2 = acc.copy()
+        for abar in (0, 1, 777, 1024, 1500, 2047):
+            emul.emul_cmux_rotate_t2(dev, acc, abar, oracle.MASK_FAITHFUL)
             r = np.zeros(2 * N, np.uint32)
             oracle.lib().orc_rotate(acc2[:N].copy(), N, abar, r[:N])
             oracle.lib().orc_rotate(acc2[N:].copy(), N, abar, r[N:])
