@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstdio>
 #include <functional>
+#include <memory>
 #include <string>
 #include "tfhe_b200.hpp"
 
@@ -24,16 +25,23 @@ static auto timeit(const std::string& title, F&& f) {   // utils::timeit! (utils
 }
 
 int main(int argc, char** argv) {
-    const uint64_t seed = argc > 1 ? std::stoull(argv[1], nullptr, 0) : 0x5EED0001ull;
+    // no argument: keys and encryptions from the OS-keyed ChaCha20 generator, like the reference's thread_rng;
+    // a seed argument selects the deterministic TEST generator (reproducible runs, NOT secure)
+    const bool seeded = argc > 1;
+    const uint64_t seed = seeded ? std::stoull(argv[1], nullptr, 0) : 0;
+    uint64_t next_index = 0;
     try {
         SecretKeyLv0 s_key_tlwelv0;
         SecretKeyLv1 s_key_tlwelv1;
-        gen_secret_keys(seed, s_key_tlwelv0, s_key_tlwelv1);
+        if (seeded) gen_secret_keys(seed, s_key_tlwelv0, s_key_tlwelv1); else gen_secret_keys(s_key_tlwelv0, s_key_tlwelv1);
         const auto t0 = Clock::now();
-        TFHE tfhe(s_key_tlwelv0, s_key_tlwelv1, seed);
+        std::unique_ptr<TFHE> tfhe_p(seeded ? new TFHE(s_key_tlwelv0, s_key_tlwelv1, TFHE::TestSeed{seed}) : new TFHE(s_key_tlwelv0, s_key_tlwelv1));
+        TFHE& tfhe = *tfhe_p;
         std::printf("%s\nTFHE::new %.1f ms (both keys generated on the device)\n", tfhe_b200_version(),
                     std::chrono::duration<double, std::milli>(Clock::now() - t0).count());
-        auto tlwelv0_ = [&](Binary b) { return Cryptor::encrypto(TLWE, s_key_tlwelv0, b, seed); };
+        auto tlwelv0_ = [&](Binary b) {
+            return seeded ? Cryptor::encrypto(TLWE, s_key_tlwelv0, b, seed, next_index++) : Cryptor::encrypto(TLWE, s_key_tlwelv0, b);
+        };
         auto dec = [&](const TLWERep& r) { return Cryptor::decrypto(TLWE, s_key_tlwelv0, r); };
         auto bin = [](int v) { return v ? Binary::One : Binary::Zero; };
 

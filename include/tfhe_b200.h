@@ -170,8 +170,22 @@ int tfhe_b200_negacyclic_mul_batch_device(tfhe_b200_ctx* ctx, const uint32_t* a_
                                           size_t B, void* stream);
 
 /* ---- host-side key generation / encryption (TFHE::new, Cryptor::{encrypto,decrypto}; tfhe.rs:21-25,
- * tlwe.rs:197-241,247-277, trgsw.rs:117-139,213-229, trlwe.rs:127-137, digest.rs:14-33).  Seeded counter-based
- * generator (the reference uses thread_rng and cannot be seeded, math.rs:421-476). */
+ * tlwe.rs:197-241,247-277, trgsw.rs:117-139,213-229, trlwe.rs:127-137, digest.rs:14-33).
+ *
+ * PRODUCTION entry points (*_csprng): ChaCha20 keyed with 256 bits -- the role of the reference's rand::thread_rng, an
+ * OS-seeded ChaCha generator (math.rs:421-476).  key = 32 bytes, or NULL: the call draws a fresh key from getrandom(2), so no
+ * (key, index) pair is ever reused.  Callers that pass their own key must never use one key for two calls of the same
+ * function, and must not derive the secret-key generator key and the public-material keys from one another. */
+int tfhe_b200_random_bytes(uint8_t* out, size_t len);   /* getrandom(2) */
+int tfhe_b200_keygen_secret_csprng(const uint8_t* key /*[32] or NULL*/, uint8_t* s0 /*[n]*/, uint8_t* s1 /*[N]*/);
+int tfhe_b200_keygen_bk_csprng(const uint8_t* key /*[32] or NULL*/, const uint8_t* s0, const uint8_t* s1, uint32_t* bk);
+int tfhe_b200_keygen_ksk_csprng(const uint8_t* key /*[32] or NULL*/, const uint8_t* s0, const uint8_t* s1, uint32_t* ksk);
+int tfhe_b200_encrypt_bits_csprng(const uint8_t* key /*[32] or NULL*/, const uint8_t* s0, const uint8_t* bits, size_t B,
+                                  uint32_t* out /*[B][n+1]*/);
+/* DETERMINISTIC TEST entry points: SplitMix64 of a 64-bit seed.  NOT SECURE -- two public mask words reveal the generator
+ * state, and with it every noise term and both secret keys; equal (seed, index) pairs repeat masks and noise.  They exist
+ * only so that parity tests can give the oracle, the host and the device identical key material (the reference cannot be
+ * seeded at all).  Never use them for data that needs protecting. */
 int tfhe_b200_keygen_secret(uint64_t seed, uint8_t* s0 /*[n]*/, uint8_t* s1 /*[N]*/);
 int tfhe_b200_keygen_bk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uint32_t* bk);
 int tfhe_b200_keygen_ksk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uint32_t* ksk);
@@ -184,6 +198,12 @@ int tfhe_b200_decrypt_bits(const uint8_t* s0, const uint32_t* ct, size_t B, uint
  * results are bit-identical to tfhe_b200_keygen_bk / _keygen_ksk / _encrypt_bits with the same seed).  Replaces the
  * host loops of BootstrappingKey::new (3810 TRLWE encryptions, tfhe.rs:119-126, trgsw.rs:117-139) and
  * KeySwitchingKey::new (24576 TLWE encryptions, tlwe.rs:247-277) that the reference marks "TODO: parallelise". ---- */
+int tfhe_b200_keygen_device_csprng(tfhe_b200_ctx* ctx, const uint8_t* key /*[32] or NULL = getrandom*/, const uint8_t* s0 /*[n] host*/,
+                                   const uint8_t* s1 /*[N] host*/);
+int tfhe_b200_encrypt_bits_device_csprng(tfhe_b200_ctx* ctx, const uint8_t* key /*[32] or NULL = getrandom*/, const uint8_t* s0 /*host*/,
+                                         const uint8_t* bits_dev /*[B] device*/, size_t B, uint32_t* out_dev /*[B][n+1] device*/,
+                                         void* stream);
+/* deterministic test forms (INSECURE, see above) */
 int tfhe_b200_keygen_device(tfhe_b200_ctx* ctx, uint64_t seed, const uint8_t* s0 /*[n] host*/, const uint8_t* s1 /*[N] host*/);
 int tfhe_b200_export_bk(tfhe_b200_ctx* ctx, uint32_t* bk_host /*[n][2l][2][N] torus domain*/);
 int tfhe_b200_export_ksk(tfhe_b200_ctx* ctx, uint32_t* ksk_host /*[N][t][3][n+1]*/);

@@ -12,8 +12,9 @@
 //   TFHE::hom_nand / and / or / xor / not / mux (tfhe.rs:27-71)   TFHE::hom_nand / ... / hom_mux  (one gate: a batch of one)
 //   --                                                            TFHE::hom_*_batch(vector<TLWERep>, ...)  one launch per batch
 //
-// Differences, all deliberate: keys and encryptions are SEEDED (the reference samples from rand::thread_rng, which is not
-// reproducible); errors are C++ exceptions (tfhe::Error carries the TFHE_B200_ERR_* code and the engine's message) where
+// Randomness: like the reference (rand::thread_rng, an OS-seeded ChaCha generator) keys and encryptions come from ChaCha20
+// keyed by getrandom(2) -- the *_csprng entry points of the C ABI.  The overloads that take a `seed` use the DETERMINISTIC
+// TEST generator instead (reproducible, NOT secure: parity tests only).  Differences, all deliberate: errors are C++ exceptions (tfhe::Error carries the TFHE_B200_ERR_* code and the engine's message) where
 // the reference aborts; there is no CPU fallback -- constructing a TFHE without a B200 throws.
 #pragma once
 #include <array>
@@ -46,9 +47,13 @@ inline void check(int rc, const tfhe_b200_ctx* ctx, const char* where) {
 using SecretKeyLv0 = std::array<Binary, TLWEHelper::N>;
 using SecretKeyLv1 = std::array<Binary, TFHEHelper::N>;
 
-// uniform secret keys from a seed (the reference draws them with BinaryDistribution::uniform(), homnand-bench.rs:10-12)
-inline void gen_secret_keys(uint64_t seed, SecretKeyLv0& s0, SecretKeyLv1& s1) {
+// uniform secret keys (the reference draws them with BinaryDistribution::uniform(), homnand-bench.rs:10-12): OS-keyed ChaCha20
+inline void gen_secret_keys(SecretKeyLv0& s0, SecretKeyLv1& s1) {
     static_assert(sizeof(Binary) == 1, "Binary is one byte: the arrays are the ABI's bit arrays");
+    check(tfhe_b200_keygen_secret_csprng(nullptr, reinterpret_cast<uint8_t*>(s0.data()), reinterpret_cast<uint8_t*>(s1.data())), nullptr, "keygen_secret");
+}
+// deterministic TEST form (NOT secure)
+inline void gen_secret_keys(uint64_t seed, SecretKeyLv0& s0, SecretKeyLv1& s1) {
     check(tfhe_b200_keygen_secret(seed, reinterpret_cast<uint8_t*>(s0.data()), reinterpret_cast<uint8_t*>(s1.data())), nullptr, "keygen_secret");
 }
 
@@ -62,8 +67,15 @@ struct TLWERep {                                        // tlwe.rs:19-41
 };
 
 struct Cryptor {                                        // digest.rs:14-33 with the TLWE strategy of tlwe.rs:197-241
-    // fresh encryption of one bit under s_key; (seed, index) select the mask and the noise
-    static TLWERep encrypto(TLWEStrategy, const SecretKeyLv0& s_key, Binary item, uint64_t seed = 0, uint64_t index = next_index()) {
+    // fresh encryption of one bit under s_key: mask and noise from ChaCha20 with a fresh getrandom(2) key per call
+    static TLWERep encrypto(TLWEStrategy, const SecretKeyLv0& s_key, Binary item) {
+        TLWERep r;
+        const uint8_t bit = (uint8_t)item;
+        check(tfhe_b200_encrypt_bits_csprng(nullptr, reinterpret_cast<const uint8_t*>(s_key.data()), &bit, 1, r.w.data()), nullptr, "encrypt_bits");
+        return r;
+    }
+    // deterministic TEST form (NOT secure): (seed, index) select the mask and the noise; the caller keeps the pairs distinct
+    static TLWERep encrypto(TLWEStrategy, const SecretKeyLv0& s_key, Binary item, uint64_t seed, uint64_t index) {
         TLWERep r;
         const uint8_t bit = (uint8_t)item;
         check(tfhe_b200_encrypt_bits(seed, index, reinterpret_cast<const uint8_t*>(s_key.data()), &bit, 1, r.w.data()), nullptr, "encrypt_bits");
@@ -74,25 +86,33 @@ struct Cryptor {                                        // digest.rs:14-33 with 
         check(tfhe_b200_decrypt_bits(reinterpret_cast<const uint8_t*>(s_key.data()), rep.w.data(), 1, &bit), nullptr, "decrypt_bits");
         return bit ? Binary::One : Binary::Zero;
     }
-    static uint64_t next_index() { static uint64_t n = 0; return n++; }
 };
 
 class TFHE {                                            // tfhe.rs:9-113
 public:
-    // TFHE::new: both evaluation keys are generated ON the device from the seed (bit-identical to the seeded host keygen)
-    TFHE(const SecretKeyLv0& s_key_tlwelv0, const SecretKeyLv1& s_key_tlwelv1, uint64_t seed = 0, int device = 0) {
+    // TFHE::new: both evaluation keys are generated ON the device, masks and noise from ChaCha20 keyed by getrandom(2)
+    TFHE(const SecretKeyLv0& s_key_tlwelv0, const SecretKeyLv1& s_key_tlwelv1, int device = 0) { init(s_key_tlwelv0, s_key_tlwelv1, nullptr, device); }
+    // deterministic TEST form (NOT secure): bit-identical to the seeded host keygen
+    struct TestSeed { uint64_t seed; };
+    TFHE(const SecretKeyLv0& s_key_tlwelv0, const SecretKeyLv1& s_key_tlwelv1, TestSeed seed, int device = 0) { init(s_key_tlwelv0, s_key_tlwelv1, &seed, device); }
+    ~TFHE() { if (ctx_) tfhe_b200_ctx_destroy(ctx_); }
+    TFHE(const TFHE&) = delete;
+    TFHE& operator=(const TFHE&) = delete;
+
+private:
+    void init(const SecretKeyLv0& s_key_tlwelv0, const SecretKeyLv1& s_key_tlwelv1, const TestSeed* seed, int device) {
         check(tfhe_b200_ctx_create(nullptr, device, &ctx_), nullptr, "ctx_create");
-        const int rc = tfhe_b200_keygen_device(ctx_, seed, reinterpret_cast<const uint8_t*>(s_key_tlwelv0.data()),
-                                               reinterpret_cast<const uint8_t*>(s_key_tlwelv1.data()));
+        const uint8_t* k0 = reinterpret_cast<const uint8_t*>(s_key_tlwelv0.data());
+        const uint8_t* k1 = reinterpret_cast<const uint8_t*>(s_key_tlwelv1.data());
+        const int rc = seed ? tfhe_b200_keygen_device(ctx_, seed->seed, k0, k1) : tfhe_b200_keygen_device_csprng(ctx_, nullptr, k0, k1);
         if (rc != TFHE_B200_OK) {
             const std::string msg = tfhe_b200_last_error(ctx_);
             tfhe_b200_ctx_destroy(ctx_);
             throw Error(rc, "keygen_device: " + msg);
         }
     }
-    ~TFHE() { if (ctx_) tfhe_b200_ctx_destroy(ctx_); }
-    TFHE(const TFHE&) = delete;
-    TFHE& operator=(const TFHE&) = delete;
+
+public:
 
     TLWERep hom_nand(const TLWERep& input_0, const TLWERep& input_1) const { return gate(TFHE_B200_NAND, input_0, &input_1); }   // tfhe.rs:41-47
     TLWERep hom_and(const TLWERep& input_0, const TLWERep& input_1) const { return gate(TFHE_B200_AND, input_0, &input_1); }     // tfhe.rs:48-54

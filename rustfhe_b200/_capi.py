@@ -29,6 +29,8 @@ SYMBOLS = [
     "tfhe_b200_keygen_device", "tfhe_b200_export_bk", "tfhe_b200_export_ksk", "tfhe_b200_export_bk_device",
     "tfhe_b200_export_ksk_device", "tfhe_b200_encrypt_bits_device",
     "tfhe_b200_decrypt_bits_device", "tfhe_b200_cmux_batch", "tfhe_b200_sample_extract_batch",
+    "tfhe_b200_random_bytes", "tfhe_b200_keygen_secret_csprng", "tfhe_b200_keygen_bk_csprng", "tfhe_b200_keygen_ksk_csprng",
+    "tfhe_b200_encrypt_bits_csprng", "tfhe_b200_keygen_device_csprng", "tfhe_b200_encrypt_bits_device_csprng",
     "tfhe_b200_file_write", "tfhe_b200_file_info", "tfhe_b200_file_read", "tfhe_b200_file_last_error",
 ]
 FILE_SECRET, FILE_BK, FILE_KSK, FILE_TLWE0, FILE_TLWE1, FILE_TRLWE, FILE_TRGSW = range(1, 8)
@@ -93,6 +95,13 @@ def lib():
         "tfhe_b200_negacyclic_mul_batch": (i32, [vp, vp, vp, vp, sz]),
         "tfhe_b200_external_product_batch_device": (i32, [vp, vp, sz, vp, vp, sz, vp]),
         "tfhe_b200_negacyclic_mul_batch_device": (i32, [vp, vp, vp, vp, sz, vp]),
+        "tfhe_b200_random_bytes": (i32, [vp, sz]),
+        "tfhe_b200_keygen_secret_csprng": (i32, [vp, vp, vp]),
+        "tfhe_b200_keygen_bk_csprng": (i32, [vp, vp, vp, vp]),
+        "tfhe_b200_keygen_ksk_csprng": (i32, [vp, vp, vp, vp]),
+        "tfhe_b200_encrypt_bits_csprng": (i32, [vp, vp, vp, sz, vp]),
+        "tfhe_b200_keygen_device_csprng": (i32, [vp, vp, vp, vp]),
+        "tfhe_b200_encrypt_bits_device_csprng": (i32, [vp, vp, vp, vp, sz, vp, vp]),
         "tfhe_b200_keygen_secret": (i32, [u64, vp, vp]),
         "tfhe_b200_keygen_bk": (i32, [u64, vp, vp, vp]),
         "tfhe_b200_keygen_ksk": (i32, [u64, vp, vp, vp]),

@@ -108,9 +108,14 @@ class SecretKeys:
         assert self.s_key_tlwelv0.shape == (K.n,) and self.s_key_tlwelv1.shape == (K.N,)
 
     @staticmethod
-    def generate(seed):
+    def generate(seed=None):
+        """seed=None (default): ChaCha20 keyed from getrandom(2), like the reference's thread_rng.  An integer seed selects the
+        DETERMINISTIC TEST generator (reproducible, NOT secure -- parity tests only; see tfhe_rng.cuh)."""
         s0, s1 = np.zeros(K.n, np.uint8), np.zeros(K.N, np.uint8)
-        _check(None, lib().tfhe_b200_keygen_secret(seed, ptr(s0), ptr(s1)))
+        if seed is None:
+            _check(None, lib().tfhe_b200_keygen_secret_csprng(None, ptr(s0), ptr(s1)))
+        else:
+            _check(None, lib().tfhe_b200_keygen_secret(seed, ptr(s0), ptr(s1)))
         return SecretKeys(s0, s1)
 
 
@@ -128,10 +133,14 @@ class KeySwitchingKey:
         assert self.words.size == K.KSK_WORDS
 
     @staticmethod
-    def new(s_key_tlwelv1, s_key_tlwelv0, seed=0):
+    def new(s_key_tlwelv1, s_key_tlwelv0, seed=None):
+        """seed=None: fresh CSPRNG key per call; integer seed: deterministic test generator (INSECURE)."""
         w = np.zeros(K.KSK_WORDS, np.uint32)
-        _check(None, lib().tfhe_b200_keygen_ksk(seed, ptr(np.ascontiguousarray(s_key_tlwelv0, np.uint8)),
-                                                ptr(np.ascontiguousarray(s_key_tlwelv1, np.uint8)), ptr(w)))
+        s0p, s1p = ptr(np.ascontiguousarray(s_key_tlwelv0, np.uint8)), ptr(np.ascontiguousarray(s_key_tlwelv1, np.uint8))
+        if seed is None:
+            _check(None, lib().tfhe_b200_keygen_ksk_csprng(None, s0p, s1p, ptr(w)))
+        else:
+            _check(None, lib().tfhe_b200_keygen_ksk(seed, s0p, s1p, ptr(w)))
         return KeySwitchingKey(w)
 
     def get(self, i, l, t):      # tlwe.rs:281-283 : get(i,l,t) = KS[i][l][t-1]
@@ -147,28 +156,37 @@ class BootstrappingKey:
         assert self.words.size == K.BK_WORDS
 
     @staticmethod
-    def new(s_key_tlwelv0, s_key_tlwelv1, seed=0):
+    def new(s_key_tlwelv0, s_key_tlwelv1, seed=None):
+        """seed=None: fresh CSPRNG key per call; integer seed: deterministic test generator (INSECURE)."""
         w = np.zeros(K.BK_WORDS, np.uint32)
-        _check(None, lib().tfhe_b200_keygen_bk(seed, ptr(np.ascontiguousarray(s_key_tlwelv0, np.uint8)),
-                                               ptr(np.ascontiguousarray(s_key_tlwelv1, np.uint8)), ptr(w)))
+        s0p, s1p = ptr(np.ascontiguousarray(s_key_tlwelv0, np.uint8)), ptr(np.ascontiguousarray(s_key_tlwelv1, np.uint8))
+        if seed is None:
+            _check(None, lib().tfhe_b200_keygen_bk_csprng(None, s0p, s1p, ptr(w)))
+        else:
+            _check(None, lib().tfhe_b200_keygen_bk(seed, s0p, s1p, ptr(w)))
         return BootstrappingKey(w)
 
 
 class Cryptor:
     """Cryptor::{encrypto, decrypto} for the TLWE strategy on bits (digest.rs:14-33; tlwe.rs:197-241)."""
 
-    _counter = 0
-
     @staticmethod
-    def encrypto(strategy, s_key, item, seed=0, ct_index0=None):
+    def encrypto(strategy, s_key, item, seed=None, ct_index0=None):
+        """seed=None (default): every call draws a fresh 256-bit ChaCha20 key from getrandom(2) -- masks and noise never repeat.
+        (seed, ct_index0) integers select the DETERMINISTIC TEST generator: reproducible, NOT secure, and the caller owns the
+        uniqueness of the pair (equal pairs repeat masks and noise)."""
         assert strategy is TLWE
         bits = np.ascontiguousarray(np.atleast_1d(item), np.uint8)
-        if ct_index0 is None:
-            ct_index0 = Cryptor._counter
-            Cryptor._counter += len(bits)
         out = np.zeros((len(bits), K.n + 1), np.uint32)
-        _check(None, lib().tfhe_b200_encrypt_bits(seed, ct_index0, ptr(np.ascontiguousarray(s_key, np.uint8)), ptr(bits),
-                                                  len(bits), ptr(out)))
+        if seed is None:
+            if ct_index0 is not None:
+                raise ValueError("ct_index0 belongs to the deterministic test generator: pass a seed with it")
+            _check(None, lib().tfhe_b200_encrypt_bits_csprng(None, ptr(np.ascontiguousarray(s_key, np.uint8)), ptr(bits), len(bits), ptr(out)))
+        else:
+            if ct_index0 is None:
+                raise ValueError("the deterministic test generator needs an explicit ct_index0 (equal (seed, index) pairs repeat noise)")
+            _check(None, lib().tfhe_b200_encrypt_bits(seed, ct_index0, ptr(np.ascontiguousarray(s_key, np.uint8)), ptr(bits),
+                                                      len(bits), ptr(out)))
         return out
 
     @staticmethod
@@ -287,9 +305,15 @@ class DeviceEngine:
         self._ck(self._l.tfhe_b200_load_ksk_device(self._ctx, C.c_void_p(dev_ptr), C.c_void_p(stream)))
 
     def keygen_device(self, seed, s_key_tlwelv0, s_key_tlwelv1):
-        """BootstrappingKey::new + KeySwitchingKey::new on the device (bit-identical to the host keygen with this seed)."""
-        self._ck(self._l.tfhe_b200_keygen_device(self._ctx, seed, ptr(np.ascontiguousarray(s_key_tlwelv0, np.uint8)),
-                                                 ptr(np.ascontiguousarray(s_key_tlwelv1, np.uint8))))
+        """BootstrappingKey::new + KeySwitchingKey::new on the device.  seed=None: ChaCha20 keyed from getrandom(2); 32 bytes: that
+        ChaCha20 key (bit-identical to the host *_csprng keygen with the same key); integer: deterministic test generator
+        (INSECURE; bit-identical to the host keygen with this seed)."""
+        s0p, s1p = ptr(np.ascontiguousarray(s_key_tlwelv0, np.uint8)), ptr(np.ascontiguousarray(s_key_tlwelv1, np.uint8))
+        if seed is None or isinstance(seed, (bytes, bytearray)):
+            key = None if seed is None else (C.c_uint8 * 32).from_buffer_copy(bytes(seed))
+            self._ck(self._l.tfhe_b200_keygen_device_csprng(self._ctx, key, s0p, s1p))
+        else:
+            self._ck(self._l.tfhe_b200_keygen_device(self._ctx, seed, s0p, s1p))
 
     def export_bk(self):
         w = np.empty(K.BK_WORDS, np.uint32)
@@ -308,6 +332,11 @@ class DeviceEngine:
         self._ck(self._l.tfhe_b200_export_ksk_device(self._ctx, C.c_void_p(dev_ptr), C.c_void_p(stream)))
 
     def encrypt_bits_device(self, seed, ct_index0, s_key, bits_ptr, B, out_ptr, stream=0):
+        """seed=None: fresh ChaCha20 key from getrandom(2) (ct_index0 ignored); integer seed: deterministic test generator."""
+        if seed is None:
+            self._ck(self._l.tfhe_b200_encrypt_bits_device_csprng(self._ctx, None, ptr(np.ascontiguousarray(s_key, np.uint8)),
+                                                                  C.c_void_p(bits_ptr), B, C.c_void_p(out_ptr), C.c_void_p(stream)))
+            return
         self._ck(self._l.tfhe_b200_encrypt_bits_device(self._ctx, seed, ct_index0, ptr(np.ascontiguousarray(s_key, np.uint8)),
                                                        C.c_void_p(bits_ptr), B, C.c_void_p(out_ptr), C.c_void_p(stream)))
 
@@ -454,7 +483,7 @@ class TFHE:
         self.engine.load_bk(bk.words)
 
     @staticmethod
-    def new_on_device(s_key_tlwelv0, s_key_tlwelv1, seed=0, device=0, decomp_mask=K.MASK_FAITHFUL):
+    def new_on_device(s_key_tlwelv0, s_key_tlwelv1, seed=None, device=0, decomp_mask=K.MASK_FAITHFUL):
         """TFHE::new with both keys generated ON the device (same seed -> same keys as `TFHE.new`); `bk` / `ksk` stay None
         until exported with `engine.export_bk()` / `engine.export_ksk()`."""
         eng = DeviceEngine(device, decomp_mask)
@@ -462,7 +491,7 @@ class TFHE:
         return TFHE(None, None, device, decomp_mask, engine=eng)
 
     @staticmethod
-    def new(s_key_tlwelv0, s_key_tlwelv1, seed=0, device=0, decomp_mask=K.MASK_FAITHFUL):
+    def new(s_key_tlwelv0, s_key_tlwelv1, seed=None, device=0, decomp_mask=K.MASK_FAITHFUL):
         """TFHE::new (tfhe.rs:21-25): ksk = KeySwitchingKey::new(lv1, &lv0); bk = BootstrappingKey::new(lv0, &lv1)."""
         ksk = KeySwitchingKey.new(s_key_tlwelv1, s_key_tlwelv0, seed)
         bk = BootstrappingKey.new(s_key_tlwelv0, s_key_tlwelv1, seed)

@@ -100,7 +100,7 @@ def build(force=False, verbose=False):
 
 def build_emul(force=False):
     """CPU emulation of the kernels' per-lane arithmetic (tests/test_host_logic.py only)."""
-    src = [os.path.join(CSRC, f) for f in ("host_emul.cpp", "ntt32.cuh", "cmux_steps.cuh", "t2_steps.cuh", "ntt_tables.h")]
+    src = [os.path.join(CSRC, f) for f in ("host_emul.cpp", "ntt32.cuh", "cmux_steps.cuh", "t2_steps.cuh", "ntt_tables.h", "tfhe_rng.cuh")]
     if not force and not _stale(EMUL, src):
         return EMUL
 

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(PM_WARPS * 32) polymul_kernel(const uint32_t* 
 // =====================================================================================================
 using tfhe_rng::Rng;
 // rows of the bootstrapping key before the a*s product: A = uniform, B = noise      bk: [n][2l][2][N], poly 0 = B, poly 1 = A
-__global__ void bk_fill_kernel(uint32_t* __restrict__ bk, uint64_t seed, long nwords /* = rows * N */) {
+__global__ void bk_fill_kernel(uint32_t* __restrict__ bk, const tfhe_rng::RngKey seed, long nwords /* = rows * N */) {
     const Rng ra(seed, tfhe_rng::BK_A), re(seed, tfhe_rng::BK_E);
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < nwords; t += (long)gridDim.x * blockDim.x) {
         const long row = t >> 10;
@@ -87,7 +87,7 @@ __global__ void bk_gadget_kernel(uint32_t* __restrict__ bk, const uint8_t* __res
 // one warp per LWE row under s0: a = uniform, b = <a, s0> + noise + message.
 //   mode 0: key-switching key, row id = (i, l, d-1), message = d * s1_i / 2^(2(l+1))      (tlwe.rs:247-283)
 //   mode 1: encryption of bits[g], row id = ct_index0 + g, message = +-1/8                  (tlwe.rs:181-186,213-228)
-__global__ void lwe_rows_kernel(uint32_t* __restrict__ out, long rows, uint64_t seed, uint64_t index0, const uint8_t* __restrict__ s0,
+__global__ void lwe_rows_kernel(uint32_t* __restrict__ out, long rows, const tfhe_rng::RngKey seed, uint64_t index0, const uint8_t* __restrict__ s0,
                                 const uint8_t* __restrict__ s1, const uint8_t* __restrict__ bits, int mode) {
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;

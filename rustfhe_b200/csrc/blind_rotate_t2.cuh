@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(G* T2_THREADS_PER_GATE, 1) blind_rotate_t2_ker
         twF[t] = g_fwdB[t];
         twI[t] = g_invB[t];
     }
-    for (int t = threadIdx.x; t < DIGIT_TAB_WORDS; t += blockDim.x) dtab[t] = g_digit_tab.v[t];
+    for (int t = threadIdx.x; t < DIGIT_TAB_WORDS; t += blockDim.x) dtab[t] = g_digit_tab2.v[t];
     // ---- prologue: gate pre-combination (tfhe.rs:27-71), rounding of (b, a) (tfhe.rs:97,107-108), acc_0 ----
     {
         uint32_t* lin = dh;
@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(G* T2_THREADS_PER_GATE, 1) blind_rotate_t2_ker
                 }
             }
         }
+#if !defined(T2_EXP_NOBAR)
         bar_sync(bar_gate, T2_THREADS_PER_GATE);   // the six spectra of this step are complete
+#endif
         {
             uint32_t y0[32], y1[32];
             if (TWREG & 2) {
@@ -125,7 +127,9 @@ __global__ void __launch_bounds__(G* T2_THREADS_PER_GATE, 1) blind_rotate_t2_ker
             } else {
                 t2_mac(lane, keyp, dh, TwRow{twI + lane * TWB_STRIDE}, y0, y1);
             }
+#if !defined(T2_EXP_NOBAR)
             bar_sync(bar_gate, T2_THREADS_PER_GATE);   // both warps have read the spectra: the own tiles are scratch now
+#endif
             t2_inv_store(lane, y0, own);
             t2_inv_store(lane, y1, own + T2_TILE_WORDS);
         }

@@ -239,6 +239,9 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     if (!ctx) return TFHE_B200_ERR_PARAM;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->keybits) cudaMemset(ctx->keybits, 0, 2048);
+    if (ctx->s1poly) cudaMemset(ctx->s1poly, 0, 1024 * 4);
+    for (auto& s : ctx->slots) if (s.s0buf) cudaMemset(s.s0buf, 0, 1024);
     cudaFree(ctx->bkdev); cudaFree(ctx->bkdev_t2); cudaFree(ctx->kskdev); cudaFree(ctx->bk_torus); cudaFree(ctx->keybits); cudaFree(ctx->s1poly);
     for (auto& s : ctx->slots) {
         cudaFree(s.ksdig); cudaFree(s.scratch); cudaFree(s.s0buf); cudaFree(s.opsbuf);
@@ -757,7 +760,7 @@ int tfhe_b200_circuit_run_device(tfhe_b200_ctx* ctx, const tfhe_b200_circuit* c,
 // ---- device-side key generation, encryption, decryption ----
 extern "C" {
 
-int tfhe_b200_keygen_device(tfhe_b200_ctx* ctx, uint64_t seed, const uint8_t* s0, const uint8_t* s1) {
+static int keygen_device_impl(tfhe_b200_ctx* ctx, const tfhe_rng::RngKey& seed, const uint8_t* s0, const uint8_t* s1) {
     if (!ctx || !s0 || !s1) return fail(ctx, TFHE_B200_ERR_PARAM, "keygen_device: null argument");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->slots[0].stream;
@@ -784,9 +787,33 @@ int tfhe_b200_keygen_device(tfhe_b200_ctx* ctx, uint64_t seed, const uint8_t* s0
     lwe_rows_kernel<<<(unsigned)((krows + 7) / 8), 256, 0, st>>>(ctx->kskdev, krows, seed, 0, ctx->keybits, ctx->keybits + 1024, nullptr, 0);
     ctx->launches++;
     CK(cudaGetLastError());
+    // the secret keys do not outlive the key generation on the device
+    CK(cudaMemsetAsync(ctx->keybits, 0, 2048, st));
+    CK(cudaMemsetAsync(ctx->s1poly, 0, 1024 * 4, st));
     CK(cudaStreamSynchronize(st));
     ctx->have_bk = ctx->have_ksk = true;
     return TFHE_B200_OK;
+}
+// generator key of a *_csprng call: the caller's 32 bytes, or fresh OS entropy (getrandom) when key == NULL
+static int csprng_key(tfhe_b200_ctx* ctx, const uint8_t* key, tfhe_rng::RngKey* out) {
+    uint8_t fresh[32];
+    if (!key) {
+        if (tfhe_b200_random_bytes(fresh, sizeof fresh) != TFHE_B200_OK) return fail(ctx, TFHE_B200_ERR_IO, "getrandom failed");
+        key = fresh;
+    }
+    *out = tfhe_rng::key_from_bytes(key);
+    volatile uint8_t* w = fresh;
+    for (size_t i = 0; i < sizeof fresh; i++) w[i] = 0;
+    return TFHE_B200_OK;
+}
+int tfhe_b200_keygen_device(tfhe_b200_ctx* ctx, uint64_t seed, const uint8_t* s0, const uint8_t* s1) {
+    return keygen_device_impl(ctx, tfhe_rng::key_from_seed(seed), s0, s1);
+}
+int tfhe_b200_keygen_device_csprng(tfhe_b200_ctx* ctx, const uint8_t* key, const uint8_t* s0, const uint8_t* s1) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    tfhe_rng::RngKey k;
+    RC(csprng_key(ctx, key, &k));
+    return keygen_device_impl(ctx, k, s0, s1);
 }
 int tfhe_b200_export_bk(tfhe_b200_ctx* ctx, uint32_t* bk_host) {
     if (!ctx || !bk_host) return fail(ctx, TFHE_B200_ERR_PARAM, "export_bk: null argument");
@@ -818,8 +845,8 @@ int tfhe_b200_export_ksk(tfhe_b200_ctx* ctx, uint32_t* ksk_host) {
     return TFHE_B200_OK;
 }
 // bits_dev: [B] bytes on the device; out_dev: [B][n+1] on the device; s0: host
-int tfhe_b200_encrypt_bits_device(tfhe_b200_ctx* ctx, uint64_t seed, uint64_t ct_index0, const uint8_t* s0, const uint8_t* bits_dev,
-                                  size_t B, uint32_t* out_dev, void* stream) {
+static int encrypt_bits_device_impl(tfhe_b200_ctx* ctx, const tfhe_rng::RngKey& seed, uint64_t ct_index0, const uint8_t* s0, const uint8_t* bits_dev,
+                                    size_t B, uint32_t* out_dev, void* stream) {
     if (!ctx || !s0 || (B && (!bits_dev || !out_dev))) return fail(ctx, TFHE_B200_ERR_PARAM, "encrypt_bits_device: null argument");
     if (B == 0) return TFHE_B200_OK;
     CK(cudaSetDevice(ctx->device));
@@ -830,7 +857,19 @@ int tfhe_b200_encrypt_bits_device(tfhe_b200_ctx* ctx, uint64_t seed, uint64_t ct
     lwe_rows_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(out_dev, (long)B, seed, ct_index0, s->s0buf, nullptr, bits_dev, 1);
     ctx->launches++;
     CK(cudaGetLastError());
+    CK(cudaMemsetAsync(s->s0buf, 0, 1024, st));   // the secret key does not stay on the device
     return slot_release(ctx, s, st);
+}
+int tfhe_b200_encrypt_bits_device(tfhe_b200_ctx* ctx, uint64_t seed, uint64_t ct_index0, const uint8_t* s0, const uint8_t* bits_dev,
+                                  size_t B, uint32_t* out_dev, void* stream) {
+    return encrypt_bits_device_impl(ctx, tfhe_rng::key_from_seed(seed), ct_index0, s0, bits_dev, B, out_dev, stream);
+}
+int tfhe_b200_encrypt_bits_device_csprng(tfhe_b200_ctx* ctx, const uint8_t* key, const uint8_t* s0, const uint8_t* bits_dev, size_t B,
+                                         uint32_t* out_dev, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    tfhe_rng::RngKey k;
+    RC(csprng_key(ctx, key, &k));
+    return encrypt_bits_device_impl(ctx, k, 0, s0, bits_dev, B, out_dev, stream);
 }
 // phase_dev / bits_dev: either may be NULL
 int tfhe_b200_decrypt_bits_device(tfhe_b200_ctx* ctx, const uint8_t* s0, const uint32_t* ct_dev, size_t B, uint8_t* bits_dev,
@@ -845,6 +884,7 @@ int tfhe_b200_decrypt_bits_device(tfhe_b200_ctx* ctx, const uint8_t* s0, const u
     lwe_phase_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(ct_dev, (long)B, s->s0buf, phase_dev, bits_dev);
     ctx->launches++;
     CK(cudaGetLastError());
+    CK(cudaMemsetAsync(s->s0buf, 0, 1024, st));   // the secret key does not stay on the device
     return slot_release(ctx, s, st);
 }
 

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 #include "t2_steps.cuh"
+#include "tfhe_rng.cuh"
 
 using namespace tfhe;
 
@@ -122,7 +123,7 @@ static void t2_step(const uint32_t* dev, uint32_t* acc, bool rotate, uint32_t ab
         }
         for (int dw = 0; dw < 3; dw++) {
             uint32_t* S = dh.data() + (3 * pw + dw) * T2_TILE_WORDS;
-            for (int lane = 0; lane < 32; lane++) t2_fwd_cols(lane, u[lane], 6 * dw, S, h_digit_tab.v);
+            for (int lane = 0; lane < 32; lane++) t2_fwd_cols(lane, u[lane], 6 * dw, S, h_digit_tab2.v);
             for (int lane = 0; lane < 32; lane++) t2_fwd_rows(lane, S, TwRow{h_fwdB + lane * TWB_STRIDE});
         }
     }
@@ -148,6 +149,8 @@ void emul_external_product_t2(const uint32_t* dev, const uint32_t* trlwe, uint32
     t2_step(dev, out, false, 0, mask);
 }
 void emul_cmux_rotate_t2(const uint32_t* dev, uint32_t* acc, uint32_t abar, uint32_t mask) { t2_step(dev, acc, true, abar, mask); }
+// one 64-bit word of the ChaCha20 block the production generator is built on (RFC 8439 known-answer test)
+uint64_t emul_chacha20_u64(const uint32_t* key, uint64_t counter, uint64_t nonce, int lane8) { return tfhe_rng::chacha20_u64(key, counter, nonce, lane8); }
 uint32_t emul_prime(void) { return P; }
 int32_t emul_key_slice(uint32_t c, int part) { return key_slice(c, part); }
 int32_t emul_key_slice2(uint32_t c, int part) { return key_slice(c, part, 2); }

@@ -6,6 +6,7 @@
 // Deliberate differences: a seeded counter-based generator (the reference cannot be seeded), full 32-bit uniform masks
 // (the reference samples Uniform<f32>, 24 random bits, math.rs:425-432) and an exact a*s product (the reference uses its FFT).
 #include <cmath>
+#include <sys/random.h>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -34,11 +35,72 @@ void add_mul_binary(const uint32_t* a, const std::vector<int>& ones, uint32_t* b
         for (int k = 0; k < j; k++) b[k] -= a[N + k - j];
     }
 }
+// 32 bytes of operating-system entropy (getrandom(2), blocking until the pool is initialised)
+bool os_random(uint8_t* out, size_t len) {
+    size_t got = 0;
+    while (got < len) {
+        const ssize_t r = getrandom(out + got, len - got, 0);
+        if (r < 0) return false;
+        got += (size_t)r;
+    }
+    return true;
+}
+// generator key of a *_csprng call: the caller's 32 bytes, or fresh OS entropy when key == NULL
+bool csprng_key(const uint8_t* key, RngKey* out) {
+    uint8_t fresh[32];
+    if (!key) {
+        if (!os_random(fresh, sizeof fresh)) return false;
+        key = fresh;
+    }
+    *out = key_from_bytes(key);
+    volatile uint8_t* w = fresh;
+    for (size_t i = 0; i < sizeof fresh; i++) w[i] = 0;
+    return true;
+}
+int keygen_secret_impl(const RngKey& seed, uint8_t* s0, uint8_t* s1);
+int keygen_bk_impl(const RngKey& seed, const uint8_t* s0, const uint8_t* s1, uint32_t* bk);
+int keygen_ksk_impl(const RngKey& seed, const uint8_t* s0, const uint8_t* s1, uint32_t* ksk);
+int encrypt_bits_impl(const RngKey& seed, uint64_t ct_index0, const uint8_t* s0, const uint8_t* bits, size_t B, uint32_t* out);
 }  // namespace
 
 extern "C" {
 
-int tfhe_b200_keygen_secret(uint64_t seed, uint8_t* s0, uint8_t* s1) {
+// ---- deterministic TEST entry points (SplitMix64 of a 64-bit seed: reproducible, NOT secure; see tfhe_rng.cuh) ----
+int tfhe_b200_keygen_secret(uint64_t seed, uint8_t* s0, uint8_t* s1) { return keygen_secret_impl(key_from_seed(seed), s0, s1); }
+int tfhe_b200_keygen_bk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uint32_t* bk) { return keygen_bk_impl(key_from_seed(seed), s0, s1, bk); }
+int tfhe_b200_keygen_ksk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uint32_t* ksk) { return keygen_ksk_impl(key_from_seed(seed), s0, s1, ksk); }
+int tfhe_b200_encrypt_bits(uint64_t seed, uint64_t ct_index0, const uint8_t* s0, const uint8_t* bits, size_t B, uint32_t* out) {
+    return encrypt_bits_impl(key_from_seed(seed), ct_index0, s0, bits, B, out);
+}
+// ---- production entry points: ChaCha20 keyed with 256 bits; key == NULL draws a fresh key from getrandom(2) per call ----
+int tfhe_b200_random_bytes(uint8_t* out, size_t len) {
+    if (!out && len) return TFHE_B200_ERR_PARAM;
+    return os_random(out, len) ? TFHE_B200_OK : TFHE_B200_ERR_IO;
+}
+int tfhe_b200_keygen_secret_csprng(const uint8_t* key, uint8_t* s0, uint8_t* s1) {
+    RngKey k;
+    if (!csprng_key(key, &k)) return TFHE_B200_ERR_IO;
+    return keygen_secret_impl(k, s0, s1);
+}
+int tfhe_b200_keygen_bk_csprng(const uint8_t* key, const uint8_t* s0, const uint8_t* s1, uint32_t* bk) {
+    RngKey k;
+    if (!csprng_key(key, &k)) return TFHE_B200_ERR_IO;
+    return keygen_bk_impl(k, s0, s1, bk);
+}
+int tfhe_b200_keygen_ksk_csprng(const uint8_t* key, const uint8_t* s0, const uint8_t* s1, uint32_t* ksk) {
+    RngKey k;
+    if (!csprng_key(key, &k)) return TFHE_B200_ERR_IO;
+    return keygen_ksk_impl(k, s0, s1, ksk);
+}
+int tfhe_b200_encrypt_bits_csprng(const uint8_t* key, const uint8_t* s0, const uint8_t* bits, size_t B, uint32_t* out) {
+    RngKey k;
+    if (!csprng_key(key, &k)) return TFHE_B200_ERR_IO;
+    return encrypt_bits_impl(k, 0, s0, bits, B, out);
+}
+}  // extern "C"
+
+namespace {
+int keygen_secret_impl(const RngKey& seed, uint8_t* s0, uint8_t* s1) {
     if (!s0 || !s1) return TFHE_B200_ERR_PARAM;
     Rng r0(seed, S0), r1(seed, S1);
     for (int i = 0; i < n; i++) s0[i] = (uint8_t)(r0.u64(i) >> 63);
@@ -48,7 +110,7 @@ int tfhe_b200_keygen_secret(uint64_t seed, uint8_t* s0, uint8_t* s1) {
 
 // BK_i = TRGSW_{s1}(s0_i): 2l fresh TRLWE_{s1}(0) rows (B = A*s1 + e, A), then mu/Bg^(j+1) added on B[0] of rows j<l and on
 // A[0] of rows l+j (trgsw.rs:118-138,213-229); alpha_bk = 2^-25 (trlwe.rs:77)
-int tfhe_b200_keygen_bk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uint32_t* bk) {
+int keygen_bk_impl(const RngKey& seed, const uint8_t* s0, const uint8_t* s1, uint32_t* bk) {
     if (!s0 || !s1 || !bk) return TFHE_B200_ERR_PARAM;
     std::vector<int> ones;
     for (int j = 0; j < N; j++) if (s1[j]) ones.push_back(j);
@@ -68,7 +130,7 @@ int tfhe_b200_keygen_bk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uin
 
 // KS[i][l][d-1] = TLWE_{s0}(d * s1_i / 2^(2(l+1))), d = 1..3 (tlwe.rs:247-283; the unreachable d=4 entry is not stored);
 // alpha = 2^-15 (tlwe.rs:176)
-int tfhe_b200_keygen_ksk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, uint32_t* ksk) {
+int keygen_ksk_impl(const RngKey& seed, const uint8_t* s0, const uint8_t* s1, uint32_t* ksk) {
     if (!s0 || !s1 || !ksk) return TFHE_B200_ERR_PARAM;
     const Rng ra(seed, KSK_A), re(seed, KSK_E);
     parallel_for(N * KS_T * 3, [&](int rowid) {
@@ -86,7 +148,7 @@ int tfhe_b200_keygen_ksk(uint64_t seed, const uint8_t* s0, const uint8_t* s1, ui
 }
 
 // Cryptor::encrypto(TLWE, &s0, Binary): One -> +1/8, Zero -> -1/8 (tlwe.rs:181-186), b = <a,s> + e + m (tlwe.rs:213-228)
-int tfhe_b200_encrypt_bits(uint64_t seed, uint64_t ct_index0, const uint8_t* s0, const uint8_t* bits, size_t B, uint32_t* out) {
+int encrypt_bits_impl(const RngKey& seed, uint64_t ct_index0, const uint8_t* s0, const uint8_t* bits, size_t B, uint32_t* out) {
     if (!s0 || (!bits && B) || (!out && B)) return TFHE_B200_ERR_PARAM;
     const Rng ra(seed, ENC_A), re(seed, ENC_E);
     for (size_t g = 0; g < B; g++) {
@@ -102,6 +164,9 @@ int tfhe_b200_encrypt_bits(uint64_t seed, uint64_t ct_index0, const uint8_t* s0,
     }
     return TFHE_B200_OK;
 }
+}  // namespace
+
+extern "C" {
 // phase = b - <a, s> (tlwe.rs:230-240)
 int tfhe_b200_phase(const uint8_t* s0, const uint32_t* ct, size_t B, uint32_t* phase) {
     if (!s0 || (!ct && B) || (!phase && B)) return TFHE_B200_ERR_PARAM;

@@ -60,18 +60,42 @@ TFHE_HD constexpr DigitTab make_digit_tab() {
     return t;
 }
 static const DigitTab h_digit_tab = make_digit_tab();
+// The same products for the throughput kernel (t2_steps.cuh), indexed by the RAW two's-complement 6-bit pattern of the digit
+// (v = d & 63: no bias to add to the index) and pre-biased by p: IOTA2[v] = (d * psi^512 mod p) + p in [p, 2p).
+TFHE_HD constexpr DigitTab make_digit_tab2() {
+    constexpr uint32_t fwdA[64] = {NTT_FWD_A_LIST};
+    DigitTab t{};
+    for (int v = 0; v < DIGIT_TAB_WORDS; v++) {
+        const int d = v < 32 ? v : v - 64;
+        const uint64_t r = (uint64_t)(d < 0 ? (int64_t)NTT_P + d : d);
+        t.v[v] = (uint32_t)(r * fwdA[2] % NTT_P) + NTT_P;
+    }
+    return t;
+}
+static const DigitTab h_digit_tab2 = make_digit_tab2();
 #if defined(__CUDACC__)
 static __device__ const DigitTab g_digit_tab = make_digit_tab();
+static __device__ const DigitTab g_digit_tab2 = make_digit_tab2();
 #endif
 
-// a + b as a THREE-input add with an opaque zero: keeps ptxas from emitting IMAD.IADD, i.e. keeps plain additions on
-// the ALU pipe and off the FMA-heavy pipe that bounds the transforms (profiles/r01_ncu_blind_rotate_v1.txt).
+// a + b on the ALU pipe: max(a + b, 0) is ONE VIADDMNMX.U32, which ptxas cannot turn into IMAD.IADD -- plain additions
+// stay off the FMA-heavy pipe that bounds the transforms (profiles/r01_ncu_blind_rotate_v1.txt).  (Round 1 used a three-input
+// add with an opaque zero from the constant bank; ptxas hoisted and re-associated that zero into extra instructions.)
 TFHE_HD uint32_t add_alu(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
-    return a + b + c_zero;
+    return __viaddmax_u32(a, b, 0u);
 #else
     return a + b;
 #endif
+}
+// pins a value: the expression that produced it stays ONE instruction (a three-input IADD3) instead of being re-associated
+// with its consumers -- ptxas otherwise splits a two-input add or subtract off it, often onto the FMA-heavy pipe (IMAD.IADD),
+// and adds the constant again at every consumer.  Emits nothing.
+TFHE_HD uint32_t pin(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    asm("" : "+r"(v));
+#endif
+    return v;
 }
 TFHE_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
@@ -94,7 +118,7 @@ TFHE_HD uint32_t shoup_mul(uint32_t y, uint32_t w, uint32_t ws) { return y * w -
 // Montgomery reduction of S < p * 2^32 : returns S * 2^-32 mod p in (0, 2p)
 TFHE_HD uint32_t redc64(uint64_t s) {
     uint32_t m = (uint32_t)s * NTT_PINV;
-    return (uint32_t)(s >> 32) + P - mulhi32(m, P);
+    return pin((uint32_t)(s >> 32) + P - mulhi32(m, P));
 }
 // centred lift of v in [0,p) to the exact signed integer (|true value| < p/2 by construction)
 TFHE_HD int32_t lift(uint32_t v) { return v > (P - 1) / 2 ? (int32_t)(v - P) : (int32_t)v; }
@@ -138,7 +162,7 @@ TFHE_HD void ct_bfly(uint32_t& a, uint32_t& b, uint32_t w, uint32_t ws) {
     const uint32_t X = CORR ? csub(a, 2u * P2) : a;
     const uint32_t T = shoup_mul(b, w, ws);
     a = add_alu(X, T);
-    b = X - T + P2;
+    b = pin(X - T + P2);
 }
 template <int S, int CORR, class TW>
 TFHE_HD void ct_stage(uint32_t (&x)[32], const TW& tw) {  // stage S = 1..4: m = 2^S blocks of half-width t = 16 >> S
@@ -226,7 +250,7 @@ TFHE_HD void gs_bfly_p(uint32_t (&x)[32], uint32_t w, uint32_t ws) {
     if constexpr (pl.cv[S][BI][0] != 0) V = csub(V, pl.cv[S][BI][0] * P);
     if constexpr (pl.cv[S][BI][1] != 0) V = csub(V, pl.cv[S][BI][1] * P);
     x[u] = add_alu(U, V);
-    x[v] = shoup_mul(U - V + pl.kv[S][BI] * P, w, ws);
+    x[v] = shoup_mul(pin(U - V + pl.kv[S][BI] * P), w, ws);
 }
 template <int IN, int S, int I, class TW, int... J>   // blocks I and I+1 of stage S (16 >> S >= 2): one 16-byte twiddle load
 TFHE_HD void gs_blockpair_p(uint32_t (&x)[32], const TW& tw, std::integer_sequence<int, J...>) {
@@ -292,7 +316,7 @@ static_assert(gs_head_is_uniform(), "gs32_head4 hard-codes the lazy plan of stag
 TFHE_HD void gs_bfly_k(uint32_t& a, uint32_t& b, uint32_t kp, uint32_t w, uint32_t ws) {
     const uint32_t U = a, V = b;
     a = add_alu(U, V);
-    b = shoup_mul(U - V + kp, w, ws);
+    b = shoup_mul(pin(U - V + kp), w, ws);
 }
 template <class TW>
 TFHE_HD void gs32_head4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, int q, const TW& tw) {

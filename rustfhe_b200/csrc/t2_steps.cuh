@@ -14,8 +14,8 @@
 //   barrier : both warps have finished reading the spectra -> the own tiles are free as transpose scratch
 //   phase 3 : inverse column passes, exact lift, acc[pw] += x0 + (x1 << 16)  (the warp is the only writer of acc[pw])
 // Per CMUX: 6 forward + 4 inverse transforms and 24 pointwise polynomial products, against 6 + 6 and 36 with three 11-bit
-// slices.  Spectra are left UNNORMALISED (< 6p): the 64-bit pointwise sums (6 * 6p * p < 2^64) and one Montgomery reduction
-// absorb the range, the inverse row pass starts from a < 6p plan (ntt32.cuh, GsPlan).
+// slices.  Spectra are left UNNORMALISED (< 8p + 32): the 64-bit pointwise sums (6 * 8p * p = 48 p^2 < 2^64) and one Montgomery
+// reduction absorb the range, the inverse row pass starts from a < 8p plan (ntt32.cuh, GsPlan).
 //
 // Tiles are 32 x 32 words, XOR-swizzled on the 16-byte chunk index (no padding: six gates of 33 KB fit one SM).
 // Every function is what ONE lane does between two warp-level synchronisation points (host_emul.cpp runs them lane by lane).
@@ -40,33 +40,61 @@ TFHE_HD size_t t2_bk_off(int i, int pw, int q, int j, int s, int lane) {
 }
 
 // ---- phase 1u: lane = column c; u[r] = masked source coefficient 32 r + c ----
-template <bool ROTATE>
-TFHE_HD void t2_u(int lane, const uint32_t* A, uint32_t abar, uint32_t mask, uint32_t (&u)[32]) {
+// u = ((X^abar A - A)[k] + mask) ^ mask with k = 32 r + lane (math.rs:85-113: X^abar A [k] = +-A[(k - abar) mod N], the sign
+// flips once where the index folds around and once more for abar >= N).  Written in byte offsets with explicit sign masks so
+// that one element costs 7 ALU instructions and two LDS: the ALU pipe is as loaded as the FMA pipe in this kernel.
+// FLIP (abar >= N) is warp-uniform: the caller branches once per step and the NOT of the sign mask folds into the LOP3 / the
+// constant of each version.
+template <bool FLIP>
+TFHE_HD void t2_u_rot(int lane, const uint32_t* A, uint32_t ap /* abar & 1023 */, uint32_t mask, uint32_t (&u)[32]) {
+    const uint32_t tb = ((uint32_t)lane - ap) * 4u;                 // byte offset of coefficient k - ap for r = 0 (may wrap below zero)
+    const uint32_t cm = FLIP ? mask + 1u : mask;                    // -(~m) = m + 1: the +1 rides on the mask addition
 #pragma unroll
     for (int r = 0; r < 32; r++) {
-        const uint32_t k = 32u * r + lane;
-        const uint32_t src = ROTATE ? rot_diff(A, k, abar) : A[k];
-        u[r] = add_alu(src, mask) ^ mask;
+        const uint32_t t4 = add_alu(tb, 128u * r);
+        const uint32_t m = (uint32_t)((int32_t)t4 >> 31);           // ~0 where the rotated index folded around
+        const uint32_t rv = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(A) + (t4 & 4092u));
+        const uint32_t a = A[32 * r + lane];
+        // FLIP = false: (rv ^ m) - m - a ;  FLIP = true: (rv ^ ~m) - ~m - a = ~(rv ^ m) + m + 1 - a
+        const uint32_t d = pin(FLIP ? (~(rv ^ m)) + m - a : (rv ^ m) - m - a);
+        u[r] = add_alu(d, cm) ^ mask;
+    }
+}
+template <bool ROTATE>
+TFHE_HD void t2_u(int lane, const uint32_t* A, uint32_t abar, uint32_t mask, uint32_t (&u)[32]) {
+    if (!ROTATE) {
+#pragma unroll
+        for (int r = 0; r < 32; r++) u[r] = add_alu(A[32 * r + lane], mask) ^ mask;
+    } else if (abar >> 10) {
+        t2_u_rot<true>(lane, A, abar & 1023u, mask, u);
+    } else {
+        t2_u_rot<false>(lane, A, abar & 1023u, mask, u);
     }
 }
 // ---- phase 1a: digit dw of the column, column pass, scatter into tile S ----
-// Stage 0 pairs rows r and r+16 with the single twiddle psi^512.  With X = d_r (a small SIGNED digit) and T = d_{r+16} psi^512
-// mod p from the 64-entry table:  a = X + T + p  in [p-32, 2p+32),  b = X - T + 2p  in (p-32, 2p+32]: no residue conversion of X.
-// The +-32 of slack is carried through the lazy bounds (8p + 32 < 2^32).
-TFHE_HD void t2_fwd_cols(int lane, const uint32_t (&u)[32], int sh /* 6 * dw */, uint32_t* S, const uint32_t* digit_tab) {
+// Stage 0 pairs rows r and r+16 with the single twiddle psi^512.  With X = d_r (a small SIGNED digit, taken straight out of
+// the masked word by an arithmetic shift) and T' = (d_{r+16} psi^512 mod p) + p from the 64-entry table indexed by the raw
+// 6-bit pattern:  a = X + T'  in [p-32, 2p+32),  b = X - T' + 3p  in (p-32, 2p+32]: no residue conversion, no index bias.
+// The +-32 of slack is carried through the lazy bounds (8p + 32 < 2^32).  Corrections: last column stage only.
+TFHE_HD void t2_fwd_cols(int lane, const uint32_t (&u)[32], int sh /* 6 * dw */, uint32_t* S, const uint32_t* digit_tab2) {
     uint32_t x[32];
+    const int sh2 = 24 - sh;
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         const uint32_t X = (uint32_t)(((int32_t)(u[r] << sh)) >> 26);
-        const uint32_t T = digit_tab[((u[r + 16] << sh) >> 26) ^ 32u];   // index d + 32 for the two's-complement 6-bit pattern of d
-        x[r] = X + T + P;
-        x[r + 16] = X - T + P2;
+        const uint32_t T = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(digit_tab2) + ((u[r + 16] >> sh2) & 0xFCu));
+        x[r] = X + T;
+        x[r + 16] = pin(X - T + 3u * P);
     }
-    ct32_after_stage0(x, TwUniform<false>());
+    // bounds: in < 2p+32; s1 4p, s2 6p, s3 8p (+32); s4 corrected (< 4p+32) -> < 6p+32
+    ct_stage<1, 0>(x, TwUniform<false>());
+    ct_stage<2, 0>(x, TwUniform<false>());
+    ct_stage<3, 0>(x, TwUniform<false>());
+    ct_stage<4, 4>(x, TwUniform<false>());
 #pragma unroll
     for (int r = 0; r < 32; r++) S[xs(r, lane)] = x[r];
 }
-// ---- phase 1b: lane = row.  Row pass, spectrum left in [0, 6p), stored back in row layout ----
+// ---- phase 1b: lane = row.  Row pass, spectrum left in [0, 8p + 32), stored back in row layout ----
 template <class TW>
 TFHE_HD void t2_fwd_rows(int lane, uint32_t* S, const TW& tw) {
     uint32_t x[32];
@@ -75,7 +103,7 @@ TFHE_HD void t2_fwd_rows(int lane, uint32_t* S, const TW& tw) {
         const uint4 v = *reinterpret_cast<const uint4*>(S + xs_chunk(lane, q));
         x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
     }
-    ct32_wide(x, tw);   // column pass leaves < 8p + 32: corrected inside stages 0, 2 and 4 -> < 6p
+    ct32_plan<0, 4, 0, 4, 0>(x, tw);   // column pass leaves < 6p+32: 8p, corrected 6p, 8p, corrected 6p, 8p (+32) -> < 8p + 32
 #pragma unroll
     for (int q = 0; q < 8; q++)
         *reinterpret_cast<uint4*>(S + xs_chunk(lane, q)) = make_uint4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
@@ -101,7 +129,7 @@ TFHE_HD void gs_tail_in(uint32_t (&x)[32], const TW& tw) {
 template <int IN, int T>
 TFHE_HD void gs_norm_in(uint32_t (&x)[32]) { gs_norm_seq<IN, T>(x, std::make_integer_sequence<int, 32>{}); }
 
-constexpr int T2_MAC_IN = 6;   // pointwise sums of six (< 6p) x (< p) products, Montgomery-reduced: < 36 p^2 / 2^32 + p < 5.5 p
+constexpr int T2_MAC_IN = 8;   // pointwise sums of six (< 8p+32) x (< p) products, Montgomery-reduced: < 48 p^2 / 2^32 + p < 7.001 p < 2^32
 
 // Montgomery reduction of S < 2^64 with S / 2^32 + p < 2^32: S * 2^-32 mod p, in (S/2^32 - p, S/2^32 + p]
 TFHE_HD uint32_t redc64_wide(uint64_t s) { return redc64(s); }
@@ -115,7 +143,9 @@ TFHE_HD void t2_mac_chunk(int lane, const uint32_t* key, const uint32_t* dh, con
 #pragma unroll
     for (int j = 0; j < BK_ROWS; j++) {
         const uint4 d = *reinterpret_cast<const uint4*>(dh + j * T2_TILE_WORDS + xs_chunk(lane, Q));
-#if defined(__CUDA_ARCH__)
+#if defined(T2_EXP_NOKEY)   // timing experiment only: no key traffic
+        const uint4 k0 = make_uint4(lane + Q, j + 7u, d.y, d.w), k1 = make_uint4(d.z, lane * 3u, Q + 1u, d.x);
+#elif defined(__CUDA_ARCH__)
         const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(key) + ((Q * BK_ROWS + j) * 2 + 0) * 32 + lane);
         const uint4 k1 = __ldg(reinterpret_cast<const uint4*>(key) + ((Q * BK_ROWS + j) * 2 + 1) * 32 + lane);
 #else

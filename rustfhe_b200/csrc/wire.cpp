@@ -16,6 +16,8 @@
 //       64     -  payload
 #include <cstdio>
 #include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
 #include <string>
 #include "../../include/tfhe_b200.h"
 
@@ -84,8 +86,11 @@ int tfhe_b200_file_write(const char* path, int kind, const void* payload, uint64
     for (int i = 0; i < 6; i++) put32(h + 16 + 4 * i, prm[i]);
     put64(h + 40, count); put64(h + 48, bytes); put64(h + 56, fnv1a((const uint8_t*)payload, bytes));
     const std::string tmp = std::string(path) + ".tmp";
-    FILE* f = fopen(tmp.c_str(), "wb");
-    if (!f) return fail(TFHE_B200_ERR_IO, tmp + ": cannot open for writing");
+    // secret keys: created with mode 0600 and O_EXCL (never through an existing, possibly world-readable, file); others 0644
+    remove(tmp.c_str());
+    const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_CLOEXEC, kind == TFHE_B200_FILE_SECRET ? 0600 : 0644);
+    FILE* f = fd >= 0 ? fdopen(fd, "wb") : nullptr;
+    if (!f) { if (fd >= 0) close(fd); return fail(TFHE_B200_ERR_IO, tmp + ": cannot open for writing"); }
     bool ok = fwrite(h, 1, 64, f) == 64 && (bytes == 0 || fwrite(payload, 1, bytes, f) == bytes);
     ok = (fclose(f) == 0) && ok;
     if (!ok) { remove(tmp.c_str()); return fail(TFHE_B200_ERR_IO, tmp + ": write failed"); }

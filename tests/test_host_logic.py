@@ -106,6 +106,8 @@ def emul():
     e.emul_key_transform_t2.argtypes = [u32p, u32p]
     e.emul_external_product_t2.argtypes = [u32p, u32p, C.c_uint32, u32p]
     e.emul_cmux_rotate_t2.argtypes = [u32p, u32p, C.c_uint32, C.c_uint32]
+    e.emul_chacha20_u64.restype = C.c_uint64
+    e.emul_chacha20_u64.argtypes = [u32p, C.c_uint64, C.c_uint64, C.c_int]
     e.emul_key_slice2.restype = C.c_int32
     e.emul_key_slice2.argtypes = [C.c_uint32, C.c_int]
     return e
@@ -184,6 +186,50 @@ def test_throughput_kernel_arithmetic_on_cpu_matches_oracle(emul, oracle, rng):
             oracle.lib().orc_external_product_exact(trgsw, (r - acc2).astype(np.uint32), oracle.MASK_FAITHFUL, pr)
             acc2 = (acc2 + pr).astype(np.uint32)
             assert np.array_equal(acc, acc2), abar
+
+
+def test_csprng_chacha20_known_answer(emul):
+    """The production generator is the ChaCha20 block function (RFC 8439 section 2.3.2 test vector: key 00..1f, block counter 1,
+    nonce 00:00:00:09:00:00:00:4a:00:00:00:00 -- in this layout words 12/13 are the 64-bit counter, 14/15 the nonce)."""
+    key = np.frombuffer(bytes(range(32)), np.uint32).copy()
+    want = [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3, 0xc7f4d1c7, 0x0368c033, 0x9aaa2204, 0x4e6cd4c3,
+            0x466482d2, 0x09aa9f07, 0x05d7c214, 0xa2028bd9, 0xd19c12b5, 0xb94e16de, 0xe883d0cb, 0x4e3c50a2]
+    for lane in range(8):
+        v = emul.emul_chacha20_u64(key, (0x09000000 << 32) | 1, 0x4a000000, lane)
+        assert (v & 0xFFFFFFFF, v >> 32) == (want[2 * lane], want[2 * lane + 1]), lane
+
+
+def test_csprng_entry_points(oracle):
+    """*_csprng: ChaCha20 keyed with 32 bytes; key=NULL draws a fresh key from getrandom(2) per call (nothing repeats), an
+    explicit key reproduces; the ciphertexts decrypt and carry the lv0 noise level."""
+    from rustfhe_b200 import _capi as K
+    import rustfhe_b200 as R
+    lib = K.lib()
+    u8 = lambda k: np.zeros(k, np.uint8)
+    key = (C.c_uint8 * 32)(*range(100, 132))
+    s0a, s1a, s0b, s1b, s0c, s1c = u8(635), u8(1024), u8(635), u8(1024), u8(635), u8(1024)
+    assert lib.tfhe_b200_keygen_secret_csprng(key, K.ptr(s0a), K.ptr(s1a)) == 0
+    assert lib.tfhe_b200_keygen_secret_csprng(key, K.ptr(s0b), K.ptr(s1b)) == 0
+    assert lib.tfhe_b200_keygen_secret_csprng(None, K.ptr(s0c), K.ptr(s1c)) == 0
+    assert np.array_equal(s0a, s0b) and np.array_equal(s1a, s1b) and not np.array_equal(s1a, s1c)
+    assert set(np.unique(s1c)) == {0, 1} and 400 < int(s1c.sum()) < 624
+    sk = R.SecretKeys.generate()          # default = CSPRNG
+    sk2 = R.SecretKeys.generate()
+    assert not np.array_equal(sk.s_key_tlwelv1, sk2.s_key_tlwelv1)
+    bits = np.random.default_rng(5).integers(0, 2, 4000).astype(np.uint8)
+    c1 = R.Cryptor.encrypto(R.TLWE, sk.s_key_tlwelv0, bits)
+    c2 = R.Cryptor.encrypto(R.TLWE, sk.s_key_tlwelv0, bits)
+    assert not np.array_equal(c1[:, 1:], c2[:, 1:])                      # fresh masks on every call
+    assert np.array_equal(R.Cryptor.decrypto(R.TLWE, sk.s_key_tlwelv0, c1), bits)
+    ph = R.Cryptor.phase(sk.s_key_tlwelv0, c1).astype(np.int64)
+    e = ((ph - np.where(bits == 1, 0x20000000, 0xE0000000) + 2 ** 31) % 2 ** 32 - 2 ** 31) / 2 ** 32
+    assert 0.8 * 2 ** -15 < e.std() < 1.25 * 2 ** -15 and abs(e.mean()) < 2 ** -19
+    masks = c1[:, 1:].reshape(-1)
+    assert abs(masks.astype(np.float64).mean() / 2 ** 32 - 0.5) < 2e-3       # full 32-bit uniform masks
+    with pytest.raises(ValueError):
+        R.Cryptor.encrypto(R.TLWE, sk.s_key_tlwelv0, bits, seed=3)        # the test generator needs an explicit index
+    buf = u8(64)
+    assert lib.tfhe_b200_random_bytes(K.ptr(buf), 64) == 0 and buf.any()
 
 
 def test_golden_fixtures(oracle, keys):
