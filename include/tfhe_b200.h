@@ -237,6 +237,33 @@ int tfhe_b200_file_info(const char* path, int* kind, uint64_t* count, uint64_t* 
 int tfhe_b200_file_read(const char* path, int kind, void* payload, uint64_t payload_bytes);
 const char* tfhe_b200_file_last_error(void);
 
+/* ---- device groups: ONE process drives several B200s of a box (rustfhe_b200/csrc/group.cu).  The reference has no
+ * counterpart (TFHE::new keeps one key pair in host memory, tfhe.rs:21-25, everything runs on the calling thread); this is
+ * independent gates of a batch are sharded over the GPUs (contiguous shards, the first B % n devices take
+ * one gate more), the bootstrapping and key-switching keys are replicated ONCE by an ncclBroadcast over NVLink (device 0 ->
+ * all, then every device transforms the bootstrapping key into its NTT domain locally); no collective runs per gate.
+ * devices == NULL and ndev <= 0: every device of the box.  One host thread at a time per group. ---- */
+typedef struct tfhe_b200_group tfhe_b200_group;
+int tfhe_b200_group_create(const tfhe_b200_params* p /* NULL = defaults */, const int* devices, int ndev, tfhe_b200_group** out);
+int tfhe_b200_group_destroy(tfhe_b200_group* g);
+const char* tfhe_b200_group_last_error(const tfhe_b200_group* g /* NULL = last error of a failed group_create */);
+int tfhe_b200_group_size(const tfhe_b200_group* g);
+tfhe_b200_ctx* tfhe_b200_group_ctx(tfhe_b200_group* g, int rank);   /* the per-device context, for the device-pointer entry points */
+int tfhe_b200_group_load_bk(tfhe_b200_group* g, const uint32_t* bk_host /*[n][2l][2][N]*/);
+int tfhe_b200_group_load_ksk(tfhe_b200_group* g, const uint32_t* ksk_host /*[N][t][3][n+1]*/);
+/* both keys generated on device 0 (tfhe_b200_keygen_device[_csprng]), then broadcast */
+int tfhe_b200_group_keygen_csprng(tfhe_b200_group* g, const uint8_t* key /*[32] or NULL = getrandom*/, const uint8_t* s0, const uint8_t* s1);
+int tfhe_b200_group_keygen(tfhe_b200_group* g, uint64_t seed /* deterministic TEST generator, INSECURE */, const uint8_t* s0, const uint8_t* s1);
+int tfhe_b200_group_reserve(tfhe_b200_group* g, size_t max_batch /* whole batch, all devices */);
+void tfhe_b200_group_shard(const tfhe_b200_group* g, size_t B, int rank, size_t* first, size_t* count);
+/* host pointers; in1 may be NULL for NOT / COPY.  _async returns once every shard is enqueued on its device (buffers should be
+ * pinned -- tfhe_b200_host_alloc -- or the host-to-device copies of the shards serialise); tfhe_b200_group_sync waits. */
+int tfhe_b200_group_gate_batch(tfhe_b200_group* g, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B);
+int tfhe_b200_group_gate_batch_async(tfhe_b200_group* g, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B);
+int tfhe_b200_group_sync(tfhe_b200_group* g);
+int tfhe_b200_host_alloc(void** out, size_t bytes);   /* pinned, portable across the devices of the box */
+int tfhe_b200_host_free(void* p);
+
 const char* tfhe_b200_version(void);
 
 #ifdef __cplusplus

@@ -16,9 +16,9 @@ from ._capi import (AND, ANDNY, COPY, MASK_CORRECTED, MASK_FAITHFUL, NAND, NOT, 
 from . import circuit
 from ._capi import (FILE_SECRET, FILE_BK, FILE_KSK, FILE_TLWE0, FILE_TLWE1, FILE_TRLWE, FILE_TRGSW)
 from .api import (TFHE, TLWE, BootstrappingKey, Cryptor, KeySwitchingKey, SecretKeys, TFHEHelper, TLWEHelper, TLWERep,
-                  TRGSWHelper, TRLWEHelper, DeviceEngine, TRLWERep, TRGSWRep, save, load)
+                  TRGSWHelper, TRLWEHelper, DeviceEngine, DeviceGroup, TRLWERep, TRGSWRep, save, load)
 
 __all__ = ["circuit", "TFHE", "TLWE", "BootstrappingKey", "Cryptor", "KeySwitchingKey", "SecretKeys", "TFHEHelper", "TLWEHelper",
-           "TLWERep", "TRGSWHelper", "TRLWEHelper", "DeviceEngine", "TfheError", "NAND", "AND", "OR", "XOR", "NOT", "COPY",
+           "TLWERep", "TRGSWHelper", "TRLWEHelper", "DeviceEngine", "DeviceGroup", "TfheError", "NAND", "AND", "OR", "XOR", "NOT", "COPY",
            "ANDNY", "MASK_FAITHFUL", "MASK_CORRECTED", "BK_WORDS", "KSK_WORDS", "TRLWERep", "TRGSWRep", "save", "load",
            "FILE_SECRET", "FILE_BK", "FILE_KSK", "FILE_TLWE0", "FILE_TLWE1", "FILE_TRLWE", "FILE_TRGSW"]

@@ -31,6 +31,10 @@ SYMBOLS = [
     "tfhe_b200_decrypt_bits_device", "tfhe_b200_cmux_batch", "tfhe_b200_sample_extract_batch",
     "tfhe_b200_random_bytes", "tfhe_b200_keygen_secret_csprng", "tfhe_b200_keygen_bk_csprng", "tfhe_b200_keygen_ksk_csprng",
     "tfhe_b200_encrypt_bits_csprng", "tfhe_b200_keygen_device_csprng", "tfhe_b200_encrypt_bits_device_csprng",
+    "tfhe_b200_group_create", "tfhe_b200_group_destroy", "tfhe_b200_group_last_error", "tfhe_b200_group_size", "tfhe_b200_group_ctx",
+    "tfhe_b200_group_load_bk", "tfhe_b200_group_load_ksk", "tfhe_b200_group_keygen_csprng", "tfhe_b200_group_keygen",
+    "tfhe_b200_group_reserve", "tfhe_b200_group_shard", "tfhe_b200_group_gate_batch", "tfhe_b200_group_gate_batch_async",
+    "tfhe_b200_group_sync", "tfhe_b200_host_alloc", "tfhe_b200_host_free",
     "tfhe_b200_file_write", "tfhe_b200_file_info", "tfhe_b200_file_read", "tfhe_b200_file_last_error",
 ]
 FILE_SECRET, FILE_BK, FILE_KSK, FILE_TLWE0, FILE_TLWE1, FILE_TRLWE, FILE_TRGSW = range(1, 8)
@@ -95,6 +99,22 @@ def lib():
         "tfhe_b200_negacyclic_mul_batch": (i32, [vp, vp, vp, vp, sz]),
         "tfhe_b200_external_product_batch_device": (i32, [vp, vp, sz, vp, vp, sz, vp]),
         "tfhe_b200_negacyclic_mul_batch_device": (i32, [vp, vp, vp, vp, sz, vp]),
+        "tfhe_b200_group_create": (i32, [C.POINTER(Params), vp, i32, C.POINTER(vp)]),
+        "tfhe_b200_group_destroy": (i32, [vp]),
+        "tfhe_b200_group_last_error": (C.c_char_p, [vp]),
+        "tfhe_b200_group_size": (i32, [vp]),
+        "tfhe_b200_group_ctx": (vp, [vp, i32]),
+        "tfhe_b200_group_load_bk": (i32, [vp, vp]),
+        "tfhe_b200_group_load_ksk": (i32, [vp, vp]),
+        "tfhe_b200_group_keygen_csprng": (i32, [vp, vp, vp, vp]),
+        "tfhe_b200_group_keygen": (i32, [vp, u64, vp, vp]),
+        "tfhe_b200_group_reserve": (i32, [vp, sz]),
+        "tfhe_b200_group_shard": (None, [vp, sz, i32, C.POINTER(sz), C.POINTER(sz)]),
+        "tfhe_b200_group_gate_batch": (i32, [vp, i32, vp, vp, vp, sz]),
+        "tfhe_b200_group_gate_batch_async": (i32, [vp, i32, vp, vp, vp, sz]),
+        "tfhe_b200_group_sync": (i32, [vp]),
+        "tfhe_b200_host_alloc": (i32, [C.POINTER(vp), sz]),
+        "tfhe_b200_host_free": (i32, [vp]),
         "tfhe_b200_random_bytes": (i32, [vp, sz]),
         "tfhe_b200_keygen_secret_csprng": (i32, [vp, vp, vp]),
         "tfhe_b200_keygen_bk_csprng": (i32, [vp, vp, vp, vp]),

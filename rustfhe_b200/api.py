@@ -262,6 +262,87 @@ class TRGSWRep:
         return engine.cmux_batch(trgsw, rep_1, rep_0)
 
 
+class DeviceGroup:
+    """Owner of one tfhe_b200_group: ONE process driving several GPUs of a box through the C ABI (rustfhe_b200/csrc/group.cu).
+    Keys are replicated once by an NCCL broadcast inside the library; a batch is cut into contiguous shards, one per GPU."""
+
+    def __init__(self, devices=None, decomp_mask=K.MASK_FAITHFUL):
+        self._l = lib()
+        self._g = C.c_void_p()
+        prm = K.Params()
+        self._l.tfhe_b200_default_params(C.byref(prm))
+        prm.decomp_mask = decomp_mask
+        if devices is None:
+            arr, n = None, 0
+        else:
+            n = len(devices)
+            arr = (C.c_int * n)(*devices)
+        rc = self._l.tfhe_b200_group_create(C.byref(prm), arr, n, C.byref(self._g))
+        if rc != K.OK:
+            self._g = None
+            msg = self._l.tfhe_b200_group_last_error(None)
+            raise TfheError(rc, msg.decode() if msg else "")
+        self.size = self._l.tfhe_b200_group_size(self._g)
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self._l.tfhe_b200_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != K.OK:
+            msg = self._l.tfhe_b200_group_last_error(self._g)
+            raise TfheError(rc, msg.decode() if msg else "")
+
+    def load_bk(self, bk_words):
+        self._ck(self._l.tfhe_b200_group_load_bk(self._g, ptr(np.ascontiguousarray(bk_words, np.uint32).reshape(-1))))
+
+    def load_ksk(self, ksk_words):
+        self._ck(self._l.tfhe_b200_group_load_ksk(self._g, ptr(np.ascontiguousarray(ksk_words, np.uint32).reshape(-1))))
+
+    def keygen(self, seed, s_key_tlwelv0, s_key_tlwelv1):
+        """seed=None: ChaCha20 keyed from getrandom(2); integer: deterministic test generator (INSECURE)."""
+        s0p, s1p = ptr(np.ascontiguousarray(s_key_tlwelv0, np.uint8)), ptr(np.ascontiguousarray(s_key_tlwelv1, np.uint8))
+        if seed is None:
+            self._ck(self._l.tfhe_b200_group_keygen_csprng(self._g, None, s0p, s1p))
+        else:
+            self._ck(self._l.tfhe_b200_group_keygen(self._g, seed, s0p, s1p))
+
+    def reserve(self, max_batch):
+        self._ck(self._l.tfhe_b200_group_reserve(self._g, max_batch))
+
+    def shard(self, B, rank):
+        first, count = C.c_size_t(), C.c_size_t()
+        self._l.tfhe_b200_group_shard(self._g, B, rank, C.byref(first), C.byref(count))
+        return first.value, count.value
+
+    def gate_batch(self, op, in0, in1=None):
+        in0 = _u32_batch(in0, K.n + 1)
+        in1 = None if in1 is None else _u32_batch(in1, K.n + 1)
+        out = np.empty_like(in0)
+        self._ck(self._l.tfhe_b200_group_gate_batch(self._g, op, ptr(in0), ptr(in1), ptr(out), len(in0)))
+        return out
+
+    def gate_batch_async(self, op, in0, in1, out):
+        """in0 / in1 / out: C-contiguous uint32 [B][n+1] arrays that stay alive (and should be pinned) until sync()."""
+        self._ck(self._l.tfhe_b200_group_gate_batch_async(self._g, op, ptr(in0), ptr(in1), ptr(out), len(in0)))
+
+    def sync(self):
+        self._ck(self._l.tfhe_b200_group_sync(self._g))
+
+    def ctx_stats(self, rank):
+        st = K.Stats()
+        ctx = self._l.tfhe_b200_group_ctx(self._g, rank)
+        _check(ctx, self._l.tfhe_b200_get_stats(ctx, C.byref(st)))
+        return {f[0]: getattr(st, f[0]) for f in K.Stats._fields_}
+
+
 class DeviceEngine:
     """Owner of one tfhe_b200_ctx (one CUDA device). Thin, explicit wrapper of the C ABI."""
 

@@ -412,6 +412,28 @@ def test_exact_mode_three_key_slices(oracle, keys, rng):
         eng.close()
 
 
+def test_gpu_against_committed_golden_vectors(engine, keys):
+    """tests/golden/gate_vectors.npz was produced in the authoring container with the reference's own FFT library
+    (tests/golden/make_golden.py); this compares the GPU output with the COMMITTED vectors directly, so the check does not
+    depend on the oracle having been rebuilt identically on this box: whole NAND ciphertexts bit for bit against the
+    exact-integer entries, decrypted bits and phases against the reference-FFT entries (P2: |e_gpu - e_ref| < 1/16), and
+    the external product against both (bit-exact / within 2 ulp)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gate_vectors.npz"))
+    assert int(g["seed"]) == keys.seed
+    c0, c1 = keys.encrypt(g["x"], 7000), keys.encrypt(g["y"], 7100)
+    assert np.array_equal(c0[:, :8], g["c0_head"]) and np.array_equal(c1[:, :8], g["c1_head"])
+    out = engine.gate_batch(0, c0, c1)
+    assert np.array_equal(out, g["nand_exact"])
+    assert np.array_equal(keys.decrypt(out), g["nand_bits"]) and np.array_equal(g["nand_bits"], 1 - (g["x"] & g["y"]))
+    e_gpu = (keys.phase(out).astype(np.int64) - g["nand_ref_phase"].astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert np.abs(e_gpu).max() < 2 ** 32 / 16
+    xp = engine.external_product_batch(keys.bk[:12 * N].reshape(1, 6, 2, N), g["xp_trlwe"].reshape(1, 2, N))[0].reshape(-1)
+    assert np.array_equal(xp, g["xp_exact"])
+    d = (xp.astype(np.int64) - g["xp_ref"].astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert np.abs(d).max() <= 2
+
+
 def test_mixed_opcode_batch(engine, oracle, keys, rng):
     """tfhe_b200_gate_batch_mixed: one launch for gates of different kinds (a circuit level) == the per-opcode launches, bit for
     bit; in1 of NOT / COPY gates is ignored."""
