@@ -31,12 +31,26 @@ CT_WORDS = N_LWE + 1
 NROT = 32                        # distinct input batches rotated through: 32 x 5.2 MB = 167 MB > 126 MB L2
 # algorithmic figures (SURVEY.md section 8d / DESIGN.md section "Roofline")
 BK_BYTES_ALGO = 62_423_040       # 635 x 12 x 1024 coefficients x 8 B (SURVEY's single-modulus basis)
-BK_BYTES_DEVICE = 635 * 36 * 1024 * 4  # this design: 3 key slices x 4 B = 12 B / coefficient
 KSK_BYTES = 1024 * 8 * 3 * 636 * 4
 MODMUL_PER_GATE = 33.81e6        # 635 x (8 x 5120 butterflies + 12288 MACs), single-modulus basis
-# this design per gate: 635 x (12 transforms x 5120 Shoup butterflies + 36864 wide MACs + 6144 REDC)
-BUTTERFLIES_PER_GATE = 635 * 12 * 5120
-FMA_SLOTS_PER_GATE = 635 * (12 * 5120 * 4 + 36864 * 2.5 + 6144 * 3)   # IMAD-issue-slot equivalents, see DESIGN.md
+WORKLOAD = ("batched 1024 independent HomNAND gates per GPU (BASELINE configs[1]), default TFHE parameters "
+            "n=635 N=1024 l=3 Bg=64 t=8 basebit=2, decomposition mask 0x02084000 (reference-faithful)")
+
+
+def design_figures(key_slices):
+    """Per-gate work of the shipped arithmetic (DESIGN.md sections 2 and 5): S key slices -> 6 forward + 2S inverse transforms of
+    5120 Shoup butterflies, 12 S x 1024 wide multiply-accumulates and 2 S x 1024 Montgomery reductions per CMUX, 635 CMUX per gate.
+    FMA-heavy issue slots: butterfly 4 (IMAD.HI 2 + 2 IMAD), IMAD.WIDE 2.5, reduction 3 (measured weights, profiles/intpipe_r01.json)."""
+    S = key_slices
+    transforms = 6 + 2 * S
+    return {"transforms_per_cmux": transforms, "butterflies_per_gate": 635 * transforms * 5120,
+            "fma_slots_per_gate": 635 * (transforms * 5120 * 4 + 12 * S * 1024 * 2.5 + 2 * S * 1024 * 3),
+            "bk_bytes_device": 635 * 12 * S * 1024 * 4}
+
+
+def workload_config(world):
+    """the keys both arms share (the driver compares them)"""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world}
 
 
 def measured_peaks():
@@ -50,9 +64,10 @@ def measured_peaks():
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one blind_rotate_kernel launch (1024 gates) from the committed
-    `ncu --set full` summary (profiles/r01_ncu_blind_rotate_latest.txt); None when the summary is missing."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_blind_rotate_latest.txt")
+    """dram__bytes_read.sum + dram__bytes_write.sum of one blind_rotate_t2_kernel launch from the committed `ncu --set full`
+    summary (profiles/r02_ncu_blind_rotate_t2_latest.txt), scaled from the profiled batch to 1024 gates (the key is read once
+    per wave, the ciphertext traffic is per gate); None when the summary is missing."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_blind_rotate_t2_latest.txt")
     try:
         tot = 0.0
         for line in open(p):
@@ -165,8 +180,8 @@ def run_reference(args):
         "impl": "reference", "metric": "bootstrapped HomNAND gates/sec", "value": v, "unit": "gates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_secs / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "batched independent HomNAND gates, default TFHE parameters (n=635,N=1024,l=3,Bg=64,t=8)",
-                   "batch_per_step": nthreads * gpt, "note": "bounded sample of the 1024-gate batch; CPU time per gate is batch independent"},
+        "config": dict(workload_config(max(1, args.gpus)), sample_gates_per_step=nthreads * gpt,
+                       note="each step is a bounded sample of the 1024-gate batch (CPU time per gate does not depend on the batch)"),
         "cpu_baseline": {"value": v, "unit": "gates/s", "cores": nthreads, "kind": "port",
                          "sample": f"{nthreads * gpt} NAND gates per step on {nthreads} threads; reference's own spqlios FFT "
                                    f"(oracle/_ref, compiled from /root/reference) + C restatement of the Rust glue (Rust toolchain absent)"},
@@ -174,6 +189,94 @@ def run_reference(args):
     }
     print(json.dumps(line))
     return 0
+
+
+def run_extras(eng, R, K, torch, dev, stream, dx, dy, s0, rank, world, dist):
+    """BASELINE.json configs 3, 4 and 5 as extra keys of the line (the headline stays configs[1]): device-resident, CUDA events,
+    best of 3 after a warm-up.  Every rank calls this (config 5 is a collective measurement); rank 0 keeps the result."""
+    import rustfhe_b200.circuit as Cq
+    out = {}
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        return best
+
+    fig = design_figures(eng.stats()["key_slices"])
+    p_int, _ = int_peak()
+    S = eng.stats()["key_slices"]
+    slots_xp = fig["fma_slots_per_gate"] / 635.0                            # one external product = one CMUX step
+    slots_pm = (1 + 2 * S) * 5120 * 4 + S * 1024 * (2.5 + 3)                # 1 + S forward, S inverse transforms, S x 1024 MAC + REDC
+    if rank == 0:
+        # ---- config 3: negacyclic poly-mul / external product at N = 1024, batch 65536 (the top of the sweep; the whole
+        #      sweep is tools/sweep_config3.py) ----
+        g = torch.Generator(device=dev).manual_seed(7)
+        B3 = 65536
+        u32 = lambda *shape: torch.randint(-2 ** 31, 2 ** 31, shape, dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+        a = u32(B3, 1024)
+        d = torch.randint(-32, 32, (B3, 1024), dtype=torch.int32, device=dev, generator=g)
+        o = torch.empty_like(a)
+        t = timed(lambda: eng.negacyclic_mul_batch_device(a.data_ptr(), d.data_ptr(), o.data_ptr(), B3, stream.cuda_stream))
+        out["config3_negacyclic_mul"] = {"batch": B3, "products_per_s": B3 / t, "int_roofline_frac": B3 / t * slots_pm / p_int}
+        del a, d, o
+        trl = u32(B3, 2, 1024)
+        res = torch.empty_like(trl)
+        trg1 = u32(1, 6, 2, 1024)
+        t = timed(lambda: eng.external_product_batch_device(trg1.data_ptr(), 1, trl.data_ptr(), res.data_ptr(), B3, stream.cuda_stream))
+        out["config3_external_product_shared_trgsw"] = {"batch": B3, "products_per_s": B3 / t, "int_roofline_frac": B3 / t * slots_xp / p_int,
+                                                        "note": "the one TRGSW is transformed inside the call (36 of 786 k transforms)"}
+        Bp = 4096
+        trgB = u32(Bp, 6, 2, 1024)
+        t = timed(lambda: eng.external_product_batch_device(trgB.data_ptr(), Bp, trl.data_ptr(), res.data_ptr(), Bp, stream.cuda_stream))
+        out["config3_external_product_per_item_trgsw"] = {"batch": Bp, "products_per_s": Bp / t,
+                                                          "note": "includes the key transforms of every item's TRGSW"}
+        del trl, res, trg1, trgB
+        # ---- config 4: 32-bit adders on encrypted operands, level-synchronous, one launch pair per level ----
+        r = np.random.default_rng(SEED + 2)
+        x, y = int(r.integers(0, 2 ** 32)), int(r.integers(0, 2 ** 32))
+        bits = np.array([(x >> i) & 1 for i in range(32)] + [(y >> i) & 1 for i in range(32)], np.uint8)
+        cts = R.Cryptor.encrypto(R.TLWE, s0, bits, seed=SEED + 300, ct_index0=0)
+        for name, nl in (("ripple_carry_nand", Cq.ripple_carry_adder(32)), ("kogge_stone_native_gates", Cq.prefix_adder(32))):
+            dc = Cq.DeviceCircuit(eng, nl)
+            dc.run(cts)
+            t0 = time.perf_counter()
+            res = dc.run(cts)
+            secs = time.perf_counter() - t0
+            got = R.Cryptor.decrypto(R.TLWE, s0, res)
+            out[f"config4_adder32_{name}"] = {"seconds": secs, "gates": dc.gates, "levels": dc.levels,
+                                              "correct": bool(sum(int(b) << i for i, b in enumerate(got)) == x + y)}
+            dc.close()
+    # ---- config 5: 2^16 random-bit NAND gates, STRONG scaling: the batch is split over the ranks ----
+    total = 1 << 16
+    mine = total // world
+    reps = -(-mine // dx.shape[0])
+    bx = dx.repeat(reps, 1)[:mine].contiguous()
+    by = dy.repeat(reps, 1)[:mine].contiguous()
+    bo = torch.empty_like(bx)
+    eng.reserve(mine)
+    eng.set_batch_overlap(0)
+
+    def sweep():
+        eng.gate_batch_device(K.NAND, bx.data_ptr(), by.data_ptr(), bo.data_ptr(), mine, stream.cuda_stream)
+
+    sweep(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream); sweep(); e1.record(stream)
+    torch.cuda.synchronize()
+    tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    eng.set_batch_overlap(-1)
+    out["config5_2pow16_gates_strong"] = {"gates": total, "n_gpus": world, "gates_per_s": total / (float(tt[0]) * 1e-3), "ms": float(tt[0])}
+    return out
 
 
 def run_gpu(args):
@@ -344,6 +447,13 @@ def run_gpu(args):
     o = (last % NROT) * BATCH
     wrong += int((got != (1 - (bx[o:o + BATCH] & by[o:o + BATCH]))).sum())
 
+    extras = None
+    if not args.no_extras:
+        try:
+            extras = run_extras(eng, R, K, torch, dev, stream, dx, dy, s0, rank, world, dist)
+        except Exception as ex:   # the headline numbers stand on their own
+            extras = {"error": str(ex)}
+
     # max over ranks
     t = torch.tensor([ms, e2e_s * 1e3, float(wrong), serial_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -353,6 +463,9 @@ def run_gpu(args):
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         p_int, p_int_src = int_peak()
+        fig = design_figures(st["key_slices"])
+        FMA_SLOTS_PER_GATE, BUTTERFLIES_PER_GATE, BK_BYTES_DEVICE = fig["fma_slots_per_gate"], fig["butterflies_per_gate"], fig["bk_bytes_device"]
+        kname = "blind_rotate_t2_kernel<6,1>" if st["key_slices"] == 2 else "blind_rotate_kernel<4,false,1,3>"
         gates = BATCH * world * args.steps
         value = gates / (ms * 1e-3)
         br_ms, ks_ms = st["avg_blind_rotate_ms"], st["avg_keyswitch_ms"]
@@ -364,14 +477,13 @@ def run_gpu(args):
             "metric": "bootstrapped HomNAND gates/sec", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "batched 1024 independent HomNAND gates per GPU (BASELINE configs[1]), default TFHE parameters "
-                                   "n=635 N=1024 l=3 Bg=64 t=8 basebit=2, decomposition mask 0x02084000 (reference-faithful)",
-                       "arithmetic": "torus words mod 2^32; exact negacyclic NTT over the 29-bit prime 536856577, three 11-bit key slices",
-                       "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world} (independent gate shards, keys replicated)",
-                       "l2": f"inputs rotate over {NROT} batches ({NROT * BATCH * 2 * CT_WORDS * 4 / 1e6:.0f} MB) > L2; keys "
-                             f"{(BK_BYTES_DEVICE + KSK_BYTES) / 1e6:.0f} MB > L2; no explicit flush",
-                       "gates_per_cta": st["gates_per_cta"], "streams": NSTREAMS,
-                       "key_slices": int(os.environ.get("TFHE_B200_KEY_SLICES", "3")) if os.environ.get("TFHE_B200_KEY_SLICES") in ("2", "3") else 3},
+            "config": dict(workload_config(world),
+                       arithmetic="torus words mod 2^32; exact negacyclic NTT over the 29-bit prime 536856577, " +
+                                  ("two 16-bit key slices (6 + 4 transforms per CMUX)" if st["key_slices"] == 2 else "three 11-bit key slices (6 + 6 transforms per CMUX)"),
+                       parallelism=f"dp{world} (independent gate shards, keys replicated)",
+                       l2=f"inputs rotate over {NROT} batches ({NROT * BATCH * 2 * CT_WORDS * 4 / 1e6:.0f} MB) > L2; keys "
+                          f"{(BK_BYTES_DEVICE + KSK_BYTES) / 1e6:.0f} MB ~ L2; no explicit flush",
+                       gates_per_cta=st["gates_per_cta"], streams=NSTREAMS, key_slices=st["key_slices"]),
             "value_serial": gates / (serial_ms * 1e-3),
             "latency_us_per_gate_amortised": 1e3 * ms / args.steps / BATCH,
             "latency_us_single_gate": latency_us,
@@ -383,20 +495,21 @@ def run_gpu(args):
             "kernels": {"blind_rotate_ms": br_ms, "keyswitch_ms": ks_ms, "timed_launches": st["timed_launches"],
                         "note": "isolated per-launch durations (CUDA events on the launching stream) from a serial K-step region of "
                                 "this same run; in the timed region consecutive batches overlap on two streams"},
-            "roofline": {"bound": "hbm", "kernel": "blind_rotate_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                          "algorithmic_bytes_per_launch": algo_bytes, "traffic": ncu_traffic(),
                          "note": "HBM is NOT the binding roof of this kernel (key bytes are read once per 1024-gate launch); "
                                  "the binding roof is the integer FMA pipe, see int_roofline"},
-            "int_roofline": {"bound": "integer FMA pipe (IMAD issue slots)", "kernel": "blind_rotate_kernel",
+            "int_roofline": {"bound": "integer FMA pipe (IMAD issue slots)", "kernel": kname,
                              "achieved": per_gpu_gps_kernel * FMA_SLOTS_PER_GATE / 1e12, "peak": p_int / 1e12, "unit": "T IMAD-slots/s",
                              "frac": per_gpu_gps_kernel * FMA_SLOTS_PER_GATE / p_int, "peak_kind": p_int_src,
                              "slots_per_gate": FMA_SLOTS_PER_GATE, "butterflies_per_gate": BUTTERFLIES_PER_GATE,
                              "modmul_per_gate_single_modulus_basis": MODMUL_PER_GATE,
                              "note": "slot weights measured on B200: IMAD 1, IMAD.HI 2, IMAD.WIDE 2.5 (profiles/intpipe_r01.json); "
-                                     "butterfly = 2 IMAD + 1 IMAD.HI = 4 slots; this design runs 12 transforms per CMUX"},
+                                     f"butterfly = 2 IMAD + 1 IMAD.HI = 4 slots; this design runs {fig['transforms_per_cmux']} transforms per CMUX"},
             "clocks": clocks,
             "key_setup_s": key_s,
+            "extras": extras,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -424,6 +537,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3 / 4 / 5 extra measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         sys.exit(run_reference(args))
@@ -432,7 +546,7 @@ def main():
         # convenience: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29541", os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
-               str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+               str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (["--no-extras"] if args.no_extras else [])
         sys.exit(subprocess.call(cmd))
     sys.exit(run_gpu(args))
 

@@ -74,6 +74,8 @@ typedef struct {
     uint64_t last_batch;
     int32_t gates_per_cta, sm_count;
     uint64_t device_key_bytes;
+    int32_t key_slices;         /* 2 or 3 (tfhe_b200_set_key_slices) */
+    int32_t reserved;
 } tfhe_b200_stats;
 
 /* ---- lifecycle (replaces Spqlios_new / Spqlios_destructor, spqlios-wrapper.cpp:9-16) ---- */

@@ -50,7 +50,7 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("last_blind_rotate_ms", C.c_float), ("last_keyswitch_ms", C.c_float),
                 ("avg_blind_rotate_ms", C.c_float), ("avg_keyswitch_ms", C.c_float), ("timed_launches", C.c_uint64),
                 ("last_batch", C.c_uint64), ("gates_per_cta", C.c_int32), ("sm_count", C.c_int32),
-                ("device_key_bytes", C.c_uint64)]
+                ("device_key_bytes", C.c_uint64), ("key_slices", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None

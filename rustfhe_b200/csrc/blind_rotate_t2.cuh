@@ -30,8 +30,9 @@ struct TwRegs {
     }
 };
 
-// TWREG bit 0: forward row twiddles in registers for the three forward transforms of a step; bit 1: same for the inverse
-template <int G, int TWREG>
+// TWREG bit 0: forward row twiddles in registers for the three forward transforms of a step; bit 1: same for the inverse.
+// EXTPROD: one plain external product per "gate" (trgsw.rs:264-306) or cmux (trgsw.rs:315-322): out = BK[g % ntrgsw] (x) (in - in0) + in0.
+template <int G, int TWREG, bool EXTPROD = false>
 __global__ void __launch_bounds__(G* T2_THREADS_PER_GATE, 1) blind_rotate_t2_kernel(const BrArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* twF = smem;
@@ -57,7 +58,11 @@ __global__ void __launch_bounds__(G* T2_THREADS_PER_GATE, 1) blind_rotate_t2_ker
     }
     for (int t = threadIdx.x; t < DIGIT_TAB_WORDS; t += blockDim.x) dtab[t] = g_digit_tab2.v[t];
     // ---- prologue: gate pre-combination (tfhe.rs:27-71), rounding of (b, a) (tfhe.rs:97,107-108), acc_0 ----
-    {
+    if (EXTPROD) {
+        const uint32_t* src = a.trlwe_in + (size_t)gate * 2048;
+        const uint32_t* sub = a.trlwe_in0 ? a.trlwe_in0 + (size_t)gate * 2048 : nullptr;   // cmux: rep_1 - rep_0
+        for (int k = tid2; k < 2048; k += T2_THREADS_PER_GATE) acc[k] = sub ? src[k] - sub[k] : src[k];
+    } else {
         uint32_t* lin = dh;
         const bool second = gate >= a.split;
         const long gsrc = second ? gate - a.split : gate;
@@ -88,13 +93,14 @@ __global__ void __launch_bounds__(G* T2_THREADS_PER_GATE, 1) blind_rotate_t2_ker
     const int bar_gate = 1 + gl;
     uint32_t* accp = acc + pw * 1024;
     uint32_t* own = dh + 3 * pw * T2_TILE_WORDS;
-    const uint32_t* keyp = a.bkdev + (size_t)pw * (T2_STEP_WORDS / 2);
+    const uint32_t* keyp = a.bkdev + (size_t)pw * (T2_STEP_WORDS / 2) + (EXTPROD ? (size_t)(gate % a.ntrgsw) * T2_STEP_WORDS : (size_t)0);
+    const int nsteps = EXTPROD ? 1 : a.nsteps;
     // ---- 635 x CMUX ----
 #pragma unroll 1
-    for (int i = 0; i < a.nsteps; i++, keyp += T2_STEP_WORDS) {
+    for (int i = 0; i < nsteps; i++, keyp += T2_STEP_WORDS) {
         {   // phase 1: u in registers, three forward transforms into the own spectrum tiles
             uint32_t u[32];
-            t2_u<true>(lane, accp, (uint32_t)abar[i], a.mask, u);
+            t2_u<!EXTPROD>(lane, accp, EXTPROD ? 0u : (uint32_t)abar[i], a.mask, u);
             if (TWREG & 1) {
                 TwRegs tw;
                 tw.load(twF + lane * TWB_STRIDE);
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(G* T2_THREADS_PER_GATE, 1) blind_rotate_t2_ker
         {   // phase 3: inverse column passes of both slices, acc[pw] += x0 + (x1 << 16)
             uint32_t z[32];
 #pragma unroll
-            for (int r = 0; r < 32; r++) z[r] = accp[32 * r + lane];
+            for (int r = 0; r < 32; r++) z[r] = EXTPROD ? 0u : accp[32 * r + lane];   // the plain product REPLACES the accumulator
 #pragma unroll 1
             for (int s = 0; s < 2; s++) t2_inv_cols(lane, own + s * T2_TILE_WORDS, 16 * s, z);
 #pragma unroll
@@ -150,7 +156,8 @@ __global__ void __launch_bounds__(G* T2_THREADS_PER_GATE, 1) blind_rotate_t2_ker
     // ---- epilogue: sample_extract_index(0) (trlwe.rs:110-121) + key-switch digits (tlwe.rs:47-64) ----
     if (a.trlwe_out) {
         uint32_t* dst = a.trlwe_out + (size_t)gate * 2048;
-        for (int k = tid2; k < 2048; k += T2_THREADS_PER_GATE) dst[k] = acc[k];
+        const uint32_t* add = (EXTPROD && a.trlwe_in0) ? a.trlwe_in0 + (size_t)gate * 2048 : nullptr;   // cmux: ... + rep_0
+        for (int k = tid2; k < 2048; k += T2_THREADS_PER_GATE) dst[k] = add ? acc[k] + add[k] : acc[k];
     }
     if (a.ksdig || a.lwe1_out) {
         for (int i = tid2; i < 1024; i += T2_THREADS_PER_GATE) {

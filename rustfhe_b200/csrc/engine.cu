@@ -204,7 +204,8 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
         auto t2attr = [&](auto kern, int G) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2_smem_bytes(G)); };
         if ((e = t2attr(blind_rotate_t2_kernel<6, 0>, 6)) != cudaSuccess || (e = t2attr(blind_rotate_t2_kernel<6, 1>, 6)) != cudaSuccess ||
             (e = t2attr(blind_rotate_t2_kernel<6, 3>, 6)) != cudaSuccess || (e = t2attr(blind_rotate_t2_kernel<4, 0>, 4)) != cudaSuccess ||
-            (e = t2attr(blind_rotate_t2_kernel<4, 1>, 4)) != cudaSuccess || (e = t2attr(blind_rotate_t2_kernel<4, 3>, 4)) != cudaSuccess)
+            (e = t2attr(blind_rotate_t2_kernel<4, 1>, 4)) != cudaSuccess || (e = t2attr(blind_rotate_t2_kernel<4, 3>, 4)) != cudaSuccess ||
+            (e = t2attr(blind_rotate_t2_kernel<6, 1, true>, 6)) != cudaSuccess)
             return bail("smem attr (t2)", e);
     }
     if (const char* v = getenv("TFHE_B200_T2_G")) ctx->t2_gates = (atoi(v) == 4) ? 4 : 6;
@@ -323,7 +324,9 @@ int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out) {
     out->last_batch = ctx->last_batch;
     out->gates_per_cta = ctx->gates_per_cta;
     out->sm_count = ctx->sm_count;
-    out->device_key_bytes = (uint64_t)LWE_N * bk_step_words(ctx->key_slices) * 4 + (uint64_t)1024 * 8 * 3 * (LWE_N + 1) * 4;
+    out->key_slices = ctx->key_slices;
+    // what the gate path streams: the two-slice key in the throughput layout (8 B per coefficient) or the three-slice key (12 B)
+    out->device_key_bytes = (uint64_t)LWE_N * (ctx->key_slices == 2 ? T2_STEP_WORDS : bk_step_words(3)) * 4 + (uint64_t)1024 * 8 * 3 * (LWE_N + 1) * 4;
     const uint64_t cnt = ctx->timed < (uint64_t)tfhe_b200_ctx::RING ? ctx->timed : (uint64_t)tfhe_b200_ctx::RING;
     double sb = 0, sk = 0;
     for (uint64_t k = 0; k < cnt; k++) {
@@ -894,10 +897,20 @@ int tfhe_b200_decrypt_bits_device(tfhe_b200_ctx* ctx, const uint8_t* s0, const u
 static int run_extprod(tfhe_b200_ctx* ctx, Slot* s, const uint32_t* trgsw_dev, size_t ntrgsw, const uint32_t* rep1, const uint32_t* rep0,
                        uint32_t* out, size_t B, cudaStream_t st) {
     RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, ntrgsw * BK_STEP_WORDS * 4));
-    RC(transform_keys(ctx, trgsw_dev, s->scratch, (int)ntrgsw, st));
     BrArgs a{};
     a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
     a.trlwe_in = rep1; a.trlwe_in0 = rep0; a.trlwe_out = out; a.ntrgsw = (long)ntrgsw; a.ns = ctx->key_slices;
+    if (a.ns == 2 && B > (size_t)ctx->sm_count) {   // two slices, throughput shape: the two-warps-per-product kernel, six products per CTA
+        const int npolys = (int)ntrgsw * 12;
+        bk_transform_t2_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(trgsw_dev, s->scratch, npolys);
+        const unsigned grid = (unsigned)((B + 5) / 6);
+        a.cta_base = (int)(B / grid); a.cta_rem = (int)(B % grid);
+        blind_rotate_t2_kernel<6, 1, true><<<grid, 6 * T2_THREADS_PER_GATE, t2_smem_bytes(6), st>>>(a);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        return TFHE_B200_OK;
+    }
+    RC(transform_keys(ctx, trgsw_dev, s->scratch, (int)ntrgsw, st));
     if (B > (size_t)ctx->sm_count) {   // throughput shape: 4 products per CTA
         const unsigned grid = (unsigned)((B + 3) / 4);
         a.cta_base = (int)(B / grid); a.cta_rem = (int)(B % grid);
