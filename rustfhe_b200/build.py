@@ -68,7 +68,7 @@ def _locked_build(target, paths, make, extra="", force=False):
 
 
 def sources():
-    names = ("engine.cu", "group.cu", "blind_rotate.cuh", "blind_rotate_t2.cuh", "t2_steps.cuh", "keyswitch.cuh", "aux_kernels.cuh", "hostkeys.cpp",
+    names = ("engine.cu", "group.cu", "blind_rotate.cuh", "blind_rotate_t2.cuh", "t2_steps.cuh", "blind_rotate_f64.cuh", "fft64.cuh", "fft64_tables.h", "keyswitch.cuh", "aux_kernels.cuh", "hostkeys.cpp",
              "wire.cpp", "csprng.hpp", "ntt32.cuh", "cmux_steps.cuh", "ntt_tables.h", "tfhe_rng.cuh")
     return [os.path.join(CSRC, f) for f in names if os.path.exists(os.path.join(CSRC, f))] + [os.path.join(ROOT, "include", "tfhe_b200.h")]
 
@@ -100,12 +100,12 @@ def build(force=False, verbose=False):
 
 def build_emul(force=False):
     """CPU emulation of the kernels' per-lane arithmetic (tests/test_host_logic.py only)."""
-    src = [os.path.join(CSRC, f) for f in ("host_emul.cpp", "ntt32.cuh", "cmux_steps.cuh", "t2_steps.cuh", "ntt_tables.h", "tfhe_rng.cuh")]
+    src = [os.path.join(CSRC, f) for f in ("host_emul.cpp", "ntt32.cuh", "cmux_steps.cuh", "t2_steps.cuh", "fft64.cuh", "fft64_tables.h", "ntt_tables.h", "tfhe_rng.cuh")]
     if not force and not _stale(EMUL, src):
         return EMUL
 
     def make(tmp):
-        subprocess.check_call([_gxx(), "-O2", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include",
+        subprocess.check_call([_gxx(), "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I/usr/local/cuda/include",
                                os.path.join(CSRC, "host_emul.cpp"), "-o", tmp])
     return _locked_build(EMUL, src, make, "", force)
 

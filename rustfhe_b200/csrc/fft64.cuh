@@ -1,0 +1,372 @@
+// fft64.cuh -- the polynomial product of the FFT64 arithmetic mode: negacyclic f64 transform over C with EXACT integer rounding.
+//
+// The reference multiplies polynomials with an f64 FFT (utils/src/spqlios/fft_processor_spqlios.cpp:58-183 driving
+// spqlios-{fft,ifft}-avx.s; pointwise stage utils/src/spqlios.rs:204-222; call sites hom_nand/src/trgsw.rs:264-306).  On the
+// B200 a DFMA issues at the rate of an IMAD (64 per clock and SM, profiles/intpipe_r01b.json), so one complex f64 transform of
+// 512 points (13.8 k DFMA-class operations) replaces a 1024-point NTT over a 29-bit prime (20.5 k IMAD slots), and -- the
+// larger gain -- a 53-bit mantissa carries the whole 32-bit key at once: 6 forward + 2 inverse transforms and 12 pointwise
+// polynomial products per CMUX instead of 6 + 4 and 24 (two 16-bit key slices) or 6 + 6 and 36 (three 11-bit slices).
+//
+// Exactness.  A coefficient of the external product is an integer of magnitude < 6144 * 32 * 2^31 < 2^49.  The transform
+// computes it with an absolute rounding error far below 1/2 (measured on honestly generated keys: < 2^-8),
+// so adding 1.5 * 2^52 leaves the EXACT integer mod 2^32 in the low word of the sum: the results are the same bits as the exact
+// NTT modes', which the parity tests check.  Not a worst-case guarantee (neither is the reference's): the NTT modes stay
+// selectable (tfhe_b200_set_key_slices).
+//
+// Mapping: a real polynomial a is folded into z_j = a_j + i a_{j+512}, j < 512, and evaluated at psi^(4k+1), psi = exp(i pi/1024).
+// One WARP owns one polynomial, 16 complex values per lane:
+//   forward  : pass A = stages 0..3 on the register index r (j = 32 r + lane; warp-uniform twiddles, immediates)
+//              transpose through 8 KB of shared memory (16-byte elements, XOR swizzle, conflict free both ways)
+//              pass B = stages 4..7 on rho = j[4:1] (lane' = 2 j[8:5] + j[0]; per-lane twiddles, 8 LDS.128)
+//              stage 8 = lane pair exchange (32 SHFL): each lane of a pair takes 8 of the 16 butterflies
+//              -> lane = p >> 4, register = p & 15 of position p, which holds the value at psi^(1 + 4 bitrev9(p))
+//   inverse  : textbook decimation in time on that order: stages 0..3 in registers (constants, mostly trivial), stage 4 = lane
+//              pair exchange, transpose, stages 5..8 on r (per-lane twiddles), z_j = psi^-j v_j, round, accumulate.
+// Twiddles of sibling nodes differ by a factor i, which costs nothing in a fused butterfly: 12 per-lane loads forward, 8 inverse.
+// 1/512 is folded into the transformed key.  Every function is what ONE lane does between two warp-level synchronisation
+// points; all arithmetic goes through F_ADD / F_MUL / F_FMA (single IEEE operations, never contracted differently), so the
+// CPU emulation (host_emul.cpp, built with -ffp-contract=off) produces the same bits as the GPU.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <utility>
+#include "fft64_tables.h"
+
+#if defined(__CUDACC__)
+#define TFHE_HD __host__ __device__ __forceinline__
+#else
+#define TFHE_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define F_ADD(a, b) __dadd_rn((a), (b))
+#define F_MUL(a, b) __dmul_rn((a), (b))
+#define F_FMA(a, b, c) __fma_rn((a), (b), (c))
+#else
+#define F_ADD(a, b) ((a) + (b))
+#define F_MUL(a, b) ((a) * (b))
+#define F_FMA(a, b, c) __builtin_fma((a), (b), (c))
+#endif
+
+namespace tfhe {
+
+struct cd { double re, im; };
+struct alignas(16) cd16 { double re, im; };   // what the tables, the transposes and the key hold (one LDS.128 / LDG.128)
+
+constexpr int F64_PTS = 512;                 // complex points per polynomial
+constexpr int F64_PER_LANE = 16;
+constexpr int F64_FWDB_ROWS = 12, F64_INVA_ROWS = 8, F64_UNTW_ROWS = 16;
+constexpr int F64_TAB_ELEMS = (F64_FWDB_ROWS + F64_INVA_ROWS + F64_UNTW_ROWS) * 32;   // per-lane tables, [row][lane] cd16
+constexpr double F64_ROUND_MAGIC = 6755399441055744.0;                             // 1.5 * 2^52
+constexpr double F64_DIGIT_BIAS = 4503599627370496.0 + 32.0;                       // 2^52 + 32
+// device key: [step i][row j < 6][output poly o < 2][register < 16][lane < 32] cd16 = 96 KB per step, 16 B per complex point
+constexpr size_t F64_CHUNK_ELEMS = 512;                                            // one (row, output) polynomial: 8 KB
+constexpr size_t F64_STEP_ELEMS = 12 * F64_CHUNK_ELEMS;
+TFHE_HD size_t f64_key_off(int i, int j, int o) { return ((size_t)i * 12 + (size_t)j * 2 + o) * F64_CHUNK_ELEMS; }
+
+static const double h_f64_fwdB[F64_FWDB_ROWS * 32 * 2] = {FFT64_FWD_B_LIST};
+static const double h_f64_invA[F64_INVA_ROWS * 32 * 2] = {FFT64_INV_A_LIST};
+static const double h_f64_untw[F64_UNTW_ROWS * 32 * 2] = {FFT64_UNTWIST_LIST};
+#if defined(__CUDACC__)
+static __device__ const double g_f64_fwdB[F64_FWDB_ROWS * 32 * 2] = {FFT64_FWD_B_LIST};
+static __device__ const double g_f64_invA[F64_INVA_ROWS * 32 * 2] = {FFT64_INV_A_LIST};
+static __device__ const double g_f64_untw[F64_UNTW_ROWS * 32 * 2] = {FFT64_UNTWIST_LIST};
+#endif
+
+template <int K> TFHE_HD constexpr double fwdA_c() { constexpr double t[] = {FFT64_FWD_A_LIST}; return t[K]; }
+template <int K> TFHE_HD constexpr double invC_c() { constexpr double t[] = {FFT64_INV_C_LIST}; return t[K]; }
+
+TFHE_HD double f64_from_words(uint32_t hi, uint32_t lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    const uint64_t b = ((uint64_t)hi << 32) | lo;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+TFHE_HD uint32_t f64_low_word(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(d);
+#else
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    return (uint32_t)b;
+#endif
+}
+TFHE_HD double f64_neg(double d) { return -d; }
+
+// ---- butterflies: (a, b) <- (a + w b, a - w b), 6 operations; the second output is 2a - (a + w b) ----
+TFHE_HD void bf_w(cd& a, cd& b, double wr, double wi) {
+    const double pr = F_FMA(wr, b.re, F_FMA(-wi, b.im, a.re));
+    const double pi = F_FMA(wr, b.im, F_FMA(wi, b.re, a.im));
+    b.re = F_FMA(2.0, a.re, -pr); b.im = F_FMA(2.0, a.im, -pi);
+    a.re = pr; a.im = pi;
+}
+// twiddle i w:  i w b = (-(wr b.im + wi b.re), wr b.re - wi b.im)
+TFHE_HD void bf_iw(cd& a, cd& b, double wr, double wi) {
+    const double pr = F_FMA(-wr, b.im, F_FMA(-wi, b.re, a.re));
+    const double pi = F_FMA(wr, b.re, F_FMA(-wi, b.im, a.im));
+    b.re = F_FMA(2.0, a.re, -pr); b.im = F_FMA(2.0, a.im, -pi);
+    a.re = pr; a.im = pi;
+}
+// twiddle -i w:  -i w b = (wr b.im + wi b.re, -(wr b.re - wi b.im))
+TFHE_HD void bf_miw(cd& a, cd& b, double wr, double wi) {
+    const double pr = F_FMA(wr, b.im, F_FMA(wi, b.re, a.re));
+    const double pi = F_FMA(-wr, b.re, F_FMA(wi, b.im, a.im));
+    b.re = F_FMA(2.0, a.re, -pr); b.im = F_FMA(2.0, a.im, -pi);
+    a.re = pr; a.im = pi;
+}
+TFHE_HD void bf_1(cd& a, cd& b) {   // w = 1
+    const double sr = F_ADD(a.re, b.re), si = F_ADD(a.im, b.im);
+    b.re = F_ADD(a.re, -b.re); b.im = F_ADD(a.im, -b.im);
+    a.re = sr; a.im = si;
+}
+TFHE_HD void bf_mi(cd& a, cd& b) {  // w = -i: w b = (b.im, -b.re)
+    const double sr = F_ADD(a.re, b.im), si = F_ADD(a.im, -b.re);
+    const double dr = F_ADD(a.re, -b.im), di = F_ADD(a.im, b.re);
+    a.re = sr; a.im = si; b.re = dr; b.im = di;
+}
+// sel: 0 = w, 1 = i w, 2 = -i w
+template <int SEL>
+TFHE_HD void bf_sel(cd& a, cd& b, double wr, double wi) {
+    if (SEL == 0) bf_w(a, b, wr, wi);
+    else if (SEL == 1) bf_iw(a, b, wr, wi);
+    else bf_miw(a, b, wr, wi);
+}
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+// pass A, stage S (0..3), butterfly I (0..7): registers r = 2 h beta + t and r + h, h = 8 >> S, warp-uniform twiddle
+template <int S, int I>
+TFHE_HD void f64_fa_bfly(cd (&x)[16]) {
+    constexpr int h = 8 >> S, beta = I / h, t = I % h, ia = 2 * h * beta + t, k = (1 << S) - 1 + beta;
+    bf_w(x[ia], x[ia + h], fwdA_c<2 * k>(), fwdA_c<2 * k + 1>());
+}
+template <int S, int... I>
+TFHE_HD void f64_fa_stage(cd (&x)[16], std::integer_sequence<int, I...>) { (f64_fa_bfly<S, I>(x), ...); }
+TFHE_HD void f64_fwd_passA(cd (&x)[16]) {
+    f64_fa_stage<0>(x, std::make_integer_sequence<int, 8>{});
+    f64_fa_stage<1>(x, std::make_integer_sequence<int, 8>{});
+    f64_fa_stage<2>(x, std::make_integer_sequence<int, 8>{});
+    f64_fa_stage<3>(x, std::make_integer_sequence<int, 8>{});
+}
+// transpose 1: element j = 32 r + lane is stored at slot j ^ ((r & 3) << 1); lane' = 2 hi + j0 then reads j = (hi, rho, j0)
+TFHE_HD void f64_t1_store(int lane, const cd (&x)[16], cd16* S) {
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        cd16 v; v.re = x[r].re; v.im = x[r].im;
+        S[(32 * r + lane) ^ ((r & 3) << 1)] = v;
+    }
+}
+TFHE_HD void f64_t1_load(int lane, const cd16* S, cd (&x)[16]) {
+    const int hi = lane >> 1, j0 = lane & 1;
+    const int base = ((hi << 5) | j0) ^ ((hi & 3) << 1);
+#pragma unroll
+    for (int rho = 0; rho < 16; rho++) {
+        const cd16 v = S[base ^ (rho << 1)];   // (rho << 1) touches bits 1..4, the swizzle bits 1..2: XOR commutes
+        x[rho].re = v.re; x[rho].im = v.im;
+    }
+}
+// pass B: stages 4..7 on rho, per-lane twiddles tb[t * 32 + lane]
+template <int SEL> TFHE_HD void f64_fb_pair(cd (&x)[16], int ia, int h, const cd16& w) { bf_sel<SEL>(x[ia], x[ia + h], w.re, w.im); }
+TFHE_HD void f64_fwd_passB(int lane, cd (&x)[16], const cd16* tb) {
+    {
+        const cd16 w = tb[0 * 32 + lane];
+#pragma unroll
+        for (int t = 0; t < 8; t++) bf_w(x[t], x[t + 8], w.re, w.im);
+    }
+    {
+        const cd16 w = tb[1 * 32 + lane];
+#pragma unroll
+        for (int t = 0; t < 4; t++) { bf_w(x[t], x[t + 4], w.re, w.im); bf_iw(x[8 + t], x[12 + t], w.re, w.im); }
+    }
+#pragma unroll
+    for (int c2 = 0; c2 < 2; c2++) {
+        const cd16 w = tb[(2 + c2) * 32 + lane];
+#pragma unroll
+        for (int t = 0; t < 2; t++) { bf_w(x[8 * c2 + t], x[8 * c2 + t + 2], w.re, w.im); bf_iw(x[8 * c2 + 4 + t], x[8 * c2 + 6 + t], w.re, w.im); }
+    }
+#pragma unroll
+    for (int c2 = 0; c2 < 4; c2++) {
+        const cd16 w = tb[(4 + c2) * 32 + lane];
+        bf_w(x[4 * c2], x[4 * c2 + 1], w.re, w.im);
+        bf_iw(x[4 * c2 + 2], x[4 * c2 + 3], w.re, w.im);
+    }
+}
+// stage 8, the lane-pair exchange.  Lane j0 owns the butterflies rho = 8 j0 + m, m < 8: it keeps its own operand of those and
+// needs the partner's; it sends the operand it holds of the partner's butterflies.
+TFHE_HD void f64_x_send(int lane, const cd (&x)[16], cd (&send)[8]) {
+    const bool odd = lane & 1;
+#pragma unroll
+    for (int m = 0; m < 8; m++) { send[m].re = odd ? x[m].re : x[m + 8].re; send[m].im = odd ? x[m].im : x[m + 8].im; }
+}
+TFHE_HD void f64_fwd_x_bfly(int lane, const cd (&x)[16], const cd (&recv)[8], const cd16* tb, cd (&y)[16]) {
+    const bool odd = lane & 1;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const cd16 w = tb[(8 + q) * 32 + lane];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int m = 2 * q + e;
+            cd a, b;   // a = element with j0 = 0, b = element with j0 = 1 of rho = 8 j0(lane) + m
+            a.re = odd ? recv[m].re : x[m].re; a.im = odd ? recv[m].im : x[m].im;
+            b.re = odd ? x[m + 8].re : recv[m].re; b.im = odd ? x[m + 8].im : recv[m].im;
+            if (e == 0) bf_w(a, b, w.re, w.im); else bf_iw(a, b, w.re, w.im);
+            y[2 * m] = a; y[2 * m + 1] = b;
+        }
+    }
+}
+
+// pointwise multiply-accumulate: acc[k] += y[k] * key[k * 32 + lane]
+TFHE_HD void f64_mac(int lane, const cd (&y)[16], const cd16* key, cd (&acc)[16]) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const cd16 w = key[k * 32 + lane];
+        acc[k].re = F_FMA(y[k].re, w.re, F_FMA(-y[k].im, w.im, acc[k].re));
+        acc[k].im = F_FMA(y[k].re, w.im, F_FMA(y[k].im, w.re, acc[k].im));
+    }
+}
+TFHE_HD void f64_mul(int lane, const cd (&y)[16], const cd16* key, cd (&acc)[16]) {   // first row: acc = y * key
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const cd16 w = key[k * 32 + lane];
+        acc[k].re = F_FMA(y[k].re, w.re, -F_MUL(y[k].im, w.im));
+        acc[k].im = F_FMA(y[k].re, w.im, F_MUL(y[k].im, w.re));
+    }
+}
+
+// =====================================================================================================
+// inverse
+// =====================================================================================================
+template <int K> TFHE_HD void f64_inv_c(cd& a, cd& b) { bf_w(a, b, invC_c<2 * K>(), invC_c<2 * K + 1>()); }
+// stages 0..3 on the register index (p & 15)
+TFHE_HD void f64_inv_low(cd (&y)[16]) {
+#pragma unroll
+    for (int m = 0; m < 8; m++) bf_1(y[2 * m], y[2 * m + 1]);
+#pragma unroll
+    for (int c = 0; c < 4; c++) { bf_1(y[4 * c], y[4 * c + 2]); bf_mi(y[4 * c + 1], y[4 * c + 3]); }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        bf_1(y[8 * c], y[8 * c + 4]);
+        f64_inv_c<1>(y[8 * c + 1], y[8 * c + 5]);
+        bf_mi(y[8 * c + 2], y[8 * c + 6]);
+        f64_inv_c<3>(y[8 * c + 3], y[8 * c + 7]);
+    }
+    bf_1(y[0], y[8]);
+    f64_inv_c<4 + 1>(y[1], y[9]); f64_inv_c<4 + 2>(y[2], y[10]); f64_inv_c<4 + 3>(y[3], y[11]);
+    bf_mi(y[4], y[12]);
+    f64_inv_c<4 + 5>(y[5], y[13]); f64_inv_c<4 + 6>(y[6], y[14]); f64_inv_c<4 + 7>(y[7], y[15]);
+}
+// stage 4 (span 16 = lane bit 0): lane parity lam owns the butterflies of registers m + 8 lam, m < 8; twiddle Wc^(16 m) (-i)^lam.
+// v[m] = result with p[4] = 0, v[8 + m] = result with p[4] = 1; the lane now holds p[3] = lam.
+template <int M> TFHE_HD void f64_inv_x_one(bool odd, const cd (&y)[16], const cd (&recv)[8], cd (&v)[16]) {
+    cd a, b;
+    a.re = odd ? recv[M].re : y[M].re; a.im = odd ? recv[M].im : y[M].im;
+    // b0 = odd ? y[M + 8] : recv[M];  b = odd ? -i b0 : b0 = odd ? (b0.im, -b0.re) : b0
+    b.re = odd ? y[M + 8].im : recv[M].re;
+    b.im = odd ? f64_neg(y[M + 8].re) : recv[M].im;
+    if (M == 0) bf_1(a, b); else f64_inv_c<12 + M>(a, b);
+    v[M] = a; v[8 + M] = b;
+}
+template <int... M>
+TFHE_HD void f64_inv_x_all(bool odd, const cd (&y)[16], const cd (&recv)[8], cd (&v)[16], std::integer_sequence<int, M...>) {
+    (f64_inv_x_one<M>(odd, y, recv, v), ...);
+}
+TFHE_HD void f64_inv_x_bfly(int lane, const cd (&y)[16], const cd (&recv)[8], cd (&v)[16]) {
+    f64_inv_x_all((lane & 1) != 0, y, recv, v, std::make_integer_sequence<int, 8>{});
+}
+// transpose 2: lane = 2 hi + lam holds p = (hi, p4, lam, m) in v[8 p4 + m]; slot = p ^ (((hi & 3) << 1) | lam);
+// lane'' = p & 31 then reads p = 32 r + lane''
+TFHE_HD void f64_t2_store(int lane, const cd (&v)[16], cd16* S) {
+    const int hi = lane >> 1, lam = lane & 1;
+    const int base = ((hi << 5) | (lam << 3)) ^ (((hi & 3) << 1) | lam);
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        cd16 t; t.re = v[e].re; t.im = v[e].im;
+        S[base ^ (((e >> 3) << 4) | (e & 7))] = t;
+    }
+}
+TFHE_HD void f64_t2_load(int lane, const cd16* S, cd (&w)[16]) {
+    const int l3 = (lane >> 3) & 1;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const cd16 t = S[(32 * r + lane) ^ (((r & 3) << 1) | l3)];
+        w[r].re = t.re; w[r].im = t.im;
+    }
+}
+// stages 5..8 on r, per-lane twiddles ta[t * 32 + lane]
+TFHE_HD void f64_inv_passA(int lane, cd (&w)[16], const cd16* ta) {
+    {
+        const cd16 t = ta[0 * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < 8; c++) bf_w(w[2 * c], w[2 * c + 1], t.re, t.im);
+    }
+    {
+        const cd16 t = ta[1 * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < 4; c++) { bf_w(w[4 * c], w[4 * c + 2], t.re, t.im); bf_miw(w[4 * c + 1], w[4 * c + 3], t.re, t.im); }
+    }
+    {
+        const cd16 t0 = ta[2 * 32 + lane], t1 = ta[3 * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            bf_w(w[8 * c], w[8 * c + 4], t0.re, t0.im);
+            bf_w(w[8 * c + 1], w[8 * c + 5], t1.re, t1.im);
+            bf_miw(w[8 * c + 2], w[8 * c + 6], t0.re, t0.im);
+            bf_miw(w[8 * c + 3], w[8 * c + 7], t1.re, t1.im);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const cd16 t = ta[(4 + k) * 32 + lane];
+        bf_w(w[k], w[k + 8], t.re, t.im);
+        bf_miw(w[k + 4], w[k + 12], t.re, t.im);
+    }
+}
+// z_j = psi^-j v_j, exact rounding; lo[r] / hi[r] = coefficients j and j + 512 (j = 32 r + lane) mod 2^32.
+// frac (host-side diagnostics only): largest distance of a value from the nearest integer.
+TFHE_HD void f64_untwist_round(int lane, const cd (&w)[16], const cd16* ut, uint32_t (&lo)[16], uint32_t (&hi)[16], double* frac = nullptr) {
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const cd16 t = ut[r * 32 + lane];
+        const double zr = F_FMA(w[r].re, t.re, -F_MUL(w[r].im, t.im));
+        const double zi = F_FMA(w[r].re, t.im, F_MUL(w[r].im, t.re));
+        const double mr = F_ADD(zr, F64_ROUND_MAGIC), mi = F_ADD(zi, F64_ROUND_MAGIC);
+        lo[r] = f64_low_word(mr);
+        hi[r] = f64_low_word(mi);
+#if !defined(__CUDA_ARCH__)
+        if (frac) {
+            const double er = zr - (mr - F64_ROUND_MAGIC), ei = zi - (mi - F64_ROUND_MAGIC);
+            const double m = (er < 0 ? -er : er) > (ei < 0 ? -ei : ei) ? (er < 0 ? -er : er) : (ei < 0 ? -ei : ei);
+            if (m > *frac) *frac = m;
+        }
+#endif
+    }
+}
+
+// ---- inputs ----
+// gadget digit from the 6-bit field f = d + 32 of a masked, sign-flipped word: (2^52 + f) - (2^52 + 32) = d, one DADD
+TFHE_HD double f64_digit(uint32_t f) { return F_ADD(f64_from_words(0x43300000u, f), -F64_DIGIT_BIAS); }
+// digit `dw` of the masked words U'[k] (k = 32 r + lane and k + 512), U' = u ^ 0x82080000 (offset-binary digits)
+constexpr uint32_t F64_SIGN_FLIP = 0x82080000u;
+TFHE_HD void f64_digits(int lane, const uint32_t* U, int dw, cd (&x)[16]) {
+    const int sh = 26 - 6 * dw;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        x[r].re = f64_digit((U[32 * r + lane] >> sh) & 63u);
+        x[r].im = f64_digit((U[512 + 32 * r + lane] >> sh) & 63u);
+    }
+}
+// key polynomial (torus words taken as centred 32-bit integers) -> folded complex input
+TFHE_HD void f64_key_input(int lane, const uint32_t* poly, cd (&x)[16]) {
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        x[r].re = (double)(int32_t)poly[32 * r + lane];
+        x[r].im = (double)(int32_t)poly[512 + 32 * r + lane];
+    }
+}
+
+}  // namespace tfhe

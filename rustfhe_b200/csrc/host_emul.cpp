@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 #include "t2_steps.cuh"
+#include "fft64.cuh"
 #include "tfhe_rng.cuh"
 
 using namespace tfhe;
@@ -149,6 +150,83 @@ void emul_external_product_t2(const uint32_t* dev, const uint32_t* trlwe, uint32
     t2_step(dev, out, false, 0, mask);
 }
 void emul_cmux_rotate_t2(const uint32_t* dev, uint32_t* acc, uint32_t abar, uint32_t mask) { t2_step(dev, acc, true, abar, mask); }
+// ---- FFT64 mode (fft64.cuh, blind_rotate_f64.cuh): one gate on ONE warp, f64 complex transform, exact rounding ----
+// TRGSW torus polys [row j][poly o][1024] -> [row j][o][register][lane] complex, scaled by 1/512
+static void f64_forward_all_lanes(cd (*x)[16], cd16* S, cd (*y)[16]) {
+    const cd16* tb = reinterpret_cast<const cd16*>(h_f64_fwdB);
+    static_assert(sizeof(cd16) == 16, "cd16 layout");
+    cd send[32][8];
+    for (int lane = 0; lane < 32; lane++) { f64_fwd_passA(x[lane]); f64_t1_store(lane, x[lane], S); }
+    for (int lane = 0; lane < 32; lane++) { f64_t1_load(lane, S, x[lane]); f64_fwd_passB(lane, x[lane], tb); f64_x_send(lane, x[lane], send[lane]); }
+    for (int lane = 0; lane < 32; lane++) f64_fwd_x_bfly(lane, x[lane], send[lane ^ 1], tb, y[lane]);
+}
+void emul_key_transform_f64(const uint32_t* trgsw, double* dev) {
+    std::vector<cd16> S(512);
+    cd16* out = reinterpret_cast<cd16*>(dev);
+    for (int j = 0; j < BK_ROWS; j++)
+        for (int o = 0; o < 2; o++) {
+            cd x[32][16], y[32][16];
+            for (int lane = 0; lane < 32; lane++) f64_key_input(lane, trgsw + (size_t)(j * 2 + o) * 1024, x[lane]);
+            f64_forward_all_lanes(x, S.data(), y);
+            for (int lane = 0; lane < 32; lane++)
+                for (int k = 0; k < 16; k++) {
+                    cd16 v; v.re = y[lane][k].re * (1.0 / 512); v.im = y[lane][k].im * (1.0 / 512);
+                    out[f64_key_off(0, j, o) + k * 32 + lane] = v;
+                }
+        }
+}
+// one step: acc <- BK (x) src + acc with src = X^abar acc - acc (rotate), or acc <- BK (x) acc (plain external product).
+// Returns the largest distance of a pre-rounding value from the nearest integer (the exactness margin: must stay far below 1/2).
+static double f64_step(const double* dev, uint32_t* acc, bool rotate, uint32_t abar, uint32_t mask) {
+    const cd16* key = reinterpret_cast<const cd16*>(dev);
+    std::vector<cd16> S(512);
+    std::vector<uint32_t> U(1024);
+    cd sum[2][32][16];
+    double frac = 0;
+    for (int pw = 0; pw < 2; pw++) {
+        for (int lane = 0; lane < 32; lane++) {
+            uint32_t u[32];
+            if (rotate) t2_u<true>(lane, acc + pw * 1024, abar, mask, u);
+            else t2_u<false>(lane, acc + pw * 1024, abar, mask, u);
+            for (int r = 0; r < 32; r++) U[32 * r + lane] = u[r] ^ F64_SIGN_FLIP;
+        }
+        for (int dw = 0; dw < 3; dw++) {
+            cd x[32][16], y[32][16];
+            for (int lane = 0; lane < 32; lane++) f64_digits(lane, U.data(), dw, x[lane]);
+            f64_forward_all_lanes(x, S.data(), y);
+            const int j = 3 * pw + dw;
+            for (int o = 0; o < 2; o++)
+                for (int lane = 0; lane < 32; lane++) {
+                    if (j == 0) f64_mul(lane, y[lane], key + f64_key_off(0, j, o), sum[o][lane]);
+                    else f64_mac(lane, y[lane], key + f64_key_off(0, j, o), sum[o][lane]);
+                }
+        }
+    }
+    const cd16* ta = reinterpret_cast<const cd16*>(h_f64_invA);
+    const cd16* ut = reinterpret_cast<const cd16*>(h_f64_untw);
+    for (int o = 0; o < 2; o++) {
+        cd send[32][8], v[32][16], w[32][16];
+        for (int lane = 0; lane < 32; lane++) { f64_inv_low(sum[o][lane]); f64_x_send(lane, sum[o][lane], send[lane]); }
+        for (int lane = 0; lane < 32; lane++) { f64_inv_x_bfly(lane, sum[o][lane], send[lane ^ 1], v[lane]); f64_t2_store(lane, v[lane], S.data()); }
+        for (int lane = 0; lane < 32; lane++) {
+            uint32_t lo[16], hi[16];
+            f64_t2_load(lane, S.data(), w[lane]);
+            f64_inv_passA(lane, w[lane], ta);
+            f64_untwist_round(lane, w[lane], ut, lo, hi, &frac);
+            for (int r = 0; r < 16; r++) {
+                uint32_t* a0 = acc + o * 1024 + 32 * r + lane;
+                a0[0] = (rotate ? a0[0] : 0u) + lo[r];
+                a0[512] = (rotate ? a0[512] : 0u) + hi[r];
+            }
+        }
+    }
+    return frac;
+}
+double emul_external_product_f64(const double* dev, const uint32_t* trlwe, uint32_t mask, uint32_t* out) {
+    memcpy(out, trlwe, 2 * 1024 * sizeof(uint32_t));
+    return f64_step(dev, out, false, 0, mask);
+}
+double emul_cmux_rotate_f64(const double* dev, uint32_t* acc, uint32_t abar, uint32_t mask) { return f64_step(dev, acc, true, abar, mask); }
 // one 64-bit word of the ChaCha20 block the production generator is built on (RFC 8439 known-answer test)
 uint64_t emul_chacha20_u64(const uint32_t* key, uint64_t counter, uint64_t nonce, int lane8) { return tfhe_rng::chacha20_u64(key, counter, nonce, lane8); }
 uint32_t emul_prime(void) { return P; }
