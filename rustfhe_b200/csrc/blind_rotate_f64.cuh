@@ -1,0 +1,244 @@
+// blind_rotate_f64.cuh -- K5F, the throughput blind rotation of the FFT64 arithmetic mode (included by engine.cu only).
+//   gate pre-combination + 635 x CMUX + sample extract (tfhe.rs:27-113, trgsw.rs:264-322, trlwe.rs:110-121)
+// One gate = ONE warp; eight gates per CTA, one CTA per SM (256 threads, up to 255 registers).  Per CMUX a warp runs six
+// forward transforms (one per gadget digit), multiplies every spectrum into BOTH output accumulators while it is still in
+// registers (2 x 16 complex values per lane = 128 registers that live for the whole step), and runs two inverse transforms:
+// no spectrum is ever written to shared memory, no barrier between warps.  The gates of a CTA only meet at the key ring:
+//   bootstrapping key: [step][row j][output o] chunks of 8 KB, in the order every warp consumes them.  One elected thread streams
+//   them with bulk (TMA) copies into a 4-deep ring in shared memory (full / empty mbarriers); all eight gates read a chunk from
+//   there, so the key crosses L2 -> SM once per CTA instead of once per gate ("reused across a batch of gates in
+//   shared memory").
+// See fft64.cuh for the transform and DESIGN.md sections 2, 3 and 5 for the operation counts and measurements.
+#pragma once
+#include "blind_rotate.cuh"
+#include "t2_steps.cuh"
+#include "fft64.cuh"
+
+constexpr int F64_GATES = 8;                    // gates (= warps) per CTA
+constexpr int F64_RING = 4;                     // key chunks in flight
+constexpr int F64_CHUNK_BYTES = (int)(F64_CHUNK_ELEMS * sizeof(cd16));   // 8192
+constexpr int F64_GATE_SMEM_BYTES = 2 * 1024 * 4 /*acc*/ + 512 * 16 /*transpose scratch*/ + 1024 * 4 /*masked source words*/ + 640 * 2 /*abar*/;
+constexpr int F64_SHARED_BYTES = F64_TAB_ELEMS * 16 + F64_RING * F64_CHUNK_BYTES + 2 * F64_RING * 8 + F64_RING * 4;
+constexpr size_t f64_smem_bytes() { return (size_t)F64_SHARED_BYTES + (size_t)F64_GATES * F64_GATE_SMEM_BYTES; }
+static_assert(f64_smem_bytes() <= 227 * 1024, "eight gates and the key ring must fit the shared memory of one SM");
+
+__device__ __forceinline__ void f64_exchange(const cd (&send)[8], cd (&recv)[8]) {
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        recv[m].re = __shfl_xor_sync(0xffffffffu, send[m].re, 1);
+        recv[m].im = __shfl_xor_sync(0xffffffffu, send[m].im, 1);
+    }
+}
+// forward transform of the 16 values a lane holds (natural order j = 32 r + lane) -> spectrum (position p = 16 lane + register)
+__device__ __forceinline__ void f64_forward(int lane, cd (&x)[16], cd16* S, const cd16* tb, cd (&y)[16]) {
+    f64_fwd_passA(x);
+    f64_t1_store(lane, x, S);
+    __syncwarp();
+    f64_t1_load(lane, S, x);
+    __syncwarp();   // the scratch is free for the next transform
+    f64_fwd_passB(lane, x, tb);
+    cd send[8], recv[8];
+    f64_x_send(lane, x, send);
+    f64_exchange(send, recv);
+    f64_fwd_x_bfly(lane, x, recv, tb, y);
+}
+
+struct F64Ring {
+    cd16* slot;        // [F64_RING][512]
+    uint64_t* full;    // [F64_RING]
+    uint64_t* empty;   // [F64_RING]
+    uint32_t* left;    // [F64_RING] warps that have handed the slot back in the current round
+    const cd16* key;   // chunk 0 of this gate batch's first step
+    long total;        // chunks the CTA consumes
+    int active;        // warps of the CTA that own a gate
+};
+// consumer side: wait for chunk n, run `use(slot)`, hand the slot back.  The LAST warp to leave a slot refills it with chunk
+// n + F64_RING: no warp is the producer, so the warps of a CTA may drift up to a ring apart (they are started staggered so that
+// the transposes and key reads of one gate fall under the arithmetic of another).
+template <class F>
+__device__ __forceinline__ void f64_with_chunk(const F64Ring& rg, long n, int lane, F&& use) {
+    const int s = (int)(n & (F64_RING - 1));
+    const uint32_t par = (uint32_t)((n / F64_RING) & 1);
+    mbar_wait(rg.full + s, par);
+    use(rg.slot + (size_t)s * F64_CHUNK_ELEMS);
+    __syncwarp();
+    if (lane == 0) {
+        mbar_arrive(rg.empty + s);
+        if (atomicAdd(rg.left + s, 1u) == (uint32_t)(rg.active - 1)) {
+            rg.left[s] = 0;
+            if (n + F64_RING < rg.total) {
+                mbar_wait(rg.empty + s, par);   // every warp's reads of the slot are ordered before the copy that overwrites it
+                bulk_fetch(rg.slot + (size_t)s * F64_CHUNK_ELEMS, rg.key + (size_t)(n + F64_RING) * F64_CHUNK_ELEMS, F64_CHUNK_BYTES, rg.full + s);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(F64_GATES * 32, 1) blind_rotate_f64_kernel(const BrArgs a, const cd16* __restrict__ key, int stagger_ns) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd16* tab = reinterpret_cast<cd16*>(smem_raw);
+    const cd16* tb = tab;                                             // forward pass B / exchange twiddles
+    const cd16* ta = tab + F64_FWDB_ROWS * 32;                        // inverse stages 5..8
+    F64Ring rg;
+    rg.slot = tab + F64_TAB_ELEMS;
+    rg.full = reinterpret_cast<uint64_t*>(rg.slot + (size_t)F64_RING * F64_CHUNK_ELEMS);
+    rg.empty = rg.full + F64_RING;
+    rg.left = reinterpret_cast<uint32_t*>(rg.empty + F64_RING);
+    const int gl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* gbase = smem_raw + F64_SHARED_BYTES + (size_t)gl * F64_GATE_SMEM_BYTES;
+    uint32_t* acc = reinterpret_cast<uint32_t*>(gbase);
+    cd16* S = reinterpret_cast<cd16*>(gbase + 2 * 1024 * 4);
+    uint32_t* U = reinterpret_cast<uint32_t*>(gbase + 2 * 1024 * 4 + 512 * 16);
+    uint16_t* abar = reinterpret_cast<uint16_t*>(gbase + 2 * 1024 * 4 + 512 * 16 + 1024 * 4);
+
+    // gates are dealt out evenly: the first cta_rem CTAs own cta_base+1 consecutive gates, the others cta_base (<= F64_GATES)
+    const long cta = blockIdx.x;
+    const long first = cta * a.cta_base + (cta < a.cta_rem ? cta : a.cta_rem);
+    const int cnt = a.cta_base + (cta < a.cta_rem ? 1 : 0);
+    const bool active = gl < cnt;
+    const long gate = active ? first + gl : a.B - 1;
+    const int nsteps = a.nsteps;
+    rg.key = key;
+    rg.total = (long)nsteps * 12;
+    rg.active = cnt;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F64_RING; s++) { mbar_init(rg.full + s, 1); mbar_init(rg.empty + s, cnt); rg.left[s] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const double* g0 = g_f64_fwdB; const double* g1 = g_f64_invA;
+        double* t = reinterpret_cast<double*>(tab);
+        for (int k = threadIdx.x; k < F64_FWDB_ROWS * 64; k += blockDim.x) t[k] = g0[k];
+        for (int k = threadIdx.x; k < F64_INVA_ROWS * 64; k += blockDim.x) t[F64_FWDB_ROWS * 64 + k] = g1[k];
+    }
+    // ---- prologue: gate pre-combination (tfhe.rs:27-71), rounding of (b, a) (tfhe.rs:97,107-108), acc_0 ----
+    {
+        uint32_t* lin = reinterpret_cast<uint32_t*>(S);
+        const bool second = gate >= a.split;
+        const long gsrc = second ? gate - a.split : gate;
+        const uint32_t* q0 = second ? a.in0b : a.in0;
+        const uint32_t* q1 = second ? a.in1b : a.in1;
+        uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
+        if (a.ops) gate_coeffs(a.ops[gate], a.mu, k0, k1, kb);
+        const uint32_t* p0 = q0 + (size_t)(a.idx0 ? (long)a.idx0[gate] : gsrc) * (LWE_N + 1);
+        const uint32_t* p1 = (q1 && k1 != 0) ? q1 + (size_t)(a.idx1 ? (long)a.idx1[gate] : gsrc) * (LWE_N + 1) : nullptr;
+        for (int c = lane; c <= LWE_N; c += 32) {
+            uint32_t v = k0 * p0[c];
+            if (p1) v += k1 * p1[c];
+            if (c == 0) v += kb;
+            lin[c] = v;
+        }
+        __syncwarp();
+        for (int i = lane; i < LWE_N; i += 32) abar[i] = (uint16_t)((lin[1 + i] + (1u << 20)) >> 21);   // round
+        const uint32_t bbar = lin[0] >> 21;                                                             // floor
+        const uint32_t nrot = (2048u - bbar) & 2047u;   // acc_0 = X^{-bbar} * (mu, ..., mu ; 0)
+        for (int k = lane; k < 1024; k += 32) {
+            const bool neg = ((uint32_t)k < (nrot & 1023u)) != (nrot >= 1024u);
+            acc[k] = neg ? 0u - a.mu : a.mu;
+            acc[1024 + k] = 0;
+        }
+    }
+    __syncthreads();   // tables, mbarriers
+    if (threadIdx.x == 0)
+        for (long n = 0; n < F64_RING && n < rg.total; n++)
+            bulk_fetch(rg.slot + (size_t)n * F64_CHUNK_ELEMS, rg.key + (size_t)n * F64_CHUNK_ELEMS, F64_CHUNK_BYTES, rg.full + n);
+    if (!active) return;   // gate slots without a gate leave here: the empty barriers count the active warps only
+    if (stagger_ns > 0 && gl > 0) __nanosleep((unsigned)(gl * stagger_ns));
+
+    // ---- 635 x CMUX ----
+    long n = 0;
+#pragma unroll 1
+    for (int i = 0; i < nsteps; i++) {
+        cd s0[16], s1[16];   // spectra of the two output polynomials
+#pragma unroll
+        for (int k = 0; k < 16; k++) { s0[k].re = 0.0; s0[k].im = 0.0; s1[k].re = 0.0; s1[k].im = 0.0; }
+        const uint32_t ab = abar[i];
+#pragma unroll 1
+        for (int pw = 0; pw < 2; pw++) {
+            {   // masked source words of polynomial pw: ((X^abar acc - acc) + mask) ^ mask, digits flipped to offset binary
+                uint32_t u[32];
+                t2_u<true>(lane, acc + pw * 1024, ab, a.mask, u);
+#pragma unroll
+                for (int r = 0; r < 32; r++) U[32 * r + lane] = u[r] ^ F64_SIGN_FLIP;
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int dw = 0; dw < 3; dw++) {
+                cd x[16], y[16];
+                f64_digits(lane, U, dw, x);
+                f64_forward(lane, x, S, tb, y);
+                f64_with_chunk(rg, n, lane, [&](const cd16* k) { f64_mac(lane, y, k, s0); });
+                f64_with_chunk(rg, n + 1, lane, [&](const cd16* k) { f64_mac(lane, y, k, s1); });
+                n += 2;
+            }
+            __syncwarp();   // every lane has read U before the next polynomial overwrites it
+        }
+#pragma unroll 1
+        for (int o = 0; o < 2; o++) {
+            cd v[16];
+            {
+                f64_inv_low(s0);
+                cd send[8], recv[8];
+                f64_x_send(lane, s0, send);
+                f64_exchange(send, recv);
+                f64_inv_x_bfly(lane, s0, recv, v);
+            }
+            f64_t2_store(lane, v, S);
+            __syncwarp();
+            f64_t2_load(lane, S, v);
+            __syncwarp();
+            f64_inv_passA(lane, v, ta);
+            uint32_t lo[16], hi[16];
+            f64_untwist_round(lane, v, ta, lo, hi);
+            uint32_t* ao = acc + o * 1024;
+#pragma unroll
+            for (int r = 0; r < 16; r++) { ao[32 * r + lane] += lo[r]; ao[512 + 32 * r + lane] += hi[r]; }
+#pragma unroll
+            for (int k = 0; k < 16; k++) s0[k] = s1[k];
+        }
+        __syncwarp();   // acc is complete before the next step's rotated reads (other lanes' words)
+    }
+
+    // ---- epilogue: sample_extract_index(0) (trlwe.rs:110-121) + key-switch digits (tlwe.rs:47-64) ----
+    if (a.trlwe_out) {
+        uint32_t* dst = a.trlwe_out + (size_t)gate * 2048;
+        for (int k = lane; k < 2048; k += 32) dst[k] = acc[k];
+    }
+    if (a.ksdig || a.lwe1_out) {
+        for (int i = lane; i < 1024; i += 32) {
+            const uint32_t ai = (i == 0) ? acc[1024] : 0u - acc[1024 + 1024 - i];
+            if (a.ksdig) a.ksdig[(size_t)gate * 1024 + i] = (uint16_t)((ai + 0x8000u) >> 16);
+            if (a.lwe1_out) a.lwe1_out[(size_t)gate * 1025 + 1 + i] = ai;
+        }
+        if (a.lwe1_out && lane == 0) a.lwe1_out[(size_t)gate * 1025] = acc[0];
+    }
+    if (a.out_init) {
+        uint32_t* dst = a.out_init + (size_t)(a.idxo ? (long)a.idxo[gate] : gate) * (LWE_N + 1);
+        for (int c = lane; c <= LWE_N; c += 32) dst[c] = (c == 0) ? acc[0] : 0u;
+    }
+}
+
+// K8F: key transform into the FFT64 layout.  One warp per (step i, row j, output poly o); 1/512 folded in.
+constexpr int KTF_WARPS = 4;
+__global__ void __launch_bounds__(KTF_WARPS * 32) bk_transform_f64_kernel(const uint32_t* __restrict__ bk, cd16* __restrict__ dev, int npolys) {
+    __shared__ __align__(16) cd16 tb[F64_FWDB_ROWS * 32];
+    __shared__ __align__(16) cd16 scratch[KTF_WARPS][512];
+    {
+        double* t = reinterpret_cast<double*>(tb);
+        for (int k = threadIdx.x; k < F64_FWDB_ROWS * 64; k += blockDim.x) t[k] = g_f64_fwdB[k];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pid = blockIdx.x * KTF_WARPS + warp;
+    if (pid >= npolys) return;
+    cd x[16], y[16];
+    f64_key_input(lane, bk + (size_t)pid * 1024, x);
+    f64_forward(lane, x, scratch[warp], tb, y);
+    cd16* dst = dev + (size_t)pid * F64_CHUNK_ELEMS;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        cd16 v; v.re = __dmul_rn(y[k].re, 1.0 / 512); v.im = __dmul_rn(y[k].im, 1.0 / 512);
+        dst[k * 32 + lane] = v;
+    }
+}

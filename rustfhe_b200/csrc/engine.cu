@@ -15,6 +15,7 @@
 #include "../../include/tfhe_b200.h"
 #include "blind_rotate.cuh"
 #include "blind_rotate_t2.cuh"
+#include "blind_rotate_f64.cuh"
 #include "keyswitch.cuh"
 #include "aux_kernels.cuh"
 
@@ -47,6 +48,7 @@ struct tfhe_b200_ctx {
     int sm_count = 0;
     uint32_t* bkdev = nullptr;   // n * BK_STEP_WORDS
     uint32_t* bkdev_t2 = nullptr;   // n * T2_STEP_WORDS: the two-slice key in the throughput kernel's layout (blind_rotate_t2.cuh)
+    cd16* bkdev_f64 = nullptr;      // n * F64_STEP_ELEMS: the f64 spectra of the FFT64 mode (blind_rotate_f64.cuh), allocated on first use
     uint32_t* kskdev = nullptr;  // [N][t][3][n+1]
     uint32_t* bk_torus = nullptr;  // [n][2l][2][N] torus-domain key as loaded / generated (kept for export: 31 MB)
     uint8_t* keybits = nullptr;    // device copy of (s0[n] | pad to 1024 | s1[N]) during device keygen
@@ -64,8 +66,11 @@ struct tfhe_b200_ctx {
     uint64_t last_batch = 0;
     int gates_per_cta = 1;
     int variant = 7;  // blind-rotate launch shape, see launch_blind_rotate
-    int key_slices = 2;  // 2 (default) = two 16-bit slices, exact for honestly generated keys (DESIGN.md section 2 has the bound);
-                         // 3 = three 11-bit slices, exact in the worst case (tfhe_b200_set_key_slices)
+    int key_slices = 2;  // arithmetic mode (tfhe_b200_set_key_slices): 2 (default) = NTT, two 16-bit key slices, exact for honestly generated
+                         // keys (DESIGN.md section 2 has the bound); 3 = NTT, three 11-bit slices, exact in the worst case; 1 = FFT64, one
+                         // f64 complex transform with exact rounding for batches above #SMs gates (latency shapes run the two-slice NTT)
+    int ns_int() const { return key_slices == 3 ? 3 : 2; }   // slices of the integer (NTT) form of the key
+    int f64_stagger_ns = 400;   // start-up offset between the warps of a CTA of the FFT64 kernel (TFHE_B200_F64_STAGGER)
     int t2_gates = 6;    // gates per CTA of the throughput kernel (TFHE_B200_T2_G: 4 or 6)
     int t2_twreg = 1;    // which row twiddles the throughput kernel keeps in registers (TFHE_B200_T2_TWREG: bit 0 forward, bit 1 inverse)
     int slab_tma = 1;     // one gate per CTA: key slabs staged by bulk copies (TFHE_B200_SLAB_TMA=0: streamed from L2 by the warps)
@@ -208,6 +213,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
             (e = t2attr(blind_rotate_t2_kernel<6, 1, true>, 6)) != cudaSuccess)
             return bail("smem attr (t2)", e);
     }
+    if (const char* v = getenv("TFHE_B200_F64_STAGGER")) ctx->f64_stagger_ns = atoi(v);
     if (const char* v = getenv("TFHE_B200_T2_G")) ctx->t2_gates = (atoi(v) == 4) ? 4 : 6;
     if (const char* v = getenv("TFHE_B200_T2_TWREG")) ctx->t2_twreg = atoi(v) & 3;
     if (const char* v = getenv("TFHE_B200_BR_VARIANT")) ctx->variant = atoi(v);
@@ -229,7 +235,9 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     }
     if (const char* v = getenv("TFHE_B200_SLAB_TMA")) ctx->slab_tma = atoi(v);
     if (const char* v = getenv("TFHE_B200_PAIR_MAX")) ctx->pair_max = std::min(atoi(v), ctx->sm_count / 2);
-    if (const char* v = getenv("TFHE_B200_KEY_SLICES")) ctx->key_slices = (atoi(v) == 3) ? 3 : 2;
+    if (const char* v = getenv("TFHE_B200_KEY_SLICES")) { const int k = atoi(v); ctx->key_slices = (k == 3 || k == 1) ? k : 2; }
+    if ((e = cudaFuncSetAttribute(blind_rotate_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
+        return bail("smem attr (f64)", e);
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (keyswitch2)", e);
     *out = ctx;
@@ -243,7 +251,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     if (ctx->keybits) cudaMemset(ctx->keybits, 0, 2048);
     if (ctx->s1poly) cudaMemset(ctx->s1poly, 0, 1024 * 4);
     for (auto& s : ctx->slots) if (s.s0buf) cudaMemset(s.s0buf, 0, 1024);
-    cudaFree(ctx->bkdev); cudaFree(ctx->bkdev_t2); cudaFree(ctx->kskdev); cudaFree(ctx->bk_torus); cudaFree(ctx->keybits); cudaFree(ctx->s1poly);
+    cudaFree(ctx->bkdev); cudaFree(ctx->bkdev_t2); cudaFree(ctx->bkdev_f64); cudaFree(ctx->kskdev); cudaFree(ctx->bk_torus); cudaFree(ctx->keybits); cudaFree(ctx->s1poly);
     for (auto& s : ctx->slots) {
         cudaFree(s.ksdig); cudaFree(s.scratch); cudaFree(s.s0buf); cudaFree(s.opsbuf);
         for (auto p : s.tmp) cudaFree(p);
@@ -285,7 +293,7 @@ int tfhe_b200_reserve(tfhe_b200_ctx* ctx, size_t max_batch) {
 // probability over the key's masks (9.8 sigma: about 1e-22 per coefficient, 3e-16 per gate), not in the worst case.
 // Re-transforms the loaded bootstrapping key.
 int tfhe_b200_set_key_slices(tfhe_b200_ctx* ctx, int slices) {
-    if (!ctx || (slices != 2 && slices != 3)) return fail(ctx, TFHE_B200_ERR_PARAM, "set_key_slices: 2 or 3");
+    if (!ctx || slices < 1 || slices > 3) return fail(ctx, TFHE_B200_ERR_PARAM, "set_key_slices: 1 (FFT64), 2 or 3");
     if (slices == ctx->key_slices) return TFHE_B200_OK;
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
@@ -326,7 +334,8 @@ int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out) {
     out->sm_count = ctx->sm_count;
     out->key_slices = ctx->key_slices;
     // what the gate path streams: the two-slice key in the throughput layout (8 B per coefficient) or the three-slice key (12 B)
-    out->device_key_bytes = (uint64_t)LWE_N * (ctx->key_slices == 2 ? T2_STEP_WORDS : bk_step_words(3)) * 4 + (uint64_t)1024 * 8 * 3 * (LWE_N + 1) * 4;
+    out->device_key_bytes = (uint64_t)LWE_N * (ctx->key_slices == 1 ? F64_STEP_ELEMS * 4 : ctx->key_slices == 2 ? T2_STEP_WORDS : bk_step_words(3)) * 4 +
+                            (uint64_t)1024 * 8 * 3 * (LWE_N + 1) * 4;
     const uint64_t cnt = ctx->timed < (uint64_t)tfhe_b200_ctx::RING ? ctx->timed : (uint64_t)tfhe_b200_ctx::RING;
     double sb = 0, sk = 0;
     for (uint64_t k = 0; k < cnt; k++) {
@@ -346,10 +355,16 @@ int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out) {
 // ---- keys ----
 static int transform_keys(tfhe_b200_ctx* ctx, const uint32_t* src_dev, uint32_t* dst_dev, int nsteps, cudaStream_t st) {
     const int npolys = nsteps * 12;
-    bk_transform_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(src_dev, dst_dev, npolys, ctx->key_slices);
+    bk_transform_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(src_dev, dst_dev, npolys, ctx->ns_int());
     ctx->launches++;
     CK(cudaGetLastError());
-    if (ctx->key_slices == 2 && dst_dev == ctx->bkdev) {   // the whole key: also in the throughput kernel's layout
+    if (ctx->key_slices == 1 && dst_dev == ctx->bkdev) {   // the whole key: also as f64 spectra
+        if (!ctx->bkdev_f64) CK(cudaMalloc(&ctx->bkdev_f64, (size_t)LWE_N * F64_STEP_ELEMS * sizeof(cd16)));
+        bk_transform_f64_kernel<<<(npolys + KTF_WARPS - 1) / KTF_WARPS, KTF_WARPS * 32, 0, st>>>(src_dev, ctx->bkdev_f64, npolys);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (ctx->ns_int() == 2 && dst_dev == ctx->bkdev) {   // the whole key: also in the throughput kernel's layout
         bk_transform_t2_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(src_dev, ctx->bkdev_t2, npolys);
         ctx->launches++;
         CK(cudaGetLastError());
@@ -419,7 +434,7 @@ static bool batches_overlap(tfhe_b200_ctx* ctx, cudaStream_t st) {
     return false;
 }
 static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, bool timed) {
-    a.bkdev = ctx->bkdev; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.ns = ctx->key_slices;
+    a.bkdev = ctx->bkdev; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.ns = ctx->ns_int();
     if (a.split <= 0) a.split = a.B;
     const int slot = (int)(ctx->timed % tfhe_b200_ctx::RING);
     if (timed) CK(cudaEventRecord(ctx->ev[slot][0], st));
@@ -450,6 +465,9 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         // best shape between one and two gates per SM (296 gates: 5.7 ms against 6.3 ms for 2-gate CTAs of the 80-register
         // kernel and 5.8 ms for 1-gate CTAs compiled for 168 registers)
         blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
+    } else if (full && ctx->key_slices == 1 && variant != 8) {   // FFT64 mode: one warp per gate, eight gates per CTA (blind_rotate_f64.cuh)
+        const unsigned grid = batches_overlap(ctx, st) ? fixed(F64_GATES) : deal(F64_GATES);
+        blind_rotate_f64_kernel<<<grid, F64_GATES * 32, f64_smem_bytes(), st>>>(a, ctx->bkdev_f64, ctx->f64_stagger_ns);
     } else if (full && a.ns == 2 && variant != 8) {   // default: the two-warps-per-gate throughput kernel (blind_rotate_t2.cuh)
         const int G = ctx->t2_gates;
         const unsigned grid = batches_overlap(ctx, st) ? fixed(G) : deal(G);
@@ -899,7 +917,7 @@ static int run_extprod(tfhe_b200_ctx* ctx, Slot* s, const uint32_t* trgsw_dev, s
     RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, ntrgsw * BK_STEP_WORDS * 4));
     BrArgs a{};
     a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
-    a.trlwe_in = rep1; a.trlwe_in0 = rep0; a.trlwe_out = out; a.ntrgsw = (long)ntrgsw; a.ns = ctx->key_slices;
+    a.trlwe_in = rep1; a.trlwe_in0 = rep0; a.trlwe_out = out; a.ntrgsw = (long)ntrgsw; a.ns = ctx->ns_int();
     if (a.ns == 2 && B > (size_t)ctx->sm_count) {   // two slices, throughput shape: the two-warps-per-product kernel, six products per CTA
         const int npolys = (int)ntrgsw * 12;
         bk_transform_t2_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(trgsw_dev, s->scratch, npolys);
