@@ -1,26 +1,32 @@
 // blind_rotate_f64.cuh -- K5F, the throughput blind rotation of the FFT64 arithmetic mode (included by engine.cu only).
 //   gate pre-combination + 635 x CMUX + sample extract (tfhe.rs:27-113, trgsw.rs:264-322, trlwe.rs:110-121)
-// One gate = ONE warp; eight gates per CTA, one CTA per SM (256 threads, up to 255 registers).  Per CMUX a warp runs six
+// One gate = ONE warp; eight gates per CTA, one CTA per SM (256 threads, 255 registers: eight gates fill the register file and
+// the shared memory of an SM; two CTAs of four gates measured 8 % slower, profiles/README.md).  Per CMUX a warp runs six
 // forward transforms (one per gadget digit), multiplies every spectrum into BOTH output accumulators while it is still in
 // registers (2 x 16 complex values per lane = 128 registers that live for the whole step), and runs two inverse transforms:
 // no spectrum is ever written to shared memory, no barrier between warps.  The gates of a CTA only meet at the key ring:
 //   bootstrapping key: [step][row j][output o] chunks of 8 KB, in the order every warp consumes them.  One elected thread streams
-//   them with bulk (TMA) copies into a 4-deep ring in shared memory (full / empty mbarriers); all eight gates read a chunk from
-//   there, so the key crosses L2 -> SM once per CTA instead of once per gate ("reused across a batch of gates in
-//   shared memory").
+//   them with bulk (TMA) copies into a four-slot ring in shared memory (full / empty mbarriers: a slot is refilled by the last
+//   warp that leaves it); the eight gates read a chunk from there, so the key crosses L2 -> SM once per CTA instead of once
+//   per gate ("reused across a batch of gates in shared memory").
 // See fft64.cuh for the transform and DESIGN.md sections 2, 3 and 5 for the operation counts and measurements.
 #pragma once
 #include "blind_rotate.cuh"
 #include "t2_steps.cuh"
 #include "fft64.cuh"
 
-constexpr int F64_GATES = 8;                    // gates (= warps) per CTA
-constexpr int F64_RING = 4;                     // key chunks in flight
+#if !defined(F64_GATES_DEF)
+#define F64_GATES_DEF 8
+#define F64_RING_DEF 4
+#endif
+constexpr int F64_GATES = F64_GATES_DEF;        // gates (= warps) per CTA
+constexpr int F64_CTAS_PER_SM = 8 / F64_GATES;
+constexpr int F64_RING = F64_RING_DEF;          // key chunks resident per CTA
 constexpr int F64_CHUNK_BYTES = (int)(F64_CHUNK_ELEMS * sizeof(cd16));   // 8192
 constexpr int F64_GATE_SMEM_BYTES = 2 * 1024 * 4 /*acc*/ + 512 * 16 /*transpose scratch*/ + 1024 * 4 /*masked source words*/ + 640 * 2 /*abar*/;
-constexpr int F64_SHARED_BYTES = F64_TAB_ELEMS * 16 + F64_RING * F64_CHUNK_BYTES + 2 * F64_RING * 8 + F64_RING * 4;
+constexpr int F64_SHARED_BYTES = ((F64_TAB_ELEMS + F64_UNTW_ROWS * 32) * 16 + F64_RING * F64_CHUNK_BYTES + 2 * F64_RING * 8 + F64_RING * 4 + 15) / 16 * 16;
 constexpr size_t f64_smem_bytes() { return (size_t)F64_SHARED_BYTES + (size_t)F64_GATES * F64_GATE_SMEM_BYTES; }
-static_assert(f64_smem_bytes() <= 227 * 1024, "eight gates and the key ring must fit the shared memory of one SM");
+static_assert(F64_CTAS_PER_SM * (f64_smem_bytes() + 1024) <= 227 * 1024, "two CTAs must fit the shared memory of one SM");
 
 __device__ __forceinline__ void f64_exchange(const cd (&send)[8], cd (&recv)[8]) {
 #pragma unroll
@@ -74,13 +80,14 @@ __device__ __forceinline__ void f64_with_chunk(const F64Ring& rg, long n, int la
     }
 }
 
-__global__ void __launch_bounds__(F64_GATES * 32, 1) blind_rotate_f64_kernel(const BrArgs a, const cd16* __restrict__ key, int stagger_ns) {
+__global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_f64_kernel(const BrArgs a, const cd16* __restrict__ key, int stagger_ns) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd16* tab = reinterpret_cast<cd16*>(smem_raw);
     const cd16* tb = tab;                                             // forward pass B / exchange twiddles
     const cd16* ta = tab + F64_FWDB_ROWS * 32;                        // inverse stages 5..8
     F64Ring rg;
-    rg.slot = tab + F64_TAB_ELEMS;
+    const cd16* ut = tab + F64_TAB_ELEMS;                             // untwist
+    rg.slot = tab + F64_TAB_ELEMS + F64_UNTW_ROWS * 32;
     rg.full = reinterpret_cast<uint64_t*>(rg.slot + (size_t)F64_RING * F64_CHUNK_ELEMS);
     rg.empty = rg.full + F64_RING;
     rg.left = reinterpret_cast<uint32_t*>(rg.empty + F64_RING);
@@ -107,10 +114,11 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) blind_rotate_f64_kernel(con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
-        const double* g0 = g_f64_fwdB; const double* g1 = g_f64_invA;
+        const double* g0 = g_f64_fwdB; const double* g1 = g_f64_invA; const double* g2 = g_f64_untw;
         double* t = reinterpret_cast<double*>(tab);
         for (int k = threadIdx.x; k < F64_FWDB_ROWS * 64; k += blockDim.x) t[k] = g0[k];
         for (int k = threadIdx.x; k < F64_INVA_ROWS * 64; k += blockDim.x) t[F64_FWDB_ROWS * 64 + k] = g1[k];
+        for (int k = threadIdx.x; k < F64_UNTW_ROWS * 64; k += blockDim.x) t[(F64_FWDB_ROWS + F64_INVA_ROWS) * 64 + k] = g2[k];
     }
     // ---- prologue: gate pre-combination (tfhe.rs:27-71), rounding of (b, a) (tfhe.rs:97,107-108), acc_0 ----
     {
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) blind_rotate_f64_kernel(con
             __syncwarp();
             f64_inv_passA(lane, v, ta);
             uint32_t lo[16], hi[16];
-            f64_untwist_round(lane, v, ta, lo, hi);
+            f64_untwist_round(lane, v, ut, lo, hi);
             uint32_t* ao = acc + o * 1024;
 #pragma unroll
             for (int r = 0; r < 16; r++) { ao[32 * r + lane] += lo[r]; ao[512 + 32 * r + lane] += hi[r]; }

@@ -55,8 +55,8 @@ struct alignas(16) cd16 { double re, im; };   // what the tables, the transposes
 
 constexpr int F64_PTS = 512;                 // complex points per polynomial
 constexpr int F64_PER_LANE = 16;
-constexpr int F64_FWDB_ROWS = 5, F64_INVA_ROWS = 5;
-constexpr int F64_TAB_ELEMS = (F64_FWDB_ROWS + F64_INVA_ROWS) * 32;   // per-lane tables, [row][lane] cd16
+constexpr int F64_FWDB_ROWS = 12, F64_INVA_ROWS = 8, F64_UNTW_ROWS = 16;
+constexpr int F64_TAB_ELEMS = (F64_FWDB_ROWS + F64_INVA_ROWS) * 32;   // per-lane twiddle tables, [row][lane] cd16 (+ the untwist table)
 constexpr double F64_ROUND_MAGIC = 6755399441055744.0;                             // 1.5 * 2^52
 constexpr double F64_DIGIT_BIAS = 4503599627370496.0 + 32.0;                       // 2^52 + 32
 // device key: [step i][row j < 6][output poly o < 2][register < 16][lane < 32] cd16 = 96 KB per step, 16 B per complex point
@@ -66,20 +66,20 @@ TFHE_HD size_t f64_key_off(int i, int j, int o) { return ((size_t)i * 12 + (size
 
 static const double h_f64_fwdB[F64_FWDB_ROWS * 32 * 2] = {FFT64_FWD_B_LIST};
 static const double h_f64_invA[F64_INVA_ROWS * 32 * 2] = {FFT64_INV_A_LIST};
+static const double h_f64_untw[F64_UNTW_ROWS * 32 * 2] = {FFT64_UNTWIST_LIST};
 #if defined(__CUDACC__)
 static __device__ const double g_f64_fwdB[F64_FWDB_ROWS * 32 * 2] = {FFT64_FWD_B_LIST};
 static __device__ const double g_f64_invA[F64_INVA_ROWS * 32 * 2] = {FFT64_INV_A_LIST};
+static __device__ const double g_f64_untw[F64_UNTW_ROWS * 32 * 2] = {FFT64_UNTWIST_LIST};
 #endif
 
 // warp-uniform twiddles: on the device they sit in the constant bank and are read as DFMA operands (c[bank][offset]); as
 // literals every one of them costs two 32-bit moves, a 64-bit immediate does not exist
 static const double h_f64_fwdA[30] = {FFT64_FWD_A_LIST};
 static const double h_f64_invC[40] = {FFT64_INV_C_LIST};
-static const double h_f64_drv[42] = {FFT64_DERIVE_LIST};
 #if defined(__CUDACC__)
 static __constant__ double c_f64_fwdA[30] = {FFT64_FWD_A_LIST};
 static __constant__ double c_f64_invC[40] = {FFT64_INV_C_LIST};
-static __constant__ double c_f64_drv[42] = {FFT64_DERIVE_LIST};
 #endif
 template <int K> TFHE_HD double fwdA_c() {
 #if defined(__CUDA_ARCH__)
@@ -94,22 +94,6 @@ template <int K> TFHE_HD double invC_c() {
 #else
     return h_f64_invC[K];
 #endif
-}
-
-template <int K> TFHE_HD double drv_c() {
-#if defined(__CUDA_ARCH__)
-    return c_f64_drv[K];
-#else
-    return h_f64_drv[K];
-#endif
-}
-// w * (constant K of FFT64_DERIVE_LIST): a per-lane twiddle derived from a loaded one.  Four operations against the eight
-// issue-cycle equivalents of an LDS.128 on the shared-memory pipe (which bounds the kernel).
-template <int K> TFHE_HD cd16 drv_mul(const cd16& w) {
-    cd16 r;
-    r.re = F_FMA(w.re, drv_c<2 * K>(), -F_MUL(w.im, drv_c<2 * K + 1>()));
-    r.im = F_FMA(w.re, drv_c<2 * K + 1>(), F_MUL(w.im, drv_c<2 * K>()));
-    return r;
 }
 
 TFHE_HD double f64_from_words(uint32_t hi, uint32_t lo) {
@@ -225,21 +209,17 @@ TFHE_HD void f64_fwd_passB(int lane, cd (&x)[16], const cd16* tb) {
 #pragma unroll
         for (int t = 0; t < 4; t++) { bf_w(x[t], x[t + 4], w.re, w.im); bf_iw(x[8 + t], x[12 + t], w.re, w.im); }
     }
-    {
-        const cd16 w0 = tb[2 * 32 + lane];
-        const cd16 w1 = drv_mul<1>(w0);   // node (6, 4 hi + 2) = node (6, 4 hi) * psi^256
 #pragma unroll
-        for (int t = 0; t < 2; t++) { bf_w(x[t], x[t + 2], w0.re, w0.im); bf_iw(x[4 + t], x[6 + t], w0.re, w0.im); }
+    for (int c2 = 0; c2 < 2; c2++) {
+        const cd16 w = tb[(2 + c2) * 32 + lane];
 #pragma unroll
-        for (int t = 0; t < 2; t++) { bf_w(x[8 + t], x[10 + t], w1.re, w1.im); bf_iw(x[12 + t], x[14 + t], w1.re, w1.im); }
+        for (int t = 0; t < 2; t++) { bf_w(x[8 * c2 + t], x[8 * c2 + t + 2], w.re, w.im); bf_iw(x[8 * c2 + 4 + t], x[8 * c2 + 6 + t], w.re, w.im); }
     }
-    {
-        const cd16 w0 = tb[3 * 32 + lane];
-        const cd16 w1 = drv_mul<1>(w0), w2 = drv_mul<0>(w0), w3 = drv_mul<2>(w0);   // q = 1, 2, 3: psi^256, psi^128, psi^384
-        bf_w(x[0], x[1], w0.re, w0.im); bf_iw(x[2], x[3], w0.re, w0.im);
-        bf_w(x[4], x[5], w1.re, w1.im); bf_iw(x[6], x[7], w1.re, w1.im);
-        bf_w(x[8], x[9], w2.re, w2.im); bf_iw(x[10], x[11], w2.re, w2.im);
-        bf_w(x[12], x[13], w3.re, w3.im); bf_iw(x[14], x[15], w3.re, w3.im);
+#pragma unroll
+    for (int c2 = 0; c2 < 4; c2++) {
+        const cd16 w = tb[(4 + c2) * 32 + lane];
+        bf_w(x[4 * c2], x[4 * c2 + 1], w.re, w.im);
+        bf_iw(x[4 * c2 + 2], x[4 * c2 + 3], w.re, w.im);
     }
 }
 // stage 8, the lane-pair exchange.  Lane j0 owns the butterflies rho = 8 j0 + m, m < 8: it keeps its own operand of those and
@@ -251,12 +231,9 @@ TFHE_HD void f64_x_send(int lane, const cd (&x)[16], cd (&send)[8]) {
 }
 TFHE_HD void f64_fwd_x_bfly(int lane, const cd (&x)[16], const cd (&recv)[8], const cd16* tb, cd (&y)[16]) {
     const bool odd = lane & 1;
-    cd16 wq[4];
-    wq[0] = tb[4 * 32 + lane];
-    wq[1] = drv_mul<1>(wq[0]); wq[2] = drv_mul<0>(wq[0]); wq[3] = drv_mul<2>(wq[0]);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const cd16 w = wq[q];
+        const cd16 w = tb[(8 + q) * 32 + lane];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const int m = 2 * q + e;
@@ -269,7 +246,16 @@ TFHE_HD void f64_fwd_x_bfly(int lane, const cd (&x)[16], const cd (&recv)[8], co
     }
 }
 
-// pointwise multiply-accumulate: acc[k] += y[k] * key[k * 32 + lane]
+// pointwise multiply-accumulate: acc[k] += y[k] * key[k * 32 + lane]; one half (registers 8 H .. 8 H + 7, 4 KB of key) at a time
+template <int H>
+TFHE_HD void f64_mac_half(int lane, const cd (&y)[16], const cd16* key /* the half's 256 values */, cd (&acc)[16]) {
+#pragma unroll
+    for (int k = 8 * H; k < 8 * H + 8; k++) {
+        const cd16 w = key[(k - 8 * H) * 32 + lane];
+        acc[k].re = F_FMA(y[k].re, w.re, F_FMA(-y[k].im, w.im, acc[k].re));
+        acc[k].im = F_FMA(y[k].re, w.im, F_FMA(y[k].im, w.re, acc[k].im));
+    }
+}
 TFHE_HD void f64_mac(int lane, const cd (&y)[16], const cd16* key, cd (&acc)[16]) {
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -365,8 +351,7 @@ TFHE_HD void f64_inv_passA(int lane, cd (&w)[16], const cd16* ta) {
         for (int c = 0; c < 4; c++) { bf_w(w[4 * c], w[4 * c + 2], t.re, t.im); bf_miw(w[4 * c + 1], w[4 * c + 3], t.re, t.im); }
     }
     {
-        const cd16 t0 = ta[2 * 32 + lane];
-        const cd16 t1 = drv_mul<4>(t0);   // Wc^(2 l + 64) = Wc^(2 l) psi^-256
+        const cd16 t0 = ta[2 * 32 + lane], t1 = ta[3 * 32 + lane];
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             bf_w(w[8 * c], w[8 * c + 4], t0.re, t0.im);
@@ -375,49 +360,36 @@ TFHE_HD void f64_inv_passA(int lane, cd (&w)[16], const cd16* ta) {
             bf_miw(w[8 * c + 3], w[8 * c + 7], t1.re, t1.im);
         }
     }
-    {
-        cd16 t[4];
-        t[0] = ta[3 * 32 + lane];
-        t[1] = drv_mul<3>(t[0]); t[2] = drv_mul<4>(t[0]); t[3] = drv_mul<5>(t[0]);   // Wc^(l + 32 k) = Wc^l psi^(-128 k)
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            bf_w(w[k], w[k + 8], t[k].re, t[k].im);
-            bf_miw(w[k + 4], w[k + 12], t[k].re, t[k].im);
-        }
+    for (int k = 0; k < 4; k++) {
+        const cd16 t = ta[(4 + k) * 32 + lane];
+        bf_w(w[k], w[k + 8], t.re, t.im);
+        bf_miw(w[k + 4], w[k + 12], t.re, t.im);
     }
 }
 // z_j = psi^-j v_j, exact rounding; lo[r] / hi[r] = coefficients j and j + 512 (j = 32 r + lane) mod 2^32.
 // frac (host-side diagnostics only): largest distance of a value from the nearest integer.
-template <int R> TFHE_HD cd16 f64_untwist_tw(const cd16& u0) {
-    if (R == 0) return u0;
-    return drv_mul<(R == 0 ? 6 : 5 + R)>(u0);   // psi^-(l + 32 r) = psi^-l psi^(-32 r)
-}
-template <int R>
-TFHE_HD void f64_untwist_one(const cd& w, const cd16& u0, uint32_t& lo, uint32_t& hi, double* frac) {
-    const cd16 t = f64_untwist_tw<R>(u0);
-    const double zr = F_FMA(w.re, t.re, -F_MUL(w.im, t.im));
-    const double zi = F_FMA(w.re, t.im, F_MUL(w.im, t.re));
-    const double mr = F_ADD(zr, F64_ROUND_MAGIC), mi = F_ADD(zi, F64_ROUND_MAGIC);
-    lo = f64_low_word(mr);
-    hi = f64_low_word(mi);
+TFHE_HD void f64_untwist_round(int lane, const cd (&w)[16], const cd16* ut, uint32_t (&lo)[16], uint32_t (&hi)[16], double* frac = nullptr) {
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const cd16 t = ut[r * 32 + lane];
+        const double zr = F_FMA(w[r].re, t.re, -F_MUL(w[r].im, t.im));
+        const double zi = F_FMA(w[r].re, t.im, F_MUL(w[r].im, t.re));
+        const double mr = F_ADD(zr, F64_ROUND_MAGIC), mi = F_ADD(zi, F64_ROUND_MAGIC);
+        lo[r] = f64_low_word(mr);
+        hi[r] = f64_low_word(mi);
 #if !defined(__CUDA_ARCH__)
-    if (frac) {
-        const double er = zr - (mr - F64_ROUND_MAGIC), ei = zi - (mi - F64_ROUND_MAGIC);
-        const double m = (er < 0 ? -er : er) > (ei < 0 ? -ei : ei) ? (er < 0 ? -er : er) : (ei < 0 ? -ei : ei);
-        if (m > *frac) *frac = m;
-    }
+        if (frac) {
+            const double er = zr - (mr - F64_ROUND_MAGIC), ei = zi - (mi - F64_ROUND_MAGIC);
+            const double m = (er < 0 ? -er : er) > (ei < 0 ? -ei : ei) ? (er < 0 ? -er : er) : (ei < 0 ? -ei : ei);
+            if (m > *frac) *frac = m;
+        }
 #else
-    (void)frac;
+        (void)frac;
 #endif
+    }
 }
-template <int... R>
-TFHE_HD void f64_untwist_all(const cd (&w)[16], const cd16& u0, uint32_t (&lo)[16], uint32_t (&hi)[16], double* frac, std::integer_sequence<int, R...>) {
-    (f64_untwist_one<R>(w[R], u0, lo[R], hi[R], frac), ...);
-}
-// ta row 4 = psi^-lane
-TFHE_HD void f64_untwist_round(int lane, const cd (&w)[16], const cd16* ta, uint32_t (&lo)[16], uint32_t (&hi)[16], double* frac = nullptr) {
-    f64_untwist_all(w, ta[4 * 32 + lane], lo, hi, frac, std::make_integer_sequence<int, 16>{});
-}
+
 // ---- inputs ----
 // gadget digit from the 6-bit field f = d + 32 of a masked, sign-flipped word: (2^52 + f) - (2^52 + 32) = d, one DADD
 TFHE_HD double f64_digit(uint32_t f) { return F_ADD(f64_from_words(0x43300000u, f), -F64_DIGIT_BIAS); }

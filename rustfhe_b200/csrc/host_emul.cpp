@@ -203,6 +203,7 @@ static double f64_step(const double* dev, uint32_t* acc, bool rotate, uint32_t a
         }
     }
     const cd16* ta = reinterpret_cast<const cd16*>(h_f64_invA);
+    const cd16* ut = reinterpret_cast<const cd16*>(h_f64_untw);
     for (int o = 0; o < 2; o++) {
         cd send[32][8], v[32][16], w[32][16];
         for (int lane = 0; lane < 32; lane++) { f64_inv_low(sum[o][lane]); f64_x_send(lane, sum[o][lane], send[lane]); }
@@ -211,7 +212,7 @@ static double f64_step(const double* dev, uint32_t* acc, bool rotate, uint32_t a
             uint32_t lo[16], hi[16];
             f64_t2_load(lane, S.data(), w[lane]);
             f64_inv_passA(lane, w[lane], ta);
-            f64_untwist_round(lane, w[lane], ta, lo, hi, &frac);
+            f64_untwist_round(lane, w[lane], ut, lo, hi, &frac);
             for (int r = 0; r < 16; r++) {
                 uint32_t* a0 = acc + o * 1024 + 32 * r + lane;
                 a0[0] = (rotate ? a0[0] : 0u) + lo[r];
