@@ -48,6 +48,20 @@ def design_figures(key_slices):
             "bk_bytes_device": 635 * 12 * S * 1024 * 4}
 
 
+def fft64_figures():
+    """Per-gate work of the FFT64 mode (fft64.cuh; DESIGN.md sections 2 and 5), counted per lane from the code and confirmed by ncu
+    (4532 FP64 warp instructions per gate and CMUX): a forward transform of 512 complex points = 32 digit conversions + 9 stages x 8
+    butterflies x 6 DFMA-class operations = 464 per lane, an inverse = 482 per lane (trivial twiddles in its first stages, untwist and
+    rounding), one spectrum x key multiply-accumulate = 64 per lane; per CMUX 6 forward + 2 inverse + 12 multiply-accumulates.
+    Shared-memory bytes per gate and CMUX: 8 transposes x 16 KB, 96 KB of key read from the ring, 60 KB of per-lane twiddle rows,
+    48 KB for the masked source words (rotated reads, one store, three digit reads), 16 KB accumulator update."""
+    fwd, inv, mac = 464 * 32, 482 * 32, 64 * 32
+    per_cmux = 6 * fwd + 2 * inv + 12 * mac
+    smem = (8 * 16 + 96 + 60 + 48 + 16) * 1024
+    return {"transforms_per_cmux": 8, "fp64_ops_per_gate": 635 * per_cmux, "smem_bytes_per_gate": 635 * smem,
+            "bk_bytes_device": 635 * 12 * 512 * 16}
+
+
 def workload_config(world):
     """the keys both arms share (the driver compares them)"""
     return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world}
@@ -67,7 +81,7 @@ def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one blind_rotate_t2_kernel launch from the committed `ncu --set full`
     summary (profiles/r02_ncu_blind_rotate_t2_latest.txt), scaled from the profiled batch to 1024 gates (the key is read once
     per wave, the ciphertext traffic is per gate); None when the summary is missing."""
-    p = os.path.join(ROOT, "profiles", "r02_ncu_blind_rotate_t2_latest.txt")
+    p = os.path.join(ROOT, "profiles", "r02_ncu_blind_rotate_f64_latest.txt")
     try:
         tot = 0.0
         for line in open(p):
@@ -79,6 +93,15 @@ def ncu_traffic():
         return tot or None
     except Exception:
         return None
+
+
+def fp64_peak():
+    """DFMA issue rate measured on this pool's B200 by tools/microbench/intpipe.cu (profiles/intpipe_r01b.json: same rate as IMAD)."""
+    p = os.path.join(ROOT, "profiles", "intpipe_r01b.json")
+    try:
+        return json.load(open(p))["dfma"]["Gops_per_s"] * 1e9, "measured (profiles/intpipe_r01b.json, dfma)"
+    except Exception:
+        return 148 * 64 * 1.965e9, "nominal 148 SM x 64 lanes x 1.965 GHz"
 
 
 def int_peak():
@@ -208,9 +231,9 @@ def run_extras(eng, R, K, torch, dev, stream, dx, dy, s0, rank, world, dist):
             best = min(best, e0.elapsed_time(e1) * 1e-3)
         return best
 
-    fig = design_figures(eng.stats()["key_slices"])
+    S = max(2, eng.stats()["key_slices"])    # the step-level entry points run the NTT (two slices in FFT64 mode)
+    fig = design_figures(S)
     p_int, _ = int_peak()
-    S = eng.stats()["key_slices"]
     slots_xp = fig["fma_slots_per_gate"] / 635.0                            # one external product = one CMUX step
     slots_pm = (1 + 2 * S) * 5120 * 4 + S * 1024 * (2.5 + 3)                # 1 + S forward, S inverse transforms, S x 1024 MAC + REDC
     if rank == 0:
@@ -463,9 +486,10 @@ def run_gpu(args):
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         p_int, p_int_src = int_peak()
-        fig = design_figures(st["key_slices"])
-        FMA_SLOTS_PER_GATE, BUTTERFLIES_PER_GATE, BK_BYTES_DEVICE = fig["fma_slots_per_gate"], fig["butterflies_per_gate"], fig["bk_bytes_device"]
-        kname = "blind_rotate_t2_kernel<6,1>" if st["key_slices"] == 2 else "blind_rotate_kernel<4,false,1,3>"
+        fft64 = st["key_slices"] == 1
+        fig = fft64_figures() if fft64 else design_figures(st["key_slices"])
+        BK_BYTES_DEVICE = fig["bk_bytes_device"]
+        kname = "blind_rotate_f64_kernel" if fft64 else "blind_rotate_t2_kernel<6,1>" if st["key_slices"] == 2 else "blind_rotate_kernel<4,false,1,3>"
         gates = BATCH * world * args.steps
         value = gates / (ms * 1e-3)
         br_ms, ks_ms = st["avg_blind_rotate_ms"], st["avg_keyswitch_ms"]
@@ -476,10 +500,13 @@ def run_gpu(args):
         line = {
             "metric": "bootstrapped HomNAND gates/sec", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64" if fft64 else "u32", "data": "synthetic",
             "config": dict(workload_config(world),
-                       arithmetic="torus words mod 2^32; exact negacyclic NTT over the 29-bit prime 536856577, " +
-                                  ("two 16-bit key slices (6 + 4 transforms per CMUX)" if st["key_slices"] == 2 else "three 11-bit key slices (6 + 6 transforms per CMUX)"),
+                       arithmetic="torus words mod 2^32; " + (
+                           "negacyclic f64 complex transform of the folded polynomial (512 points), products rounded to the exact integer "
+                           "(6 + 2 transforms per CMUX); results bit-identical to the exact NTT modes" if fft64 else
+                           "exact negacyclic NTT over the 29-bit prime 536856577, " +
+                           ("two 16-bit key slices (6 + 4 transforms per CMUX)" if st["key_slices"] == 2 else "three 11-bit key slices (6 + 6 transforms per CMUX)")),
                        parallelism=f"dp{world} (independent gate shards, keys replicated)",
                        l2=f"inputs rotate over {NROT} batches ({NROT * BATCH * 2 * CT_WORDS * 4 / 1e6:.0f} MB) > L2; keys "
                           f"{(BK_BYTES_DEVICE + KSK_BYTES) / 1e6:.0f} MB ~ L2; no explicit flush",
@@ -499,18 +526,35 @@ def run_gpu(args):
                          "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                          "algorithmic_bytes_per_launch": algo_bytes, "traffic": ncu_traffic(),
                          "note": "HBM is NOT the binding roof of this kernel (key bytes are read once per 1024-gate launch); "
-                                 "the binding roof is the integer FMA pipe, see int_roofline"},
-            "int_roofline": {"bound": "integer FMA pipe (IMAD issue slots)", "kernel": kname,
-                             "achieved": per_gpu_gps_kernel * FMA_SLOTS_PER_GATE / 1e12, "peak": p_int / 1e12, "unit": "T IMAD-slots/s",
-                             "frac": per_gpu_gps_kernel * FMA_SLOTS_PER_GATE / p_int, "peak_kind": p_int_src,
-                             "slots_per_gate": FMA_SLOTS_PER_GATE, "butterflies_per_gate": BUTTERFLIES_PER_GATE,
-                             "modmul_per_gate_single_modulus_basis": MODMUL_PER_GATE,
-                             "note": "slot weights measured on B200: IMAD 1, IMAD.HI 2, IMAD.WIDE 2.5 (profiles/intpipe_r01.json); "
-                                     f"butterfly = 2 IMAD + 1 IMAD.HI = 4 slots; this design runs {fig['transforms_per_cmux']} transforms per CMUX"},
+                                 "the binding roofs are on-chip, see " + ("smem_roofline and fp64_roofline" if fft64 else "int_roofline")},
             "clocks": clocks,
             "key_setup_s": key_s,
             "extras": extras,
         }
+        if fft64:
+            p64, p64_src = fp64_peak()
+            smem_peak = 148 * 128 * (peaks.get("sm_max_mhz", 1965.0) * 1e6)    # 128 B per clock and SM (B300_MICROARCH.md, LDS/STS)
+            line["fp64_roofline"] = {"bound": "FP64 pipe (DFMA issue slots)", "kernel": kname, "achieved": per_gpu_gps_kernel * fig["fp64_ops_per_gate"] / 1e12,
+                                     "peak": p64 / 1e12, "unit": "T DFMA-class ops/s", "frac": per_gpu_gps_kernel * fig["fp64_ops_per_gate"] / p64,
+                                     "peak_kind": p64_src, "ops_per_gate": fig["fp64_ops_per_gate"], "roof_gates_per_s": p64 / fig["fp64_ops_per_gate"],
+                                     "note": "DFMA / DADD / DMUL, one issue slot each; ncu: sm__pipe_fp64_cycles_active"}
+            line["smem_roofline"] = {"bound": "shared-memory bandwidth (the binding roof of this kernel)", "kernel": kname,
+                                     "achieved": per_gpu_gps_kernel * fig["smem_bytes_per_gate"] / 1e9, "peak": smem_peak / 1e9, "unit": "GB/s",
+                                     "frac": per_gpu_gps_kernel * fig["smem_bytes_per_gate"] / smem_peak, "peak_kind": "148 SM x 128 B/clk x SM clock",
+                                     "bytes_per_gate": fig["smem_bytes_per_gate"], "roof_gates_per_s": smem_peak / fig["smem_bytes_per_gate"],
+                                     "note": "algorithmic shared-memory bytes of the design (transposes, key ring reads, per-lane twiddles, source words, "
+                                             "accumulator); ncu: l1tex__data_pipe_lsu_wavefronts_mem_shared"}
+            line["int_roofline"] = dict(line["fp64_roofline"], note="FFT64 mode: the arithmetic runs on the FP64 pipe, whose issue rate equals the IMAD rate "
+                                        "(profiles/intpipe_r01b.json); see fp64_roofline / smem_roofline")
+        else:
+            FMA_SLOTS_PER_GATE, BUTTERFLIES_PER_GATE = fig["fma_slots_per_gate"], fig["butterflies_per_gate"]
+            line["int_roofline"] = {"bound": "integer FMA pipe (IMAD issue slots)", "kernel": kname,
+                                    "achieved": per_gpu_gps_kernel * FMA_SLOTS_PER_GATE / 1e12, "peak": p_int / 1e12, "unit": "T IMAD-slots/s",
+                                    "frac": per_gpu_gps_kernel * FMA_SLOTS_PER_GATE / p_int, "peak_kind": p_int_src,
+                                    "slots_per_gate": FMA_SLOTS_PER_GATE, "butterflies_per_gate": BUTTERFLIES_PER_GATE,
+                                    "modmul_per_gate_single_modulus_basis": MODMUL_PER_GATE,
+                                    "note": "slot weights measured on B200: IMAD 1, IMAD.HI 2, IMAD.WIDE 2.5 (profiles/intpipe_r01.json); "
+                                            f"butterfly = 2 IMAD + 1 IMAD.HI = 4 slots; this design runs {fig['transforms_per_cmux']} transforms per CMUX"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 nthreads = os.cpu_count() or 1

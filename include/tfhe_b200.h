@@ -74,7 +74,7 @@ typedef struct {
     uint64_t last_batch;
     int32_t gates_per_cta, sm_count;
     uint64_t device_key_bytes;
-    int32_t key_slices;         /* 2 or 3 (tfhe_b200_set_key_slices) */
+    int32_t key_slices;         /* arithmetic mode: 1 = FFT64, 2 or 3 = NTT key slices (tfhe_b200_set_key_slices) */
     int32_t reserved;
 } tfhe_b200_stats;
 
@@ -84,11 +84,17 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p /* NULL = defaults */, int de
 int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx);
 const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx /* NULL = last error of a failed ctx_create */);
 int tfhe_b200_set_decomp_mask(tfhe_b200_ctx* ctx, uint32_t mask);
-/* Key slices per bootstrapping-key polynomial.  2 (default): two 16-bit slices, 6 + 4 transforms per CMUX; the external
- * product is the exact integer product for every honestly generated key (uniform masks): a slice sum would have to exceed
- * 9.8 standard deviations, probability about 1e-22 per coefficient and 3e-16 per gate over the key's masks (DESIGN.md section
- * 2; tests/test_host_logic.py measures the distribution).  3: three 11-bit slices, 6 + 6 transforms, exact in the worst case
- * (any key, any digits).  Switching re-transforms the loaded bootstrapping key. */
+/* Arithmetic of the polynomial products of the gate path (every mode returns the same ciphertext bits for honestly generated keys;
+ * the parity tests compare all three against the exact-integer oracle):
+ *   1 (default) FFT64: one f64 complex transform of the folded polynomial, 6 + 2 transforms per CMUX, every product rounded to
+ *     the EXACT integer (the reference computes the same products with an f64 FFT, fft_processor_spqlios.cpp:58-183).  Measured
+ *     rounding margin on uniform keys: |value - nearest integer| < 2^-8 against the 1/2 that would flip a bit (DESIGN.md
+ *     section 2; tests/test_host_logic.py asserts it).  Used for batches above #SMs gates; smaller batches and the step-level
+ *     entry points (external product, cmux) run mode 2.
+ *   2 NTT over a 29-bit prime, two 16-bit key slices, 6 + 4 transforms per CMUX; exact unless a slice sum exceeds 9.8 standard
+ *     deviations (about 1e-22 per coefficient, 3e-16 per gate over the key's masks).
+ *   3 NTT, three 11-bit key slices, 6 + 6 transforms: exact in the worst case (any key, any digits).
+ * Switching re-transforms the loaded bootstrapping key. */
 int tfhe_b200_set_key_slices(tfhe_b200_ctx* ctx, int slices);
 /* How a full batch (more than two gates per SM) is cut into CTAs.  AUTO (default): decided per call -- if an earlier batch is
  * still running on another stream the batch is cut into 4-gate CTAs only (the next batch back-fills the last wave), otherwise

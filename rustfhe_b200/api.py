@@ -429,7 +429,8 @@ class DeviceEngine:
         self._ck(self._l.tfhe_b200_set_decomp_mask(self._ctx, mask))
 
     def set_key_slices(self, slices):
-        """2 (default) = two 16-bit key slices, exact for honest keys; 3 = exact in the worst case."""
+        """1 (default) = FFT64 with exact rounding, 2 = NTT with two 16-bit key slices (both exact for honest keys), 3 = NTT with three
+        11-bit slices, exact in the worst case (include/tfhe_b200.h)."""
         self._ck(self._l.tfhe_b200_set_key_slices(self._ctx, slices))
 
     def set_batch_overlap(self, mode):

@@ -66,9 +66,10 @@ struct tfhe_b200_ctx {
     uint64_t last_batch = 0;
     int gates_per_cta = 1;
     int variant = 7;  // blind-rotate launch shape, see launch_blind_rotate
-    int key_slices = 2;  // arithmetic mode (tfhe_b200_set_key_slices): 2 (default) = NTT, two 16-bit key slices, exact for honestly generated
-                         // keys (DESIGN.md section 2 has the bound); 3 = NTT, three 11-bit slices, exact in the worst case; 1 = FFT64, one
-                         // f64 complex transform with exact rounding for batches above #SMs gates (latency shapes run the two-slice NTT)
+    int key_slices = 1;  // arithmetic mode (tfhe_b200_set_key_slices): 1 (default) = FFT64, one f64 complex transform with exact rounding
+                         // for batches above #SMs gates (latency shapes and step-level entry points run the two-slice NTT); 2 = NTT, two
+                         // 16-bit key slices; both exact for honestly generated keys (DESIGN.md section 2 has the margins);
+                         // 3 = NTT, three 11-bit slices, exact in the worst case
     int ns_int() const { return key_slices == 3 ? 3 : 2; }   // slices of the integer (NTT) form of the key
     int f64_stagger_ns = 400;   // start-up offset between the warps of a CTA of the FFT64 kernel (TFHE_B200_F64_STAGGER)
     int t2_gates = 6;    // gates per CTA of the throughput kernel (TFHE_B200_T2_G: 4 or 6)
@@ -141,7 +142,7 @@ static cudaError_t set_smem(Kern k, int G) { return cudaFuncSetAttribute(k, cuda
 
 extern "C" {
 
-const char* tfhe_b200_version(void) { return "rustfhe_b200 0.3 (sm_100a, p=536856577, 2x16-bit key slices; 3x11-bit selectable)"; }
+const char* tfhe_b200_version(void) { return "rustfhe_b200 0.4 (sm_100a; FFT64 with exact rounding; NTT p=536856577 with 2x16-bit / 3x11-bit key slices selectable)"; }
 
 int tfhe_b200_default_params(tfhe_b200_params* p) {
     if (!p) return TFHE_B200_ERR_PARAM;
@@ -235,7 +236,7 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     }
     if (const char* v = getenv("TFHE_B200_SLAB_TMA")) ctx->slab_tma = atoi(v);
     if (const char* v = getenv("TFHE_B200_PAIR_MAX")) ctx->pair_max = std::min(atoi(v), ctx->sm_count / 2);
-    if (const char* v = getenv("TFHE_B200_KEY_SLICES")) { const int k = atoi(v); ctx->key_slices = (k == 3 || k == 1) ? k : 2; }
+    if (const char* v = getenv("TFHE_B200_KEY_SLICES")) { const int k = atoi(v); if (k >= 1 && k <= 3) ctx->key_slices = k; }
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64)", e);
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
@@ -287,11 +288,8 @@ int tfhe_b200_reserve(tfhe_b200_ctx* ctx, size_t max_batch) {
     return TFHE_B200_OK;
 }
 
-// Key slices per bootstrapping-key polynomial.  3 (default): 11/11/10-bit slices, every slice product is below p/2 in the WORST
-// case, the result is the exact external product unconditionally.  2 (opt-in fast mode): 16/16-bit slices, two inverse
-// transforms and a third of the pointwise work less per CMUX; a slice product then stays below p/2 only with overwhelming
-// probability over the key's masks (9.8 sigma: about 1e-22 per coefficient, 3e-16 per gate), not in the worst case.
-// Re-transforms the loaded bootstrapping key.
+// Arithmetic mode of the gate path: 1 = FFT64 (default), 2 / 3 = NTT with two 16-bit / three 11-bit key slices (include/tfhe_b200.h
+// has the exactness statement of each).  Re-transforms the loaded bootstrapping key.
 int tfhe_b200_set_key_slices(tfhe_b200_ctx* ctx, int slices) {
     if (!ctx || slices < 1 || slices > 3) return fail(ctx, TFHE_B200_ERR_PARAM, "set_key_slices: 1 (FFT64), 2 or 3");
     if (slices == ctx->key_slices) return TFHE_B200_OK;

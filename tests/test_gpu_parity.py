@@ -14,9 +14,10 @@ from conftest import phase_err
 pytestmark = pytest.mark.gpu
 
 N, n = 1024, 635
-# Default arithmetic: two 16-bit key slices -- exact on random and real keys (every slice sum stays 9.8 sigma below p/2), but by
-# design not on the adversarial worst-case KEY below; that vector runs in the worst-case-exact three-slice
-# mode (test_exact_mode_three_key_slices, or the whole suite with TFHE_B200_KEY_SLICES=3).
+# Default arithmetic: FFT64 (f64 transform with exact rounding) for batches above #SMs gates, the two-slice NTT below and for
+# the step-level entry points.  Both are exact on random and real keys (DESIGN.md section 2 has the margins) but by design not on
+# the adversarial worst-case KEY below; that vector runs in the worst-case-exact three-slice mode
+# (test_exact_mode_three_key_slices, or the whole suite with TFHE_B200_KEY_SLICES=3).
 FAST_MODE = __import__("os").environ.get("TFHE_B200_KEY_SLICES") != "3"
 
 
@@ -375,24 +376,29 @@ def test_batch_overlap_modes_same_bits(engine, keys, rng):
 
 
 def test_exact_mode_three_key_slices(oracle, keys, rng):
-    """tfhe_b200_set_key_slices(ctx, 3): three 11-bit key slices, exact in the WORST case (every slice sum < p/2 for any key and
-    any digits).  On real keys the default two-slice mode gives the same ciphertext bits; the adversarial
-    key (all words 0x7FFFFFFF) against all digits -32 is exact in this mode only.  Switching re-transforms the loaded key."""
+    """tfhe_b200_set_key_slices: 1 = FFT64 (default), 2 = NTT with two 16-bit key slices, 3 = NTT with three 11-bit slices, exact
+    in the WORST case (every slice sum < p/2 for any key and any digits).  On real keys all three modes give
+    the same ciphertext bits; the adversarial key (all words 0x7FFFFFFF) against all digits -32 is exact by construction in the
+    three-slice mode only.  Switching re-transforms the loaded key."""
     import rustfhe_b200 as R
     eng = R.DeviceEngine(0)
     try:
+        default_mode = eng.stats()["key_slices"]
         eng.load_ksk(keys.ksk)
         eng.load_bk(keys.bk)
         B = 300
         x = rng.integers(0, 2, B).astype(np.uint8)
         y = rng.integers(0, 2, B).astype(np.uint8)
         c0, c1 = keys.encrypt(x, 61000), keys.encrypt(y, 62000)
+        eng.set_key_slices(1)
+        fft = eng.gate_batch(R.NAND, c0, c1)
         eng.set_key_slices(2)
         fast = eng.gate_batch(R.NAND, c0, c1)
         eng.set_key_slices(3)
         exact = eng.gate_batch(R.NAND, c0, c1)
         assert np.array_equal(keys.decrypt(exact), 1 - (x & y))
         assert np.array_equal(fast, exact)
+        assert np.array_equal(fft, exact)
         idx = rng.choice(B, 8, replace=False)
         assert np.array_equal(exact[idx], oracle.gate_exact(keys, oracle.NAND, c0[idx], c1[idx]))
         few = eng.gate_batch(R.XOR, c0[:3], c1[:3])          # latency shape (cluster pair), three slices
@@ -406,8 +412,53 @@ def test_exact_mode_three_key_slices(oracle, keys, rng):
             ref = np.zeros(2 * N, np.uint32)
             oracle.lib().orc_external_product_exact(trgsw[g].reshape(-1), trlwe[g].reshape(-1), 0x02084000, ref)
             assert np.array_equal(out[g].reshape(-1), ref), g
-        eng.set_key_slices(2)
-        assert np.array_equal(eng.gate_batch(R.NAND, c0[:40], c1[:40]), exact[:40])
+        eng.set_key_slices(default_mode)
+        assert np.array_equal(eng.gate_batch(R.NAND, c0[:200], c1[:200]), exact[:200])
+        with pytest.raises(R.TfheError):
+            eng.set_key_slices(4)
+    finally:
+        eng.close()
+
+
+def test_fft64_mode_exact(oracle, keys, rng):
+    """The FFT64 throughput kernel (blind_rotate_f64_kernel: f64 transform, exact rounding, one warp per gate, key ring in shared
+    memory) against the exact-integer oracle: raw accumulators after 0, 1, 2 and 17 CMUX steps with the rounding edge cases of
+    (b, a), whole-gate ciphertexts on a sample of a ragged batch (8 gates per CTA: 1185 = full CTAs + uneven dealing), the same
+    bits run after run, and all decrypts right."""
+    import rustfhe_b200 as R
+    eng = R.DeviceEngine(0)
+    try:
+        eng.set_key_slices(1)
+        eng.load_ksk(keys.ksk)
+        eng.load_bk(keys.bk)
+        sms = eng.stats()["sm_count"]
+        B = sms + 13                                             # above #SMs: the FFT64 kernel, not a latency shape
+        bits = rng.integers(0, 2, B).astype(np.uint8)
+        lin = oracle.gate_linear(oracle.NAND, keys.encrypt(bits, 0), keys.encrypt(1 - bits, 1000))
+        lin[0, 0] = 0                      # bbar = 0
+        lin[3, 0] = 0xFFE00000             # bbar = 2047
+        lin[4, 0] = 0x80000000             # bbar = 1024
+        lin[4, 1] = 0xFFF00000             # abar rounds up to 2048 -> 0
+        lin[4, 2] = 0x7FF00000             # abar = 1024
+        for nsteps in (0, 1, 2, 17):
+            out = eng.blind_rotate_batch(lin, nsteps)
+            for g in (0, 1, 3, 4, 7, 8, B - 1):
+                ref = np.zeros(2 * N, np.uint32)
+                oracle.lib().orc_blind_rotate_exact(keys.exact_handle(), lin[g], 0x02084000, nsteps, ref)
+                assert np.array_equal(out[g].reshape(-1), ref), (nsteps, g)
+        B = 8 * sms + 1
+        x = rng.integers(0, 2, B).astype(np.uint8)
+        y = rng.integers(0, 2, B).astype(np.uint8)
+        c0, c1 = keys.encrypt(x, 81000), keys.encrypt(y, 82000)
+        outs = [eng.gate_batch(R.XOR, c0, c1) for _ in range(3)]
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+        assert np.array_equal(keys.decrypt(outs[0]), x ^ y)
+        idx = np.concatenate([rng.choice(B, 6, replace=False), [0, B - 1]])
+        assert np.array_equal(outs[0][idx], oracle.gate_exact(keys, oracle.XOR, c0[idx], c1[idx]))
+        ops = rng.integers(0, 7, B).astype(np.uint8)            # a circuit level of mixed gates in one launch
+        mixed = eng.gate_batch_mixed(ops, c0, c1)
+        sel = np.flatnonzero(ops == R.XOR)
+        assert np.array_equal(mixed[sel], outs[0][sel])
     finally:
         eng.close()
 

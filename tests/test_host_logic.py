@@ -110,6 +110,12 @@ def emul():
     e.emul_chacha20_u64.argtypes = [u32p, C.c_uint64, C.c_uint64, C.c_int]
     e.emul_key_slice2.restype = C.c_int32
     e.emul_key_slice2.argtypes = [C.c_uint32, C.c_int]
+    f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+    e.emul_key_transform_f64.argtypes = [u32p, f64p]
+    e.emul_external_product_f64.restype = C.c_double
+    e.emul_external_product_f64.argtypes = [f64p, u32p, C.c_uint32, u32p]
+    e.emul_cmux_rotate_f64.restype = C.c_double
+    e.emul_cmux_rotate_f64.argtypes = [f64p, u32p, C.c_uint32, C.c_uint32]
     return e
 
 
@@ -186,6 +192,50 @@ def test_throughput_kernel_arithmetic_on_cpu_matches_oracle(emul, oracle, rng):
             oracle.lib().orc_external_product_exact(trgsw, (r - acc2).astype(np.uint32), oracle.MASK_FAITHFUL, pr)
             acc2 = (acc2 + pr).astype(np.uint32)
             assert np.array_equal(acc, acc2), abar
+
+
+def test_fft64_kernel_arithmetic_on_cpu_matches_oracle(emul, oracle, rng):
+    """the per-lane code of the FFT64 kernel (fft64.cuh: f64 complex transform of the folded polynomial, one warp per polynomial,
+    swizzled 16-byte transposes, lane-pair exchange stages, spectra accumulated per lane, exact rounding by the 1.5 * 2^52 trick)
+    executed on the CPU -- same IEEE operations in the same order as the GPU (explicit fma, -ffp-contract=off) -- against the
+    exact-integer oracle.  The margin of the rounding (distance of a pre-rounding value from the nearest integer) is asserted:
+    < 2^-6 on uniform keys (1/2 would be a wrong bit), and the adversarial extreme vectors still round correctly."""
+    def u32(k):
+        return rng.integers(0, 2 ** 32, k, dtype=np.uint64).astype(np.uint32)
+    worst = 0.0
+    for trial in range(5):
+        trgsw, trlwe = u32(12 * N), u32(2 * N)
+        if trial == 3:
+            trgsw[:], trlwe[:] = 0x7FFFFFFF, 0x7DF7C000        # key words maximal, all digits -32
+        if trial == 4:
+            trgsw[:], trlwe[:] = 0x80000000, 0x7DF7C000        # key words -2^31
+        dev = np.zeros(12 * 512 * 2, np.float64)
+        emul.emul_key_transform_f64(trgsw, dev)
+        for mask in (oracle.MASK_FAITHFUL, oracle.MASK_TESTED):
+            out, ref = np.zeros(2 * N, np.uint32), np.zeros(2 * N, np.uint32)
+            frac = emul.emul_external_product_f64(dev, trlwe, mask, out)
+            oracle.lib().orc_external_product_exact(trgsw, trlwe, mask, ref)
+            assert np.array_equal(out, ref), (trial, hex(mask))
+            if trial < 3:
+                worst = max(worst, frac)
+            else:
+                assert frac <= 0.25
+    assert 0 < worst < 2 ** -6
+    trgsw = u32(12 * N)
+    dev = np.zeros(12 * 512 * 2, np.float64)
+    emul.emul_key_transform_f64(trgsw, dev)
+    acc = u32(2 * N)
+    acc2 = acc.copy()
+    for abar in (0, 1, 777, 1024, 1500, 2047):
+        frac = emul.emul_cmux_rotate_f64(dev, acc, abar, oracle.MASK_FAITHFUL)
+        r = np.zeros(2 * N, np.uint32)
+        oracle.lib().orc_rotate(acc2[:N].copy(), N, abar, r[:N])
+        oracle.lib().orc_rotate(acc2[N:].copy(), N, abar, r[N:])
+        pr = np.zeros(2 * N, np.uint32)
+        oracle.lib().orc_external_product_exact(trgsw, (r - acc2).astype(np.uint32), oracle.MASK_FAITHFUL, pr)
+        acc2 = (acc2 + pr).astype(np.uint32)
+        assert np.array_equal(acc, acc2), abar
+        assert frac < 2 ** -6
 
 
 def test_csprng_chacha20_known_answer(emul):
