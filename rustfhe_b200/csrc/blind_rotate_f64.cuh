@@ -6,8 +6,8 @@
 // registers (2 x 16 complex values per lane = 128 registers that live for the whole step), and runs two inverse transforms:
 // no spectrum is ever written to shared memory, no barrier between warps.  The gates of a CTA only meet at the key ring:
 //   bootstrapping key: [step][row j][output o] chunks of 8 KB, in the order every warp consumes them.  One elected thread streams
-//   them with bulk (TMA) copies into a four-slot ring in shared memory (full / empty mbarriers: a slot is refilled by the last
-//   warp that leaves it); the eight gates read a chunk from there, so the key crosses L2 -> SM once per CTA instead of once
+//   them with bulk (TMA) copies, 16 KB (one row, both output polynomials) at a time, into a two-slot ring in shared memory (full /
+//   empty mbarriers: a slot is refilled by the last warp that leaves it); the eight gates read a chunk from there, so the key crosses L2 -> SM once per CTA instead of once
 //   per gate ("reused across a batch of gates in shared memory").
 // See fft64.cuh for the transform and DESIGN.md sections 2, 3 and 5 for the operation counts and measurements.
 #pragma once
@@ -17,13 +17,14 @@
 
 #if !defined(F64_GATES_DEF)
 #define F64_GATES_DEF 8
-#define F64_RING_DEF 4
+#define F64_RING_DEF 2
 #endif
 constexpr int F64_GATES = F64_GATES_DEF;        // gates (= warps) per CTA
 constexpr int F64_CTAS_PER_SM = 8 / F64_GATES;
 constexpr int F64_RING = F64_RING_DEF;          // key chunks resident per CTA
-constexpr int F64_CHUNK_BYTES = (int)(F64_CHUNK_ELEMS * sizeof(cd16));   // 8192
-constexpr int F64_GATE_SMEM_BYTES = 2 * 1024 * 4 /*acc*/ + 512 * 16 /*transpose scratch*/ + 1024 * 4 /*masked source words*/ + 640 * 2 /*abar*/;
+constexpr int F64_SLOT_ELEMS = 2 * (int)F64_CHUNK_ELEMS;                 // one ring slot = both output polynomials of a row: 16 KB
+constexpr int F64_CHUNK_BYTES = (int)(F64_SLOT_ELEMS * sizeof(cd16));
+constexpr int F64_GATE_SMEM_BYTES = 2 * 1024 * 4 /*acc*/ + 512 * 16 /*transpose scratch*/ + 6 * 32 * 16 /*digit planes*/ + 640 * 2 /*abar*/;
 constexpr int F64_SHARED_BYTES = ((F64_TAB_ELEMS + F64_UNTW_ROWS * 32) * 16 + F64_RING * F64_CHUNK_BYTES + 2 * F64_RING * 8 + F64_RING * 4 + 15) / 16 * 16;
 constexpr size_t f64_smem_bytes() { return (size_t)F64_SHARED_BYTES + (size_t)F64_GATES * F64_GATE_SMEM_BYTES; }
 static_assert(F64_CTAS_PER_SM * (f64_smem_bytes() + 1024) <= 227 * 1024, "two CTAs must fit the shared memory of one SM");
@@ -49,6 +50,27 @@ __device__ __forceinline__ void f64_forward(int lane, cd (&x)[16], cd16* S, cons
     f64_fwd_x_bfly(lane, x, recv, tb, y);
 }
 
+// inverse transform of one output spectrum (destroyed), rounded to the exact integers and added to the accumulator polynomial
+__device__ __forceinline__ void f64_inverse_acc(int lane, cd (&sp)[16], cd16* S, const cd16* ta, const cd16* ut, uint32_t* ao) {
+    cd v[16];
+    {
+        f64_inv_low(sp);
+        cd send[8], recv[8];
+        f64_x_send(lane, sp, send);
+        f64_exchange(send, recv);
+        f64_inv_x_bfly(lane, sp, recv, v);
+    }
+    f64_t2_store(lane, v, S);
+    __syncwarp();
+    f64_t2_load(lane, S, v);
+    __syncwarp();
+    f64_inv_passA(lane, v, ta);
+    uint32_t lo[16], hi[16];
+    f64_untwist_round(lane, v, ut, lo, hi);
+#pragma unroll
+    for (int r = 0; r < 16; r++) { ao[32 * r + lane] += lo[r]; ao[512 + 32 * r + lane] += hi[r]; }
+}
+
 struct F64Ring {
     cd16* slot;        // [F64_RING][512]
     uint64_t* full;    // [F64_RING]
@@ -66,7 +88,7 @@ __device__ __forceinline__ void f64_with_chunk(const F64Ring& rg, long n, int la
     const int s = (int)(n & (F64_RING - 1));
     const uint32_t par = (uint32_t)((n / F64_RING) & 1);
     mbar_wait(rg.full + s, par);
-    use(rg.slot + (size_t)s * F64_CHUNK_ELEMS);
+    use(rg.slot + (size_t)s * F64_SLOT_ELEMS);
     __syncwarp();
     if (lane == 0) {
         mbar_arrive(rg.empty + s);
@@ -74,7 +96,7 @@ __device__ __forceinline__ void f64_with_chunk(const F64Ring& rg, long n, int la
             rg.left[s] = 0;
             if (n + F64_RING < rg.total) {
                 mbar_wait(rg.empty + s, par);   // every warp's reads of the slot are ordered before the copy that overwrites it
-                bulk_fetch(rg.slot + (size_t)s * F64_CHUNK_ELEMS, rg.key + (size_t)(n + F64_RING) * F64_CHUNK_ELEMS, F64_CHUNK_BYTES, rg.full + s);
+                bulk_fetch(rg.slot + (size_t)s * F64_SLOT_ELEMS, rg.key + (size_t)(n + F64_RING) * F64_SLOT_ELEMS, F64_CHUNK_BYTES, rg.full + s);
             }
         }
     }
@@ -88,15 +110,15 @@ __global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_
     F64Ring rg;
     const cd16* ut = tab + F64_TAB_ELEMS;                             // untwist
     rg.slot = tab + F64_TAB_ELEMS + F64_UNTW_ROWS * 32;
-    rg.full = reinterpret_cast<uint64_t*>(rg.slot + (size_t)F64_RING * F64_CHUNK_ELEMS);
+    rg.full = reinterpret_cast<uint64_t*>(rg.slot + (size_t)F64_RING * F64_SLOT_ELEMS);
     rg.empty = rg.full + F64_RING;
     rg.left = reinterpret_cast<uint32_t*>(rg.empty + F64_RING);
     const int gl = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* gbase = smem_raw + F64_SHARED_BYTES + (size_t)gl * F64_GATE_SMEM_BYTES;
     uint32_t* acc = reinterpret_cast<uint32_t*>(gbase);
     cd16* S = reinterpret_cast<cd16*>(gbase + 2 * 1024 * 4);
-    uint32_t* U = reinterpret_cast<uint32_t*>(gbase + 2 * 1024 * 4 + 512 * 16);
-    uint16_t* abar = reinterpret_cast<uint16_t*>(gbase + 2 * 1024 * 4 + 512 * 16 + 1024 * 4);
+    uint4* D = reinterpret_cast<uint4*>(gbase + 2 * 1024 * 4 + 512 * 16);   // digit planes [digit][re / im][lane]
+    uint16_t* abar = reinterpret_cast<uint16_t*>(gbase + 2 * 1024 * 4 + 512 * 16 + 6 * 32 * 16);
 
     // gates are dealt out evenly: the first cta_rem CTAs own cta_base+1 consecutive gates, the others cta_base (<= F64_GATES)
     const long cta = blockIdx.x;
@@ -106,7 +128,7 @@ __global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_
     const long gate = active ? first + gl : a.B - 1;
     const int nsteps = a.nsteps;
     rg.key = key;
-    rg.total = (long)nsteps * 12;
+    rg.total = (long)nsteps * 6;
     rg.active = cnt;
 
     if (threadIdx.x == 0) {
@@ -150,7 +172,7 @@ __global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_
     __syncthreads();   // tables, mbarriers
     if (threadIdx.x == 0)
         for (long n = 0; n < F64_RING && n < rg.total; n++)
-            bulk_fetch(rg.slot + (size_t)n * F64_CHUNK_ELEMS, rg.key + (size_t)n * F64_CHUNK_ELEMS, F64_CHUNK_BYTES, rg.full + n);
+            bulk_fetch(rg.slot + (size_t)n * F64_SLOT_ELEMS, rg.key + (size_t)n * F64_SLOT_ELEMS, F64_CHUNK_BYTES, rg.full + n);
     if (!active) return;   // gate slots without a gate leave here: the empty barriers count the active warps only
     if (stagger_ns > 0 && gl > 0) __nanosleep((unsigned)(gl * stagger_ns));
 
@@ -164,47 +186,36 @@ __global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_
         const uint32_t ab = abar[i];
 #pragma unroll 1
         for (int pw = 0; pw < 2; pw++) {
-            {   // masked source words of polynomial pw: ((X^abar acc - acc) + mask) ^ mask, digits flipped to offset binary
+            {   // masked source words of polynomial pw, ((X^abar acc - acc) + mask) ^ mask: lane-private, parked as three byte planes
                 uint32_t u[32];
                 t2_u<true>(lane, acc + pw * 1024, ab, a.mask, u);
-#pragma unroll
-                for (int r = 0; r < 32; r++) U[32 * r + lane] = u[r] ^ F64_SIGN_FLIP;
+                u4 re, im;
+                f64_pack_plane<0>(u, re, im);
+                D[0 * 32 + lane] = make_uint4(re.x, re.y, re.z, re.w); D[1 * 32 + lane] = make_uint4(im.x, im.y, im.z, im.w);
+                f64_pack_plane<1>(u, re, im);
+                D[2 * 32 + lane] = make_uint4(re.x, re.y, re.z, re.w); D[3 * 32 + lane] = make_uint4(im.x, im.y, im.z, im.w);
+                f64_pack_plane<2>(u, re, im);
+                D[4 * 32 + lane] = make_uint4(re.x, re.y, re.z, re.w); D[5 * 32 + lane] = make_uint4(im.x, im.y, im.z, im.w);
             }
-            __syncwarp();
 #pragma unroll 1
             for (int dw = 0; dw < 3; dw++) {
                 cd x[16], y[16];
-                f64_digits(lane, U, dw, x);
+                {
+                    const uint4 a4 = D[(2 * dw) * 32 + lane], b4 = D[(2 * dw + 1) * 32 + lane];
+                    u4 re, im;
+                    re.x = a4.x; re.y = a4.y; re.z = a4.z; re.w = a4.w; im.x = b4.x; im.y = b4.y; im.z = b4.z; im.w = b4.w;
+                    f64_digits(re, im, x);
+                }
                 f64_forward(lane, x, S, tb, y);
-                f64_with_chunk(rg, n, lane, [&](const cd16* k) { f64_mac(lane, y, k, s0); });
-                f64_with_chunk(rg, n + 1, lane, [&](const cd16* k) { f64_mac(lane, y, k, s1); });
-                n += 2;
+                f64_with_chunk(rg, n, lane, [&](const cd16* k) {
+                    f64_mac(lane, y, k, s0);
+                    f64_mac(lane, y, k + F64_CHUNK_ELEMS, s1);
+                });
+                n++;
             }
-            __syncwarp();   // every lane has read U before the next polynomial overwrites it
         }
-#pragma unroll 1
-        for (int o = 0; o < 2; o++) {
-            cd v[16];
-            {
-                f64_inv_low(s0);
-                cd send[8], recv[8];
-                f64_x_send(lane, s0, send);
-                f64_exchange(send, recv);
-                f64_inv_x_bfly(lane, s0, recv, v);
-            }
-            f64_t2_store(lane, v, S);
-            __syncwarp();
-            f64_t2_load(lane, S, v);
-            __syncwarp();
-            f64_inv_passA(lane, v, ta);
-            uint32_t lo[16], hi[16];
-            f64_untwist_round(lane, v, ut, lo, hi);
-            uint32_t* ao = acc + o * 1024;
-#pragma unroll
-            for (int r = 0; r < 16; r++) { ao[32 * r + lane] += lo[r]; ao[512 + 32 * r + lane] += hi[r]; }
-#pragma unroll
-            for (int k = 0; k < 16; k++) s0[k] = s1[k];
-        }
+        f64_inverse_acc(lane, s0, S, ta, ut, acc);
+        f64_inverse_acc(lane, s1, S, ta, ut, acc + 1024);
         __syncwarp();   // acc is complete before the next step's rotated reads (other lanes' words)
     }
 
@@ -246,7 +257,7 @@ __global__ void __launch_bounds__(KTF_WARPS * 32) bk_transform_f64_kernel(const 
     cd16* dst = dev + (size_t)pid * F64_CHUNK_ELEMS;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        cd16 v; v.re = __dmul_rn(y[k].re, 1.0 / 512); v.im = __dmul_rn(y[k].im, 1.0 / 512);
+        cd16 v; v.re = __dmul_rn(y[k].re, F64_KEY_SCALE); v.im = __dmul_rn(y[k].im, F64_KEY_SCALE);
         dst[k * 32 + lane] = v;
     }
 }

@@ -391,17 +391,46 @@ TFHE_HD void f64_untwist_round(int lane, const cd (&w)[16], const cd16* ut, uint
 }
 
 // ---- inputs ----
-// gadget digit from the 6-bit field f = d + 32 of a masked, sign-flipped word: (2^52 + f) - (2^52 + 32) = d, one DADD
-TFHE_HD double f64_digit(uint32_t f) { return F_ADD(f64_from_words(0x43300000u, f), -F64_DIGIT_BIAS); }
-// digit `dw` of the masked words U'[k] (k = 32 r + lane and k + 512), U' = u ^ 0x82080000 (offset-binary digits)
-constexpr uint32_t F64_SIGN_FLIP = 0x82080000u;
-TFHE_HD void f64_digits(int lane, const uint32_t* U, int dw, cd (&x)[16]) {
-    const int sh = 26 - 6 * dw;
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-        x[r].re = f64_digit((U[32 * r + lane] >> sh) & 63u);
-        x[r].im = f64_digit((U[512 + 32 * r + lane] >> sh) & 63u);
-    }
+// The masked source words of a polynomial are LANE-PRIVATE: lane l computes u[r] for the coefficients 32 r + l, r < 32, and the
+// folded input of its transforms is x[r] = (digit(u[r]), digit(u[r + 16])), r < 16.  The three gadget digits of the 32 words are
+// packed as bytes, one plane of 2 x 16 bytes per digit, and parked in shared memory between the transforms (32 live registers
+// less): byte = top byte of (u << 6 dw) with its two low bits cleared = 4 * digit as a signed byte (the factor 4 is folded into
+// the key scale).  A digit then costs ONE instruction (I2F.F64.S8 with a byte selector) and 1/16 of an LDS.128.
+struct u4 { uint32_t x, y, z, w; };
+constexpr double F64_KEY_SCALE = 1.0 / 2048.0;   // 1/512 of the inverse transform, 1/4 of the digit bytes
+TFHE_HD uint32_t f64_byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, s);
+#else
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t)((v >> (8 * ((s >> (4 * k)) & 7))) & 0xFF) << (8 * k);
+    return r;
+#endif
+}
+// plane word q (q < 8) of digit dw: bytes of u[4 q .. 4 q + 3]
+template <int DW>
+TFHE_HD uint32_t f64_pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const uint32_t lo = f64_byte_perm(a << (6 * DW), b << (6 * DW), 0x0073u), hi = f64_byte_perm(c << (6 * DW), d << (6 * DW), 0x0073u);
+    return f64_byte_perm(lo, hi, 0x5410u) & 0xFCFCFCFCu;
+}
+template <int DW>
+TFHE_HD void f64_pack_plane(const uint32_t (&u)[32], u4& re, u4& im) {
+    re.x = f64_pack4<DW>(u[0], u[1], u[2], u[3]);     re.y = f64_pack4<DW>(u[4], u[5], u[6], u[7]);
+    re.z = f64_pack4<DW>(u[8], u[9], u[10], u[11]);   re.w = f64_pack4<DW>(u[12], u[13], u[14], u[15]);
+    im.x = f64_pack4<DW>(u[16], u[17], u[18], u[19]); im.y = f64_pack4<DW>(u[20], u[21], u[22], u[23]);
+    im.z = f64_pack4<DW>(u[24], u[25], u[26], u[27]); im.w = f64_pack4<DW>(u[28], u[29], u[30], u[31]);
+}
+TFHE_HD double f64_byte(uint32_t w, int k) { return (double)(int8_t)(w >> (8 * k)); }
+TFHE_HD void f64_unpack4(uint32_t w, double& a, double& b, double& c, double& d) {
+    a = f64_byte(w, 0); b = f64_byte(w, 1); c = f64_byte(w, 2); d = f64_byte(w, 3);
+}
+// folded input (scaled by 4) from one digit plane
+TFHE_HD void f64_digits(const u4& re, const u4& im, cd (&x)[16]) {
+    f64_unpack4(re.x, x[0].re, x[1].re, x[2].re, x[3].re);     f64_unpack4(re.y, x[4].re, x[5].re, x[6].re, x[7].re);
+    f64_unpack4(re.z, x[8].re, x[9].re, x[10].re, x[11].re);   f64_unpack4(re.w, x[12].re, x[13].re, x[14].re, x[15].re);
+    f64_unpack4(im.x, x[0].im, x[1].im, x[2].im, x[3].im);     f64_unpack4(im.y, x[4].im, x[5].im, x[6].im, x[7].im);
+    f64_unpack4(im.z, x[8].im, x[9].im, x[10].im, x[11].im);   f64_unpack4(im.w, x[12].im, x[13].im, x[14].im, x[15].im);
 }
 // key polynomial (torus words taken as centred 32-bit integers) -> folded complex input
 TFHE_HD void f64_key_input(int lane, const uint32_t* poly, cd (&x)[16]) {

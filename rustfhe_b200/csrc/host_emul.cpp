@@ -170,7 +170,7 @@ void emul_key_transform_f64(const uint32_t* trgsw, double* dev) {
             f64_forward_all_lanes(x, S.data(), y);
             for (int lane = 0; lane < 32; lane++)
                 for (int k = 0; k < 16; k++) {
-                    cd16 v; v.re = y[lane][k].re * (1.0 / 512); v.im = y[lane][k].im * (1.0 / 512);
+                    cd16 v; v.re = y[lane][k].re * F64_KEY_SCALE; v.im = y[lane][k].im * F64_KEY_SCALE;
                     out[f64_key_off(0, j, o) + k * 32 + lane] = v;
                 }
         }
@@ -180,7 +180,7 @@ void emul_key_transform_f64(const uint32_t* trgsw, double* dev) {
 static double f64_step(const double* dev, uint32_t* acc, bool rotate, uint32_t abar, uint32_t mask) {
     const cd16* key = reinterpret_cast<const cd16*>(dev);
     std::vector<cd16> S(512);
-    std::vector<uint32_t> U(1024);
+    std::vector<u4> planes(6 * 32);   // [digit][re / im][lane]
     cd sum[2][32][16];
     double frac = 0;
     for (int pw = 0; pw < 2; pw++) {
@@ -188,11 +188,13 @@ static double f64_step(const double* dev, uint32_t* acc, bool rotate, uint32_t a
             uint32_t u[32];
             if (rotate) t2_u<true>(lane, acc + pw * 1024, abar, mask, u);
             else t2_u<false>(lane, acc + pw * 1024, abar, mask, u);
-            for (int r = 0; r < 32; r++) U[32 * r + lane] = u[r] ^ F64_SIGN_FLIP;
+            f64_pack_plane<0>(u, planes[0 * 32 + lane], planes[1 * 32 + lane]);
+            f64_pack_plane<1>(u, planes[2 * 32 + lane], planes[3 * 32 + lane]);
+            f64_pack_plane<2>(u, planes[4 * 32 + lane], planes[5 * 32 + lane]);
         }
         for (int dw = 0; dw < 3; dw++) {
             cd x[32][16], y[32][16];
-            for (int lane = 0; lane < 32; lane++) f64_digits(lane, U.data(), dw, x[lane]);
+            for (int lane = 0; lane < 32; lane++) f64_digits(planes[(2 * dw) * 32 + lane], planes[(2 * dw + 1) * 32 + lane], x[lane]);
             f64_forward_all_lanes(x, S.data(), y);
             const int j = 3 * pw + dw;
             for (int o = 0; o < 2; o++)
