@@ -50,14 +50,15 @@ def design_figures(key_slices):
 
 def fft64_figures():
     """Per-gate work of the FFT64 mode (fft64.cuh; DESIGN.md sections 2 and 5), counted per lane from the code and confirmed by ncu
-    (4532 FP64 warp instructions per gate and CMUX): a forward transform of 512 complex points = 32 digit conversions + 9 stages x 8
-    butterflies x 6 DFMA-class operations = 464 per lane, an inverse = 482 per lane (trivial twiddles in its first stages, untwist and
-    rounding), one spectrum x key multiply-accumulate = 64 per lane; per CMUX 6 forward + 2 inverse + 12 multiply-accumulates.
+    (4340 FP64 warp instructions per gate and CMUX): a forward transform of 512 complex points = 9 stages x 8 butterflies x 6
+    DFMA-class operations = 432 per lane (the digits enter through I2F.F64.S8, not on the FP64 pipe's DFMA count), an inverse =
+    482 per lane (trivial twiddles in its first stages, untwist and rounding), one spectrum x key multiply-accumulate = 64 per
+    lane; per CMUX 6 forward + 2 inverse + 12 multiply-accumulates.
     Shared-memory bytes per gate and CMUX: 8 transposes x 16 KB, 96 KB of key read from the ring, 60 KB of per-lane twiddle rows,
-    48 KB for the masked source words (rotated reads, one store, three digit reads), 16 KB accumulator update."""
-    fwd, inv, mac = 464 * 32, 482 * 32, 64 * 32
+    22 KB for the source words (rotated reads, digit byte planes), 16 KB accumulator update."""
+    fwd, inv, mac = 432 * 32, 482 * 32, 64 * 32
     per_cmux = 6 * fwd + 2 * inv + 12 * mac
-    smem = (8 * 16 + 96 + 60 + 48 + 16) * 1024
+    smem = (8 * 16 + 96 + 60 + 22 + 16) * 1024
     return {"transforms_per_cmux": 8, "fp64_ops_per_gate": 635 * per_cmux, "smem_bytes_per_gate": 635 * smem,
             "bk_bytes_device": 635 * 12 * 512 * 16}
 

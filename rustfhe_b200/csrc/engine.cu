@@ -463,7 +463,9 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         // best shape between one and two gates per SM (296 gates: 5.7 ms against 6.3 ms for 2-gate CTAs of the 80-register
         // kernel and 5.8 ms for 1-gate CTAs compiled for 168 registers)
         blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-    } else if (full && ctx->key_slices == 1 && variant != 8) {   // FFT64 mode: one warp per gate, eight gates per CTA (blind_rotate_f64.cuh)
+    } else if (full && ctx->key_slices == 1 && variant != 8 && a.B > 2L * ctx->sm_count) {
+        // FFT64 mode: one warp per gate, eight gates per CTA (blind_rotate_f64.cuh).  Up to two gates per SM the two-warps-per-gate
+        // NTT kernel below is faster (296 gates: 6.4 ms against 7.8 ms), from three gates per SM on this one is
         const unsigned grid = batches_overlap(ctx, st) ? fixed(F64_GATES) : deal(F64_GATES);
         blind_rotate_f64_kernel<<<grid, F64_GATES * 32, f64_smem_bytes(), st>>>(a, ctx->bkdev_f64, ctx->f64_stagger_ns);
     } else if (full && a.ns == 2 && variant != 8) {   // default: the two-warps-per-gate throughput kernel (blind_rotate_t2.cuh)

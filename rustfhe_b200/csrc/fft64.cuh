@@ -191,7 +191,8 @@ TFHE_HD void f64_t1_load(int lane, const cd16* S, cd (&x)[16]) {
 #pragma unroll
     for (int k = 0; k < 4; k++) b[k] = S + (base ^ (k << 1));
 #pragma unroll
-    for (int rho = 0; rho < 16; rho++) {
+    for (int k = 0; k < 16; k++) {
+        const int rho = (k >> 1) | ((k & 1) << 3);   // 0, 8, 1, 9, ...: the operands of the first butterflies of pass B arrive first
         const cd16 v = b[rho & 3][(rho >> 2) << 3];
         x[rho].re = v.re; x[rho].im = v.im;
     }

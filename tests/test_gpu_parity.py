@@ -432,7 +432,7 @@ def test_fft64_mode_exact(oracle, keys, rng):
         eng.load_ksk(keys.ksk)
         eng.load_bk(keys.bk)
         sms = eng.stats()["sm_count"]
-        B = sms + 13                                             # above #SMs: the FFT64 kernel, not a latency shape
+        B = 2 * sms + 13                                         # above 2 #SMs: the FFT64 kernel, not a latency shape or the NTT kernel
         bits = rng.integers(0, 2, B).astype(np.uint8)
         lin = oracle.gate_linear(oracle.NAND, keys.encrypt(bits, 0), keys.encrypt(1 - bits, 1000))
         lin[0, 0] = 0                      # bbar = 0
