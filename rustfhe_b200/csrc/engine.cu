@@ -71,7 +71,9 @@ struct tfhe_b200_ctx {
                          // 16-bit key slices; both exact for honestly generated keys (DESIGN.md section 2 has the margins);
                          // 3 = NTT, three 11-bit slices, exact in the worst case
     int ns_int() const { return key_slices == 3 ? 3 : 2; }   // slices of the integer (NTT) form of the key
-    int f64_stagger_ns = 400;   // start-up offset between the warps of a CTA of the FFT64 kernel (TFHE_B200_F64_STAGGER)
+    int f64_latency = 1;        // FFT64 mode: batches of at most #SMs gates run one gate per CTA on six warps (TFHE_B200_F64_LATENCY=0: the NTT
+                                // latency shapes)
+    int f64_stagger_ns = 0;   // start-up offset between the warps of a CTA of the FFT64 kernel (TFHE_B200_F64_STAGGER)
     int t2_gates = 6;    // gates per CTA of the throughput kernel (TFHE_B200_T2_G: 4 or 6)
     int t2_twreg = 1;    // which row twiddles the throughput kernel keeps in registers (TFHE_B200_T2_TWREG: bit 0 forward, bit 1 inverse)
     int slab_tma = 1;     // one gate per CTA: key slabs staged by bulk copies (TFHE_B200_SLAB_TMA=0: streamed from L2 by the warps)
@@ -239,6 +241,9 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if (const char* v = getenv("TFHE_B200_KEY_SLICES")) { const int k = atoi(v); if (k >= 1 && k <= 3) ctx->key_slices = k; }
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64)", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L_SMEM_BYTES)) != cudaSuccess)
+        return bail("smem attr (f64 latency)", e);
+    if (const char* v = getenv("TFHE_B200_F64_LATENCY")) ctx->f64_latency = atoi(v);
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (keyswitch2)", e);
     *out = ctx;
@@ -487,6 +492,12 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         const unsigned grid = batches_overlap(ctx, st) ? fixed(4) : deal(4);
         if (a.ns == 2) blind_rotate_kernel<4, false, 1, 2><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
         else blind_rotate_kernel<4, false, 1, 3><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
+    } else if (!full && ctx->key_slices == 1 && ctx->f64_latency && variant != 9 && (a.B > (long)ctx->pair_max || ctx->f64_latency > 1)) {
+        // FFT64 latency shape, one gate per SM on six warps: 3.2 ms per gate whatever the batch, so it takes the batches the 2-SM
+        // clusters (2.7 ms, at most #SMs/2 gates) cannot: 148 gates 3.24 ms against 3.57 ms (TFHE_B200_F64_LATENCY=2 forces it)
+        a.cta_base = 1; a.cta_rem = 0;
+        ctx->gates_per_cta = 1;
+        blind_rotate_f64_latency_kernel<<<(unsigned)a.B, F64L_THREADS, F64L_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
     } else if (a.B <= (long)ctx->pair_max && variant != 9) {   // latency shape: one gate on a cluster of two SMs, as long as
                                                                 // the clusters fit in one wave (74 gates: 3.66 ms against 3.92 ms
                                                                 // with one CTA per gate; TFHE_B200_PAIR_MAX moves the limit)

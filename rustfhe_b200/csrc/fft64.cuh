@@ -197,31 +197,41 @@ TFHE_HD void f64_t1_load(int lane, const cd16* S, cd (&x)[16]) {
         x[rho].re = v.re; x[rho].im = v.im;
     }
 }
-// pass B: stages 4..7 on rho, per-lane twiddles tb[t * 32 + lane]
-template <int SEL> TFHE_HD void f64_fb_pair(cd (&x)[16], int ia, int h, const cd16& w) { bf_sel<SEL>(x[ia], x[ia + h], w.re, w.im); }
-TFHE_HD void f64_fwd_passB(int lane, cd (&x)[16], const cd16* tb) {
+// pass B: stages 4..7 on rho, per-lane twiddles tb[t * 32 + lane].  The eight rows are loaded by f64_fwd_twB BEFORE the
+// transpose (nothing can be hoisted above a warp barrier by the compiler), so their latency is under pass A and the transpose.
+struct F64TwB { cd16 w[8]; };
+TFHE_HD void f64_fwd_twB(int lane, const cd16* tb, F64TwB& t) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) t.w[k] = tb[k * 32 + lane];
+}
+TFHE_HD void f64_fwd_passB(cd (&x)[16], const F64TwB& tw) {
     {
-        const cd16 w = tb[0 * 32 + lane];
+        const cd16 w = tw.w[0];
 #pragma unroll
         for (int t = 0; t < 8; t++) bf_w(x[t], x[t + 8], w.re, w.im);
     }
     {
-        const cd16 w = tb[1 * 32 + lane];
+        const cd16 w = tw.w[1];
 #pragma unroll
         for (int t = 0; t < 4; t++) { bf_w(x[t], x[t + 4], w.re, w.im); bf_iw(x[8 + t], x[12 + t], w.re, w.im); }
     }
 #pragma unroll
     for (int c2 = 0; c2 < 2; c2++) {
-        const cd16 w = tb[(2 + c2) * 32 + lane];
+        const cd16 w = tw.w[2 + c2];
 #pragma unroll
         for (int t = 0; t < 2; t++) { bf_w(x[8 * c2 + t], x[8 * c2 + t + 2], w.re, w.im); bf_iw(x[8 * c2 + 4 + t], x[8 * c2 + 6 + t], w.re, w.im); }
     }
 #pragma unroll
     for (int c2 = 0; c2 < 4; c2++) {
-        const cd16 w = tb[(4 + c2) * 32 + lane];
+        const cd16 w = tw.w[4 + c2];
         bf_w(x[4 * c2], x[4 * c2 + 1], w.re, w.im);
         bf_iw(x[4 * c2 + 2], x[4 * c2 + 3], w.re, w.im);
     }
+}
+TFHE_HD void f64_fwd_passB(int lane, cd (&x)[16], const cd16* tb) {
+    F64TwB tw;
+    f64_fwd_twB(lane, tb, tw);
+    f64_fwd_passB(x, tw);
 }
 // stage 8, the lane-pair exchange.  Lane j0 owns the butterflies rho = 8 j0 + m, m < 8: it keeps its own operand of those and
 // needs the partner's; it sends the operand it holds of the partner's butterflies.
@@ -339,20 +349,25 @@ TFHE_HD void f64_t2_load(int lane, const cd16* S, cd (&w)[16]) {
         w[r].re = t.re; w[r].im = t.im;
     }
 }
-// stages 5..8 on r, per-lane twiddles ta[t * 32 + lane]
-TFHE_HD void f64_inv_passA(int lane, cd (&w)[16], const cd16* ta) {
+// stages 5..8 on r, per-lane twiddles ta[t * 32 + lane] (loaded by f64_inv_twA before the transpose, like the forward rows)
+struct F64TwA { cd16 w[8]; };
+TFHE_HD void f64_inv_twA(int lane, const cd16* ta, F64TwA& t) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) t.w[k] = ta[k * 32 + lane];
+}
+TFHE_HD void f64_inv_passA(cd (&w)[16], const F64TwA& tw) {
     {
-        const cd16 t = ta[0 * 32 + lane];
+        const cd16 t = tw.w[0];
 #pragma unroll
         for (int c = 0; c < 8; c++) bf_w(w[2 * c], w[2 * c + 1], t.re, t.im);
     }
     {
-        const cd16 t = ta[1 * 32 + lane];
+        const cd16 t = tw.w[1];
 #pragma unroll
         for (int c = 0; c < 4; c++) { bf_w(w[4 * c], w[4 * c + 2], t.re, t.im); bf_miw(w[4 * c + 1], w[4 * c + 3], t.re, t.im); }
     }
     {
-        const cd16 t0 = ta[2 * 32 + lane], t1 = ta[3 * 32 + lane];
+        const cd16 t0 = tw.w[2], t1 = tw.w[3];
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             bf_w(w[8 * c], w[8 * c + 4], t0.re, t0.im);
@@ -363,10 +378,15 @@ TFHE_HD void f64_inv_passA(int lane, cd (&w)[16], const cd16* ta) {
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const cd16 t = ta[(4 + k) * 32 + lane];
+        const cd16 t = tw.w[4 + k];
         bf_w(w[k], w[k + 8], t.re, t.im);
         bf_miw(w[k + 4], w[k + 12], t.re, t.im);
     }
+}
+TFHE_HD void f64_inv_passA(int lane, cd (&w)[16], const cd16* ta) {
+    F64TwA tw;
+    f64_inv_twA(lane, ta, tw);
+    f64_inv_passA(w, tw);
 }
 // z_j = psi^-j v_j, exact rounding; lo[r] / hi[r] = coefficients j and j + 512 (j = 32 r + lane) mod 2^32.
 // frac (host-side diagnostics only): largest distance of a value from the nearest integer.
