@@ -44,16 +44,28 @@ __device__ __forceinline__ void f64_forward(int lane, cd (&x)[16], cd16* S, cons
     F64TwB tw;
     if (PREFETCH) f64_fwd_twB(lane, tb, tw);
     f64_fwd_passA(x);
+#if !defined(F64_X_NOT1)   // timing experiment: no transpose
     f64_t1_store(lane, x, S);
     __syncwarp();
     f64_t1_load(lane, S, x);
     __syncwarp();   // the scratch is free for the next transform
+#endif
     if (!PREFETCH) f64_fwd_twB(lane, tb, tw);
     f64_fwd_passB(x, tw);
+#if defined(F64_X_NOX)   // timing experiment: the last stage without the lane-pair exchange
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const cd16 w = tb[(8 + (m >> 1)) * 32 + lane];
+        cd a2 = x[m], b2 = x[m + 8];
+        bf_w(a2, b2, w.re, w.im);
+        y[2 * m] = a2; y[2 * m + 1] = b2;
+    }
+#else
     cd send[8], recv[8];
     f64_x_send(lane, x, send);
     f64_exchange(send, recv);
     f64_fwd_x_bfly(lane, x, recv, tb, y);
+#endif
 }
 
 // inverse transform of one output spectrum (destroyed), rounded to the exact integers and added to the accumulator polynomial
@@ -196,7 +208,12 @@ __global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_
         for (int pw = 0; pw < 2; pw++) {
             {   // masked source words of polynomial pw, ((X^abar acc - acc) + mask) ^ mask: lane-private, parked as three byte planes
                 uint32_t u[32];
+#if defined(F64_X_NOU)   // timing experiment: no rotated reads, no masking
+#pragma unroll
+                for (int r = 0; r < 32; r++) u[r] = acc[pw * 1024 + lane] * (r + 1);
+#else
                 t2_u<true>(lane, acc + pw * 1024, ab, a.mask, u);
+#endif
                 u4 re, im;
                 f64_pack_plane<0>(u, re, im);
                 D[0 * 32 + lane] = make_uint4(re.x, re.y, re.z, re.w); D[1 * 32 + lane] = make_uint4(im.x, im.y, im.z, im.w);
@@ -215,10 +232,15 @@ __global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_
                     f64_digits(re, im, x);
                 }
                 f64_forward(lane, x, S, tb, y);
+#if defined(F64_X_NOKEY)   // timing experiment: no ring, key values from the twiddle table
+                f64_mac(0, y, tb, s0);
+                f64_mac(1, y, tb, s1);
+#else
                 f64_with_chunk(rg, n, lane, [&](const cd16* k) {
                     f64_mac(lane, y, k, s0);
                     f64_mac(lane, y, k + F64_CHUNK_ELEMS, s1);
                 });
+#endif
                 n++;
             }
         }

@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <climits>
+#include <cstdint>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -736,6 +738,32 @@ int tfhe_b200_circuit_create(tfhe_b200_ctx* ctx, size_t n_levels, const size_t* 
             (!one && (in1[g] < 0 || (size_t)in1[g] >= n_wires))) {
             delete c;
             return fail(ctx, TFHE_B200_ERR_PARAM, "circuit_create: opcode or wire index out of range");
+        }
+    }
+    // A level is evaluated in place on one wire table by gates that run concurrently: within a level no wire may be written
+    // twice, and no wire may be both read and written (the reader could see either value).  Sizes must fit the 32-bit grid math.
+    if (n_wires > (size_t)INT32_MAX || c->max_level > ((size_t)1 << 30)) {
+        delete c;
+        return fail(ctx, TFHE_B200_ERR_PARAM, "circuit_create: more than 2^31 - 1 wires or 2^30 gates in a level");
+    }
+    {
+        std::vector<uint32_t> written(n_wires, 0u), read(n_wires, 0u);   // level number + 1 of the last write / read
+        size_t g = 0;
+        for (size_t l = 0; l < n_levels; l++) {
+            const uint32_t tag = (uint32_t)l + 1u;
+            for (size_t k = 0; k < level_gates[l]; k++, g++) {
+                const bool one = ops[g] == TFHE_B200_NOT || ops[g] == TFHE_B200_COPY;
+                read[in0[g]] = tag;
+                if (!one) read[in1[g]] = tag;
+            }
+            g -= level_gates[l];
+            for (size_t k = 0; k < level_gates[l]; k++, g++) {
+                if (written[out[g]] == tag || read[out[g]] == tag) {
+                    delete c;
+                    return fail(ctx, TFHE_B200_ERR_PARAM, "circuit_create: a wire is written twice, or read and written, within one level");
+                }
+                written[out[g]] = tag;
+            }
         }
     }
     if (c->total) {

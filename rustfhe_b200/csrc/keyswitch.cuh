@@ -80,15 +80,16 @@ constexpr int KS2_THREADS = KS2_GATES * 32;
 #endif
 constexpr int KS2_LV = KS2_LVDEF;                  // levels per stage
 constexpr int KS2_ROWS = KS2_LV * 3;               // rows per stage
-constexpr int KS2_ROW_WORDS = 640;                 // 636 words padded to a multiple of 16 bytes x 32 lanes x 5
+constexpr int KS2_ROW_WORDS = LWE_N + 1;           // 636 words = 159 x 16 bytes: the rows of a stage are contiguous in the key, one bulk copy
 constexpr int KS2_RING = 3;
 constexpr int KS2_STAGE_WORDS = KS2_ROWS * KS2_ROW_WORDS;
-constexpr size_t KS2_SMEM_BYTES = (size_t)KS2_RING * KS2_STAGE_WORDS * 4 + (size_t)KS_ICHUNK * KS2_GATES * 2;
+constexpr size_t KS2_SMEM_BYTES = (size_t)KS2_RING * KS2_STAGE_WORDS * 4 + (size_t)KS_ICHUNK * KS2_GATES * 2 + KS2_RING * 8;
 __global__ void __launch_bounds__(KS2_THREADS) keyswitch2_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
                                                                 uint32_t* __restrict__ out, long B, const int32_t* __restrict__ idxo) {
     extern __shared__ __align__(16) uint32_t ks_smem[];
     uint32_t* ring = ks_smem;
     uint16_t* dg = reinterpret_cast<uint16_t*>(ks_smem + KS2_RING * KS2_STAGE_WORDS);   // [ichunk][16]
+    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(ks_smem) + KS2_SMEM_BYTES - KS2_RING * 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long g0 = (long)blockIdx.x * KS2_GATES;
     const int ichunk = 1024 / (int)gridDim.y;
@@ -98,28 +99,30 @@ __global__ void __launch_bounds__(KS2_THREADS) keyswitch2_kernel(const uint4* __
         const int g = t / ichunk, ii = t % ichunk;
         dg[ii * KS2_GATES + g] = (g0 + g < B) ? dig[(size_t)(g0 + g) * 1024 + i0 + ii] : (uint16_t)0;
     }
-    auto stage_in = [&](int k) {   // rows (key index i0 + k / SPI, KS2_LV levels, all three multiples) -> ring slot k % 3
+    // rows (key index i0 + k / SPI, KS2_LV levels, all three multiples) -> ring slot k % 3: ONE bulk (TMA) copy of 30 KB issued by
+    // one thread, completing on the slot's mbarrier (the per-thread cp.async version spent 16 of its 58 instructions per gate,
+    // index and level on the addresses of the 16-byte pieces)
+    auto stage_in = [&](int k) {
         constexpr int SPI = 8 / KS2_LV;   // stages per key index
         const uint4* src = ksk + ((size_t)(i0 + k / SPI) * 8 + (size_t)(k % SPI) * KS2_LV) * 3 * KS_CHUNKS;
-        const uint32_t dst = smem_u32(ring + (k % KS2_RING) * KS2_STAGE_WORDS);
-        for (int t = threadIdx.x; t < KS2_ROWS * KS_CHUNKS; t += KS2_THREADS) {
-            const int row = t / KS_CHUNKS, c = t - row * KS_CHUNKS;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(row * KS2_ROW_WORDS + 4 * c) * 4u), "l"(src + t)
-                         : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        bulk_fetch(ring + (k % KS2_RING) * KS2_STAGE_WORDS, src, KS2_STAGE_WORDS * 4, full + k % KS2_RING);
     };
-    stage_in(0);
-    if (nstages > 1) stage_in(1); else asm volatile("cp.async.commit_group;" ::: "memory");
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < KS2_RING; r++) mbar_init(full + r, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        stage_in(0);
+        if (nstages > 1) stage_in(1);
+    }
+    __syncthreads();   // digits staged, mbarriers initialised
     uint4 acc[5];
 #pragma unroll
     for (int q = 0; q < 5; q++) acc[q] = make_uint4(0, 0, 0, 0);
     const bool live = g0 + warp < B;
 #pragma unroll 1
     for (int k = 0; k < nstages; k++) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // stage k has landed (at most the newest group is still in flight)
-        __syncthreads();                                          // ... for every thread; and everybody is done with stage k-1
-        if (k + 2 < nstages) stage_in(k + 2); else asm volatile("cp.async.commit_group;" ::: "memory");
+        if (k > 0) __syncthreads();                               // everybody is done with stage k-1: its slot takes stage k+2
+        if (threadIdx.x == 0 && k + 2 < nstages) stage_in(k + 2);
+        mbar_wait(full + k % KS2_RING, (uint32_t)((k / KS2_RING) & 1));   // stage k has landed
         if (live) {
             constexpr int SPI = 8 / KS2_LV;
             const uint32_t d16 = dg[(k / SPI) * KS2_GATES + warp];

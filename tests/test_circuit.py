@@ -141,3 +141,29 @@ def test_device_resident_circuit_matches_host_evaluator():
             assert sum(int(b) << i for i, b in enumerate(got)) == x + y
     finally:
         tfhe.close()
+
+
+@pytest.mark.gpu
+def test_device_circuit_rejects_racy_netlists(engine):
+    """tfhe_b200_circuit_create: a level runs in place on one wire table with all its gates concurrent, so a wire written twice
+    in a level, or read by one gate and written by another of the same level, is rejected (it would be a silent data race)."""
+    import ctypes as C
+    import rustfhe_b200 as R
+    from rustfhe_b200 import _capi as K
+
+    def create(level_sizes, ops, i0, i1, out, n_wires):
+        h = C.c_void_p()
+        sizes = (C.c_size_t * len(level_sizes))(*level_sizes)
+        rc = engine._l.tfhe_b200_circuit_create(engine._ctx, len(level_sizes), sizes, K.ptr(np.asarray(ops, np.uint8)), K.ptr(np.asarray(i0, np.int32)),
+                                                K.ptr(np.asarray(i1, np.int32)), K.ptr(np.asarray(out, np.int32)), n_wires, C.byref(h))
+        if rc == 0:
+            engine._l.tfhe_b200_circuit_destroy(engine._ctx, h)
+        return rc
+    assert create([2, 1], [R.NAND, R.AND, R.OR], [0, 0, 2], [1, 1, 3], [2, 3, 4], 5) == 0            # well formed
+    assert create([2], [R.NAND, R.AND], [0, 0], [1, 1], [2, 2], 3) != 0                               # two gates write wire 2
+    assert create([2], [R.NAND, R.AND], [0, 2], [1, 1], [2, 3], 4) != 0                               # wire 2 written and read in one level
+    assert create([1], [R.NOT], [0], [0], [0], 1) != 0                                                # in place on its own input
+    assert create([1], [R.NAND], [0], [5], [1], 3) != 0                                               # index out of range
+    msg = engine._l.tfhe_b200_last_error(engine._ctx)
+    msg = msg.decode() if isinstance(msg, bytes) else str(msg)
+    assert "out of range" in msg
