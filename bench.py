@@ -59,8 +59,11 @@ def fft64_figures():
     fwd, inv, mac = 432 * 32, 482 * 32, 64 * 32
     per_cmux = 6 * fwd + 2 * inv + 12 * mac
     smem = (8 * 16 + 96 + 60 + 22 + 16) * 1024
+    # issue slots: a DFMA-class instruction keeps the issue port for two cycles (profiles/r02_dfma_mix.json); the other 3911 warp
+    # instructions of a gate and CMUX (ncu, profiles/r02_ncu_blind_rotate_f64_latest.txt) take one each
+    issue = 2 * per_cmux / 32 + 3911
     return {"transforms_per_cmux": 8, "fp64_ops_per_gate": 635 * per_cmux, "smem_bytes_per_gate": 635 * smem,
-            "bk_bytes_device": 635 * 12 * 512 * 16}
+            "issue_cycles_per_gate": 635 * issue, "bk_bytes_device": 635 * 12 * 512 * 16}
 
 
 def workload_config(world):
@@ -527,7 +530,7 @@ def run_gpu(args):
                          "frac": achieved / peaks["hbm_gbs"], "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                          "algorithmic_bytes_per_launch": algo_bytes, "traffic": ncu_traffic(),
                          "note": "HBM is NOT the binding roof of this kernel (key bytes are read once per 1024-gate launch); "
-                                 "the binding roofs are on-chip, see " + ("smem_roofline and fp64_roofline" if fft64 else "int_roofline")},
+                                 "the binding roofs are on-chip, see " + ("issue_roofline, smem_roofline and fp64_roofline" if fft64 else "int_roofline")},
             "clocks": clocks,
             "key_setup_s": key_s,
             "extras": extras,
@@ -539,12 +542,19 @@ def run_gpu(args):
                                      "peak": p64 / 1e12, "unit": "T DFMA-class ops/s", "frac": per_gpu_gps_kernel * fig["fp64_ops_per_gate"] / p64,
                                      "peak_kind": p64_src, "ops_per_gate": fig["fp64_ops_per_gate"], "roof_gates_per_s": p64 / fig["fp64_ops_per_gate"],
                                      "note": "DFMA / DADD / DMUL, one issue slot each; ncu: sm__pipe_fp64_cycles_active"}
-            line["smem_roofline"] = {"bound": "shared-memory bandwidth (the binding roof of this kernel)", "kernel": kname,
+            line["smem_roofline"] = {"bound": "shared-memory bandwidth", "kernel": kname,
                                      "achieved": per_gpu_gps_kernel * fig["smem_bytes_per_gate"] / 1e9, "peak": smem_peak / 1e9, "unit": "GB/s",
                                      "frac": per_gpu_gps_kernel * fig["smem_bytes_per_gate"] / smem_peak, "peak_kind": "148 SM x 128 B/clk x SM clock",
                                      "bytes_per_gate": fig["smem_bytes_per_gate"], "roof_gates_per_s": smem_peak / fig["smem_bytes_per_gate"],
                                      "note": "algorithmic shared-memory bytes of the design (transposes, key ring reads, per-lane twiddles, source words, "
                                              "accumulator); ncu: l1tex__data_pipe_lsu_wavefronts_mem_shared"}
+            issue_peak = 148 * 4 * (peaks.get("sm_max_mhz", 1965.0) * 1e6)      # one warp instruction per scheduler and clock
+            line["issue_roofline"] = {"bound": "instruction issue slots (the binding roof: a DFMA holds the issue port for two cycles)", "kernel": kname,
+                                      "achieved": per_gpu_gps_kernel * fig["issue_cycles_per_gate"] / 1e9, "peak": issue_peak / 1e9, "unit": "G issue cycles/s",
+                                      "frac": per_gpu_gps_kernel * fig["issue_cycles_per_gate"] / issue_peak, "peak_kind": "148 SM x 4 schedulers x SM clock",
+                                      "issue_cycles_per_gate": fig["issue_cycles_per_gate"], "roof_gates_per_s": issue_peak / fig["issue_cycles_per_gate"],
+                                      "note": "2 x 4324 FP64 + 3911 other warp instructions per gate and CMUX; measured DFMA + FFMA mixes add up instead of "
+                                              "overlapping (profiles/r02_dfma_mix.json), and a third warp per scheduler does not raise the issue rate"}
             line["int_roofline"] = dict(line["fp64_roofline"], note="FFT64 mode: the arithmetic runs on the FP64 pipe, whose issue rate equals the IMAD rate "
                                         "(profiles/intpipe_r01b.json); see fp64_roofline / smem_roofline")
         else:

@@ -18,6 +18,7 @@
 #include "blind_rotate.cuh"
 #include "blind_rotate_t2.cuh"
 #include "blind_rotate_f64.cuh"
+#include "blind_rotate_f64t.cuh"
 #include "keyswitch.cuh"
 #include "aux_kernels.cuh"
 
@@ -73,6 +74,8 @@ struct tfhe_b200_ctx {
                          // 16-bit key slices; both exact for honestly generated keys (DESIGN.md section 2 has the margins);
                          // 3 = NTT, three 11-bit slices, exact in the worst case
     int ns_int() const { return key_slices == 3 ? 3 : 2; }   // slices of the integer (NTT) form of the key
+    int f64_tmem = 0;           // FFT64 throughput kernel: 0 = K5F, eight gates per SM (default); 1 = per-gate state in tensor memory, twelve gates
+                                // per SM (K5FT, TFHE_B200_F64_TMEM=1): measured 10 % slower -- the kernel is bound by issue slots, not by latency
     int f64_latency = 1;        // FFT64 mode: batches of at most #SMs gates run one gate per CTA on six warps (TFHE_B200_F64_LATENCY=0: the NTT
                                 // latency shapes)
     int f64_stagger_ns = 0;   // start-up offset between the warps of a CTA of the FFT64 kernel (TFHE_B200_F64_STAGGER)
@@ -246,6 +249,9 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (f64 latency)", e);
     if (const char* v = getenv("TFHE_B200_F64_LATENCY")) ctx->f64_latency = atoi(v);
+    if ((e = cudaFuncSetAttribute(blind_rotate_f64t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64t_smem_bytes())) != cudaSuccess)
+        return bail("smem attr (f64 tmem)", e);
+    if (const char* v = getenv("TFHE_B200_F64_TMEM")) ctx->f64_tmem = atoi(v);
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (keyswitch2)", e);
     *out = ctx;
@@ -473,8 +479,13 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
     } else if (full && ctx->key_slices == 1 && variant != 8 && a.B > 2L * ctx->sm_count) {
         // FFT64 mode: one warp per gate, eight gates per CTA (blind_rotate_f64.cuh).  Up to two gates per SM the two-warps-per-gate
         // NTT kernel below is faster (296 gates: 6.4 ms against 7.8 ms), from three gates per SM on this one is
-        const unsigned grid = batches_overlap(ctx, st) ? fixed(F64_GATES) : deal(F64_GATES);
-        blind_rotate_f64_kernel<<<grid, F64_GATES * 32, f64_smem_bytes(), st>>>(a, ctx->bkdev_f64, ctx->f64_stagger_ns);
+        if (ctx->f64_tmem) {
+            const unsigned grid = batches_overlap(ctx, st) ? fixed(F64T_GATES) : deal(F64T_GATES);
+            blind_rotate_f64t_kernel<<<grid, F64T_GATES * 32, f64t_smem_bytes(), st>>>(a, ctx->bkdev_f64);
+        } else {
+            const unsigned grid = batches_overlap(ctx, st) ? fixed(F64_GATES) : deal(F64_GATES);
+            blind_rotate_f64_kernel<<<grid, F64_GATES * 32, f64_smem_bytes(), st>>>(a, ctx->bkdev_f64, ctx->f64_stagger_ns);
+        }
     } else if (full && a.ns == 2 && variant != 8) {   // default: the two-warps-per-gate throughput kernel (blind_rotate_t2.cuh)
         const int G = ctx->t2_gates;
         const unsigned grid = batches_overlap(ctx, st) ? fixed(G) : deal(G);

@@ -463,6 +463,32 @@ def test_fft64_mode_exact(oracle, keys, rng):
         eng.close()
 
 
+def test_fft64_tensor_memory_variant_same_bits(keys, rng, monkeypatch):
+    """The opt-in K5FT variant (TFHE_B200_F64_TMEM=1: output spectra, digit planes and the rounded mask of a gate live in tensor
+    memory, twelve gates per SM) returns the same ciphertext bits as the default kernel, on a batch with uneven dealing."""
+    import rustfhe_b200 as R
+    outs = []
+    x = y = c0 = c1 = None
+    for flag in ("0", "1"):
+        monkeypatch.setenv("TFHE_B200_F64_TMEM", flag)
+        eng = R.DeviceEngine(0)
+        try:
+            eng.set_key_slices(1)
+            eng.load_ksk(keys.ksk)
+            eng.load_bk(keys.bk)
+            if x is None:
+                B = 12 * eng.stats()["sm_count"] + 5
+                x = rng.integers(0, 2, B).astype(np.uint8)
+                y = rng.integers(0, 2, B).astype(np.uint8)
+                c0, c1 = keys.encrypt(x, 91000), keys.encrypt(y, 92000)
+            outs.append(eng.gate_batch(R.NAND, c0, c1))
+            assert eng.stats()["gates_per_cta"] == (12 if flag == "1" else 8)
+        finally:
+            eng.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(keys.decrypt(outs[1]), 1 - (x & y))
+
+
 def test_gpu_against_committed_golden_vectors(engine, keys):
     """tests/golden/gate_vectors.npz was produced in the authoring container with the reference's own FFT library
     (tests/golden/make_golden.py); this compares the GPU output with the COMMITTED vectors directly, so the check does not
