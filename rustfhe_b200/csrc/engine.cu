@@ -243,7 +243,14 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     }
     if (const char* v = getenv("TFHE_B200_SLAB_TMA")) ctx->slab_tma = atoi(v);
     if (const char* v = getenv("TFHE_B200_PAIR_MAX")) ctx->pair_max = std::min(atoi(v), ctx->sm_count / 2);
-    if (const char* v = getenv("TFHE_B200_KEY_SLICES")) { const int k = atoi(v); if (k >= 1 && k <= 3) ctx->key_slices = k; }
+    if (const char* v = getenv("TFHE_B200_KEY_SLICES")) {   // A/B and test runs: say so, the arithmetic mode is not a silent setting
+        const int k = atoi(v);
+        if (k >= 1 && k <= 3 && k != ctx->key_slices) {
+            ctx->key_slices = k;
+            fprintf(stderr, "rustfhe_b200: TFHE_B200_KEY_SLICES=%d selects arithmetic mode %d (%s) for this context\n", k, k,
+                    k == 1 ? "FFT64" : k == 2 ? "NTT, two key slices" : "NTT, three key slices");
+        }
+    }
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64)", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L_SMEM_BYTES)) != cudaSuccess)
