@@ -19,6 +19,7 @@
 #include "blind_rotate_t2.cuh"
 #include "blind_rotate_f64.cuh"
 #include "blind_rotate_f64t.cuh"
+#include "blind_rotate_f64l2.cuh"
 #include "keyswitch.cuh"
 #include "aux_kernels.cuh"
 
@@ -76,8 +77,8 @@ struct tfhe_b200_ctx {
     int ns_int() const { return key_slices == 3 ? 3 : 2; }   // slices of the integer (NTT) form of the key
     int f64_tmem = 0;           // FFT64 throughput kernel: 0 = K5F, eight gates per SM (default); 1 = per-gate state in tensor memory, twelve gates
                                 // per SM (K5FT, TFHE_B200_F64_TMEM=1): measured 10 % slower -- the kernel is bound by issue slots, not by latency
-    int f64_latency = 1;        // FFT64 mode: batches of at most #SMs gates run one gate per CTA on six warps (TFHE_B200_F64_LATENCY=0: the NTT
-                                // latency shapes)
+    int f64_latency = 1;        // FFT64 mode: batches of at most #SMs gates run one gate per SM, two warps per transform (K5FL2);
+                                // TFHE_B200_F64_LATENCY=3: one warp per transform (K5FL), =0: the NTT latency shapes
     int f64_stagger_ns = 0;   // start-up offset between the warps of a CTA of the FFT64 kernel (TFHE_B200_F64_STAGGER)
     int t2_gates = 6;    // gates per CTA of the throughput kernel (TFHE_B200_T2_G: 4 or 6)
     int t2_twreg = 1;    // which row twiddles the throughput kernel keeps in registers (TFHE_B200_T2_TWREG: bit 0 forward, bit 1 inverse)
@@ -256,6 +257,8 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (f64 latency)", e);
     if (const char* v = getenv("TFHE_B200_F64_LATENCY")) ctx->f64_latency = atoi(v);
+    if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L2_SMEM_BYTES)) != cudaSuccess)
+        return bail("smem attr (f64 latency 2)", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_f64t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64t_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64 tmem)", e);
     if (const char* v = getenv("TFHE_B200_F64_TMEM")) ctx->f64_tmem = atoi(v);
@@ -512,12 +515,14 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         const unsigned grid = batches_overlap(ctx, st) ? fixed(4) : deal(4);
         if (a.ns == 2) blind_rotate_kernel<4, false, 1, 2><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
         else blind_rotate_kernel<4, false, 1, 3><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
-    } else if (!full && ctx->key_slices == 1 && ctx->f64_latency && variant != 9 && (a.B > (long)ctx->pair_max || ctx->f64_latency > 1)) {
-        // FFT64 latency shape, one gate per SM on six warps: 3.2 ms per gate whatever the batch, so it takes the batches the 2-SM
-        // clusters (2.7 ms, at most #SMs/2 gates) cannot: 148 gates 3.24 ms against 3.57 ms (TFHE_B200_F64_LATENCY=2 forces it)
+    } else if (!full && ctx->key_slices == 1 && ctx->f64_latency && variant != 9) {
+        // FFT64 latency shape, one gate per SM on twelve warps (two per transform): 2.58 ms per gate from 1 to #SMs gates, against
+        // 2.66-2.73 ms for the NTT cluster kernel (two SMs per gate, at most #SMs/2 gates) and 3.57 ms for the one-CTA NTT kernel at
+        // 148 gates.  TFHE_B200_F64_LATENCY=3: one warp per transform (K5FL, 3.2 ms); =0: the NTT latency shapes.
         a.cta_base = 1; a.cta_rem = 0;
         ctx->gates_per_cta = 1;
-        blind_rotate_f64_latency_kernel<<<(unsigned)a.B, F64L_THREADS, F64L_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
+        if (ctx->f64_latency == 3) blind_rotate_f64_latency_kernel<<<(unsigned)a.B, F64L_THREADS, F64L_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
+        else blind_rotate_f64_latency2_kernel<<<(unsigned)a.B, F64L2_THREADS, F64L2_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
     } else if (a.B <= (long)ctx->pair_max && variant != 9) {   // latency shape: one gate on a cluster of two SMs, as long as
                                                                 // the clusters fit in one wave (74 gates: 3.66 ms against 3.92 ms
                                                                 // with one CTA per gate; TFHE_B200_PAIR_MAX moves the limit)
