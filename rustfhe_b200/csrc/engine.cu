@@ -481,14 +481,24 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         ctx->gates_per_cta = G;
         return (unsigned)nctas;
     };
-    if (full && (variant == 3 || a.B <= 2L * ctx->sm_count) && a.ns == 3) {
+    // FFT64 mode: up to two gates per SM run as waves of the one-gate-per-SM latency kernel (2.6 ms a wave: 296 gates 5.25 ms against
+    // 6.4 ms for K5T; three waves take 7.9 ms, K5F with three gates per SM 7.7 ms)
+    const bool f64_waves = ctx->key_slices == 1 && ctx->f64_latency && variant != 9 && variant != 8 && a.B <= 2L * ctx->sm_count;
+    if (f64_waves) {
+        // FFT64 latency shape, one gate per SM on twelve warps (two per transform): 2.58 ms per gate from 1 to #SMs gates, against
+        // 2.66-2.73 ms for the NTT cluster kernel (two SMs per gate, at most #SMs/2 gates) and 3.57 ms for the one-CTA NTT kernel at
+        // 148 gates.  TFHE_B200_F64_LATENCY=3: one warp per transform (K5FL, 3.2 ms); =0: the NTT latency shapes.
+        a.cta_base = 1; a.cta_rem = 0;
+        ctx->gates_per_cta = 1;
+        if (ctx->f64_latency == 3) blind_rotate_f64_latency_kernel<<<(unsigned)a.B, F64L_THREADS, F64L_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
+        else blind_rotate_f64_latency2_kernel<<<(unsigned)a.B, F64L2_THREADS, F64L2_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
+    } else if (full && (variant == 3 || a.B <= 2L * ctx->sm_count) && a.ns == 3) {
         // 1-gate CTAs, up to three per SM (96 registers): the earlier default (TFHE_B200_BR_VARIANT=3 for A/B runs) and still the
         // best shape between one and two gates per SM (296 gates: 5.7 ms against 6.3 ms for 2-gate CTAs of the 80-register
         // kernel and 5.8 ms for 1-gate CTAs compiled for 168 registers)
         blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
     } else if (full && ctx->key_slices == 1 && variant != 8 && a.B > 2L * ctx->sm_count) {
-        // FFT64 mode: one warp per gate, eight gates per CTA (blind_rotate_f64.cuh).  Up to two gates per SM the two-warps-per-gate
-        // NTT kernel below is faster (296 gates: 6.4 ms against 7.8 ms), from three gates per SM on this one is
+        // FFT64 mode: one warp per gate, eight gates per CTA (blind_rotate_f64.cuh), from three gates per SM on
         if (ctx->f64_tmem) {
             const unsigned grid = batches_overlap(ctx, st) ? fixed(F64T_GATES) : deal(F64T_GATES);
             blind_rotate_f64t_kernel<<<grid, F64T_GATES * 32, f64t_smem_bytes(), st>>>(a, ctx->bkdev_f64);
@@ -515,14 +525,6 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         const unsigned grid = batches_overlap(ctx, st) ? fixed(4) : deal(4);
         if (a.ns == 2) blind_rotate_kernel<4, false, 1, 2><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
         else blind_rotate_kernel<4, false, 1, 3><<<grid, 4 * THREADS_PER_GATE, br_smem_bytes(4), st>>>(a);
-    } else if (!full && ctx->key_slices == 1 && ctx->f64_latency && variant != 9) {
-        // FFT64 latency shape, one gate per SM on twelve warps (two per transform): 2.58 ms per gate from 1 to #SMs gates, against
-        // 2.66-2.73 ms for the NTT cluster kernel (two SMs per gate, at most #SMs/2 gates) and 3.57 ms for the one-CTA NTT kernel at
-        // 148 gates.  TFHE_B200_F64_LATENCY=3: one warp per transform (K5FL, 3.2 ms); =0: the NTT latency shapes.
-        a.cta_base = 1; a.cta_rem = 0;
-        ctx->gates_per_cta = 1;
-        if (ctx->f64_latency == 3) blind_rotate_f64_latency_kernel<<<(unsigned)a.B, F64L_THREADS, F64L_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
-        else blind_rotate_f64_latency2_kernel<<<(unsigned)a.B, F64L2_THREADS, F64L2_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
     } else if (a.B <= (long)ctx->pair_max && variant != 9) {   // latency shape: one gate on a cluster of two SMs, as long as
                                                                 // the clusters fit in one wave (74 gates: 3.66 ms against 3.92 ms
                                                                 // with one CTA per gate; TFHE_B200_PAIR_MAX moves the limit)
