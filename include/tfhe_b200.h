@@ -89,8 +89,8 @@ int tfhe_b200_set_decomp_mask(tfhe_b200_ctx* ctx, uint32_t mask);
  *   1 (default) FFT64: one f64 complex transform of the folded polynomial, 6 + 2 transforms per CMUX, every product rounded to
  *     the EXACT integer (the reference computes the same products with an f64 FFT, fft_processor_spqlios.cpp:58-183).  Measured
  *     rounding margin on uniform keys: |value - nearest integer| < 2^-8 against the 1/2 that would flip a bit (DESIGN.md
- *     section 2; tests/test_host_logic.py asserts it).  Used for batches above #SMs gates; smaller batches and the step-level
- *     entry points (external product, cmux) run mode 2.
+ *     section 2; tests/test_host_logic.py asserts it).  Used by every gate batch, whatever its size; the step-level entry
+ *     points (external product, cmux) run mode 2.
  *   2 NTT over a 29-bit prime, two 16-bit key slices, 6 + 4 transforms per CMUX; exact unless a slice sum exceeds 9.8 standard
  *     deviations (about 1e-22 per coefficient, 3e-16 per gate over the key's masks).
  *   3 NTT, three 11-bit key slices, 6 + 6 transforms: exact in the worst case (any key, any digits).

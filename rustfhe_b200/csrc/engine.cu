@@ -71,7 +71,7 @@ struct tfhe_b200_ctx {
     int gates_per_cta = 1;
     int variant = 7;  // blind-rotate launch shape, see launch_blind_rotate
     int key_slices = 1;  // arithmetic mode (tfhe_b200_set_key_slices): 1 (default) = FFT64, one f64 complex transform with exact rounding
-                         // for batches above #SMs gates (latency shapes and step-level entry points run the two-slice NTT); 2 = NTT, two
+                         // for every gate batch (the step-level entry points run the two-slice NTT); 2 = NTT, two
                          // 16-bit key slices; both exact for honestly generated keys (DESIGN.md section 2 has the margins);
                          // 3 = NTT, three 11-bit slices, exact in the worst case
     int ns_int() const { return key_slices == 3 ? 3 : 2; }   // slices of the integer (NTT) form of the key
