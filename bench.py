@@ -256,8 +256,14 @@ def run_extras(eng, R, K, torch, dev, stream, dx, dy, s0, rank, world, dist):
         res = torch.empty_like(trl)
         trg1 = u32(1, 6, 2, 1024)
         t = timed(lambda: eng.external_product_batch_device(trg1.data_ptr(), 1, trl.data_ptr(), res.data_ptr(), B3, stream.cuda_stream))
-        out["config3_external_product_shared_trgsw"] = {"batch": B3, "products_per_s": B3 / t, "int_roofline_frac": B3 / t * slots_xp / p_int,
-                                                        "note": "the one TRGSW is transformed inside the call (36 of 786 k transforms)"}
+        if eng.stats()["key_slices"] == 1:   # FFT64: the persistent external_product_f64_kernel, bound by issue slots like the gate kernel
+            issue_xp = fft64_figures()["issue_cycles_per_gate"] / 635.0
+            out["config3_external_product_shared_trgsw"] = {"batch": B3, "products_per_s": B3 / t, "issue_roofline_frac": B3 / t * issue_xp / (148 * 4 * 1.965e9),
+                                                            "hbm_gbs": B3 / t * 2 * 8192 / 1e9,
+                                                            "note": "FFT64 arithmetic, one product per warp, the TRGSW transformed inside the call and kept on the key ring"}
+        else:
+            out["config3_external_product_shared_trgsw"] = {"batch": B3, "products_per_s": B3 / t, "int_roofline_frac": B3 / t * slots_xp / p_int,
+                                                            "note": "the one TRGSW is transformed inside the call (36 of 786 k transforms)"}
         Bp = 4096
         trgB = u32(Bp, 6, 2, 1024)
         t = timed(lambda: eng.external_product_batch_device(trgB.data_ptr(), Bp, trl.data_ptr(), res.data_ptr(), Bp, stream.cuda_stream))

@@ -69,6 +69,8 @@ __device__ __forceinline__ void f64_forward(int lane, cd (&x)[16], cd16* S, cons
 }
 
 // inverse transform of one output spectrum (destroyed), rounded to the exact integers and added to the accumulator polynomial
+// REPLACE: the result overwrites the accumulator polynomial (plain external product) instead of being added to it
+template <bool REPLACE = false>
 __device__ __forceinline__ void f64_inverse_acc(int lane, cd (&sp)[16], cd16* S, const cd16* ta, const cd16* ut, uint32_t* ao) {
     cd v[16];
     {
@@ -88,7 +90,10 @@ __device__ __forceinline__ void f64_inverse_acc(int lane, cd (&sp)[16], cd16* S,
     uint32_t lo[16], hi[16];
     f64_untwist_round(lane, v, ut, lo, hi);
 #pragma unroll
-    for (int r = 0; r < 16; r++) { ao[32 * r + lane] += lo[r]; ao[512 + 32 * r + lane] += hi[r]; }
+    for (int r = 0; r < 16; r++) {
+        if (REPLACE) { ao[32 * r + lane] = lo[r]; ao[512 + 32 * r + lane] = hi[r]; }
+        else { ao[32 * r + lane] += lo[r]; ao[512 + 32 * r + lane] += hi[r]; }
+    }
 }
 
 struct F64Ring {
@@ -99,6 +104,7 @@ struct F64Ring {
     const cd16* key;   // chunk 0 of this gate batch's first step
     long total;        // chunks the CTA consumes
     int active;        // warps of the CTA that own a gate
+    long period;       // 0: chunk n of the stream is chunk n of the key; > 0: chunk n is chunk n % period (one TRGSW used over and over)
 };
 // consumer side: wait for chunk n, run `use(slot)`, hand the slot back.  The LAST warp to leave a slot refills it with chunk
 // n + F64_RING: no warp is the producer, so the warps of a CTA may drift up to a ring apart (they are started staggered so that
@@ -116,7 +122,8 @@ __device__ __forceinline__ void f64_with_chunk(const F64Ring& rg, long n, int la
             rg.left[s] = 0;
             if (n + F64_RING < rg.total) {
                 mbar_wait(rg.empty + s, par);   // every warp's reads of the slot are ordered before the copy that overwrites it
-                bulk_fetch(rg.slot + (size_t)s * F64_SLOT_ELEMS, rg.key + (size_t)(n + F64_RING) * F64_SLOT_ELEMS, F64_CHUNK_BYTES, rg.full + s);
+                const long c = rg.period ? (n + F64_RING) % rg.period : n + F64_RING;
+                bulk_fetch(rg.slot + (size_t)s * F64_SLOT_ELEMS, rg.key + (size_t)c * F64_SLOT_ELEMS, F64_CHUNK_BYTES, rg.full + s);
             }
         }
     }
@@ -150,6 +157,7 @@ __global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_
     rg.key = key;
     rg.total = (long)nsteps * 6;
     rg.active = cnt;
+    rg.period = 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < F64_RING; s++) { mbar_init(rg.full + s, 1); mbar_init(rg.empty + s, cnt); rg.left[s] = 0; }
@@ -289,6 +297,104 @@ __global__ void __launch_bounds__(KTF_WARPS * 32) bk_transform_f64_kernel(const 
     for (int k = 0; k < 16; k++) {
         cd16 v; v.re = __dmul_rn(y[k].re, F64_KEY_SCALE); v.im = __dmul_rn(y[k].im, F64_KEY_SCALE);
         dst[k * 32 + lane] = v;
+    }
+}
+
+// =====================================================================================================
+// K5FX: plain external products / cmux with ONE shared TRGSW in the FFT64 arithmetic (trgsw.rs:264-322; BASELINE config 3):
+//   out[g] = TRGSW (x) (in[g] - in0[g]) + in0[g]        (in0 = null: out[g] = TRGSW (x) in[g])
+// Persistent CTAs of eight warps, one product per warp and round; the six 16 KB key chunks of the TRGSW go round the same ring
+// as in K5F (chunk n of the stream = chunk n % 6 of the key), so the key crosses L2 -> SM once per eight products.
+// =====================================================================================================
+__global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel(const BrArgs a, const cd16* __restrict__ key) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd16* tab = reinterpret_cast<cd16*>(smem_raw);
+    const cd16* tb = tab;
+    const cd16* ta = tab + F64_FWDB_ROWS * 32;
+    F64Ring rg;
+    const cd16* ut = tab + F64_TAB_ELEMS;
+    rg.slot = tab + F64_TAB_ELEMS + F64_UNTW_ROWS * 32;
+    rg.full = reinterpret_cast<uint64_t*>(rg.slot + (size_t)F64_RING * F64_SLOT_ELEMS);
+    rg.empty = rg.full + F64_RING;
+    rg.left = reinterpret_cast<uint32_t*>(rg.empty + F64_RING);
+    const int gl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* gbase = smem_raw + F64_SHARED_BYTES + (size_t)gl * F64_GATE_SMEM_BYTES;
+    uint32_t* acc = reinterpret_cast<uint32_t*>(gbase);
+    cd16* S = reinterpret_cast<cd16*>(gbase + 2 * 1024 * 4);
+    uint4* D = reinterpret_cast<uint4*>(gbase + 2 * 1024 * 4 + 512 * 16);
+    const long ngroups = (a.B + F64_GATES - 1) / F64_GATES;
+    const long mine = blockIdx.x < ngroups ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // rounds of this CTA
+    rg.key = key;
+    rg.total = mine * 6;
+    rg.active = F64_GATES;   // every warp takes part in every round (a warp without a product repeats the last one and does not store)
+    rg.period = 6;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F64_RING; s++) { mbar_init(rg.full + s, 1); mbar_init(rg.empty + s, F64_GATES); rg.left[s] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        double* t = reinterpret_cast<double*>(tab);
+        for (int k = threadIdx.x; k < F64_FWDB_ROWS * 64; k += blockDim.x) t[k] = g_f64_fwdB[k];
+        for (int k = threadIdx.x; k < F64_INVA_ROWS * 64; k += blockDim.x) t[F64_FWDB_ROWS * 64 + k] = g_f64_invA[k];
+        for (int k = threadIdx.x; k < F64_UNTW_ROWS * 64; k += blockDim.x) t[(F64_FWDB_ROWS + F64_INVA_ROWS) * 64 + k] = g_f64_untw[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (long n = 0; n < F64_RING && n < rg.total; n++)
+            bulk_fetch(rg.slot + (size_t)n * F64_SLOT_ELEMS, rg.key + (size_t)(n % 6) * F64_SLOT_ELEMS, F64_CHUNK_BYTES, rg.full + n);
+    long n = 0;
+#pragma unroll 1
+    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long want = grp * F64_GATES + gl;
+        const long g = want < a.B ? want : a.B - 1;
+        {
+            const uint32_t* src = a.trlwe_in + (size_t)g * 2048;
+            const uint32_t* sub = a.trlwe_in0 ? a.trlwe_in0 + (size_t)g * 2048 : nullptr;   // cmux: rep_1 - rep_0
+            for (int k = lane; k < 2048; k += 32) acc[k] = sub ? src[k] - sub[k] : src[k];
+        }
+        __syncwarp();
+        cd s0[16], s1[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) { s0[k].re = 0.0; s0[k].im = 0.0; s1[k].re = 0.0; s1[k].im = 0.0; }
+#pragma unroll 1
+        for (int pw = 0; pw < 2; pw++) {
+            {
+                uint32_t u[32];
+                t2_u<false>(lane, acc + pw * 1024, 0u, a.mask, u);
+                u4 re, im;
+                f64_pack_plane<0>(u, re, im);
+                D[0 * 32 + lane] = make_uint4(re.x, re.y, re.z, re.w); D[1 * 32 + lane] = make_uint4(im.x, im.y, im.z, im.w);
+                f64_pack_plane<1>(u, re, im);
+                D[2 * 32 + lane] = make_uint4(re.x, re.y, re.z, re.w); D[3 * 32 + lane] = make_uint4(im.x, im.y, im.z, im.w);
+                f64_pack_plane<2>(u, re, im);
+                D[4 * 32 + lane] = make_uint4(re.x, re.y, re.z, re.w); D[5 * 32 + lane] = make_uint4(im.x, im.y, im.z, im.w);
+            }
+#pragma unroll 1
+            for (int dw = 0; dw < 3; dw++) {
+                cd x[16], y[16];
+                {
+                    const uint4 a4 = D[(2 * dw) * 32 + lane], b4 = D[(2 * dw + 1) * 32 + lane];
+                    u4 re, im;
+                    re.x = a4.x; re.y = a4.y; re.z = a4.z; re.w = a4.w; im.x = b4.x; im.y = b4.y; im.z = b4.z; im.w = b4.w;
+                    f64_digits(re, im, x);
+                }
+                f64_forward(lane, x, S, tb, y);
+                f64_with_chunk(rg, n, lane, [&](const cd16* k) {
+                    f64_mac(lane, y, k, s0);
+                    f64_mac(lane, y, k + F64_CHUNK_ELEMS, s1);
+                });
+                n++;
+            }
+        }
+        f64_inverse_acc<true>(lane, s0, S, ta, ut, acc);
+        f64_inverse_acc<true>(lane, s1, S, ta, ut, acc + 1024);
+        __syncwarp();
+        if (want < a.B) {
+            uint32_t* dst = a.trlwe_out + (size_t)g * 2048;
+            const uint32_t* add = a.trlwe_in0 ? a.trlwe_in0 + (size_t)g * 2048 : nullptr;   // cmux: ... + rep_0
+            for (int k = lane; k < 2048; k += 32) dst[k] = add ? acc[k] + add[k] : acc[k];
+        }
+        __syncwarp();
     }
 }
 

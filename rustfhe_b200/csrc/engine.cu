@@ -254,6 +254,8 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     }
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64)", e);
+    if ((e = cudaFuncSetAttribute(external_product_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
+        return bail("smem attr (f64 external product)", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (f64 latency)", e);
     if (const char* v = getenv("TFHE_B200_F64_LATENCY")) ctx->f64_latency = atoi(v);
@@ -982,6 +984,16 @@ static int run_extprod(tfhe_b200_ctx* ctx, Slot* s, const uint32_t* trgsw_dev, s
     BrArgs a{};
     a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
     a.trlwe_in = rep1; a.trlwe_in0 = rep0; a.trlwe_out = out; a.ntrgsw = (long)ntrgsw; a.ns = ctx->ns_int();
+    if (ctx->key_slices == 1 && ntrgsw == 1 && B > (size_t)ctx->sm_count) {   // FFT64, one shared TRGSW: persistent CTAs, one product per warp
+        cd16* kx = reinterpret_cast<cd16*>(s->scratch);   // 96 KB of the slot scratch (BK_STEP_WORDS * 4 = 144 KB were reserved above)
+        bk_transform_f64_kernel<<<(12 + KTF_WARPS - 1) / KTF_WARPS, KTF_WARPS * 32, 0, st>>>(trgsw_dev, kx, 12);
+        const long ngroups = ((long)B + F64_GATES - 1) / F64_GATES;
+        const unsigned grid = (unsigned)std::min<long>(ngroups, (long)ctx->sm_count);
+        external_product_f64_kernel<<<grid, F64_GATES * 32, f64_smem_bytes(), st>>>(a, kx);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        return TFHE_B200_OK;
+    }
     if (a.ns == 2 && B > (size_t)ctx->sm_count) {   // two slices, throughput shape: the two-warps-per-product kernel, six products per CTA
         const int npolys = (int)ntrgsw * 12;
         bk_transform_t2_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(trgsw_dev, s->scratch, npolys);

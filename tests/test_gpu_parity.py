@@ -72,6 +72,27 @@ def test_external_product_exact(engine, oracle, rng, mask):
         engine.set_decomp_mask(0x02084000)
 
 
+def test_external_product_large_batch_shared_trgsw(engine, oracle, rng):
+    """config 3(ii) at throughput size: one shared TRGSW against a batch above #SMs products (in the default mode the persistent
+    FFT64 kernel external_product_f64_kernel: one product per warp, the TRGSW going round the key ring; ragged last round), plain
+    product and cmux form, bit-exact vs the integer oracle on a sample, and identical to the small-batch (NTT) path."""
+    B = 8 * 148 * 2 + 3
+    trlwe, rep0 = u32(rng, B, 2, N), u32(rng, B, 2, N)
+    trlwe[1] = 0x7DF7C000            # all digits -32
+    trgsw = u32(rng, 1, 6, 2, N)
+    out = engine.external_product_batch(trgsw, trlwe)
+    cm = engine.cmux_batch(trgsw, trlwe, rep0)
+    idx = np.concatenate([[0, 1, B - 1, B - 2], rng.choice(B, 6, replace=False)])
+    for g in idx:
+        ref = np.zeros(2 * N, np.uint32)
+        oracle.lib().orc_external_product_exact(trgsw[0].reshape(-1), trlwe[g].reshape(-1), 0x02084000, ref)
+        assert np.array_equal(out[g].reshape(-1), ref), g
+        oracle.lib().orc_external_product_exact(trgsw[0].reshape(-1), (trlwe[g] - rep0[g]).reshape(-1), 0x02084000, ref)
+        assert np.array_equal(cm[g].reshape(-1), ref + rep0[g].reshape(-1)), g
+    small = engine.external_product_batch(trgsw, trlwe[:40])
+    assert np.array_equal(small, out[:40])
+
+
 def test_external_product_vs_reference_fft(engine, oracle, rng):
     """P1: against the reference's own FFT (oracle/_ref): |diff| <= 2 ulp per coefficient (measured -1/0/+1)."""
     if not oracle.ref_init():
