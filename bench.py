@@ -250,7 +250,12 @@ def run_extras(eng, R, K, torch, dev, stream, dx, dy, s0, rank, world, dist):
         d = torch.randint(-32, 32, (B3, 1024), dtype=torch.int32, device=dev, generator=g)
         o = torch.empty_like(a)
         t = timed(lambda: eng.negacyclic_mul_batch_device(a.data_ptr(), d.data_ptr(), o.data_ptr(), B3, stream.cuda_stream))
-        out["config3_negacyclic_mul"] = {"batch": B3, "products_per_s": B3 / t, "int_roofline_frac": B3 / t * slots_pm / p_int}
+        if eng.stats()["key_slices"] == 1:   # FFT64: polymul_f64_kernel, two forward + one inverse transform per product, I/O straight from HBM
+            issue_pm = 2 * (2 * 432 + 482 + 16 * 6) + 700
+            out["config3_negacyclic_mul"] = {"batch": B3, "products_per_s": B3 / t, "issue_roofline_frac": B3 / t * issue_pm / (148 * 4 * 1.965e9),
+                                             "hbm_gbs": B3 / t * 3 * 4096 / 1e9, "note": "FFT64 arithmetic, one product per warp"}
+        else:
+            out["config3_negacyclic_mul"] = {"batch": B3, "products_per_s": B3 / t, "int_roofline_frac": B3 / t * slots_pm / p_int}
         del a, d, o
         trl = u32(B3, 2, 1024)
         res = torch.empty_like(trl)
@@ -266,6 +271,8 @@ def run_extras(eng, R, K, torch, dev, stream, dx, dy, s0, rank, world, dist):
                                                             "note": "the one TRGSW is transformed inside the call (36 of 786 k transforms)"}
         Bp = 4096
         trgB = u32(Bp, 6, 2, 1024)
+        for _ in range(4):   # every work slot of the ring grows its scratch (604 MB of transformed TRGSWs) on its first use
+            eng.external_product_batch_device(trgB.data_ptr(), Bp, trl.data_ptr(), res.data_ptr(), Bp, stream.cuda_stream)
         t = timed(lambda: eng.external_product_batch_device(trgB.data_ptr(), Bp, trl.data_ptr(), res.data_ptr(), Bp, stream.cuda_stream))
         out["config3_external_product_per_item_trgsw"] = {"batch": Bp, "products_per_s": Bp / t,
                                                           "note": "includes the key transforms of every item's TRGSW"}

@@ -399,6 +399,50 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel
 }
 
 // =====================================================================================================
+// K7F: exact negacyclic product a * d mod (X^N + 1, 2^32) in the FFT64 arithmetic (Polynomial::fft_cross, math.rs:337-347;
+// Spqlios_poly_mul, spqlios-wrapper.cpp:38-53; BASELINE config 3).  a = torus words taken as centred 32-bit integers, |d| <= 192:
+// a coefficient of the product is below 1024 * 2^31 * 192 < 2^49, as in the external product.  One product per warp (two forward
+// transforms, a pointwise product, one inverse), persistent CTAs of twelve warps; inputs are read and the result is written
+// straight from / to global memory (coalesced 128-byte rows), shared memory holds only the twiddle tables and the transpose scratch.
+// =====================================================================================================
+constexpr int PMF_WARPS = 12;
+constexpr int PMF_SMEM_BYTES = (F64_TAB_ELEMS + F64_UNTW_ROWS * 32) * 16 + PMF_WARPS * 512 * 16;
+__global__ void __launch_bounds__(PMF_WARPS * 32, 1) polymul_f64_kernel(const uint32_t* __restrict__ a, const int32_t* __restrict__ d,
+                                                                       uint32_t* __restrict__ out, long B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd16* tab = reinterpret_cast<cd16*>(smem_raw);
+    const cd16* tb = tab;
+    const cd16* ta = tab + F64_FWDB_ROWS * 32;
+    const cd16* ut = tab + F64_TAB_ELEMS;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    cd16* S = tab + F64_TAB_ELEMS + F64_UNTW_ROWS * 32 + (size_t)w * 512;
+    {
+        double* t = reinterpret_cast<double*>(tab);
+        for (int k = threadIdx.x; k < F64_FWDB_ROWS * 64; k += blockDim.x) t[k] = g_f64_fwdB[k];
+        for (int k = threadIdx.x; k < F64_INVA_ROWS * 64; k += blockDim.x) t[F64_FWDB_ROWS * 64 + k] = g_f64_invA[k];
+        for (int k = threadIdx.x; k < F64_UNTW_ROWS * 64; k += blockDim.x) t[(F64_FWDB_ROWS + F64_INVA_ROWS) * 64 + k] = g_f64_untw[k];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (long g = (long)blockIdx.x * PMF_WARPS + w; g < B; g += (long)gridDim.x * PMF_WARPS) {
+        cd x[16], ya[16], yd[16];
+        f64_key_input(lane, a + (size_t)g * 1024, x);
+        f64_forward(lane, x, S, tb, ya);
+        const int32_t* dp = d + (size_t)g * 1024;
+#pragma unroll
+        for (int r = 0; r < 16; r++) { x[r].re = (double)dp[32 * r + lane]; x[r].im = (double)dp[512 + 32 * r + lane]; }
+        f64_forward(lane, x, S, tb, yd);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {   // pointwise product, with the 1/512 of the inverse transform (exact power of two)
+            const double pr = F_FMA(ya[k].re, yd[k].re, -F_MUL(ya[k].im, yd[k].im));
+            const double pi = F_FMA(ya[k].re, yd[k].im, F_MUL(ya[k].im, yd[k].re));
+            ya[k].re = F_MUL(pr, 1.0 / 512); ya[k].im = F_MUL(pi, 1.0 / 512);
+        }
+        f64_inverse_acc<true>(lane, ya, S, ta, ut, out + (size_t)g * 1024);
+    }
+}
+
+// =====================================================================================================
 // K5FL: latency shape of the FFT64 mode -- ONE gate per CTA, six warps.  Warp w = 3 pw + dw transforms gadget digit dw of
 // accumulator polynomial pw (the six forward transforms of a CMUX run concurrently), multiplies its spectrum by its two key
 // polynomials (requested from L2 into 128 registers before the transform starts, so the load latency is under the transform)

@@ -254,6 +254,8 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     }
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64)", e);
+    if ((e = cudaFuncSetAttribute(polymul_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PMF_SMEM_BYTES)) != cudaSuccess)
+        return bail("smem attr (f64 polymul)", e);
     if ((e = cudaFuncSetAttribute(external_product_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64 external product)", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L_SMEM_BYTES)) != cudaSuccess)
@@ -1107,27 +1109,31 @@ int tfhe_b200_external_product_batch_device(tfhe_b200_ctx* ctx, const uint32_t* 
     RC(run_extprod(ctx, s, trgsw_dev, ntrgsw, trlwe_dev, nullptr, out_dev, B, st));
     return slot_release(ctx, s, st);
 }
+// exact negacyclic products: FFT64 mode and more than a wave of products -> polymul_f64_kernel, otherwise the NTT kernel
+static int launch_polymul(tfhe_b200_ctx* ctx, const uint32_t* a_dev, const int32_t* d_dev, uint32_t* out_dev, size_t B, cudaStream_t st) {
+    if (ctx->key_slices == 1 && B > (size_t)ctx->sm_count) {
+        const long nctas = std::min<long>(((long)B + PMF_WARPS - 1) / PMF_WARPS, (long)ctx->sm_count);
+        polymul_f64_kernel<<<(unsigned)nctas, PMF_WARPS * 32, PMF_SMEM_BYTES, st>>>(a_dev, d_dev, out_dev, (long)B);
+    } else {
+        polymul_kernel<<<(unsigned)((B + PM_WARPS - 1) / PM_WARPS), PM_WARPS * 32, 0, st>>>(a_dev, d_dev, out_dev, (long)B, 1024, 1024, 1024, 0);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TFHE_B200_OK;
+}
 int tfhe_b200_negacyclic_mul_batch_device(tfhe_b200_ctx* ctx, const uint32_t* a_dev, const int32_t* d_dev, uint32_t* out_dev, size_t B,
                                           void* stream) {
     if (!ctx || !a_dev || !d_dev || !out_dev) return fail(ctx, TFHE_B200_ERR_PARAM, "negacyclic_mul_batch_device: null argument");
     if (B == 0) return TFHE_B200_OK;
     CK(cudaSetDevice(ctx->device));
-    polymul_kernel<<<(unsigned)((B + PM_WARPS - 1) / PM_WARPS), PM_WARPS * 32, 0, (cudaStream_t)stream>>>(a_dev, d_dev, out_dev, (long)B, 1024, 1024,
-                                                                                                           1024, 0);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return TFHE_B200_OK;
+    return launch_polymul(ctx, a_dev, d_dev, out_dev, B, (cudaStream_t)stream);
 }
 int tfhe_b200_negacyclic_mul_batch(tfhe_b200_ctx* ctx, const uint32_t* a, const int32_t* d, uint32_t* out, size_t B) {
     if (!ctx || !a || !d || !out) return fail(ctx, TFHE_B200_ERR_PARAM, "negacyclic_mul_batch: null argument");
     if (B == 0) return TFHE_B200_OK;
     HostIo io; io.in[0] = a; io.in_bytes[0] = B * 4096; io.in[1] = d; io.in_bytes[1] = B * 4096; io.out = out; io.out_bytes = B * 4096;
     return with_host_io(ctx, io, [&](Slot*, cudaStream_t st, uint32_t* const* di, uint32_t* dout) {
-        polymul_kernel<<<(unsigned)((B + PM_WARPS - 1) / PM_WARPS), PM_WARPS * 32, 0, st>>>(di[0], (const int32_t*)di[1], dout, (long)B, 1024, 1024,
-                                                                                             1024, 0);
-        ctx->launches++;
-        CK(cudaGetLastError());
-        return TFHE_B200_OK;
+        return launch_polymul(ctx, di[0], (const int32_t*)di[1], dout, B, st);
     });
 }
 

@@ -41,6 +41,24 @@ def test_negacyclic_mul_exact(engine, oracle, rng):
         assert np.array_equal(out[g], ref), g
 
 
+def test_negacyclic_mul_large_batch(engine, oracle, rng):
+    """config 3(i) at throughput size (above #SMs products: in the default mode the persistent FFT64 kernel polymul_f64_kernel),
+    with the extreme vectors of the small test in it, bit-exact vs schoolbook on a sample and identical to the small-batch path."""
+    B = 12 * 148 + 7
+    a = u32(rng, B, N)
+    d = rng.integers(-32, 32, size=(B, N)).astype(np.int32)
+    a[2], d[2] = 0xFFFFFFFF, 31
+    a[3], d[3] = 0x80000000, -32
+    a[5], d[5] = 0x7FFFFFFF, 192                     # the documented bound of the entry, all coefficients extreme
+    d[4] = rng.integers(-192, 193, size=N)
+    out = engine.negacyclic_mul_batch(a, d)
+    for g in np.concatenate([[0, 2, 3, 4, 5, B - 1], rng.choice(B, 4, replace=False)]):
+        ref = np.zeros(N, np.uint32)
+        oracle.lib().orc_negacyclic_mul_schoolbook(a[g], d[g], N, ref)
+        assert np.array_equal(out[g], ref), g
+    assert np.array_equal(engine.negacyclic_mul_batch(a[:33], d[:33]), out[:33])
+
+
 def test_negacyclic_mul_kat_via_device(engine):
     """reference KAT math.rs:761-843: [2,3,4]*[4,5,6] = [-30,-2,43] mod X^3+1 embeds in N=1024 only as a linear product;
     use the N-independent identities X^k * a instead: a * X^1023 * X = -a."""
