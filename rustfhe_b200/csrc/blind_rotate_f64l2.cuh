@@ -40,41 +40,6 @@ constexpr int F64L2_SMEM_BYTES = F64L2_TAB_ELEMS * 16 + 2 * 1024 * 4 /*acc*/ + F
                                  F64L2_KEY_BYTES + 2 * 1024 * 4 /*masked source words*/ + 640 * 2 /*abar*/ + 16 /*mbarrier*/;
 static_assert(F64L2_SMEM_BYTES <= 227 * 1024, "one gate must fit the shared memory of one SM");
 
-// three butterfly stages on 8 registers with warp-uniform twiddles: pass 1 of the forward transform (nodes (s, e >> (3 - s)))
-template <int S, int I>
-__device__ __forceinline__ void l2_f1_bfly(cd (&x)[8]) {
-    constexpr int h = 4 >> S, beta = I / h, t = I % h, ia = 2 * h * beta + t, k = (1 << S) - 1 + beta;
-    bf_w(x[ia], x[ia + h], fwdA_c<2 * k>(), fwdA_c<2 * k + 1>());
-}
-__device__ __forceinline__ void l2_fwd_pass1(cd (&x)[8]) {
-    l2_f1_bfly<0, 0>(x); l2_f1_bfly<0, 1>(x); l2_f1_bfly<0, 2>(x); l2_f1_bfly<0, 3>(x);
-    l2_f1_bfly<1, 0>(x); l2_f1_bfly<1, 1>(x); l2_f1_bfly<1, 2>(x); l2_f1_bfly<1, 3>(x);
-    l2_f1_bfly<2, 0>(x); l2_f1_bfly<2, 1>(x); l2_f1_bfly<2, 2>(x); l2_f1_bfly<2, 3>(x);
-}
-// three stages with per-thread twiddles w[0] (first stage), w[1] (second; odd node: times i), w[2], w[3] (third; odd nodes: times i)
-__device__ __forceinline__ void l2_fwd_pass23(cd (&x)[8], const cd16 (&w)[4]) {
-#pragma unroll
-    for (int m = 0; m < 4; m++) bf_w(x[m], x[m + 4], w[0].re, w[0].im);
-    bf_w(x[0], x[2], w[1].re, w[1].im); bf_w(x[1], x[3], w[1].re, w[1].im);
-    bf_iw(x[4], x[6], w[1].re, w[1].im); bf_iw(x[5], x[7], w[1].re, w[1].im);
-    bf_w(x[0], x[1], w[2].re, w[2].im); bf_iw(x[2], x[3], w[2].re, w[2].im);
-    bf_w(x[4], x[5], w[3].re, w[3].im); bf_iw(x[6], x[7], w[3].re, w[3].im);
-}
-// inverse pass 1': stages 0..2 on p[2:0], constants
-__device__ __forceinline__ void l2_inv_pass1(cd (&y)[8]) {
-    bf_1(y[0], y[1]); bf_1(y[2], y[3]); bf_1(y[4], y[5]); bf_1(y[6], y[7]);
-    bf_1(y[0], y[2]); bf_mi(y[1], y[3]); bf_1(y[4], y[6]); bf_mi(y[5], y[7]);
-    bf_1(y[0], y[4]); f64_inv_c<1>(y[1], y[5]); bf_mi(y[2], y[6]); f64_inv_c<3>(y[3], y[7]);
-}
-// inverse passes 2', 3': twiddles v[0] (first stage), v[1] (second; odd: times -i), v[2], v[3] (third: m = 0, 1; m = 2, 3: times -i)
-__device__ __forceinline__ void l2_inv_pass23(cd (&y)[8], const cd16 (&v)[4]) {
-#pragma unroll
-    for (int c = 0; c < 4; c++) bf_w(y[2 * c], y[2 * c + 1], v[0].re, v[0].im);
-    bf_w(y[0], y[2], v[1].re, v[1].im); bf_miw(y[1], y[3], v[1].re, v[1].im);
-    bf_w(y[4], y[6], v[1].re, v[1].im); bf_miw(y[5], y[7], v[1].re, v[1].im);
-    bf_w(y[0], y[4], v[2].re, v[2].im); bf_w(y[1], y[5], v[3].re, v[3].im);
-    bf_miw(y[2], y[6], v[2].re, v[2].im); bf_miw(y[3], y[7], v[3].re, v[3].im);
-}
 __device__ __forceinline__ void l2_store(cd16* p, const cd& v) { cd16 t; t.re = v.re; t.im = v.im; *p = t; }
 __device__ __forceinline__ void l2_load(const cd16* p, cd& v) { const cd16 t = *p; v.re = t.re; v.im = t.im; }
 

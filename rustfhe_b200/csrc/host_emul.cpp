@@ -229,6 +229,102 @@ double emul_external_product_f64(const double* dev, const uint32_t* trlwe, uint3
     return f64_step(dev, out, false, 0, mask);
 }
 double emul_cmux_rotate_f64(const double* dev, uint32_t* acc, uint32_t abar, uint32_t mask) { return f64_step(dev, acc, true, abar, mask); }
+// ---- FFT64 latency kernel (blind_rotate_f64l2.cuh): one transform on two warps (64 threads x 8 values), three radix-8 passes.
+// Plain external product with the key in the one-warp layout (emul_key_transform_f64): the same transposes, swizzle and tables
+// as the kernel, thread by thread.
+static void l2_forward64(cd (*x)[8], cd16* A, cd16* Bb) {   // x[t][e] = z_{t + 64 e}  ->  x[t][e] = spectrum position 8 t + e
+    const cd16* tf2 = reinterpret_cast<const cd16*>(h_l2_fwd2);
+    const cd16* tf3 = reinterpret_cast<const cd16*>(h_l2_fwd3);
+    for (int t = 0; t < 64; t++) {
+        l2_fwd_pass1(x[t]);
+        for (int e = 0; e < 8; e++) { A[t + 64 * e].re = x[t][e].re; A[t + 64 * e].im = x[t][e].im; }
+    }
+    for (int t = 0; t < 64; t++) {
+        const int hi3 = t >> 3, lo3 = t & 7;
+        cd16 w[4];
+        for (int k = 0; k < 4; k++) w[k] = tf2[k * 8 + hi3];
+        for (int m = 0; m < 8; m++) { x[t][m].re = A[64 * hi3 + 8 * m + lo3].re; x[t][m].im = A[64 * hi3 + 8 * m + lo3].im; }
+        l2_fwd_pass23(x[t], w);
+        for (int m = 0; m < 8; m++) { Bb[64 * hi3 + 8 * m + (lo3 ^ m)].re = x[t][m].re; Bb[64 * hi3 + 8 * m + (lo3 ^ m)].im = x[t][m].im; }
+    }
+    for (int t = 0; t < 64; t++) {
+        const int lo3 = t & 7;
+        cd16 w[4];
+        for (int k = 0; k < 4; k++) w[k] = tf3[k * 64 + t];
+        for (int e = 0; e < 8; e++) { x[t][e].re = Bb[8 * t + (e ^ lo3)].re; x[t][e].im = Bb[8 * t + (e ^ lo3)].im; }
+        l2_fwd_pass23(x[t], w);
+    }
+}
+static void l2_inverse64(cd (*y)[8], cd16* A, cd16* Bb, uint32_t* out /*[1024]*/) {   // y[t][e] = spectrum position 8 t + e
+    const cd16* ti2 = reinterpret_cast<const cd16*>(h_l2_inv2);
+    const cd16* ti3 = reinterpret_cast<const cd16*>(h_l2_inv3);
+    const cd16* tut = reinterpret_cast<const cd16*>(h_l2_untw);
+    for (int t = 0; t < 64; t++) {
+        const int lo3 = t & 7;
+        l2_inv_pass1(y[t]);
+        for (int e = 0; e < 8; e++) { Bb[8 * t + (e ^ lo3)].re = y[t][e].re; Bb[8 * t + (e ^ lo3)].im = y[t][e].im; }
+    }
+    for (int t = 0; t < 64; t++) {
+        const int hi3 = t >> 3, lo3 = t & 7;
+        cd16 v[4];
+        for (int k = 0; k < 4; k++) v[k] = ti2[k * 8 + lo3];
+        for (int m = 0; m < 8; m++) { y[t][m].re = Bb[64 * hi3 + 8 * m + (lo3 ^ m)].re; y[t][m].im = Bb[64 * hi3 + 8 * m + (lo3 ^ m)].im; }
+        l2_inv_pass23(y[t], v);
+        for (int m = 0; m < 8; m++) { A[64 * hi3 + 8 * m + lo3].re = y[t][m].re; A[64 * hi3 + 8 * m + lo3].im = y[t][m].im; }
+    }
+    for (int t = 0; t < 64; t++) {
+        cd16 v[4];
+        for (int k = 0; k < 4; k++) v[k] = ti3[k * 64 + t];
+        for (int e = 0; e < 8; e++) { y[t][e].re = A[t + 64 * e].re; y[t][e].im = A[t + 64 * e].im; }
+        l2_inv_pass23(y[t], v);
+        for (int e = 0; e < 8; e++) {
+            const cd16 u = tut[e * 64 + t];
+            const double zr = F_FMA(y[t][e].re, u.re, -F_MUL(y[t][e].im, u.im));
+            const double zi = F_FMA(y[t][e].re, u.im, F_MUL(y[t][e].im, u.re));
+            out[t + 64 * e] = f64_low_word(F_ADD(zr, F64_ROUND_MAGIC));
+            out[512 + t + 64 * e] = f64_low_word(F_ADD(zi, F64_ROUND_MAGIC));
+        }
+    }
+}
+void emul_external_product_f64l2(const double* dev, const uint32_t* trlwe, uint32_t mask, uint32_t* out) {
+    const cd16* key = reinterpret_cast<const cd16*>(dev);
+    std::vector<cd16> A(512), Bb(512);
+    std::vector<cd16> prod(12 * 512);   // [row j][output o][register e][thread t]
+    for (int pair = 0; pair < 6; pair++) {
+        const int pw = pair / 3, dw = pair % 3, sh = 6 * dw;
+        cd x[64][8];
+        for (int t = 0; t < 64; t++)
+            for (int e = 0; e < 8; e++) {
+                const uint32_t ur = add_alu(trlwe[pw * 1024 + t + 64 * e], mask) ^ mask;
+                const uint32_t ui = add_alu(trlwe[pw * 1024 + 512 + t + 64 * e], mask) ^ mask;
+                x[t][e].re = (double)((((int32_t)(ur << sh)) >> 24) & ~3);
+                x[t][e].im = (double)((((int32_t)(ui << sh)) >> 24) & ~3);
+            }
+        l2_forward64(x, A.data(), Bb.data());
+        for (int t = 0; t < 64; t++)
+            for (int e = 0; e < 8; e++)
+                for (int o = 0; o < 2; o++) {
+                    const cd16 k = key[f64_key_off(0, pair, o) + (size_t)(8 * (t & 1) + e) * 32 + (t >> 1)];
+                    cd16 q;
+                    q.re = F_FMA(x[t][e].re, k.re, -F_MUL(x[t][e].im, k.im));
+                    q.im = F_FMA(x[t][e].re, k.im, F_MUL(x[t][e].im, k.re));
+                    prod[((size_t)(2 * pair + o) * 8 + e) * 64 + t] = q;
+                }
+    }
+    for (int o = 0; o < 2; o++) {
+        cd y[64][8];
+        for (int t = 0; t < 64; t++)
+            for (int e = 0; e < 8; e++) {
+                cd16 v = prod[((size_t)o * 8 + e) * 64 + t];
+                for (int j = 1; j < 6; j++) {
+                    const cd16 q = prod[((size_t)(2 * j + o) * 8 + e) * 64 + t];
+                    v.re = F_ADD(v.re, q.re); v.im = F_ADD(v.im, q.im);
+                }
+                y[t][e].re = v.re; y[t][e].im = v.im;
+            }
+        l2_inverse64(y, A.data(), Bb.data(), out + o * 1024);
+    }
+}
 // one 64-bit word of the ChaCha20 block the production generator is built on (RFC 8439 known-answer test)
 uint64_t emul_chacha20_u64(const uint32_t* key, uint64_t counter, uint64_t nonce, int lane8) { return tfhe_rng::chacha20_u64(key, counter, nonce, lane8); }
 uint32_t emul_prime(void) { return P; }

@@ -116,6 +116,7 @@ def emul():
     e.emul_external_product_f64.argtypes = [f64p, u32p, C.c_uint32, u32p]
     e.emul_cmux_rotate_f64.restype = C.c_double
     e.emul_cmux_rotate_f64.argtypes = [f64p, u32p, C.c_uint32, C.c_uint32]
+    e.emul_external_product_f64l2.argtypes = [f64p, u32p, C.c_uint32, u32p]
     return e
 
 
@@ -236,6 +237,27 @@ def test_fft64_kernel_arithmetic_on_cpu_matches_oracle(emul, oracle, rng):
         acc2 = (acc2 + pr).astype(np.uint32)
         assert np.array_equal(acc, acc2), abar
         assert frac < 2 ** -6
+
+
+def test_fft64_two_warp_transform_on_cpu_matches_oracle(emul, oracle, rng):
+    """the transform of the FFT64 latency kernel (blind_rotate_f64l2.cuh: one transform on two warps, 8 values per thread, three
+    radix-8 passes, two transposes with the XOR swizzle, per-thread twiddle tables, the key read in the one-warp layout) executed on
+    the CPU thread by thread: one external product, bit-exact vs the integer oracle, the extreme vectors included."""
+    def u32(k):
+        return rng.integers(0, 2 ** 32, k, dtype=np.uint64).astype(np.uint32)
+    for trial in range(4):
+        trgsw, trlwe = u32(12 * N), u32(2 * N)
+        if trial == 2:
+            trgsw[:], trlwe[:] = 0x7FFFFFFF, 0x7DF7C000
+        if trial == 3:
+            trgsw[:], trlwe[:] = 0x80000000, 0x7DF7C000
+        dev = np.zeros(12 * 512 * 2, np.float64)
+        emul.emul_key_transform_f64(trgsw, dev)
+        for mask in (oracle.MASK_FAITHFUL, oracle.MASK_TESTED):
+            out, ref = np.zeros(2 * N, np.uint32), np.zeros(2 * N, np.uint32)
+            emul.emul_external_product_f64l2(dev, trlwe, mask, out)
+            oracle.lib().orc_external_product_exact(trgsw, trlwe, mask, ref)
+            assert np.array_equal(out, ref), (trial, hex(mask))
 
 
 def test_csprng_chacha20_known_answer(emul):
