@@ -10,7 +10,8 @@
 //     pass 2 : j = 64 hi + 8 m + lo     stages 3..5 on m   (thread = 8 hi + lo; twiddles per hi: 4 loads from a 512-byte table)
 //     pass 3 : p = 8 tt + e''           stages 6..8 on e'' (thread tt; 4 loads from a 4 KB table)
 //   The spectrum positions are those of the one-warp transform (in-place Cooley-Tukey: position p holds psi^(1 + 4 bitrev9 p)), so
-//   the SAME transformed key is used ([register 16][lane 32] layout of fft64.cuh, read here as 16-byte pieces of two rows).
+//   the same transformed key values are used, re-laid-out per polynomial as [register 8][thread 64] (f64l2_key_layout_kernel): in
+//   the one-warp layout a quarter warp would read two rows 4 KB apart, a two-way bank conflict on every key load.
 //   The 96 KB of key of a step arrive by ONE bulk (TMA) copy, requested as soon as the previous step's products are done, i.e.
 //   a whole inverse transform ahead (loads into registers were tried first: ptxas sinks them next to their use and the products
 //   then wait 3 000 cycles for L2).  Each pair multiplies its spectrum by its two key polynomials and leaves the products in its
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(F64L2_THREADS, 1) blind_rotate_f64_latency2_ke
 #pragma unroll
     for (int k = 0; k < 4; k++) { wf2[k] = tf2[k * 8 + hi3]; wf3[k] = tf3[k * 64 + t]; }
     // this thread's 8 spectrum points p = 8 t + e in the [register 16][lane 32] key layout: (p & 15) * 32 + (p >> 4)
-    const cd16* kp = keybuf + (size_t)(2 * pair) * F64_CHUNK_ELEMS + (size_t)(8 * (t & 1)) * 32 + (t >> 1);
+    const cd16* kp = keybuf + (size_t)(2 * pair) * F64_CHUNK_ELEMS + t;   // [register e][thread t]
     const uint32_t* A = (F64L2_SHARED_U ? uw : acc) + pw * 1024;
     const int sh = 6 * dw;
 
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(F64L2_THREADS, 1) blind_rotate_f64_latency2_ke
 #if F64L2_KEYREG
         mbar_wait(kfull, (uint32_t)(i & 1));   // this step's key has landed (it was requested an inverse transform ago)
 #pragma unroll
-        for (int e = 0; e < 8; e++) { k0r[e] = kp[e * 32]; k1r[e] = kp[F64_CHUNK_ELEMS + e * 32]; }
+        for (int e = 0; e < 8; e++) { k0r[e] = kp[e * 64]; k1r[e] = kp[F64_CHUNK_ELEMS + e * 64]; }
         l2_fwd_pass23(x, wf3);
         bar_sync(bar_id, 64);                  // the pair has read buffer B: both buffers take the products now
 #else
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(F64L2_THREADS, 1) blind_rotate_f64_latency2_ke
         mbar_wait(kfull, (uint32_t)(i & 1));
         bar_sync(bar_id, 64);
 #pragma unroll
-        for (int e = 0; e < 8; e++) { k0r[e] = kp[e * 32]; k1r[e] = kp[F64_CHUNK_ELEMS + e * 32]; }
+        for (int e = 0; e < 8; e++) { k0r[e] = kp[e * 64]; k1r[e] = kp[F64_CHUNK_ELEMS + e * 64]; }
 #endif
         {
             cd16* po = prod + (size_t)(2 * pair) * 512 + t;
@@ -240,5 +241,16 @@ __global__ void __launch_bounds__(F64L2_THREADS, 1) blind_rotate_f64_latency2_ke
     if (a.out_init) {
         uint32_t* dst = a.out_init + (size_t)(a.idxo ? (long)a.idxo[gate] : gate) * (LWE_N + 1);
         for (int c = threadIdx.x; c <= LWE_N; c += F64L2_THREADS) dst[c] = (c == 0) ? acc[0] : 0u;
+    }
+}
+
+// the transformed key, polynomial by polynomial, from the one-warp layout [register 16][lane 32] (position p at (p & 15) * 32 + (p >> 4))
+// to the two-warp layout [register 8][thread 64] (position p = 8 t + e at e * 64 + t)
+__global__ void f64l2_key_layout_kernel(const cd16* __restrict__ src, cd16* __restrict__ dst, long npolys) {
+    const long poly = blockIdx.x;
+    if (poly >= npolys) return;
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) {
+        const int e = k >> 6, t = k & 63, p = 8 * t + e;
+        dst[poly * 512 + k] = src[poly * 512 + (p & 15) * 32 + (p >> 4)];
     }
 }

@@ -53,6 +53,7 @@ struct tfhe_b200_ctx {
     uint32_t* bkdev = nullptr;   // n * BK_STEP_WORDS
     uint32_t* bkdev_t2 = nullptr;   // n * T2_STEP_WORDS: the two-slice key in the throughput kernel's layout (blind_rotate_t2.cuh)
     cd16* bkdev_f64 = nullptr;      // n * F64_STEP_ELEMS: the f64 spectra of the FFT64 mode (blind_rotate_f64.cuh), allocated on first use
+    cd16* bkdev_f64l = nullptr;     // the same values in the layout of the latency kernel (blind_rotate_f64l2.cuh)
     uint32_t* kskdev = nullptr;  // [N][t][3][n+1]
     uint32_t* bk_torus = nullptr;  // [n][2l][2][N] torus-domain key as loaded / generated (kept for export: 31 MB)
     uint8_t* keybits = nullptr;    // device copy of (s0[n] | pad to 1024 | s1[N]) during device keygen
@@ -279,7 +280,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     if (ctx->keybits) cudaMemset(ctx->keybits, 0, 2048);
     if (ctx->s1poly) cudaMemset(ctx->s1poly, 0, 1024 * 4);
     for (auto& s : ctx->slots) if (s.s0buf) cudaMemset(s.s0buf, 0, 1024);
-    cudaFree(ctx->bkdev); cudaFree(ctx->bkdev_t2); cudaFree(ctx->bkdev_f64); cudaFree(ctx->kskdev); cudaFree(ctx->bk_torus); cudaFree(ctx->keybits); cudaFree(ctx->s1poly);
+    cudaFree(ctx->bkdev); cudaFree(ctx->bkdev_t2); cudaFree(ctx->bkdev_f64); cudaFree(ctx->bkdev_f64l); cudaFree(ctx->kskdev); cudaFree(ctx->bk_torus); cudaFree(ctx->keybits); cudaFree(ctx->s1poly);
     for (auto& s : ctx->slots) {
         cudaFree(s.ksdig); cudaFree(s.scratch); cudaFree(s.s0buf); cudaFree(s.opsbuf);
         for (auto p : s.tmp) cudaFree(p);
@@ -359,7 +360,7 @@ int tfhe_b200_get_stats(tfhe_b200_ctx* ctx, tfhe_b200_stats* out) {
     out->sm_count = ctx->sm_count;
     out->key_slices = ctx->key_slices;
     // what the gate path streams: the two-slice key in the throughput layout (8 B per coefficient) or the three-slice key (12 B)
-    out->device_key_bytes = (uint64_t)LWE_N * (ctx->key_slices == 1 ? F64_STEP_ELEMS * 4 : ctx->key_slices == 2 ? T2_STEP_WORDS : bk_step_words(3)) * 4 +
+    out->device_key_bytes = (uint64_t)LWE_N * (ctx->key_slices == 1 ? F64_STEP_ELEMS * 4 /* one of the two layouts is streamed per launch */ : ctx->key_slices == 2 ? T2_STEP_WORDS : bk_step_words(3)) * 4 +
                             (uint64_t)1024 * 8 * 3 * (LWE_N + 1) * 4;
     const uint64_t cnt = ctx->timed < (uint64_t)tfhe_b200_ctx::RING ? ctx->timed : (uint64_t)tfhe_b200_ctx::RING;
     double sb = 0, sk = 0;
@@ -386,7 +387,9 @@ static int transform_keys(tfhe_b200_ctx* ctx, const uint32_t* src_dev, uint32_t*
     if (ctx->key_slices == 1 && dst_dev == ctx->bkdev) {   // the whole key: also as f64 spectra
         if (!ctx->bkdev_f64) CK(cudaMalloc(&ctx->bkdev_f64, (size_t)LWE_N * F64_STEP_ELEMS * sizeof(cd16)));
         bk_transform_f64_kernel<<<(npolys + KTF_WARPS - 1) / KTF_WARPS, KTF_WARPS * 32, 0, st>>>(src_dev, ctx->bkdev_f64, npolys);
-        ctx->launches++;
+        if (!ctx->bkdev_f64l) CK(cudaMalloc(&ctx->bkdev_f64l, (size_t)LWE_N * F64_STEP_ELEMS * sizeof(cd16)));
+        f64l2_key_layout_kernel<<<(unsigned)npolys, 256, 0, st>>>(ctx->bkdev_f64, ctx->bkdev_f64l, (long)npolys);
+        ctx->launches += 2;
         CK(cudaGetLastError());
     }
     if (ctx->ns_int() == 2 && dst_dev == ctx->bkdev) {   // the whole key: also in the throughput kernel's layout
@@ -485,17 +488,17 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         ctx->gates_per_cta = G;
         return (unsigned)nctas;
     };
-    // FFT64 mode: up to two gates per SM run as waves of the one-gate-per-SM latency kernel (2.6 ms a wave: 296 gates 5.25 ms against
+    // FFT64 mode: up to two gates per SM run as waves of the one-gate-per-SM latency kernel (2.4 ms a wave: 296 gates 4.8 ms against
     // 6.4 ms for K5T; three waves take 7.9 ms, K5F with three gates per SM 7.7 ms)
     const bool f64_waves = ctx->key_slices == 1 && ctx->f64_latency && variant != 9 && variant != 8 && a.B <= 2L * ctx->sm_count;
     if (f64_waves) {
-        // FFT64 latency shape, one gate per SM on twelve warps (two per transform): 2.58 ms per gate from 1 to #SMs gates, against
+        // FFT64 latency shape, one gate per SM on twelve warps (two per transform): 2.37 ms per gate from 1 to #SMs gates, against
         // 2.66-2.73 ms for the NTT cluster kernel (two SMs per gate, at most #SMs/2 gates) and 3.57 ms for the one-CTA NTT kernel at
         // 148 gates.  TFHE_B200_F64_LATENCY=3: one warp per transform (K5FL, 3.2 ms); =0: the NTT latency shapes.
         a.cta_base = 1; a.cta_rem = 0;
         ctx->gates_per_cta = 1;
         if (ctx->f64_latency == 3) blind_rotate_f64_latency_kernel<<<(unsigned)a.B, F64L_THREADS, F64L_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
-        else blind_rotate_f64_latency2_kernel<<<(unsigned)a.B, F64L2_THREADS, F64L2_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
+        else blind_rotate_f64_latency2_kernel<<<(unsigned)a.B, F64L2_THREADS, F64L2_SMEM_BYTES, st>>>(a, ctx->bkdev_f64l);
     } else if (full && (variant == 3 || a.B <= 2L * ctx->sm_count) && a.ns == 3) {
         // 1-gate CTAs, up to three per SM (96 registers): the earlier default (TFHE_B200_BR_VARIANT=3 for A/B runs) and still the
         // best shape between one and two gates per SM (296 gates: 5.7 ms against 6.3 ms for 2-gate CTAs of the 80-register

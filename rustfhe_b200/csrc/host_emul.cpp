@@ -304,7 +304,8 @@ void emul_external_product_f64l2(const double* dev, const uint32_t* trlwe, uint3
         for (int t = 0; t < 64; t++)
             for (int e = 0; e < 8; e++)
                 for (int o = 0; o < 2; o++) {
-                    const cd16 k = key[f64_key_off(0, pair, o) + (size_t)(8 * (t & 1) + e) * 32 + (t >> 1)];
+                    const int pp = 8 * t + e;   // the kernel reads the same value from the [register 8][thread 64] copy of the key
+                    const cd16 k = key[f64_key_off(0, pair, o) + (size_t)(pp & 15) * 32 + (pp >> 4)];
                     cd16 q;
                     q.re = F_FMA(x[t][e].re, k.re, -F_MUL(x[t][e].im, k.im));
                     q.im = F_FMA(x[t][e].re, k.im, F_MUL(x[t][e].im, k.re));
