@@ -488,9 +488,9 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         ctx->gates_per_cta = G;
         return (unsigned)nctas;
     };
-    // FFT64 mode: up to two gates per SM run as waves of the one-gate-per-SM latency kernel (2.4 ms a wave: 296 gates 4.8 ms against
-    // 6.4 ms for K5T; three waves take 7.9 ms, K5F with three gates per SM 7.7 ms)
-    const bool f64_waves = ctx->key_slices == 1 && ctx->f64_latency && variant != 9 && variant != 8 && a.B <= 2L * ctx->sm_count;
+    // FFT64 mode: up to three gates per SM run as waves of the one-gate-per-SM latency kernel (2.4 ms a wave: 296 gates 4.8 ms against
+    // 6.4 ms for K5T, 444 gates 7.2 ms against 7.7 ms for K5F with three gates per SM; four waves would take 9.5 ms against 7.9 ms)
+    const bool f64_waves = ctx->key_slices == 1 && ctx->f64_latency && variant != 9 && variant != 8 && a.B <= 3L * ctx->sm_count;
     if (f64_waves) {
         // FFT64 latency shape, one gate per SM on twelve warps (two per transform): 2.37 ms per gate from 1 to #SMs gates, against
         // 2.66-2.73 ms for the NTT cluster kernel (two SMs per gate, at most #SMs/2 gates) and 3.57 ms for the one-CTA NTT kernel at
@@ -504,8 +504,8 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         // best shape between one and two gates per SM (296 gates: 5.7 ms against 6.3 ms for 2-gate CTAs of the 80-register
         // kernel and 5.8 ms for 1-gate CTAs compiled for 168 registers)
         blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
-    } else if (full && ctx->key_slices == 1 && variant != 8 && a.B > 2L * ctx->sm_count) {
-        // FFT64 mode: one warp per gate, eight gates per CTA (blind_rotate_f64.cuh), from three gates per SM on
+    } else if (full && ctx->key_slices == 1 && variant != 8) {
+        // FFT64 mode: one warp per gate, eight gates per CTA (blind_rotate_f64.cuh), above three gates per SM
         if (ctx->f64_tmem) {
             const unsigned grid = batches_overlap(ctx, st) ? fixed(F64T_GATES) : deal(F64T_GATES);
             blind_rotate_f64t_kernel<<<grid, F64T_GATES * 32, f64t_smem_bytes(), st>>>(a, ctx->bkdev_f64);

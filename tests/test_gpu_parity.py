@@ -355,7 +355,7 @@ def test_cmux_exact_and_selects(engine, oracle, keys, rng):
 
 @pytest.mark.parametrize("B", [5, 49, 74, 75, 148, 149, 297, 445, 601, 889])
 def test_launch_shapes_deterministic_and_exact(engine, oracle, keys, rng, B):
-    """Every launch shape of the default mode (one gate per SM on twelve warps -- K5FL2 -- in one and two waves up to 2 #SMs
+    """Every launch shape of the default mode (one gate per SM on twelve warps -- K5FL2 -- in one, two and three waves up to 3 #SMs
     gates, the one-warp-per-gate throughput kernel K5F with uneven dealing above; with TFHE_B200_KEY_SLICES=2/3 the NTT shapes:
     2-SM cluster per gate, one gate per CTA, K5T / K5) gives the same bits run after run (a shared-memory race would not) and
     matches the exact oracle on a sample; all decrypts are right."""
@@ -472,7 +472,7 @@ def test_fft64_mode_exact(oracle, keys, rng):
         eng.load_ksk(keys.ksk)
         eng.load_bk(keys.bk)
         sms = eng.stats()["sm_count"]
-        B = 2 * sms + 13                                         # above 2 #SMs: the FFT64 throughput kernel, not waves of the latency kernel
+        B = 3 * sms + 13                                         # above 3 #SMs: the FFT64 throughput kernel, not waves of the latency kernel
         bits = rng.integers(0, 2, B).astype(np.uint8)
         lin = oracle.gate_linear(oracle.NAND, keys.encrypt(bits, 0), keys.encrypt(1 - bits, 1000))
         lin[0, 0] = 0                      # bbar = 0
