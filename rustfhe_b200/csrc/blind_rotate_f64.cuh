@@ -38,34 +38,22 @@ __device__ __forceinline__ void f64_exchange(const cd (&send)[8], cd (&recv)[8])
 }
 // forward transform of the 16 values a lane holds (natural order j = 32 r + lane) -> spectrum (position p = 16 lane + register)
 // PREFETCH: the per-lane twiddle rows of pass B are requested before pass A (32 registers for the length of pass A and the
-// transpose; +3 % in the throughput kernel, not affordable next to the 128 key registers of the latency kernel)
+// transpose; +3 % in the throughput kernel)
 template <bool PREFETCH = true>
 __device__ __forceinline__ void f64_forward(int lane, cd (&x)[16], cd16* S, const cd16* tb, cd (&y)[16]) {
     F64TwB tw;
     if (PREFETCH) f64_fwd_twB(lane, tb, tw);
     f64_fwd_passA(x);
-#if !defined(F64_X_NOT1)   // timing experiment: no transpose
     f64_t1_store(lane, x, S);
     __syncwarp();
     f64_t1_load(lane, S, x);
     __syncwarp();   // the scratch is free for the next transform
-#endif
     if (!PREFETCH) f64_fwd_twB(lane, tb, tw);
     f64_fwd_passB(x, tw);
-#if defined(F64_X_NOX)   // timing experiment: the last stage without the lane-pair exchange
-#pragma unroll
-    for (int m = 0; m < 8; m++) {
-        const cd16 w = tb[(8 + (m >> 1)) * 32 + lane];
-        cd a2 = x[m], b2 = x[m + 8];
-        bf_w(a2, b2, w.re, w.im);
-        y[2 * m] = a2; y[2 * m + 1] = b2;
-    }
-#else
     cd send[8], recv[8];
     f64_x_send(lane, x, send);
     f64_exchange(send, recv);
     f64_fwd_x_bfly(lane, x, recv, tb, y);
-#endif
 }
 
 // inverse transform of one output spectrum (destroyed), rounded to the exact integers and added to the accumulator polynomial
@@ -216,12 +204,7 @@ __global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_
         for (int pw = 0; pw < 2; pw++) {
             {   // masked source words of polynomial pw, ((X^abar acc - acc) + mask) ^ mask: lane-private, parked as three byte planes
                 uint32_t u[32];
-#if defined(F64_X_NOU)   // timing experiment: no rotated reads, no masking
-#pragma unroll
-                for (int r = 0; r < 32; r++) u[r] = acc[pw * 1024 + lane] * (r + 1);
-#else
                 t2_u<true>(lane, acc + pw * 1024, ab, a.mask, u);
-#endif
                 u4 re, im;
                 f64_pack_plane<0>(u, re, im);
                 D[0 * 32 + lane] = make_uint4(re.x, re.y, re.z, re.w); D[1 * 32 + lane] = make_uint4(im.x, im.y, im.z, im.w);
@@ -240,15 +223,10 @@ __global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_
                     f64_digits(re, im, x);
                 }
                 f64_forward(lane, x, S, tb, y);
-#if defined(F64_X_NOKEY)   // timing experiment: no ring, key values from the twiddle table
-                f64_mac(0, y, tb, s0);
-                f64_mac(1, y, tb, s1);
-#else
                 f64_with_chunk(rg, n, lane, [&](const cd16* k) {
                     f64_mac(lane, y, k, s0);
                     f64_mac(lane, y, k + F64_CHUNK_ELEMS, s1);
                 });
-#endif
                 n++;
             }
         }
@@ -439,137 +417,5 @@ __global__ void __launch_bounds__(PMF_WARPS * 32, 1) polymul_f64_kernel(const ui
             ya[k].re = F_MUL(pr, 1.0 / 512); ya[k].im = F_MUL(pi, 1.0 / 512);
         }
         f64_inverse_acc<true>(lane, ya, S, ta, ut, out + (size_t)g * 1024);
-    }
-}
-
-// =====================================================================================================
-// K5FL: latency shape of the FFT64 mode -- ONE gate per CTA, six warps.  Warp w = 3 pw + dw transforms gadget digit dw of
-// accumulator polynomial pw (the six forward transforms of a CMUX run concurrently), multiplies its spectrum by its two key
-// polynomials (requested from L2 into 128 registers before the transform starts, so the load latency is under the transform)
-// and leaves the two products in shared memory; after one CTA barrier warps 0 and 1 add the six products of "their" output
-// polynomial, run the inverse transform and update the accumulator; a second barrier ends the step.
-// Critical path per CMUX: source words + one forward transform + one inverse transform, instead of the six + two that the
-// one-warp-per-gate throughput kernel runs back to back.
-// =====================================================================================================
-constexpr int F64L_WARPS = 6;
-constexpr int F64L_THREADS = F64L_WARPS * 32;
-constexpr int F64L_SMEM_BYTES = (F64_TAB_ELEMS + F64_UNTW_ROWS * 32) * 16 /*twiddle tables*/ + 2 * 1024 * 4 /*acc*/ + F64L_WARPS * 512 * 16 /*transpose scratch*/ +
-                                F64L_WARPS * 2 * 512 * 16 /*products*/ + 640 * 2 /*abar*/;
-static_assert(F64L_SMEM_BYTES <= 227 * 1024, "one gate must fit the shared memory of one SM");
-
-__global__ void __launch_bounds__(F64L_THREADS, 1) blind_rotate_f64_latency_kernel(const BrArgs a, const cd16* __restrict__ key) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd16* tab = reinterpret_cast<cd16*>(smem_raw);
-    const cd16* tb = tab;
-    const cd16* ta = tab + F64_FWDB_ROWS * 32;
-    const cd16* ut = tab + F64_TAB_ELEMS;
-    uint32_t* acc = reinterpret_cast<uint32_t*>(tab + F64_TAB_ELEMS + F64_UNTW_ROWS * 32);
-    cd16* scratch = reinterpret_cast<cd16*>(acc + 2048);
-    cd16* prod = scratch + F64L_WARPS * 512;                    // [warp][output][register][lane]
-    uint16_t* abar = reinterpret_cast<uint16_t*>(prod + F64L_WARPS * 2 * 512);
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pw = w / 3, dw = w - 3 * pw;
-    cd16* S = scratch + w * 512;
-    const long gate = blockIdx.x;
-    const int nsteps = a.nsteps;
-    {
-        const double* g0 = g_f64_fwdB; const double* g1 = g_f64_invA; const double* g2 = g_f64_untw;
-        double* t = reinterpret_cast<double*>(tab);
-        for (int k = threadIdx.x; k < F64_FWDB_ROWS * 64; k += blockDim.x) t[k] = g0[k];
-        for (int k = threadIdx.x; k < F64_INVA_ROWS * 64; k += blockDim.x) t[F64_FWDB_ROWS * 64 + k] = g1[k];
-        for (int k = threadIdx.x; k < F64_UNTW_ROWS * 64; k += blockDim.x) t[(F64_FWDB_ROWS + F64_INVA_ROWS) * 64 + k] = g2[k];
-    }
-    // ---- prologue: gate pre-combination (tfhe.rs:27-71), rounding of (b, a) (tfhe.rs:97,107-108), acc_0 ----
-    {
-        uint32_t* lin = reinterpret_cast<uint32_t*>(scratch);
-        const bool second = gate >= a.split;
-        const long gsrc = second ? gate - a.split : gate;
-        const uint32_t* q0 = second ? a.in0b : a.in0;
-        const uint32_t* q1 = second ? a.in1b : a.in1;
-        uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
-        if (a.ops) gate_coeffs(a.ops[gate], a.mu, k0, k1, kb);
-        const uint32_t* p0 = q0 + (size_t)(a.idx0 ? (long)a.idx0[gate] : gsrc) * (LWE_N + 1);
-        const uint32_t* p1 = (q1 && k1 != 0) ? q1 + (size_t)(a.idx1 ? (long)a.idx1[gate] : gsrc) * (LWE_N + 1) : nullptr;
-        for (int c = threadIdx.x; c <= LWE_N; c += F64L_THREADS) {
-            uint32_t v = k0 * p0[c];
-            if (p1) v += k1 * p1[c];
-            if (c == 0) v += kb;
-            lin[c] = v;
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < LWE_N; i += F64L_THREADS) abar[i] = (uint16_t)((lin[1 + i] + (1u << 20)) >> 21);   // round
-        const uint32_t bbar = lin[0] >> 21;                                                                           // floor
-        const uint32_t nrot = (2048u - bbar) & 2047u;
-        for (int k = threadIdx.x; k < 1024; k += F64L_THREADS) {
-            const bool neg = ((uint32_t)k < (nrot & 1023u)) != (nrot >= 1024u);
-            acc[k] = neg ? 0u - a.mu : a.mu;
-            acc[1024 + k] = 0;
-        }
-    }
-    __syncthreads();
-
-    const double2* kp = reinterpret_cast<const double2*>(key) + (size_t)(2 * w) * F64_CHUNK_ELEMS + lane;   // rows j = w, outputs 0 and 1
-#pragma unroll 1
-    for (int i = 0; i < nsteps; i++, kp += F64_STEP_ELEMS) {
-        double2 k0r[16], k1r[16];   // this warp's two key polynomials: in flight while the transform runs
-#pragma unroll
-        for (int k = 0; k < 16; k++) { k0r[k] = __ldg(kp + k * 32); k1r[k] = __ldg(kp + F64_CHUNK_ELEMS + k * 32); }
-        cd x[16], y[16];
-        {
-            uint32_t u[32];
-            t2_u<true>(lane, acc + pw * 1024, (uint32_t)abar[i], a.mask, u);
-            const int sh = 6 * dw;
-#pragma unroll
-            for (int r = 0; r < 16; r++) {
-                x[r].re = (double)(((int32_t)(u[r] << sh)) >> 26);
-                x[r].im = (double)(((int32_t)(u[r + 16] << sh)) >> 26);
-            }
-        }
-        f64_forward<false>(lane, x, S, tb, y);
-        cd16* po = prod + (size_t)(2 * w) * 512 + lane;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {   // the digits are not pre-scaled by 4 here: the key carries 1/2048, so multiply by 4 (exact)
-            cd16 p0, p1;
-            p0.re = F_FMA(y[k].re, k0r[k].x, -F_MUL(y[k].im, k0r[k].y)); p0.im = F_FMA(y[k].re, k0r[k].y, F_MUL(y[k].im, k0r[k].x));
-            p1.re = F_FMA(y[k].re, k1r[k].x, -F_MUL(y[k].im, k1r[k].y)); p1.im = F_FMA(y[k].re, k1r[k].y, F_MUL(y[k].im, k1r[k].x));
-            po[k * 32] = p0;
-            po[512 + k * 32] = p1;
-        }
-        __syncthreads();   // the twelve products are complete
-        if (w < 2) {
-            cd s[16];
-            const cd16* pi = prod + (size_t)w * 512 + lane;
-#pragma unroll
-            for (int k = 0; k < 16; k++) { const cd16 v = pi[k * 32]; s[k].re = v.re; s[k].im = v.im; }
-#pragma unroll
-            for (int j = 1; j < F64L_WARPS; j++)
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const cd16 v = pi[(size_t)(2 * j) * 512 + k * 32];
-                    s[k].re = F_ADD(s[k].re, v.re); s[k].im = F_ADD(s[k].im, v.im);
-                }
-#pragma unroll
-            for (int k = 0; k < 16; k++) { s[k].re = F_MUL(s[k].re, 4.0); s[k].im = F_MUL(s[k].im, 4.0); }
-            f64_inverse_acc(lane, s, S, ta, ut, acc + w * 1024);
-        }
-        __syncthreads();   // acc is complete before the next step's rotated reads
-    }
-
-    // ---- epilogue: sample_extract_index(0) (trlwe.rs:110-121) + key-switch digits (tlwe.rs:47-64) ----
-    if (a.trlwe_out) {
-        uint32_t* dst = a.trlwe_out + (size_t)gate * 2048;
-        for (int k = threadIdx.x; k < 2048; k += F64L_THREADS) dst[k] = acc[k];
-    }
-    if (a.ksdig || a.lwe1_out) {
-        for (int i = threadIdx.x; i < 1024; i += F64L_THREADS) {
-            const uint32_t ai = (i == 0) ? acc[1024] : 0u - acc[1024 + 1024 - i];
-            if (a.ksdig) a.ksdig[(size_t)gate * 1024 + i] = (uint16_t)((ai + 0x8000u) >> 16);
-            if (a.lwe1_out) a.lwe1_out[(size_t)gate * 1025 + 1 + i] = ai;
-        }
-        if (a.lwe1_out && threadIdx.x == 0) a.lwe1_out[(size_t)gate * 1025] = acc[0];
-    }
-    if (a.out_init) {
-        uint32_t* dst = a.out_init + (size_t)(a.idxo ? (long)a.idxo[gate] : gate) * (LWE_N + 1);
-        for (int c = threadIdx.x; c <= LWE_N; c += F64L_THREADS) dst[c] = (c == 0) ? acc[0] : 0u;
     }
 }

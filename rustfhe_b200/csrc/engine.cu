@@ -78,8 +78,8 @@ struct tfhe_b200_ctx {
     int ns_int() const { return key_slices == 3 ? 3 : 2; }   // slices of the integer (NTT) form of the key
     int f64_tmem = 0;           // FFT64 throughput kernel: 0 = K5F, eight gates per SM (default); 1 = per-gate state in tensor memory, twelve gates
                                 // per SM (K5FT, TFHE_B200_F64_TMEM=1): measured 10 % slower -- the kernel is bound by issue slots, not by latency
-    int f64_latency = 1;        // FFT64 mode: batches of at most #SMs gates run one gate per SM, two warps per transform (K5FL2);
-                                // TFHE_B200_F64_LATENCY=3: one warp per transform (K5FL), =0: the NTT latency shapes
+    int f64_latency = 1;        // FFT64 mode: batches of at most 3 #SMs gates run one gate per SM, two warps per transform (K5FL2);
+                                // TFHE_B200_F64_LATENCY=0: the NTT latency shapes / K5T / K5F instead
     int f64_stagger_ns = 0;   // start-up offset between the warps of a CTA of the FFT64 kernel (TFHE_B200_F64_STAGGER)
     int t2_gates = 6;    // gates per CTA of the throughput kernel (TFHE_B200_T2_G: 4 or 6)
     int t2_twreg = 1;    // which row twiddles the throughput kernel keeps in registers (TFHE_B200_T2_TWREG: bit 0 forward, bit 1 inverse)
@@ -259,8 +259,6 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
         return bail("smem attr (f64 polymul)", e);
     if ((e = cudaFuncSetAttribute(external_product_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64 external product)", e);
-    if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L_SMEM_BYTES)) != cudaSuccess)
-        return bail("smem attr (f64 latency)", e);
     if (const char* v = getenv("TFHE_B200_F64_LATENCY")) ctx->f64_latency = atoi(v);
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (f64 latency 2)", e);
@@ -494,11 +492,10 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
     if (f64_waves) {
         // FFT64 latency shape, one gate per SM on twelve warps (two per transform): 2.37 ms per gate from 1 to #SMs gates, against
         // 2.66-2.73 ms for the NTT cluster kernel (two SMs per gate, at most #SMs/2 gates) and 3.57 ms for the one-CTA NTT kernel at
-        // 148 gates.  TFHE_B200_F64_LATENCY=3: one warp per transform (K5FL, 3.2 ms); =0: the NTT latency shapes.
+        // 148 gates.  TFHE_B200_F64_LATENCY=0: the NTT latency shapes.  (One warp per transform on six warps measured 3.2 ms.)
         a.cta_base = 1; a.cta_rem = 0;
         ctx->gates_per_cta = 1;
-        if (ctx->f64_latency == 3) blind_rotate_f64_latency_kernel<<<(unsigned)a.B, F64L_THREADS, F64L_SMEM_BYTES, st>>>(a, ctx->bkdev_f64);
-        else blind_rotate_f64_latency2_kernel<<<(unsigned)a.B, F64L2_THREADS, F64L2_SMEM_BYTES, st>>>(a, ctx->bkdev_f64l);
+        blind_rotate_f64_latency2_kernel<<<(unsigned)a.B, F64L2_THREADS, F64L2_SMEM_BYTES, st>>>(a, ctx->bkdev_f64l);
     } else if (full && (variant == 3 || a.B <= 2L * ctx->sm_count) && a.ns == 3) {
         // 1-gate CTAs, up to three per SM (96 registers): the earlier default (TFHE_B200_BR_VARIANT=3 for A/B runs) and still the
         // best shape between one and two gates per SM (296 gates: 5.7 ms against 6.3 ms for 2-gate CTAs of the 80-register
