@@ -254,3 +254,223 @@ __global__ void f64l2_key_layout_kernel(const cd16* __restrict__ src, cd16* __re
         dst[poly * 512 + k] = src[poly * 512 + (p & 15) * 32 + (p >> 4)];
     }
 }
+
+// =====================================================================================================
+// K5FL3: the same step on a CLUSTER OF TWO SMs (batches of at most #SMs/2 gates).  K5FL2 is bound by the shared-memory bandwidth
+// of its SM; here CTA c owns accumulator polynomial c: its three warp pairs transform the three digits of that polynomial (half of
+// the transposes, products and key traffic per SM), multiply by the key of BOTH output polynomials, and the CTA then
+//   * adds its three products of output (1 - c) and sends that partial sum (8 KB) to the peer with ONE bulk DSMEM copy that counts
+//     its bytes on the peer's mbarrier (warp pair 1),
+//   * adds its three products of output c, waits for the peer's partial sum, adds it, runs the inverse transform of output c and
+//     updates ITS accumulator polynomial (warp pair 0).
+// Send and receive buffers are double buffered by step parity: the peer sends step i only after it has finished step i - 1, for
+// which it needed my step i - 1, which I sent after consuming its step i - 2 -- no reverse signal is needed (the argument of the
+// NTT cluster kernel, blind_rotate.cuh).  One cluster barrier at the start, one at the end.
+// =====================================================================================================
+constexpr int F64L3_THREADS = 3 * 64;
+constexpr int F64L3_KEY_BYTES = 6 * 512 * 16;   // this CTA's three rows, both outputs
+constexpr int F64L3_SMEM_BYTES = F64L2_TAB_ELEMS * 16 + 1024 * 4 /*own accumulator polynomial*/ + 3 * 2 * 512 * 16 /*transpose buffers = products*/ +
+                                 F64L3_KEY_BYTES + 2 * 512 * 16 /*send*/ + 2 * 512 * 16 /*recv*/ + 640 * 2 /*abar*/ + 32 /*mbarriers*/;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F64L3_THREADS, 1) blind_rotate_f64_latency3_kernel(const BrArgs a, const cd16* __restrict__ key) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();   // accumulator / output polynomial of this CTA
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd16* tab = reinterpret_cast<cd16*>(smem_raw);
+    const cd16* tf2 = tab;
+    const cd16* tf3 = tab + 32;
+    const cd16* ti2 = tab + 288;
+    const cd16* ti3 = tab + 320;
+    const cd16* tut = tab + 576;
+    uint32_t* acc = reinterpret_cast<uint32_t*>(tab + F64L2_TAB_ELEMS);   // polynomial c only
+    cd16* scratch = reinterpret_cast<cd16*>(acc + 1024);
+    cd16* prod = scratch;                         // [digit dw][output o][register][thread]
+    cd16* keybuf = scratch + 3 * 2 * 512;         // [digit dw][output o][register 8][thread 64]
+    cd16* sendb = keybuf + 6 * 512;               // [parity][512]
+    cd16* recvb = sendb + 2 * 512;                // [parity][512]
+    uint16_t* abar = reinterpret_cast<uint16_t*>(recvb + 2 * 512);
+    uint64_t* kfull = reinterpret_cast<uint64_t*>(abar + 640);
+    uint64_t* pfull = kfull + 1;                  // [parity]
+    const int pair = threadIdx.x >> 6, t = threadIdx.x & 63;   // pair = digit dw of polynomial c
+    cd16* bufA = scratch + (size_t)pair * 1024;
+    cd16* bufB = bufA + 512;
+    const int bar_id = 1 + pair;
+    const long gate = blockIdx.x >> 1;
+    const int nsteps = a.nsteps;
+    {
+        double* d = reinterpret_cast<double*>(tab);
+        for (int k = threadIdx.x; k < 64; k += blockDim.x) { d[k] = g_l2_fwd2[k]; d[2 * 288 + k] = g_l2_inv2[k]; }
+        for (int k = threadIdx.x; k < 512; k += blockDim.x) { d[2 * 32 + k] = g_l2_fwd3[k]; d[2 * 320 + k] = g_l2_inv3[k]; }
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) d[2 * 576 + k] = g_l2_untw[k];
+    }
+    // ---- prologue (both CTAs): gate pre-combination (tfhe.rs:27-71), rounding of (b, a) (tfhe.rs:97,107-108), acc_0 ----
+    {
+        uint32_t* lin = reinterpret_cast<uint32_t*>(scratch);
+        const bool second = gate >= a.split;
+        const long gsrc = second ? gate - a.split : gate;
+        const uint32_t* q0 = second ? a.in0b : a.in0;
+        const uint32_t* q1 = second ? a.in1b : a.in1;
+        uint32_t k0 = (uint32_t)(second ? a.c0b : a.c0), k1 = (uint32_t)(second ? a.c1b : a.c1), kb = second ? a.cbb : a.cb;
+        if (a.ops) gate_coeffs(a.ops[gate], a.mu, k0, k1, kb);
+        const uint32_t* p0 = q0 + (size_t)(a.idx0 ? (long)a.idx0[gate] : gsrc) * (LWE_N + 1);
+        const uint32_t* p1 = (q1 && k1 != 0) ? q1 + (size_t)(a.idx1 ? (long)a.idx1[gate] : gsrc) * (LWE_N + 1) : nullptr;
+        for (int k = threadIdx.x; k <= LWE_N; k += F64L3_THREADS) {
+            uint32_t v = k0 * p0[k];
+            if (p1) v += k1 * p1[k];
+            if (k == 0) v += kb;
+            lin[k] = v;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 640; i += F64L3_THREADS) abar[i] = i < LWE_N ? (uint16_t)((lin[1 + i] + (1u << 20)) >> 21) : (uint16_t)0;
+        const uint32_t bbar = lin[0] >> 21;
+        const uint32_t nrot = (2048u - bbar) & 2047u;
+        __syncthreads();   // lin (the scratch) has been read
+        for (int k = threadIdx.x; k < 1024; k += F64L3_THREADS) {
+            const bool neg = ((uint32_t)k < (nrot & 1023u)) != (nrot >= 1024u);
+            acc[k] = c == 0 ? (neg ? 0u - a.mu : a.mu) : 0u;
+        }
+    }
+    const cd16* mykey = key + (size_t)(6 * c) * F64_CHUNK_ELEMS;   // rows 3 c .. 3 c + 2 of every step: 6 consecutive chunks
+    if (threadIdx.x == 0) {
+        mbar_init(kfull, 1);
+        mbar_init(pfull, 1);
+        mbar_init(pfull + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (nsteps > 0) bulk_fetch(keybuf, mykey, F64L3_KEY_BYTES, kfull);
+    }
+    __syncthreads();
+    cluster.sync();   // both CTAs are set up (mbarriers) before the first remote copy
+
+    const uint32_t remote_recv = map_to_cta(smem_u32(recvb), (uint32_t)(c ^ 1));
+    const uint32_t remote_bar = map_to_cta(smem_u32(pfull), (uint32_t)(c ^ 1));
+    const int hi3 = t >> 3, lo3 = t & 7;
+    cd16 wf2[4], wf3[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { wf2[k] = tf2[k * 8 + hi3]; wf3[k] = tf3[k * 64 + t]; }
+    const cd16* kp = keybuf + (size_t)(2 * pair) * F64_CHUNK_ELEMS + t;
+    const int sh = 6 * pair;
+
+#pragma unroll 1
+    for (int i = 0; i < nsteps; i++) {
+        if (threadIdx.x == 0) mbar_expect_tx(pfull + (i & 1), 512u * 16u);   // arm this step's arrival of the peer's partial sum
+        cd x[8];
+        {
+            const uint32_t ab = abar[i];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const uint32_t ur = add_alu(rot_diff(acc, (uint32_t)(t + 64 * e), ab), a.mask) ^ a.mask;
+                const uint32_t ui = add_alu(rot_diff(acc, (uint32_t)(512 + t + 64 * e), ab), a.mask) ^ a.mask;
+                x[e].re = (double)((((int32_t)(ur << sh)) >> 24) & ~3);
+                x[e].im = (double)((((int32_t)(ui << sh)) >> 24) & ~3);
+            }
+        }
+        l2_fwd_pass1(x);
+#pragma unroll
+        for (int e = 0; e < 8; e++) l2_store(bufA + t + 64 * e, x[e]);
+        bar_sync(bar_id, 64);
+#pragma unroll
+        for (int m = 0; m < 8; m++) l2_load(bufA + 64 * hi3 + 8 * m + lo3, x[m]);
+        l2_fwd_pass23(x, wf2);
+#pragma unroll
+        for (int m = 0; m < 8; m++) l2_store(bufB + 64 * hi3 + 8 * m + (lo3 ^ m), x[m]);
+        bar_sync(bar_id, 64);
+#pragma unroll
+        for (int e = 0; e < 8; e++) l2_load(bufB + 8 * t + (e ^ lo3), x[e]);
+        mbar_wait(kfull, (uint32_t)(i & 1));
+        cd16 k0r[8], k1r[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) { k0r[e] = kp[e * 64]; k1r[e] = kp[F64_CHUNK_ELEMS + e * 64]; }
+        l2_fwd_pass23(x, wf3);
+        bar_sync(bar_id, 64);   // the pair has read buffer B: both buffers take the products now
+        {
+            cd16* po = prod + (size_t)(2 * pair) * 512 + t;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const cd16 k0 = k0r[e], k1 = k1r[e];
+                cd16 q0, q1;
+                q0.re = F_FMA(x[e].re, k0.re, -F_MUL(x[e].im, k0.im)); q0.im = F_FMA(x[e].re, k0.im, F_MUL(x[e].im, k0.re));
+                q1.re = F_FMA(x[e].re, k1.re, -F_MUL(x[e].im, k1.im)); q1.im = F_FMA(x[e].re, k1.im, F_MUL(x[e].im, k1.re));
+                po[e * 64] = q0;
+                po[512 + e * 64] = q1;
+            }
+        }
+        __syncthreads();   // the six products are complete, the key buffer is free
+        if (threadIdx.x == 0 && i + 1 < nsteps) bulk_fetch(keybuf, mykey + (size_t)(i + 1) * F64_STEP_ELEMS, F64L3_KEY_BYTES, kfull);
+        if (pair == 1) {   // the three products of the PEER's output polynomial: add, send
+            cd16* sb = sendb + (size_t)(i & 1) * 512;
+            const cd16* pi = prod + (size_t)(c ^ 1) * 512 + t;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                cd16 v = pi[e * 64];
+                const cd16 v1 = pi[(size_t)2 * 512 + e * 64], v2 = pi[(size_t)4 * 512 + e * 64];
+                v.re = F_ADD(F_ADD(v.re, v1.re), v2.re); v.im = F_ADD(F_ADD(v.im, v1.im), v2.im);
+                sb[e * 64 + t] = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the sums are visible to the copy engine
+            bar_sync(7, 128);   // ... of every thread of the pair; and pairs 0 and 1 have both read the products
+            if (t == 0) bulk_send(remote_recv + (uint32_t)(i & 1) * 512u * 16u, sb, 512u * 16u, remote_bar + 8u * (uint32_t)(i & 1));
+        } else if (pair == 0) {   // the three products of MY output polynomial, the peer's partial sum, the inverse transform
+            cd16 wi2[4], wi3[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { wi2[k] = ti2[k * 8 + lo3]; wi3[k] = ti3[k * 64 + t]; }
+            cd y[8];
+            const cd16* pi = prod + (size_t)c * 512 + t;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const cd16 v0 = pi[e * 64], v1 = pi[(size_t)2 * 512 + e * 64], v2 = pi[(size_t)4 * 512 + e * 64];
+                y[e].re = F_ADD(F_ADD(v0.re, v1.re), v2.re); y[e].im = F_ADD(F_ADD(v0.im, v1.im), v2.im);
+            }
+            bar_sync(7, 128);   // pairs 0 and 1 have both read the products: the buffers are transpose scratch again
+            mbar_wait(pfull + (i & 1), (uint32_t)(i >> 1) & 1u);
+            {
+                const cd16* rb = recvb + (size_t)(i & 1) * 512 + t;
+#pragma unroll
+                for (int e = 0; e < 8; e++) { const cd16 v = rb[e * 64]; y[e].re = F_ADD(y[e].re, v.re); y[e].im = F_ADD(y[e].im, v.im); }
+            }
+            l2_inv_pass1(y);
+#pragma unroll
+            for (int e = 0; e < 8; e++) l2_store(bufB + 8 * t + (e ^ lo3), y[e]);
+            bar_sync(bar_id, 64);
+#pragma unroll
+            for (int m = 0; m < 8; m++) l2_load(bufB + 64 * hi3 + 8 * m + (lo3 ^ m), y[m]);
+            l2_inv_pass23(y, wi2);
+#pragma unroll
+            for (int m = 0; m < 8; m++) l2_store(bufA + 64 * hi3 + 8 * m + lo3, y[m]);
+            bar_sync(bar_id, 64);
+#pragma unroll
+            for (int e = 0; e < 8; e++) l2_load(bufA + t + 64 * e, y[e]);
+            l2_inv_pass23(y, wi3);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const cd16 u = tut[e * 64 + t];
+                const double zr = F_FMA(y[e].re, u.re, -F_MUL(y[e].im, u.im));
+                const double zi = F_FMA(y[e].re, u.im, F_MUL(y[e].im, u.re));
+                acc[t + 64 * e] += f64_low_word(F_ADD(zr, F64_ROUND_MAGIC));
+                acc[512 + t + 64 * e] += f64_low_word(F_ADD(zi, F64_ROUND_MAGIC));
+            }
+        }
+        __syncthreads();   // my accumulator polynomial is complete before the next step's rotated reads
+    }
+    cluster.sync();   // no CTA leaves while its peer may still copy into its shared memory
+
+    // ---- epilogue: sample_extract_index(0) (trlwe.rs:110-121) + key-switch digits (tlwe.rs:47-64): CTA 0 has b, CTA 1 has a ----
+    if (a.trlwe_out) {
+        uint32_t* dst = a.trlwe_out + (size_t)gate * 2048 + (size_t)c * 1024;
+        for (int k = threadIdx.x; k < 1024; k += F64L3_THREADS) dst[k] = acc[k];
+    }
+    if (c == 1 && (a.ksdig || a.lwe1_out)) {
+        for (int i = threadIdx.x; i < 1024; i += F64L3_THREADS) {
+            const uint32_t ai = (i == 0) ? acc[0] : 0u - acc[1024 - i];
+            if (a.ksdig) a.ksdig[(size_t)gate * 1024 + i] = (uint16_t)((ai + 0x8000u) >> 16);
+            if (a.lwe1_out) a.lwe1_out[(size_t)gate * 1025 + 1 + i] = ai;
+        }
+    }
+    if (c == 0) {
+        if (a.lwe1_out && threadIdx.x == 0) a.lwe1_out[(size_t)gate * 1025] = acc[0];
+        if (a.out_init) {
+            uint32_t* dst = a.out_init + (size_t)(a.idxo ? (long)a.idxo[gate] : gate) * (LWE_N + 1);
+            for (int k = threadIdx.x; k <= LWE_N; k += F64L3_THREADS) dst[k] = (k == 0) ? acc[0] : 0u;
+        }
+    }
+}

@@ -78,6 +78,7 @@ struct tfhe_b200_ctx {
     int ns_int() const { return key_slices == 3 ? 3 : 2; }   // slices of the integer (NTT) form of the key
     int f64_tmem = 0;           // FFT64 throughput kernel: 0 = K5F, eight gates per SM (default); 1 = per-gate state in tensor memory, twelve gates
                                 // per SM (K5FT, TFHE_B200_F64_TMEM=1): measured 10 % slower -- the kernel is bound by issue slots, not by latency
+    int f64_cluster = 1;        // FFT64 latency shape on a cluster of two SMs for batches of at most #SMs/2 gates (TFHE_B200_F64_CLUSTER=0: one SM)
     int f64_latency = 1;        // FFT64 mode: batches of at most 3 #SMs gates run one gate per SM, two warps per transform (K5FL2);
                                 // TFHE_B200_F64_LATENCY=0: the NTT latency shapes / K5T / K5F instead
     int f64_stagger_ns = 0;   // start-up offset between the warps of a CTA of the FFT64 kernel (TFHE_B200_F64_STAGGER)
@@ -260,6 +261,9 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
     if ((e = cudaFuncSetAttribute(external_product_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64 external product)", e);
     if (const char* v = getenv("TFHE_B200_F64_LATENCY")) ctx->f64_latency = atoi(v);
+    if (const char* v = getenv("TFHE_B200_F64_CLUSTER")) ctx->f64_cluster = atoi(v);
+    if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L3_SMEM_BYTES)) != cudaSuccess)
+        return bail("smem attr (f64 latency 3)", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (f64 latency 2)", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_f64t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64t_smem_bytes())) != cudaSuccess)
@@ -495,7 +499,10 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         // 148 gates.  TFHE_B200_F64_LATENCY=0: the NTT latency shapes.  (One warp per transform on six warps measured 3.2 ms.)
         a.cta_base = 1; a.cta_rem = 0;
         ctx->gates_per_cta = 1;
-        blind_rotate_f64_latency2_kernel<<<(unsigned)a.B, F64L2_THREADS, F64L2_SMEM_BYTES, st>>>(a, ctx->bkdev_f64l);
+        if (ctx->f64_cluster && a.B <= (long)ctx->pair_max)   // one gate on a cluster of two SMs (K5FL3)
+            blind_rotate_f64_latency3_kernel<<<(unsigned)(2 * a.B), F64L3_THREADS, F64L3_SMEM_BYTES, st>>>(a, ctx->bkdev_f64l);
+        else
+            blind_rotate_f64_latency2_kernel<<<(unsigned)a.B, F64L2_THREADS, F64L2_SMEM_BYTES, st>>>(a, ctx->bkdev_f64l);
     } else if (full && (variant == 3 || a.B <= 2L * ctx->sm_count) && a.ns == 3) {
         // 1-gate CTAs, up to three per SM (96 registers): the earlier default (TFHE_B200_BR_VARIANT=3 for A/B runs) and still the
         // best shape between one and two gates per SM (296 gates: 5.7 ms against 6.3 ms for 2-gate CTAs of the 80-register
