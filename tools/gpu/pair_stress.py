@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
-"""Stress of the 2-SM cluster kernel's spectra exchange (GPU box only): the same random gate batches through the cluster
-shape and through the one-CTA-per-gate shape (TFHE_B200_BR_VARIANT=9) of the library in TFHE_B200_LIB; every output
-ciphertext must be the same bits.  usage: python tools/gpu/pair_stress.py [rounds] [B]"""
+"""Stress of the 2-SM cluster latency kernel's DSMEM exchange (GPU box only): the same random gate batches through the cluster
+shape (K5FL3, default for batches of at most #SMs/2 gates) and through the one-SM-per-gate shape (K5FL2,
+TFHE_B200_F64_CLUSTER=0) of the library in TFHE_B200_LIB; every output ciphertext must be the same bits.
+With TFHE_B200_KEY_SLICES=2/3 in the environment: the NTT cluster kernel against the NTT one-CTA kernel (TFHE_B200_BR_VARIANT=9).
+usage: python tools/gpu/pair_stress.py [rounds] [B]"""
 import os
 import sys
 
@@ -19,9 +21,13 @@ def main():
     sk = R.SecretKeys.generate(seed)
     os.environ.pop("TFHE_B200_BR_VARIANT", None)
     os.environ.pop("TFHE_B200_SLAB_TMA", None)
+    os.environ.pop("TFHE_B200_F64_CLUSTER", None)
     pair = R.TFHE.new_on_device(sk.s_key_tlwelv0, sk.s_key_tlwelv1, seed).engine
-    os.environ["TFHE_B200_BR_VARIANT"] = "9"
-    os.environ["TFHE_B200_SLAB_TMA"] = "0"     # the plain one-CTA-per-gate kernel (keys streamed from L2) is the reference shape
+    if os.environ.get("TFHE_B200_KEY_SLICES") in ("2", "3"):
+        os.environ["TFHE_B200_BR_VARIANT"] = "9"
+        os.environ["TFHE_B200_SLAB_TMA"] = "0"     # NTT modes: the plain one-CTA-per-gate kernel (keys streamed from L2)
+    else:
+        os.environ["TFHE_B200_F64_CLUSTER"] = "0"  # FFT64 mode: one SM per gate is the reference shape
     solo = R.TFHE.new_on_device(sk.s_key_tlwelv0, sk.s_key_tlwelv1, seed).engine
     rng = np.random.default_rng(7)
     bad = 0
