@@ -68,7 +68,7 @@ def _locked_build(target, paths, make, extra="", force=False):
 
 
 def sources():
-    names = ("engine.cu", "group.cu", "blind_rotate.cuh", "blind_rotate_t2.cuh", "t2_steps.cuh", "blind_rotate_f64.cuh", "blind_rotate_f64t.cuh", "blind_rotate_f64l2.cuh", "fft64.cuh", "fft64_tables.h", "keyswitch.cuh", "aux_kernels.cuh", "hostkeys.cpp",
+    names = ("engine.cu", "group.cu", "blind_rotate.cuh", "blind_rotate_t2.cuh", "t2_steps.cuh", "blind_rotate_f64.cuh", "blind_rotate_f64t.cuh", "blind_rotate_f64l2.cuh", "blind_rotate_f64w2.cuh", "fft64.cuh", "fft64_tables.h", "keyswitch.cuh", "aux_kernels.cuh", "hostkeys.cpp",
              "wire.cpp", "csprng.hpp", "ntt32.cuh", "cmux_steps.cuh", "ntt_tables.h", "tfhe_rng.cuh")
     return [os.path.join(CSRC, f) for f in names if os.path.exists(os.path.join(CSRC, f))] + [os.path.join(ROOT, "include", "tfhe_b200.h")]
 

@@ -20,6 +20,7 @@
 #include "blind_rotate_f64.cuh"
 #include "blind_rotate_f64t.cuh"
 #include "blind_rotate_f64l2.cuh"
+#include "blind_rotate_f64w2.cuh"
 #include "keyswitch.cuh"
 #include "aux_kernels.cuh"
 
@@ -76,7 +77,7 @@ struct tfhe_b200_ctx {
                          // 16-bit key slices; both exact for honestly generated keys (DESIGN.md section 2 has the margins);
                          // 3 = NTT, three 11-bit slices, exact in the worst case
     int ns_int() const { return key_slices == 3 ? 3 : 2; }   // slices of the integer (NTT) form of the key
-    int f64_tmem = 0;           // FFT64 throughput kernel: 0 = K5F, eight gates per SM (default); 1 = per-gate state in tensor memory, twelve gates
+    int f64_tmem = 0;           // FFT64 throughput kernel: 0 = K5F, eight gates per SM (default); 2 = K5F2, a gate on two warps, six gates; 1 = per-gate state in tensor memory, twelve gates
                                 // per SM (K5FT, TFHE_B200_F64_TMEM=1): measured 10 % slower -- the kernel is bound by issue slots, not by latency
     int f64_cluster = 1;        // FFT64 latency shape on a cluster of two SMs for batches of at most #SMs/2 gates (TFHE_B200_F64_CLUSTER=0: one SM)
     int f64_latency = 1;        // FFT64 mode: batches of at most 3 #SMs gates run one gate per SM, two warps per transform (K5FL2);
@@ -268,7 +269,11 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
         return bail("smem attr (f64 latency 2)", e);
     if ((e = cudaFuncSetAttribute(blind_rotate_f64t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64t_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64 tmem)", e);
+    if ((e = cudaFuncSetAttribute(blind_rotate_f64w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64w2_smem_bytes())) != cudaSuccess)
+        return bail("smem attr (f64 two warps)", e);
     if (const char* v = getenv("TFHE_B200_F64_TMEM")) ctx->f64_tmem = atoi(v);
+    if (const char* v = getenv("TFHE_B200_F64_KERNEL"))   // "k5f" (default), "tmem" (K5FT), "w2" (K5F2): the measured alternatives
+        ctx->f64_tmem = !strcmp(v, "tmem") ? 1 : !strcmp(v, "w2") ? 2 : 0;
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (keyswitch2)", e);
     *out = ctx;
@@ -510,7 +515,10 @@ static int launch_blind_rotate(tfhe_b200_ctx* ctx, BrArgs& a, cudaStream_t st, b
         blind_rotate_kernel<1, false, 3><<<fixed(1), THREADS_PER_GATE, br_smem_bytes(1), st>>>(a);
     } else if (full && ctx->key_slices == 1 && variant != 8) {
         // FFT64 mode: one warp per gate, eight gates per CTA (blind_rotate_f64.cuh), above three gates per SM
-        if (ctx->f64_tmem) {
+        if (ctx->f64_tmem == 2) {
+            const unsigned grid = batches_overlap(ctx, st) ? fixed(F64W2_GATES) : deal(F64W2_GATES);
+            blind_rotate_f64w2_kernel<<<grid, F64W2_THREADS, f64w2_smem_bytes(), st>>>(a, ctx->bkdev_f64l);
+        } else if (ctx->f64_tmem) {
             const unsigned grid = batches_overlap(ctx, st) ? fixed(F64T_GATES) : deal(F64T_GATES);
             blind_rotate_f64t_kernel<<<grid, F64T_GATES * 32, f64t_smem_bytes(), st>>>(a, ctx->bkdev_f64);
         } else {

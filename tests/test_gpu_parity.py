@@ -529,6 +529,33 @@ def test_fft64_tensor_memory_variant_same_bits(keys, rng, monkeypatch):
     assert np.array_equal(keys.decrypt(outs[1]), 1 - (x & y))
 
 
+def test_fft64_two_warp_throughput_variant_same_bits(keys, rng, monkeypatch):
+    """The opt-in K5F2 variant (TFHE_B200_F64_KERNEL=w2: one gate on two warps, three radix-8 passes per transform, six gates
+    per SM) returns the same ciphertext bits as the default kernel, on a batch with uneven dealing."""
+    import rustfhe_b200 as R
+    outs = []
+    x = y = c0 = c1 = None
+    monkeypatch.setenv("TFHE_B200_F64_LATENCY", "0")
+    for name in ("k5f", "w2"):
+        monkeypatch.setenv("TFHE_B200_F64_KERNEL", name)
+        eng = R.DeviceEngine(0)
+        try:
+            eng.set_key_slices(1)
+            eng.load_ksk(keys.ksk)
+            eng.load_bk(keys.bk)
+            if x is None:
+                B = 6 * eng.stats()["sm_count"] + 5
+                x = rng.integers(0, 2, B).astype(np.uint8)
+                y = rng.integers(0, 2, B).astype(np.uint8)
+                c0, c1 = keys.encrypt(x, 93000), keys.encrypt(y, 94000)
+            outs.append(eng.gate_batch(R.XOR, c0, c1))
+            assert eng.stats()["gates_per_cta"] == (6 if name == "w2" else 8)
+        finally:
+            eng.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(keys.decrypt(outs[1]), x ^ y)
+
+
 def test_gpu_against_committed_golden_vectors(engine, keys):
     """tests/golden/gate_vectors.npz was produced in the authoring container with the reference's own FFT library
     (tests/golden/make_golden.py); this compares the GPU output with the COMMITTED vectors directly, so the check does not
