@@ -148,6 +148,16 @@ int tfhe_b200_circuit_create(tfhe_b200_ctx* ctx, size_t n_levels, const size_t* 
 int tfhe_b200_circuit_run_device(tfhe_b200_ctx* ctx, const tfhe_b200_circuit* circuit, uint32_t* wires_dev /*[n_wires][n+1]*/,
                                  void* stream);
 int tfhe_b200_circuit_destroy(tfhe_b200_ctx* ctx, tfhe_b200_circuit* circuit);
+/* Pieces of a run, for evaluators that spread one level over several devices (the group entry points below use them):
+ * the shape of a circuit; gates [first, first + count) of one level, results either to their wires (rows_out == NULL) or
+ * to row k = gate first + k of rows_out with the wire table only read; and the scatter of a whole level's rows
+ * (rows_dev[k] = output of gate k of the level) into the wire table. */
+int tfhe_b200_circuit_shape(const tfhe_b200_circuit* circuit, size_t* n_levels, size_t* n_wires, size_t* max_level_gates);
+int tfhe_b200_circuit_level_gates(const tfhe_b200_circuit* circuit, size_t level, size_t* gates);
+int tfhe_b200_circuit_run_level_device(tfhe_b200_ctx* ctx, const tfhe_b200_circuit* circuit, size_t level, size_t first, size_t count,
+                                       uint32_t* wires_dev, uint32_t* rows_out /* NULL or [count][n+1] */, void* stream);
+int tfhe_b200_circuit_scatter_level_device(tfhe_b200_ctx* ctx, const tfhe_b200_circuit* circuit, size_t level,
+                                           const uint32_t* rows_dev /*[level gates][n+1]*/, uint32_t* wires_dev, void* stream);
 int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t B); /* TFHE::bootstrap */
 /* hom_mux(control, input_0, input_1) = (input_1 & control) | (input_0 & !control): three bootstraps, tfhe.rs:27-40 */
 int tfhe_b200_mux_batch(tfhe_b200_ctx* ctx, const uint32_t* control, const uint32_t* in0, const uint32_t* in1,
@@ -269,6 +279,20 @@ void tfhe_b200_group_shard(const tfhe_b200_group* g, size_t B, int rank, size_t*
 int tfhe_b200_group_gate_batch(tfhe_b200_group* g, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B);
 int tfhe_b200_group_gate_batch_async(tfhe_b200_group* g, int op, const uint32_t* in0, const uint32_t* in1, uint32_t* out, size_t B);
 int tfhe_b200_group_sync(tfhe_b200_group* g);
+/* A levelised netlist (arguments as tfhe_b200_circuit_create) on every device of the group.  A level of at least shard_min
+ * gates (0 = default: more than one wave of the latency kernel, #SMs / 2 + 1) is cut into contiguous shards, one per device,
+ * and its output ciphertexts are exchanged over NCCL before the next level (2544 B per gate); narrower levels are evaluated
+ * by every device on its own copy of the wire table, without an exchange.  The reference evaluates a logic expression
+ * depth-first, one gate at a time, on the calling thread (nander/src/lib.rs:72-89).
+ * _run: wires_host [n_wires][n+1] with the input and constant wires filled in; on return every wire of the circuit. */
+typedef struct tfhe_b200_group_circuit tfhe_b200_group_circuit;
+int tfhe_b200_group_circuit_create(tfhe_b200_group* g, size_t n_levels, const size_t* level_gates, const uint8_t* ops,
+                                   const int32_t* in0, const int32_t* in1, const int32_t* out, size_t n_wires, size_t shard_min,
+                                   tfhe_b200_group_circuit** circuit);
+int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* circuit, uint32_t* wires_host);
+int tfhe_b200_group_circuit_stats(const tfhe_b200_group_circuit* circuit, uint64_t* sharded_levels, uint64_t* replicated_levels,
+                                  size_t* shard_min);
+int tfhe_b200_group_circuit_destroy(tfhe_b200_group* g, tfhe_b200_group_circuit* circuit);
 int tfhe_b200_host_alloc(void** out, size_t bytes);   /* pinned, portable across the devices of the box */
 int tfhe_b200_host_free(void* p);
 

@@ -35,6 +35,8 @@ SYMBOLS = [
     "tfhe_b200_group_load_bk", "tfhe_b200_group_load_ksk", "tfhe_b200_group_keygen_csprng", "tfhe_b200_group_keygen",
     "tfhe_b200_group_reserve", "tfhe_b200_group_shard", "tfhe_b200_group_gate_batch", "tfhe_b200_group_gate_batch_async",
     "tfhe_b200_group_sync", "tfhe_b200_host_alloc", "tfhe_b200_host_free",
+    "tfhe_b200_circuit_shape", "tfhe_b200_circuit_level_gates", "tfhe_b200_circuit_run_level_device", "tfhe_b200_circuit_scatter_level_device",
+    "tfhe_b200_group_circuit_create", "tfhe_b200_group_circuit_run", "tfhe_b200_group_circuit_stats", "tfhe_b200_group_circuit_destroy",
     "tfhe_b200_file_write", "tfhe_b200_file_info", "tfhe_b200_file_read", "tfhe_b200_file_last_error",
 ]
 FILE_SECRET, FILE_BK, FILE_KSK, FILE_TLWE0, FILE_TLWE1, FILE_TRLWE, FILE_TRGSW = range(1, 8)
@@ -89,6 +91,14 @@ def lib():
         "tfhe_b200_circuit_create": (i32, [vp, sz, vp, vp, vp, vp, vp, sz, C.POINTER(vp)]),
         "tfhe_b200_circuit_run_device": (i32, [vp, vp, vp, vp]),
         "tfhe_b200_circuit_destroy": (i32, [vp, vp]),
+        "tfhe_b200_circuit_shape": (i32, [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]),
+        "tfhe_b200_circuit_level_gates": (i32, [vp, sz, C.POINTER(sz)]),
+        "tfhe_b200_circuit_run_level_device": (i32, [vp, vp, sz, sz, sz, vp, vp, vp]),
+        "tfhe_b200_circuit_scatter_level_device": (i32, [vp, vp, sz, vp, vp, vp]),
+        "tfhe_b200_group_circuit_create": (i32, [vp, sz, vp, vp, vp, vp, vp, sz, sz, C.POINTER(vp)]),
+        "tfhe_b200_group_circuit_run": (i32, [vp, vp, vp]),
+        "tfhe_b200_group_circuit_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(sz)]),
+        "tfhe_b200_group_circuit_destroy": (i32, [vp, vp]),
         "tfhe_b200_bootstrap_batch": (i32, [vp, vp, vp, sz]),
         "tfhe_b200_mux_batch": (i32, [vp, vp, vp, vp, vp, sz]),
         "tfhe_b200_mux_batch_device": (i32, [vp, vp, vp, vp, vp, sz, vp]),

@@ -202,6 +202,25 @@ def prefix_adder(nbits=32):
     return nl
 
 
+def side_by_side(netlist, k):
+    """k disjoint copies of a netlist in one: inputs of copy c are inputs [c * n_inputs, (c + 1) * n_inputs), outputs are
+    concatenated in copy order.  Levels become k times as wide (a SIMD batch of the same circuit on independent operands) --
+    the shape on which sharding a level over the GPUs of a group pays."""
+    nl = Netlist()
+    nl.add_inputs(k * netlist.n_inputs)
+    inner = netlist.n_wires - netlist.n_inputs
+    base = k * netlist.n_inputs
+    nl.n_wires += k * inner
+    for c in range(k):
+        m = lambda w, c=c: c * netlist.n_inputs + w if w < netlist.n_inputs else base + c * inner + (w - netlist.n_inputs)
+        for w, bit in netlist.consts.items():
+            nl.consts[m(w)] = bit
+        for op, a, b, out in netlist.gates:
+            nl.gates.append((op, m(a), m(b) if b >= 0 else -1, m(out)))
+        nl.outputs += [m(w) for w in netlist.outputs]
+    return nl
+
+
 def expr_to_netlist(expr):
     """Compile a LogicExpr with the TFHE Logip mapping (native and/or/xor/not gates, nander/src/lib.rs:40-62)."""
     nl = Netlist()
@@ -261,19 +280,12 @@ class DeviceCircuit:
     def __init__(self, engine, netlist):
         import ctypes as C
         self.engine, self.netlist = engine, netlist
-        levels = netlist.levels()
-        sizes, ops, i0, i1, o = [], [], [], [], []
-        for lev in levels:
-            n = 0
-            for op, (a, b, c) in lev.items():
-                ops.append(np.full(len(c), op, np.uint8)); i0.append(a); i1.append(b); o.append(c); n += len(c)
-            sizes.append(n)
-        cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0), dt)
+        sizes, ops, i0, i1, o = _flatten_levels(netlist)
         self._sizes = (C.c_size_t * max(1, len(sizes)))(*sizes)
         self._h = C.c_void_p()
-        self.levels, self.gates = len(levels), int(sum(sizes))
-        rc = engine._l.tfhe_b200_circuit_create(engine._ctx, len(sizes), self._sizes, K.ptr(cat(ops, np.uint8)), K.ptr(cat(i0, np.int32)),
-                                                K.ptr(cat(i1, np.int32)), K.ptr(cat(o, np.int32)), netlist.n_wires, C.byref(self._h))
+        self.levels, self.gates, self.sizes = len(sizes), int(sum(sizes)), sizes
+        rc = engine._l.tfhe_b200_circuit_create(engine._ctx, len(sizes), self._sizes, K.ptr(ops), K.ptr(i0), K.ptr(i1), K.ptr(o),
+                                                netlist.n_wires, C.byref(self._h))
         engine._ck(rc)
 
     def run(self, inputs=None):
@@ -295,6 +307,69 @@ class DeviceCircuit:
     def close(self):
         if self._h:
             self.engine._l.tfhe_b200_circuit_destroy(self.engine._ctx, self._h)
+            self._h = None
+
+
+def _flatten_levels(netlist):
+    """The levels of a netlist as the concatenated arrays the C ABI takes: sizes, ops, in0, in1, out."""
+    sizes, ops, i0, i1, o = [], [], [], [], []
+    for lev in netlist.levels():
+        n = 0
+        for op, (a, b, c) in lev.items():
+            ops.append(np.full(len(c), op, np.uint8)); i0.append(a); i1.append(b); o.append(c); n += len(c)
+        sizes.append(n)
+    cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0), dt)
+    return sizes, cat(ops, np.uint8), cat(i0, np.int32), cat(i1, np.int32), cat(o, np.int32)
+
+
+def level_plan(sizes, world, shard_min):
+    """What tfhe_b200_group_circuit_run does with each level on `world` devices: ("replicated", width) when the level is
+    evaluated by every device on its own wire table, or ("sharded", [(first, count) per device]) when it is cut into
+    contiguous shards whose outputs are exchanged (the first width % world devices take one gate more)."""
+    plan = []
+    for w in sizes:
+        if world == 1 or w < shard_min:
+            plan.append(("replicated", w))
+        else:
+            base, rem = divmod(w, world)
+            plan.append(("sharded", [(r * base + min(r, rem), base + (1 if r < rem else 0)) for r in range(world)]))
+    return plan
+
+
+class GroupCircuit:
+    """A levelised netlist on every GPU of a DeviceGroup (tfhe_b200_group_circuit_*): wide levels are sharded over the devices
+    and their outputs exchanged over NCCL, narrow ones are evaluated by every device.  `run(inputs)` returns the
+    output ciphertexts; `last` holds how many levels of the run were sharded / replicated."""
+
+    def __init__(self, group, netlist, shard_min=0):
+        import ctypes as C
+        self.group, self.netlist = group, netlist
+        sizes, ops, i0, i1, o = _flatten_levels(netlist)
+        self._sizes = (C.c_size_t * max(1, len(sizes)))(*sizes)
+        self._h = C.c_void_p()
+        self.levels, self.gates, self.sizes = len(sizes), int(sum(sizes)), sizes
+        group._ck(group._l.tfhe_b200_group_circuit_create(group._g, len(sizes), self._sizes, K.ptr(ops), K.ptr(i0), K.ptr(i1), K.ptr(o),
+                                                         netlist.n_wires, shard_min, C.byref(self._h)))
+        self.last = {}
+
+    def run(self, inputs=None):
+        import ctypes as C
+        nl, W = self.netlist, K.n + 1
+        wires = np.zeros((nl.n_wires, W), np.uint32)
+        if nl.n_inputs:
+            wires[:nl.n_inputs] = np.ascontiguousarray(inputs, np.uint32).reshape(nl.n_inputs, W)
+        for w, bit in nl.consts.items():
+            wires[w, 0] = 0x20000000 if bit else 0xE0000000
+        g = self.group
+        g._ck(g._l.tfhe_b200_group_circuit_run(g._g, self._h, K.ptr(wires)))
+        sh, rep, smin = C.c_uint64(), C.c_uint64(), C.c_size_t()
+        g._l.tfhe_b200_group_circuit_stats(self._h, C.byref(sh), C.byref(rep), C.byref(smin))
+        self.last = {"sharded_levels": sh.value, "replicated_levels": rep.value, "shard_min": smin.value}
+        return wires[nl.outputs] if nl.outputs else wires
+
+    def close(self):
+        if self._h:
+            self.group._l.tfhe_b200_group_circuit_destroy(self.group._g, self._h)
             self._h = None
 
 

@@ -142,3 +142,12 @@ __global__ void sample_extract_kernel(const uint32_t* __restrict__ trlwe, uint32
     if (threadIdx.x == 0) o[0] = b[index];
 }
 
+// wires[out[g]] = rows[g]: one level's ciphertexts, gathered from every device of a group, into the wire table (one warp per row)
+__global__ void wire_scatter_kernel(const uint4* __restrict__ rows, const int32_t* __restrict__ idxo, uint32_t* __restrict__ wires, long n) {
+    const long g = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n) return;
+    const uint4* src = rows + (size_t)g * ((LWE_N + 1) / 4);
+    uint4* dst = reinterpret_cast<uint4*>(wires + (size_t)idxo[g] * (LWE_N + 1));
+    for (int c = threadIdx.x & 31; c < (LWE_N + 1) / 4; c += 32) dst[c] = src[c];
+}
+

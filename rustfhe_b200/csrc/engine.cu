@@ -859,6 +859,55 @@ int tfhe_b200_circuit_run_device(tfhe_b200_ctx* ctx, const tfhe_b200_circuit* c,
     }
     return slot_release(ctx, s, st);
 }
+// ---- pieces of a run for evaluators that spread a level over several devices (group.cu, SURVEY 8e: "per level, all-gather of
+// that level's outputs so every GPU holds all wires") ----
+int tfhe_b200_circuit_shape(const tfhe_b200_circuit* c, size_t* n_levels, size_t* n_wires, size_t* max_level_gates) {
+    if (!c) return TFHE_B200_ERR_PARAM;
+    if (n_levels) *n_levels = c->level_gates.size();
+    if (n_wires) *n_wires = c->n_wires;
+    if (max_level_gates) *max_level_gates = c->max_level;
+    return TFHE_B200_OK;
+}
+int tfhe_b200_circuit_level_gates(const tfhe_b200_circuit* c, size_t level, size_t* gates) {
+    if (!c || !gates || level >= c->level_gates.size()) return TFHE_B200_ERR_PARAM;
+    *gates = c->level_gates[level];
+    return TFHE_B200_OK;
+}
+// gates [first, first + count) of one level.  rows_out == NULL: results go to their wires (as circuit_run_device does);
+// otherwise row k of rows_out receives the output of gate first + k and the wire table is only read.
+int tfhe_b200_circuit_run_level_device(tfhe_b200_ctx* ctx, const tfhe_b200_circuit* c, size_t level, size_t first, size_t count,
+                                       uint32_t* wires_dev, uint32_t* rows_out, void* stream) {
+    if (!ctx || !c || !wires_dev) return fail(ctx, TFHE_B200_ERR_PARAM, "circuit_run_level: null argument");
+    if (!ctx->have_bk || !ctx->have_ksk) return fail(ctx, TFHE_B200_ERR_STATE, "circuit_run_level: keys not loaded");
+    if (level >= c->level_gates.size() || first > c->level_gates[level] || count > c->level_gates[level] - first)
+        return fail(ctx, TFHE_B200_ERR_PARAM, "circuit_run_level: level or gate range out of bounds");
+    if (count == 0) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Slot* s;
+    RC(slot_acquire(ctx, &st, false, &s));
+    const size_t f = c->level_first[level] + first;
+    BrArgs a{};
+    a.ops = c->ops + f;
+    a.idx0 = c->idx + f; a.idx1 = c->idx + c->total + f; a.idxo = rows_out ? nullptr : c->idx + 2 * c->total + f;
+    a.in0 = wires_dev; a.in1 = wires_dev; a.B = (long)count;
+    RC(run_gates(ctx, s, a, rows_out ? rows_out : wires_dev, st));
+    return slot_release(ctx, s, st);
+}
+// wires[out wire of gate k of the level] = rows[k] for every gate of the level
+int tfhe_b200_circuit_scatter_level_device(tfhe_b200_ctx* ctx, const tfhe_b200_circuit* c, size_t level, const uint32_t* rows_dev,
+                                           uint32_t* wires_dev, void* stream) {
+    if (!ctx || !c || !rows_dev || !wires_dev) return fail(ctx, TFHE_B200_ERR_PARAM, "circuit_scatter_level: null argument");
+    if (level >= c->level_gates.size()) return fail(ctx, TFHE_B200_ERR_PARAM, "circuit_scatter_level: level out of bounds");
+    const size_t n = c->level_gates[level];
+    if (n == 0) return TFHE_B200_OK;
+    CK(cudaSetDevice(ctx->device));
+    wire_scatter_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(rows_dev),
+                                                                                 c->idx + 2 * c->total + c->level_first[level], wires_dev, (long)n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TFHE_B200_OK;
+}
 }  // extern "C"
 
 // ---- device-side key generation, encryption, decryption ----

@@ -9,6 +9,8 @@
 //   group_keygen[_csprng]            both keys generated ON device 0, then the same broadcast
 //   group_gate_batch[_async]         contiguous shards of ceil/floor(B / n) gates per GPU, every GPU fed from the caller's host
 //                                    buffers on its own streams (tfhe_b200_gate_batch_async per context); group_sync waits
+//   group_circuit_create / _run      a levelised netlist on all GPUs: wide levels sharded + outputs exchanged over NCCL, narrow
+//                                    levels replicated (the one place of the path with a per-level exchange step)
 // The per-device contexts stay reachable (group_ctx) for the device-pointer entry points.  One host thread at a time, like a ctx.
 #include <cuda_runtime.h>
 #include <nccl.h>
@@ -230,6 +232,126 @@ int tfhe_b200_group_gate_batch(tfhe_b200_group* g, int op, const uint32_t* in0, 
     const int rc = tfhe_b200_group_gate_batch_async(g, op, in0, in1, out, B);
     if (rc) { if (g) tfhe_b200_group_sync(g); return rc; }
     return tfhe_b200_group_sync(g);
+}
+// ---- circuits on a group: every device holds the whole wire table; a level of at least `shard_min` gates is cut
+// into contiguous shards, one per device, whose outputs are exchanged before the next level -- each device broadcasts its
+// shard of the level's output rows to the others (N ncclBroadcast in one NCCL group call = an all-gather with uneven shards,
+// 2544 B per gate over NVLink) and every device scatters the rows into its wire table.  Narrower levels are evaluated by
+// EVERY device on its own copy (the kernels are deterministic, the copies stay bit-identical): no exchange where a level
+// fits one wave of the latency kernel anyway.  Everything is enqueued on one stream per device; the host waits once.
+struct tfhe_b200_group_circuit {
+    std::vector<tfhe_b200_circuit*> per_dev;
+    std::vector<uint32_t*> wires, rows;
+    std::vector<size_t> level_gates;
+    size_t n_wires = 0, max_level = 0, shard_min = 0;
+    uint64_t sharded_levels = 0, replicated_levels = 0;   // of the last run
+};
+int tfhe_b200_group_circuit_destroy(tfhe_b200_group* g, tfhe_b200_group_circuit* c) {
+    if (!g || !c) return TFHE_B200_ERR_PARAM;
+    for (size_t r = 0; r < c->per_dev.size(); r++) {
+        cudaSetDevice(g->devices[r]);
+        if (c->per_dev[r]) tfhe_b200_circuit_destroy(g->ctx[r], c->per_dev[r]);
+        if (r < c->wires.size()) cudaFree(c->wires[r]);
+        if (r < c->rows.size()) cudaFree(c->rows[r]);
+    }
+    delete c;
+    return TFHE_B200_OK;
+}
+int tfhe_b200_group_circuit_create(tfhe_b200_group* g, size_t n_levels, const size_t* level_gates, const uint8_t* ops, const int32_t* in0,
+                                   const int32_t* in1, const int32_t* out, size_t n_wires, size_t shard_min,
+                                   tfhe_b200_group_circuit** circuit) {
+    if (!g || !circuit) return TFHE_B200_ERR_PARAM;
+    *circuit = nullptr;
+    tfhe_b200_group_circuit* c = new tfhe_b200_group_circuit();
+    c->n_wires = n_wires;
+    if (shard_min == 0) {   // default: a level is cut up when it does not fit one wave of the 2-SM cluster latency kernel (#SMs / 2 gates)
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->devices[0]);
+        shard_min = (size_t)sms / 2 + 1;
+    }
+    c->shard_min = shard_min;
+    for (size_t l = 0; l < n_levels; l++) {
+        c->level_gates.push_back(level_gates[l]);
+        if (level_gates[l] > c->max_level) c->max_level = level_gates[l];
+    }
+    for (size_t r = 0; r < g->ctx.size(); r++) {
+        tfhe_b200_circuit* pc = nullptr;
+        const int rc = tfhe_b200_circuit_create(g->ctx[r], n_levels, level_gates, ops, in0, in1, out, n_wires, &pc);
+        if (rc != TFHE_B200_OK) {
+            g->err = "device " + std::to_string(g->devices[r]) + ": " + tfhe_b200_last_error(g->ctx[r]);
+            tfhe_b200_group_circuit_destroy(g, c);
+            return rc;
+        }
+        c->per_dev.push_back(pc);
+        uint32_t *w = nullptr, *rows = nullptr;
+        if (cudaSetDevice(g->devices[r]) != cudaSuccess || cudaMalloc(&w, (n_wires ? n_wires : 1) * CT_WORDS * 4) != cudaSuccess ||
+            cudaMalloc(&rows, (c->max_level ? c->max_level : 1) * CT_WORDS * 4) != cudaSuccess) {
+            g->err = std::string("group_circuit_create: ") + cudaGetErrorString(cudaGetLastError());
+            cudaFree(w);
+            tfhe_b200_group_circuit_destroy(g, c);
+            return TFHE_B200_ERR_NOMEM;
+        }
+        c->wires.push_back(w);
+        c->rows.push_back(rows);
+    }
+    *circuit = c;
+    return TFHE_B200_OK;
+}
+// wires_host [n_wires][n+1]: in = input and constant wires filled in (the others are ignored), out = every wire of the circuit
+int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* c, uint32_t* wires_host) {
+    if (!g || !c || !wires_host) return TFHE_B200_ERR_PARAM;
+    const int n = (int)g->ctx.size();
+    const size_t bytes = c->n_wires * CT_WORDS * 4;
+    for (int r = 0; r < n; r++) {
+        GCK(cudaSetDevice(g->devices[r]));
+        GCK(cudaMemcpyAsync(c->wires[r], wires_host, bytes, cudaMemcpyHostToDevice, g->stream[r]));
+    }
+    c->sharded_levels = c->replicated_levels = 0;
+    for (size_t l = 0; l < c->level_gates.size(); l++) {
+        const size_t width = c->level_gates[l];
+        if (width == 0) continue;
+        if (n == 1 || width < c->shard_min) {
+            for (int r = 0; r < n; r++)
+                GCTX(r, tfhe_b200_circuit_run_level_device(g->ctx[r], c->per_dev[r], l, 0, width, c->wires[r], nullptr, g->stream[r]));
+            c->replicated_levels++;
+            continue;
+        }
+        for (int r = 0; r < n; r++) {
+            size_t first, count;
+            tfhe_b200_group_shard(g, width, r, &first, &count);
+            GCTX(r, tfhe_b200_circuit_run_level_device(g->ctx[r], c->per_dev[r], l, first, count, c->wires[r], c->rows[r] + first * CT_WORDS,
+                                                      g->stream[r]));
+        }
+        GNCCL(ncclGroupStart());
+        for (int root = 0; root < n; root++) {
+            size_t first, count;
+            tfhe_b200_group_shard(g, width, root, &first, &count);
+            if (count == 0) continue;
+            for (int r = 0; r < n; r++) {
+                uint32_t* p = c->rows[r] + first * CT_WORDS;
+                const ncclResult_t rr = ncclBroadcast(p, p, count * CT_WORDS, ncclUint32, root, g->comm[r], g->stream[r]);
+                if (rr != ncclSuccess) {
+                    ncclGroupEnd();
+                    g->err = std::string("ncclBroadcast (level outputs): ") + ncclGetErrorString(rr);
+                    return TFHE_B200_ERR_CUDA;
+                }
+            }
+        }
+        GNCCL(ncclGroupEnd());
+        for (int r = 0; r < n; r++)
+            GCTX(r, tfhe_b200_circuit_scatter_level_device(g->ctx[r], c->per_dev[r], l, c->rows[r], c->wires[r], g->stream[r]));
+        c->sharded_levels++;
+    }
+    GCK(cudaSetDevice(g->devices[0]));
+    GCK(cudaMemcpyAsync(wires_host, c->wires[0], bytes, cudaMemcpyDeviceToHost, g->stream[0]));
+    return sync_streams(g);
+}
+int tfhe_b200_group_circuit_stats(const tfhe_b200_group_circuit* c, uint64_t* sharded_levels, uint64_t* replicated_levels, size_t* shard_min) {
+    if (!c) return TFHE_B200_ERR_PARAM;
+    if (sharded_levels) *sharded_levels = c->sharded_levels;
+    if (replicated_levels) *replicated_levels = c->replicated_levels;
+    if (shard_min) *shard_min = c->shard_min;
+    return TFHE_B200_OK;
 }
 // pinned host memory that every device of the box can copy from / to asynchronously (pageable buffers serialise the shards)
 int tfhe_b200_host_alloc(void** out, size_t bytes) {

@@ -167,3 +167,76 @@ def test_device_circuit_rejects_racy_netlists(engine):
     msg = engine._l.tfhe_b200_last_error(engine._ctx)
     msg = msg.decode() if isinstance(msg, bytes) else str(msg)
     assert "out of range" in msg
+
+
+def test_side_by_side_and_level_plan(rng):
+    """Host logic of the multi-GPU circuit evaluator: k disjoint copies of a netlist (levels k times as wide) simulate like k
+    separate runs; the level plan shards a level of at least shard_min gates contiguously (every gate exactly once, the first
+    width % world devices one gate more) and replicates the narrower ones."""
+    base = Cq.prefix_adder(8)
+    k = 5
+    wide = Cq.side_by_side(base, k)
+    assert wide.n_inputs == k * base.n_inputs and len(wide.gates) == k * len(base.gates)
+    assert [sum(len(o) for (_, _, o) in lev.values()) for lev in wide.levels()] == \
+           [k * sum(len(o) for (_, _, o) in lev.values()) for lev in base.levels()]
+    bits = rng.integers(0, 2, (k, base.n_inputs)).astype(np.uint8)
+    got = wide.simulate(bits.reshape(-1)).reshape(k, -1)
+    for c in range(k):
+        assert np.array_equal(got[c], base.simulate(bits[c]))
+    sizes = [3, 75, 0, 1531, 74, 8]
+    plan = Cq.level_plan(sizes, 8, 75)
+    assert [p[0] for p in plan] == ["replicated", "sharded", "replicated", "sharded", "replicated", "replicated"]
+    for w, (kind, what) in zip(sizes, plan):
+        if kind == "replicated":
+            assert what == w
+        else:
+            assert what[0][0] == 0 and all(what[r][0] + what[r][1] == what[r + 1][0] for r in range(7)) and what[7][0] + what[7][1] == w
+            counts = [c for _, c in what]
+            assert max(counts) - min(counts) <= 1 and counts == sorted(counts, reverse=True)
+    assert all(p[0] == "replicated" for p in Cq.level_plan(sizes, 1, 1))
+
+
+@pytest.mark.gpu
+def test_circuit_level_pieces_match_whole_run(engine, keys, rng):
+    """tfhe_b200_circuit_run_level_device / _scatter_level_device (what a group does per device): every level evaluated as two
+    shards into a row buffer and then scattered gives the same wire table, bit for bit, as tfhe_b200_circuit_run_device."""
+    import ctypes as C
+    import torch
+    import rustfhe_b200 as R
+    from rustfhe_b200 import _capi as K
+    nl = Cq.prefix_adder(16)
+    bits = rng.integers(0, 2, nl.n_inputs).astype(np.uint8)
+    cts = keys.encrypt(bits, 95000)
+    dc = Cq.DeviceCircuit(engine, nl)
+    try:
+        W = K.n + 1
+        wires = np.zeros((nl.n_wires, W), np.uint32)
+        wires[:nl.n_inputs] = cts
+        dev = torch.device("cuda", engine.device)
+        st = torch.cuda.current_stream(dev)
+        whole = torch.from_numpy(wires.view(np.int32)).to(dev)
+        engine._ck(engine._l.tfhe_b200_circuit_run_device(engine._ctx, dc._h, C.c_void_p(whole.data_ptr()), C.c_void_p(st.cuda_stream)))
+        nlev, nw, mx = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        assert engine._l.tfhe_b200_circuit_shape(dc._h, C.byref(nlev), C.byref(nw), C.byref(mx)) == 0
+        assert (nlev.value, nw.value, mx.value) == (dc.levels, nl.n_wires, max(dc.sizes))
+        pieces = torch.from_numpy(wires.view(np.int32)).to(dev)
+        rows = torch.zeros((mx.value, W), dtype=torch.int32, device=dev)
+        for l in range(nlev.value):
+            g = C.c_size_t()
+            assert engine._l.tfhe_b200_circuit_level_gates(dc._h, l, C.byref(g)) == 0 and g.value == dc.sizes[l]
+            cut = g.value // 3
+            for first, count in ((0, cut), (cut, g.value - cut)):
+                engine._ck(engine._l.tfhe_b200_circuit_run_level_device(engine._ctx, dc._h, l, first, count, C.c_void_p(pieces.data_ptr()),
+                                                                        C.c_void_p(rows.data_ptr() + first * W * 4), C.c_void_p(st.cuda_stream)))
+            engine._ck(engine._l.tfhe_b200_circuit_scatter_level_device(engine._ctx, dc._h, l, C.c_void_p(rows.data_ptr()),
+                                                                        C.c_void_p(pieces.data_ptr()), C.c_void_p(st.cuda_stream)))
+        torch.cuda.synchronize()
+        assert torch.equal(whole, pieces)
+        got = keys.decrypt(whole[torch.as_tensor(nl.outputs, device=dev)].cpu().numpy().view(np.uint32))
+        assert np.array_equal(got, nl.simulate(bits))
+        assert engine._l.tfhe_b200_circuit_run_level_device(engine._ctx, dc._h, nlev.value, 0, 1, C.c_void_p(pieces.data_ptr()), None,
+                                                            C.c_void_p(st.cuda_stream)) != 0          # level out of bounds
+        assert engine._l.tfhe_b200_circuit_run_level_device(engine._ctx, dc._h, 0, 1, dc.sizes[0], C.c_void_p(pieces.data_ptr()), None,
+                                                            C.c_void_p(st.cuda_stream)) != 0          # range past the level
+    finally:
+        dc.close()

@@ -70,3 +70,64 @@ def test_group_two_devices_bit_exact(engine, oracle, keys, rng):
         assert np.array_equal(g.gate_batch(R.XOR, c0[:300], c1[:300]), out[:300])
     finally:
         g.close()
+
+
+@pytest.mark.gpu
+def test_group_circuit_one_device_matches_device_circuit(engine, keys, rng):
+    """tfhe_b200_group_circuit_* on a group of one device (every level takes the replicated path): same output bits as the
+    single-context device circuit, and the decrypted sum is right."""
+    import rustfhe_b200 as R
+    from rustfhe_b200 import circuit as Cq
+    nl = Cq.ripple_carry_adder(8)
+    bits = rng.integers(0, 2, nl.n_inputs).astype(np.uint8)
+    cts = keys.encrypt(bits, 96000)
+    dc = Cq.DeviceCircuit(engine, nl)
+    want = dc.run(cts)
+    dc.close()
+    g = R.DeviceGroup([0])
+    try:
+        g.load_ksk(keys.ksk)
+        g.load_bk(keys.bk)
+        gc = Cq.GroupCircuit(g, nl, shard_min=1)
+        got = gc.run(cts)
+        assert gc.last["sharded_levels"] == 0 and gc.last["replicated_levels"] == gc.levels
+        gc.close()
+        assert np.array_equal(got, want)
+        assert np.array_equal(keys.decrypt(got), nl.simulate(bits))
+    finally:
+        g.close()
+
+
+@pytest.mark.gpu
+def test_group_circuit_two_devices_sharded_levels_bit_exact(engine, keys, rng):
+    """>= 2 GPUs: twelve 8-bit prefix adders side by side; with shard_min = 2 nearly every level is cut over the devices and its
+    outputs exchanged by the library's NCCL broadcasts, with the default shard_min (one wave of the latency kernel) only the
+    levels wider than that are.  Both runs equal the single-device circuit bit for bit."""
+    import torch
+    import rustfhe_b200 as R
+    from rustfhe_b200 import circuit as Cq
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs two GPUs")
+    nl = Cq.side_by_side(Cq.prefix_adder(8), 12)
+    bits = rng.integers(0, 2, nl.n_inputs).astype(np.uint8)
+    cts = keys.encrypt(bits, 97000)
+    dc = Cq.DeviceCircuit(engine, nl)
+    want = dc.run(cts)
+    dc.close()
+    assert np.array_equal(keys.decrypt(want), nl.simulate(bits))
+    g = R.DeviceGroup(list(range(min(ndev, 8))))
+    try:
+        g.load_ksk(keys.ksk)
+        g.load_bk(keys.bk)
+        for smin in (2, 0):
+            gc = Cq.GroupCircuit(g, nl, shard_min=smin)
+            got = gc.run(cts)
+            plan = Cq.level_plan(gc.sizes, g.size, gc.last["shard_min"])
+            assert gc.last["sharded_levels"] == sum(1 for p in plan if p[0] == "sharded") > 0
+            assert gc.last["sharded_levels"] + gc.last["replicated_levels"] == gc.levels
+            got2 = gc.run(cts)                       # a second run reuses the device tables
+            gc.close()
+            assert np.array_equal(got, want) and np.array_equal(got2, want)
+    finally:
+        g.close()
