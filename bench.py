@@ -316,6 +316,40 @@ def run_extras(eng, R, K, torch, dev, stream, dx, dy, s0, rank, world, dist):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     eng.set_batch_overlap(-1)
     out["config5_2pow16_gates_strong"] = {"gates": total, "n_gpus": world, "gates_per_s": total / (float(tt[0]) * 1e-3), "ms": float(tt[0])}
+    # ---- config 4 on all GPUs of the run: ONE process (rank 0) drives them as a device group through the C ABI; wide levels are
+    # sharded and their outputs exchanged over NCCL, levels narrower than one wave of the latency kernel are replicated ----
+    cpu_wait = dist.new_group(backend="gloo") if world > 1 else None   # the other ranks wait on the CPU: an NCCL barrier would spin on their GPUs
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_wait)
+    if rank == 0:
+        try:
+            g = R.DeviceGroup(list(range(world)))
+            try:
+                sk = R.SecretKeys.generate(SEED)
+                g.keygen(SEED, sk.s_key_tlwelv0, sk.s_key_tlwelv1)
+                r = np.random.default_rng(SEED + 4)
+                for name, nl, k in (("ripple_carry_nand", Cq.ripple_carry_adder(32), 1), ("kogge_stone_x64", Cq.side_by_side(Cq.prefix_adder(32), 64), 64)):
+                    xs = [int(v) for v in r.integers(0, 2 ** 32, k, dtype=np.uint64)]
+                    ys = [int(v) for v in r.integers(0, 2 ** 32, k, dtype=np.uint64)]
+                    bits = np.array([(v >> i) & 1 for x, y in zip(xs, ys) for v in (x, y) for i in range(32)], np.uint8)
+                    cts = R.Cryptor.encrypto(R.TLWE, sk.s_key_tlwelv0, bits, seed=SEED + 400, ct_index0=0)
+                    gc = Cq.GroupCircuit(g, nl)
+                    gc.run(cts)
+                    t0 = time.perf_counter()
+                    res = gc.run(cts)
+                    secs = time.perf_counter() - t0
+                    got = R.Cryptor.decrypto(R.TLWE, sk.s_key_tlwelv0, res).reshape(k, 33)
+                    ok = all(sum(int(b) << i for i, b in enumerate(row)) == x + y for row, x, y in zip(got, xs, ys))
+                    out[f"config4_group_{name}"] = {"n_gpus": world, "seconds": secs, "gates": gc.gates, "levels": gc.levels,
+                                                    "gates_per_s": gc.gates / secs, "correct": bool(ok), **gc.last}
+                    gc.close()
+            finally:
+                g.close()
+        except Exception as ex:
+            out["config4_group_error"] = str(ex)
+    if world > 1:
+        dist.barrier(group=cpu_wait)
     return out
 
 

@@ -284,12 +284,15 @@ int tfhe_b200_group_sync(tfhe_b200_group* g);
  * and its output ciphertexts are exchanged over NCCL before the next level (2544 B per gate); narrower levels are evaluated
  * by every device on its own copy of the wire table, without an exchange.  The reference evaluates a logic expression
  * depth-first, one gate at a time, on the calling thread (nander/src/lib.rs:72-89).
- * _run: wires_host [n_wires][n+1] with the input and constant wires filled in; on return every wire of the circuit. */
+ * _run: inputs_host [n_inputs][n+1] are the wires 0 .. n_inputs-1 (one host-to-device copy, then an NCCL broadcast); the wires
+ * const_wires[k] are set to the trivial ciphertext of const_bits[k]; outputs_host [n_out][n+1] receives the wires out_wires[]. */
 typedef struct tfhe_b200_group_circuit tfhe_b200_group_circuit;
 int tfhe_b200_group_circuit_create(tfhe_b200_group* g, size_t n_levels, const size_t* level_gates, const uint8_t* ops,
                                    const int32_t* in0, const int32_t* in1, const int32_t* out, size_t n_wires, size_t shard_min,
                                    tfhe_b200_group_circuit** circuit);
-int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* circuit, uint32_t* wires_host);
+int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* circuit, const uint32_t* inputs_host, size_t n_inputs,
+                                const int32_t* const_wires, const uint8_t* const_bits, size_t n_consts, const int32_t* out_wires,
+                                size_t n_out, uint32_t* outputs_host);
 int tfhe_b200_group_circuit_stats(const tfhe_b200_group_circuit* circuit, uint64_t* sharded_levels, uint64_t* replicated_levels,
                                   size_t* shard_min);
 int tfhe_b200_group_circuit_destroy(tfhe_b200_group* g, tfhe_b200_group_circuit* circuit);

@@ -96,7 +96,7 @@ def lib():
         "tfhe_b200_circuit_run_level_device": (i32, [vp, vp, sz, sz, sz, vp, vp, vp]),
         "tfhe_b200_circuit_scatter_level_device": (i32, [vp, vp, sz, vp, vp, vp]),
         "tfhe_b200_group_circuit_create": (i32, [vp, sz, vp, vp, vp, vp, vp, sz, sz, C.POINTER(vp)]),
-        "tfhe_b200_group_circuit_run": (i32, [vp, vp, vp]),
+        "tfhe_b200_group_circuit_run": (i32, [vp, vp, vp, sz, vp, vp, sz, vp, sz, vp]),
         "tfhe_b200_group_circuit_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(sz)]),
         "tfhe_b200_group_circuit_destroy": (i32, [vp, vp]),
         "tfhe_b200_bootstrap_batch": (i32, [vp, vp, vp, sz]),

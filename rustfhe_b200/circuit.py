@@ -355,17 +355,17 @@ class GroupCircuit:
     def run(self, inputs=None):
         import ctypes as C
         nl, W = self.netlist, K.n + 1
-        wires = np.zeros((nl.n_wires, W), np.uint32)
-        if nl.n_inputs:
-            wires[:nl.n_inputs] = np.ascontiguousarray(inputs, np.uint32).reshape(nl.n_inputs, W)
-        for w, bit in nl.consts.items():
-            wires[w, 0] = 0x20000000 if bit else 0xE0000000
+        ins = np.ascontiguousarray(inputs, np.uint32).reshape(nl.n_inputs, W) if nl.n_inputs else np.zeros((0, W), np.uint32)
+        cw = np.ascontiguousarray(list(nl.consts.keys()), np.int32)
+        cb = np.ascontiguousarray(list(nl.consts.values()), np.uint8)
+        ow = np.ascontiguousarray(nl.outputs if nl.outputs else np.arange(nl.n_wires), np.int32)
+        out = np.empty((len(ow), W), np.uint32)
         g = self.group
-        g._ck(g._l.tfhe_b200_group_circuit_run(g._g, self._h, K.ptr(wires)))
+        g._ck(g._l.tfhe_b200_group_circuit_run(g._g, self._h, K.ptr(ins), len(ins), K.ptr(cw), K.ptr(cb), len(cw), K.ptr(ow), len(ow), K.ptr(out)))
         sh, rep, smin = C.c_uint64(), C.c_uint64(), C.c_size_t()
         g._l.tfhe_b200_group_circuit_stats(self._h, C.byref(sh), C.byref(rep), C.byref(smin))
         self.last = {"sharded_levels": sh.value, "replicated_levels": rep.value, "shard_min": smin.value}
-        return wires[nl.outputs] if nl.outputs else wires
+        return out
 
     def close(self):
         if self._h:

@@ -32,6 +32,7 @@ struct tfhe_b200_group {
     std::vector<ncclComm_t> comm;
     std::vector<cudaStream_t> stream;     // one per device: broadcasts and key loads
     std::vector<uint32_t*> stage;         // one per device: KSK_WORDS words, receive buffer of the broadcasts
+    uint32_t mu = 0x20000000u;            // 1/8: the message of a trivial ciphertext (constant wires of a circuit)
     std::string err;
 };
 
@@ -108,6 +109,7 @@ int tfhe_b200_group_create(const tfhe_b200_params* p, const int* devices, int nd
     if (ndev <= 0 && !devices) ndev = have;   // all devices of the box
     if (ndev <= 0 || ndev > have) { g_group_create_err = "group_create: bad device count"; return TFHE_B200_ERR_PARAM; }
     tfhe_b200_group* g = new tfhe_b200_group();
+    if (p) g->mu = p->mu;
     for (int r = 0; r < ndev; r++) {
         const int d = devices ? devices[r] : r;
         for (int q = 0; q < r; q++)
@@ -245,7 +247,18 @@ struct tfhe_b200_group_circuit {
     std::vector<size_t> level_gates;
     size_t n_wires = 0, max_level = 0, shard_min = 0;
     uint64_t sharded_levels = 0, replicated_levels = 0;   // of the last run
+    int32_t* out_idx = nullptr;                           // device 0: the output wires of a run and their gathered rows
+    uint32_t* out_rows = nullptr;
+    size_t out_cap = 0;
 };
+// rows[k] = table[idx[k]] (one warp per 2544-byte ciphertext)
+__global__ void gather_rows_kernel(const uint4* __restrict__ table, const int32_t* __restrict__ idx, uint4* __restrict__ rows, long n) {
+    const long k = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const uint4* src = table + (size_t)idx[k] * (CT_WORDS / 4);
+    uint4* dst = rows + (size_t)k * (CT_WORDS / 4);
+    for (int c = threadIdx.x & 31; c < (int)(CT_WORDS / 4); c += 32) dst[c] = src[c];
+}
 int tfhe_b200_group_circuit_destroy(tfhe_b200_group* g, tfhe_b200_group_circuit* c) {
     if (!g || !c) return TFHE_B200_ERR_PARAM;
     for (size_t r = 0; r < c->per_dev.size(); r++) {
@@ -254,6 +267,9 @@ int tfhe_b200_group_circuit_destroy(tfhe_b200_group* g, tfhe_b200_group_circuit*
         if (r < c->wires.size()) cudaFree(c->wires[r]);
         if (r < c->rows.size()) cudaFree(c->rows[r]);
     }
+    if (!g->devices.empty()) cudaSetDevice(g->devices[0]);
+    cudaFree(c->out_idx);
+    cudaFree(c->out_rows);
     delete c;
     return TFHE_B200_OK;
 }
@@ -297,14 +313,43 @@ int tfhe_b200_group_circuit_create(tfhe_b200_group* g, size_t n_levels, const si
     *circuit = c;
     return TFHE_B200_OK;
 }
-// wires_host [n_wires][n+1]: in = input and constant wires filled in (the others are ignored), out = every wire of the circuit
-int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* c, uint32_t* wires_host) {
-    if (!g || !c || !wires_host) return TFHE_B200_ERR_PARAM;
+// inputs_host [n_inputs][n+1] = wires 0 .. n_inputs-1 (uploaded to device 0 once and broadcast over NCCL); constant wires are
+// set to trivial ciphertexts on every device; outputs_host [n_out][n+1] = the wires out_wires[], gathered on device 0.
+int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* c, const uint32_t* inputs_host, size_t n_inputs,
+                                const int32_t* const_wires, const uint8_t* const_bits, size_t n_consts, const int32_t* out_wires, size_t n_out,
+                                uint32_t* outputs_host) {
+    if (!g || !c || (n_inputs && !inputs_host) || (n_consts && (!const_wires || !const_bits)) || (n_out && (!out_wires || !outputs_host)))
+        return TFHE_B200_ERR_PARAM;
+    if (n_inputs > c->n_wires) { g->err = "group_circuit_run: more inputs than wires"; return TFHE_B200_ERR_PARAM; }
+    for (size_t k = 0; k < n_consts; k++)
+        if (const_wires[k] < 0 || (size_t)const_wires[k] >= c->n_wires) { g->err = "group_circuit_run: constant wire out of range"; return TFHE_B200_ERR_PARAM; }
+    for (size_t k = 0; k < n_out; k++)
+        if (out_wires[k] < 0 || (size_t)out_wires[k] >= c->n_wires) { g->err = "group_circuit_run: output wire out of range"; return TFHE_B200_ERR_PARAM; }
     const int n = (int)g->ctx.size();
-    const size_t bytes = c->n_wires * CT_WORDS * 4;
+    std::vector<uint32_t> trivial(2 * CT_WORDS, 0u);   // [0] = Zero, [1] = One: (b, a) = (-+1/8, 0)  (tlwe.rs:181-186); alive until the final sync
+    trivial[0] = 0u - g->mu;
+    trivial[CT_WORDS] = g->mu;
     for (int r = 0; r < n; r++) {
         GCK(cudaSetDevice(g->devices[r]));
-        GCK(cudaMemcpyAsync(c->wires[r], wires_host, bytes, cudaMemcpyHostToDevice, g->stream[r]));
+        GCK(cudaMemsetAsync(c->wires[r], 0, c->n_wires * CT_WORDS * 4, g->stream[r]));
+    }
+    if (n_inputs) {
+        GCK(cudaSetDevice(g->devices[0]));
+        GCK(cudaMemcpyAsync(c->wires[0], inputs_host, n_inputs * CT_WORDS * 4, cudaMemcpyHostToDevice, g->stream[0]));
+        if (n > 1) {
+            GNCCL(ncclGroupStart());
+            for (int r = 0; r < n; r++) {
+                const ncclResult_t rr = ncclBroadcast(c->wires[r], c->wires[r], n_inputs * CT_WORDS, ncclUint32, 0, g->comm[r], g->stream[r]);
+                if (rr != ncclSuccess) { ncclGroupEnd(); g->err = std::string("ncclBroadcast (inputs): ") + ncclGetErrorString(rr); return TFHE_B200_ERR_CUDA; }
+            }
+            GNCCL(ncclGroupEnd());
+        }
+    }
+    for (int r = 0; r < n; r++) {
+        GCK(cudaSetDevice(g->devices[r]));
+        for (size_t k = 0; k < n_consts; k++)
+            GCK(cudaMemcpyAsync(c->wires[r] + (size_t)const_wires[k] * CT_WORDS, trivial.data() + (const_bits[k] ? CT_WORDS : 0), CT_WORDS * 4,
+                                cudaMemcpyHostToDevice, g->stream[r]));
     }
     c->sharded_levels = c->replicated_levels = 0;
     for (size_t l = 0; l < c->level_gates.size(); l++) {
@@ -342,8 +387,22 @@ int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* c, 
             GCTX(r, tfhe_b200_circuit_scatter_level_device(g->ctx[r], c->per_dev[r], l, c->rows[r], c->wires[r], g->stream[r]));
         c->sharded_levels++;
     }
-    GCK(cudaSetDevice(g->devices[0]));
-    GCK(cudaMemcpyAsync(wires_host, c->wires[0], bytes, cudaMemcpyDeviceToHost, g->stream[0]));
+    if (n_out) {
+        GCK(cudaSetDevice(g->devices[0]));
+        if (n_out > c->out_cap) {
+            GCK(cudaStreamSynchronize(g->stream[0]));
+            cudaFree(c->out_idx); cudaFree(c->out_rows);
+            c->out_idx = nullptr; c->out_rows = nullptr; c->out_cap = 0;
+            GCK(cudaMalloc(&c->out_idx, n_out * sizeof(int32_t)));
+            GCK(cudaMalloc(&c->out_rows, n_out * CT_WORDS * 4));
+            c->out_cap = n_out;
+        }
+        GCK(cudaMemcpyAsync(c->out_idx, out_wires, n_out * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream[0]));
+        gather_rows_kernel<<<(unsigned)((n_out + 7) / 8), 256, 0, g->stream[0]>>>(reinterpret_cast<const uint4*>(c->wires[0]), c->out_idx,
+                                                                                 reinterpret_cast<uint4*>(c->out_rows), (long)n_out);
+        GCK(cudaGetLastError());
+        GCK(cudaMemcpyAsync(outputs_host, c->out_rows, n_out * CT_WORDS * 4, cudaMemcpyDeviceToHost, g->stream[0]));
+    }
     return sync_streams(g);
 }
 int tfhe_b200_group_circuit_stats(const tfhe_b200_group_circuit* c, uint64_t* sharded_levels, uint64_t* replicated_levels, size_t* shard_min) {

@@ -94,6 +94,11 @@ def test_group_circuit_one_device_matches_device_circuit(engine, keys, rng):
         gc.close()
         assert np.array_equal(got, want)
         assert np.array_equal(keys.decrypt(got), nl.simulate(bits))
+        # constants only (a nander expression): trivial ciphertexts are set on the device, no inputs are uploaded
+        ex = Cq.expr_to_netlist(Cq.parse_logic_expr("!(1&0)^(0|1)&1"))
+        gc = Cq.GroupCircuit(g, ex)
+        assert np.array_equal(keys.decrypt(gc.run()), ex.simulate([]))
+        gc.close()
     finally:
         g.close()
 
