@@ -4,6 +4,9 @@
 use std::os::raw::{c_char, c_int, c_void};
 
 pub enum Ctx {}
+pub enum Circuit {}
+pub enum Group {}
+pub enum GroupCircuit {}
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -65,6 +68,31 @@ extern "C" {
     pub fn tfhe_b200_export_ksk(ctx: *mut Ctx, ksk: *mut u32) -> c_int;
     pub fn tfhe_b200_encrypt_bits_device(ctx: *mut Ctx, seed: u64, ct_index0: u64, s0: *const u8, bits_dev: *const u8, b: usize, out_dev: *mut u32, stream: *mut c_void) -> c_int;
     pub fn tfhe_b200_decrypt_bits_device(ctx: *mut Ctx, s0: *const u8, ct_dev: *const u32, b: usize, bits_dev: *mut u8, phase_dev: *mut u32, stream: *mut c_void) -> c_int;
+    // device-resident circuits (the level-synchronous evaluator behind nander's LogicExpr, nander/src/lib.rs:72-89)
+    pub fn tfhe_b200_circuit_create(ctx: *mut Ctx, n_levels: usize, level_gates: *const usize, ops: *const u8, in0: *const i32, in1: *const i32,
+                                    out: *const i32, n_wires: usize, circuit: *mut *mut Circuit) -> c_int;
+    pub fn tfhe_b200_circuit_run_device(ctx: *mut Ctx, circuit: *const Circuit, wires_dev: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn tfhe_b200_circuit_destroy(ctx: *mut Ctx, circuit: *mut Circuit) -> c_int;
+    // several GPUs from one process: keys replicated by an NCCL broadcast, batches sharded, circuits with a per-level exchange
+    pub fn tfhe_b200_group_create(p: *const Params, devices: *const c_int, ndev: c_int, out: *mut *mut Group) -> c_int;
+    pub fn tfhe_b200_group_destroy(g: *mut Group) -> c_int;
+    pub fn tfhe_b200_group_last_error(g: *const Group) -> *const c_char;
+    pub fn tfhe_b200_group_size(g: *const Group) -> c_int;
+    pub fn tfhe_b200_group_load_bk(g: *mut Group, bk: *const u32) -> c_int;
+    pub fn tfhe_b200_group_load_ksk(g: *mut Group, ksk: *const u32) -> c_int;
+    pub fn tfhe_b200_group_keygen_csprng(g: *mut Group, key: *const u8, s0: *const u8, s1: *const u8) -> c_int;
+    pub fn tfhe_b200_group_reserve(g: *mut Group, max_batch: usize) -> c_int;
+    pub fn tfhe_b200_group_gate_batch(g: *mut Group, op: c_int, in0: *const u32, in1: *const u32, out: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_group_gate_batch_async(g: *mut Group, op: c_int, in0: *const u32, in1: *const u32, out: *mut u32, b: usize) -> c_int;
+    pub fn tfhe_b200_group_sync(g: *mut Group) -> c_int;
+    pub fn tfhe_b200_group_circuit_create(g: *mut Group, n_levels: usize, level_gates: *const usize, ops: *const u8, in0: *const i32,
+                                          in1: *const i32, out: *const i32, n_wires: usize, shard_min: usize,
+                                          circuit: *mut *mut GroupCircuit) -> c_int;
+    pub fn tfhe_b200_group_circuit_run(g: *mut Group, circuit: *mut GroupCircuit, inputs: *const u32, n_inputs: usize, const_wires: *const i32,
+                                       const_bits: *const u8, n_consts: usize, out_wires: *const i32, n_out: usize, outputs: *mut u32) -> c_int;
+    pub fn tfhe_b200_group_circuit_destroy(g: *mut Group, circuit: *mut GroupCircuit) -> c_int;
+    pub fn tfhe_b200_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
+    pub fn tfhe_b200_host_free(p: *mut c_void) -> c_int;
     // flat file format (the reference has no serialisation)
     pub fn tfhe_b200_file_write(path: *const c_char, kind: c_int, payload: *const c_void, count: u64) -> c_int;
     pub fn tfhe_b200_file_info(path: *const c_char, kind: *mut c_int, count: *mut u64, payload_bytes: *mut u64) -> c_int;
