@@ -34,6 +34,12 @@ def main():
     except Exception:
         p_int = 148 * 64 * 1.965e9
     eng = R.DeviceEngine(0)
+    fft64 = eng.stats()["key_slices"] == 1
+    # FFT64 arithmetic (the default): both kernels are bound by issue slots like the gate kernel (bench.py fft64_figures; a DFMA holds
+    # the issue port for two cycles): cycles per product = 2 x FP64 instructions + the others
+    issue_peak = 148 * 4 * 1.965e9
+    issue_pm = 2 * (2 * 432 + 482 + 16 * 6) + 700
+    issue_xp = 2 * (6 * 432 + 2 * 482 + 12 * 64) + 3911
     dev = torch.device("cuda", 0)
     st = torch.cuda.current_stream()
     g = torch.Generator(device=dev).manual_seed(7)
@@ -53,7 +59,7 @@ def main():
             best = min(best, e0.elapsed_time(e1) * 1e-3)
         return best
 
-    res = {"gpu": torch.cuda.get_device_name(0), "int_peak_slots_per_s": p_int, "hbm_gbs": peaks["hbm_gbs"], "negacyclic_mul": [],
+    res = {"gpu": torch.cuda.get_device_name(0), "arithmetic": "FFT64" if fft64 else "NTT", "issue_peak_cycles_per_s": issue_peak, "int_peak_slots_per_s": p_int, "hbm_gbs": peaks["hbm_gbs"], "negacyclic_mul": [],
            "external_product_shared_trgsw": [], "external_product_per_item_trgsw": []}
     for lb in range(0, args.max_log2 + 1, 2):
         B = 1 << lb
@@ -61,14 +67,15 @@ def main():
         d = torch.randint(-32, 32, (B, 1024), dtype=torch.int32, device=dev, generator=g)
         o = torch.empty_like(a)
         t = timed(lambda: eng.negacyclic_mul_batch_device(a.data_ptr(), d.data_ptr(), o.data_ptr(), B, st.cuda_stream))
-        res["negacyclic_mul"].append({"batch": B, "seconds": t, "products_per_s": B / t, "int_roofline_frac": B / t * SLOTS_PM / p_int,
+        res["negacyclic_mul"].append({"batch": B, "seconds": t, "products_per_s": B / t,
+                                      **({"issue_roofline_frac": B / t * issue_pm / issue_peak} if fft64 else {"int_roofline_frac": B / t * SLOTS_PM / p_int}),
                                       "hbm_roofline_frac": B / t * 3 * 4096 / (peaks["hbm_gbs"] * 1e9)})
         trl = u32(B, 2, 1024)
         out = torch.empty_like(trl)
         trg1 = u32(1, 6, 2, 1024)
         t = timed(lambda: eng.external_product_batch_device(trg1.data_ptr(), 1, trl.data_ptr(), out.data_ptr(), B, st.cuda_stream))
         res["external_product_shared_trgsw"].append({"batch": B, "seconds": t, "products_per_s": B / t,
-                                                     "int_roofline_frac": B / t * SLOTS_XP / p_int,
+                                                     **({"issue_roofline_frac": B / t * issue_xp / issue_peak} if fft64 else {"int_roofline_frac": B / t * SLOTS_XP / p_int}),
                                                      "hbm_roofline_frac": B / t * 2 * 8192 / (peaks["hbm_gbs"] * 1e9)})
         if B <= 4096:
             trgB = u32(B, 6, 2, 1024)
