@@ -325,10 +325,19 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel
     for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const long want = grp * F64_GATES + gl;
         const long g = want < a.B ? want : a.B - 1;
-        {
-            const uint32_t* src = a.trlwe_in + (size_t)g * 2048;
-            const uint32_t* sub = a.trlwe_in0 ? a.trlwe_in0 + (size_t)g * 2048 : nullptr;   // cmux: rep_1 - rep_0
-            for (int k = lane; k < 2048; k += 32) acc[k] = sub ? src[k] - sub[k] : src[k];
+        {   // 16 independent 16-byte loads per lane (one memory latency per product, not one per 128-byte row)
+            const uint4* src = reinterpret_cast<const uint4*>(a.trlwe_in + (size_t)g * 2048) + lane;
+            uint4* dst = reinterpret_cast<uint4*>(acc) + lane;
+            uint4 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) v[q] = src[32 * q];
+            if (a.trlwe_in0) {   // cmux: rep_1 - rep_0
+                const uint4* sub = reinterpret_cast<const uint4*>(a.trlwe_in0 + (size_t)g * 2048) + lane;
+#pragma unroll
+                for (int q = 0; q < 16; q++) { const uint4 w = sub[32 * q]; v[q].x -= w.x; v[q].y -= w.y; v[q].z -= w.z; v[q].w -= w.w; }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; q++) dst[32 * q] = v[q];
         }
         __syncwarp();
         cd s0[16], s1[16];
@@ -368,9 +377,18 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel
         f64_inverse_acc<true>(lane, s1, S, ta, ut, acc + 1024);
         __syncwarp();
         if (want < a.B) {
-            uint32_t* dst = a.trlwe_out + (size_t)g * 2048;
-            const uint32_t* add = a.trlwe_in0 ? a.trlwe_in0 + (size_t)g * 2048 : nullptr;   // cmux: ... + rep_0
-            for (int k = lane; k < 2048; k += 32) dst[k] = add ? acc[k] + add[k] : acc[k];
+            uint4* dst = reinterpret_cast<uint4*>(a.trlwe_out + (size_t)g * 2048) + lane;
+            const uint4* res = reinterpret_cast<const uint4*>(acc) + lane;
+            uint4 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) v[q] = res[32 * q];
+            if (a.trlwe_in0) {   // cmux: ... + rep_0
+                const uint4* add = reinterpret_cast<const uint4*>(a.trlwe_in0 + (size_t)g * 2048) + lane;
+#pragma unroll
+                for (int q = 0; q < 16; q++) { const uint4 w = add[32 * q]; v[q].x += w.x; v[q].y += w.y; v[q].z += w.z; v[q].w += w.w; }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; q++) dst[32 * q] = v[q];
         }
         __syncwarp();
     }

@@ -1050,7 +1050,8 @@ static int run_extprod(tfhe_b200_ctx* ctx, Slot* s, const uint32_t* trgsw_dev, s
     BrArgs a{};
     a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
     a.trlwe_in = rep1; a.trlwe_in0 = rep0; a.trlwe_out = out; a.ntrgsw = (long)ntrgsw; a.ns = ctx->ns_int();
-    if (ctx->key_slices == 1 && ntrgsw == 1 && B > (size_t)ctx->sm_count) {   // FFT64, one shared TRGSW: persistent CTAs, one product per warp
+    const bool rows16 = (((uintptr_t)rep1 | (uintptr_t)rep0 | (uintptr_t)out) & 15) == 0;   // the FFT64 kernel moves its rows as 16-byte words
+    if (ctx->key_slices == 1 && ntrgsw == 1 && B > (size_t)ctx->sm_count && rows16) {   // FFT64, one shared TRGSW: persistent CTAs, one product per warp
         cd16* kx = reinterpret_cast<cd16*>(s->scratch);   // 96 KB of the slot scratch (BK_STEP_WORDS * 4 = 144 KB were reserved above)
         bk_transform_f64_kernel<<<(12 + KTF_WARPS - 1) / KTF_WARPS, KTF_WARPS * 32, 0, st>>>(trgsw_dev, kx, 12);
         const long ngroups = ((long)B + F64_GATES - 1) / F64_GATES;
