@@ -89,7 +89,7 @@ struct tfhe_b200_ctx {
     int pair_max = 0;     // largest batch that runs on 2-SM clusters (set at create: #SMs / 2)
     int deal_fixed = -1;  // how a full batch is cut into CTAs: 0 = dealt evenly over whole waves (best for a batch running alone),
                           // 1 = 4-gate CTAs only (best when batches on other streams back-fill the last wave), -1 = decide per call
-    int ks_variant = 2;  // key-switch kernel: 2 = rows staged in shared memory, one warp per gate; 1 = register tiles
+    int ks_variant = 3;  // key-switch kernel: 3 = rows staged in shared memory, one warp per gate, producer / consumer ring; 2 = the same with a CTA barrier per stage; 1 = register tiles
     std::string err;
 };
 static thread_local std::string g_create_err;
@@ -276,6 +276,9 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
         ctx->f64_tmem = !strcmp(v, "tmem") ? 1 : !strcmp(v, "w2") ? 2 : 0;
     if ((e = cudaFuncSetAttribute(keyswitch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS2_SMEM_BYTES)) != cudaSuccess)
         return bail("smem attr (keyswitch2)", e);
+    if ((e = cudaFuncSetAttribute(keyswitch_p_kernel<KSP_GATES, KSP_RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)KsP<KSP_GATES, KSP_RING>::SMEM_BYTES)) != cudaSuccess)
+        return bail("smem attr (keyswitch pipeline)", e);
     *out = ctx;
     return TFHE_B200_OK;
 }
@@ -574,7 +577,13 @@ static int launch_keyswitch(tfhe_b200_ctx* ctx, const uint16_t* dig, uint32_t* o
         while (isplit < 128 && tiles * isplit < 2L * ctx->sm_count) isplit *= 2;
         dim3 grid((unsigned)tiles, isplit);
         keyswitch_kernel<<<grid, dim3(KS_THREADS, KS_GROUPS), 0, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B, idxo);
-    } else {                      // shared-memory staged kernel, one warp per gate (default)
+    } else if (ctx->ks_variant == 3) {   // producer / consumer pipeline over the staged rows, one warp per gate (default)
+        const long tiles = (B + KSP_GATES - 1) / KSP_GATES;
+        int isplit = KS_ISPLIT_MIN;
+        while (isplit < 128 && tiles * isplit < 2L * ctx->sm_count) isplit *= 2;
+        keyswitch_p_kernel<KSP_GATES, KSP_RING><<<dim3((unsigned)tiles, isplit), (KSP_GATES + 1) * 32, KsP<KSP_GATES, KSP_RING>::SMEM_BYTES, st>>>(
+            reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B, idxo);
+    } else {                      // the same with one __syncthreads per stage instead of empty barriers (TFHE_B200_KS_VARIANT=2)
         const long tiles = (B + KS2_GATES - 1) / KS2_GATES;
         int isplit = KS_ISPLIT_MIN;
         while (isplit < 128 && tiles * isplit < 2L * ctx->sm_count) isplit *= 2;

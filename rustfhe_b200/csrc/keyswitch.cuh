@@ -156,6 +156,103 @@ __global__ void __launch_bounds__(KS2_THREADS) keyswitch2_kernel(const uint4* __
         }
     }
 }
+// ---- K6p: the same kernel as a producer / consumer pipeline ----
+// K6b synchronises its 16 warps with one __syncthreads per stage (the slot of stage k - 1 takes stage k + 2) and every 16-gate
+// tile stages its whole key slice from L2: 64 tiles x 62.5 MB = 4-6 GB per 1024 gates, 9.5 TB/s at 0.62 ms -- as close to the L2
+// as to the shared-memory floor.  Here NG consumer warps (one gate each) and one producer warp share a ring of RING slots with
+// full / empty mbarriers: a consumer waits for `full`, adds its rows, and its lane 0 arrives on `empty`; the producer waits for
+// `empty` before it overwrites a slot.  No CTA-wide barrier in the loop: 0.54 ms per 1024 gates against 0.62.  More gates per CTA
+// (24 or 31 with a ring of six, one CTA per SM: half the L2 traffic) measured the same 0.54-0.60 ms -- the kernel sits on its
+// shared-memory floor (0.43 ms), not on the L2 (profiles/r02_keyswitch_pipeline_variants.log).
+#if !defined(KSP_NG)
+#define KSP_NG 16
+#endif
+#if !defined(KSP_NR)
+#define KSP_NR 3
+#endif
+constexpr int KSP_GATES = KSP_NG, KSP_RING = KSP_NR;   // shipped shape: 16 gates + producer, ring of three: two CTAs per SM
+template <int NG, int RING>
+struct KsP {
+    static constexpr int THREADS = (NG + 1) * 32;
+    static constexpr size_t SMEM_BYTES = (size_t)RING * KS2_STAGE_WORDS * 4 + (size_t)KS_ICHUNK * NG * 2 + 2 * RING * 8;
+};
+template <int NG, int RING>
+__global__ void __launch_bounds__((NG + 1) * 32) keyswitch_p_kernel(const uint4* __restrict__ ksk, const uint16_t* __restrict__ dig,
+                                                                    uint32_t* __restrict__ out, long B, const int32_t* __restrict__ idxo) {
+    extern __shared__ __align__(16) uint32_t ks_smem[];
+    uint32_t* ring = ks_smem;
+    uint16_t* dg = reinterpret_cast<uint16_t*>(ks_smem + RING * KS2_STAGE_WORDS);   // [ichunk][NG]
+    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(ks_smem) + KsP<NG, RING>::SMEM_BYTES - 2 * RING * 8);
+    uint64_t* empty = full + RING;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long g0 = (long)blockIdx.x * NG;
+    const int ichunk = 1024 / (int)gridDim.y;
+    const int i0 = blockIdx.y * ichunk;
+    const int nstages = ichunk * (8 / KS2_LV);
+    constexpr int SPI = 8 / KS2_LV;   // stages per key index
+    for (int t = threadIdx.x; t < ichunk * NG; t += (NG + 1) * 32) {
+        const int g = t / ichunk, ii = t % ichunk;
+        dg[ii * NG + g] = (g0 + g < B) ? dig[(size_t)(g0 + g) * 1024 + i0 + ii] : (uint16_t)0;
+    }
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < RING; r++) { mbar_init(full + r, 1); mbar_init(empty + r, NG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();   // digits staged, mbarriers initialised
+    if (warp == NG) {   // producer
+        if (lane == 0) {
+#pragma unroll 1
+            for (int k = 0; k < nstages; k++) {
+                const int s = k % RING;
+                if (k >= RING) mbar_wait(empty + s, (uint32_t)((k / RING - 1) & 1));   // every consumer has left the slot's previous stage
+                const uint4* src = ksk + ((size_t)(i0 + k / SPI) * 8 + (size_t)(k % SPI) * KS2_LV) * 3 * KS_CHUNKS;
+                bulk_fetch(ring + s * KS2_STAGE_WORDS, src, KS2_STAGE_WORDS * 4, full + s);
+            }
+        }
+        return;
+    }
+    uint4 acc[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) acc[q] = make_uint4(0, 0, 0, 0);
+    const bool live = g0 + warp < B;   // warps without a gate still hand their slots back
+#pragma unroll 1
+    for (int k = 0; k < nstages; k++) {
+        const int s = k % RING;
+        mbar_wait(full + s, (uint32_t)((k / RING) & 1));
+        if (live) {
+            const uint32_t d16 = dg[(k / SPI) * NG + warp];
+            const uint32_t* rows = ring + s * KS2_STAGE_WORDS;
+#pragma unroll
+            for (int l = 0; l < KS2_LV; l++) {
+                const uint32_t d = (d16 >> (14 - 2 * ((k % SPI) * KS2_LV + l))) & 3u;   // level 0 in bits 15:14
+                if (d != 0) {
+                    const uint4* r = reinterpret_cast<const uint4*>(rows + (l * 3 + (int)d - 1) * KS2_ROW_WORDS) + lane;
+#pragma unroll
+                    for (int q = 0; q < 5; q++) {
+                        if (q < 4 || lane < KS_CHUNKS - 128) {
+                            const uint4 v = r[32 * q];
+                            acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+    if (!live) return;
+    uint32_t* o = out + (size_t)(idxo ? (long)idxo[g0 + warp] : g0 + warp) * (LWE_N + 1);
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        const int c = lane + 32 * q;
+        if (c < KS_CHUNKS) {
+            atomicAdd(o + 4 * c + 0, 0u - acc[q].x);
+            atomicAdd(o + 4 * c + 1, 0u - acc[q].y);
+            atomicAdd(o + 4 * c + 2, 0u - acc[q].z);
+            atomicAdd(o + 4 * c + 3, 0u - acc[q].w);
+        }
+    }
+}
 // prepares the key-switch inputs from explicit level-1 samples (step-level entry tfhe_b200_keyswitch_batch)
 __global__ void lwe1_prepare_kernel(const uint32_t* __restrict__ lwe1, uint16_t* __restrict__ dig, uint32_t* __restrict__ out, long B) {
     const long g = blockIdx.x;
