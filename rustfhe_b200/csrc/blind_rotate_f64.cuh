@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel
 // straight from / to global memory (coalesced 128-byte rows), shared memory holds only the twiddle tables and the transpose scratch.
 // =====================================================================================================
 constexpr int PMF_WARPS = 12;
-constexpr int PMF_SMEM_BYTES = (F64_TAB_ELEMS + F64_UNTW_ROWS * 32) * 16 + PMF_WARPS * 512 * 16;
+constexpr int PMF_SMEM_BYTES = (F64_TAB_ELEMS + F64_UNTW_ROWS * 32) * 16 + 2 * PMF_WARPS * 512 * 16;   // per warp: transpose scratch + the first spectrum
 __global__ void __launch_bounds__(PMF_WARPS * 32, 1) polymul_f64_kernel(const uint32_t* __restrict__ a, const int32_t* __restrict__ d,
                                                                        uint32_t* __restrict__ out, long B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -411,7 +411,8 @@ __global__ void __launch_bounds__(PMF_WARPS * 32, 1) polymul_f64_kernel(const ui
     const cd16* ta = tab + F64_FWDB_ROWS * 32;
     const cd16* ut = tab + F64_TAB_ELEMS;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    cd16* S = tab + F64_TAB_ELEMS + F64_UNTW_ROWS * 32 + (size_t)w * 512;
+    cd16* S = tab + F64_TAB_ELEMS + F64_UNTW_ROWS * 32 + (size_t)w * 1024;
+    cd16* Y = S + 512 + lane;   // the first spectrum waits here while the second transform has the registers (168 per thread at twelve warps)
     {
         double* t = reinterpret_cast<double*>(tab);
         for (int k = threadIdx.x; k < F64_FWDB_ROWS * 64; k += blockDim.x) t[k] = g_f64_fwdB[k];
@@ -421,19 +422,22 @@ __global__ void __launch_bounds__(PMF_WARPS * 32, 1) polymul_f64_kernel(const ui
     __syncthreads();
 #pragma unroll 1
     for (long g = (long)blockIdx.x * PMF_WARPS + w; g < B; g += (long)gridDim.x * PMF_WARPS) {
-        cd x[16], ya[16], yd[16];
+        cd x[16], y[16];
         f64_key_input(lane, a + (size_t)g * 1024, x);
-        f64_forward(lane, x, S, tb, ya);
+        f64_forward(lane, x, S, tb, y);
+#pragma unroll
+        for (int k = 0; k < 16; k++) { cd16 v; v.re = y[k].re; v.im = y[k].im; Y[32 * k] = v; }
         const int32_t* dp = d + (size_t)g * 1024;
 #pragma unroll
         for (int r = 0; r < 16; r++) { x[r].re = (double)dp[32 * r + lane]; x[r].im = (double)dp[512 + 32 * r + lane]; }
-        f64_forward(lane, x, S, tb, yd);
+        f64_forward(lane, x, S, tb, y);
 #pragma unroll
         for (int k = 0; k < 16; k++) {   // pointwise product, with the 1/512 of the inverse transform (exact power of two)
-            const double pr = F_FMA(ya[k].re, yd[k].re, -F_MUL(ya[k].im, yd[k].im));
-            const double pi = F_FMA(ya[k].re, yd[k].im, F_MUL(ya[k].im, yd[k].re));
-            ya[k].re = F_MUL(pr, 1.0 / 512); ya[k].im = F_MUL(pi, 1.0 / 512);
+            const cd16 ya = Y[32 * k];
+            const double pr = F_FMA(ya.re, y[k].re, -F_MUL(ya.im, y[k].im));
+            const double pi = F_FMA(ya.re, y[k].im, F_MUL(ya.im, y[k].re));
+            y[k].re = F_MUL(pr, 1.0 / 512); y[k].im = F_MUL(pi, 1.0 / 512);
         }
-        f64_inverse_acc<true>(lane, ya, S, ta, ut, out + (size_t)g * 1024);
+        f64_inverse_acc<true>(lane, y, S, ta, ut, out + (size_t)g * 1024);
     }
 }

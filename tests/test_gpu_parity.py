@@ -173,6 +173,30 @@ def test_sample_extract_and_keyswitch_exact(engine, oracle, keys, rng):
     assert np.array_equal(keys.decrypt(out), bits)
 
 
+def test_keyswitch_kernel_variants_same_bits(oracle, keys, rng, monkeypatch):
+    """The three key-switch kernels (TFHE_B200_KS_VARIANT: 3 = producer / consumer ring, the default; 2 = CTA barrier per stage;
+    1 = register tiles) give the same words on ragged batches (1, 17, 33 and 1500 samples: partial tiles, several tiles, every
+    split of the key indices), and the oracle's on a sample."""
+    import rustfhe_b200 as R
+    outs = {}
+    xs = {B: u32(rng, B, N + 1) for B in (1, 17, 33, 1500)}
+    for v in ("3", "2", "1"):
+        monkeypatch.setenv("TFHE_B200_KS_VARIANT", v)
+        eng = R.DeviceEngine(0)
+        try:
+            eng.load_ksk(keys.ksk)
+            eng.load_bk(keys.bk)
+            outs[v] = {B: eng.keyswitch_batch(x) for B, x in xs.items()}
+        finally:
+            eng.close()
+    for B, x in xs.items():
+        assert np.array_equal(outs["3"][B], outs["2"][B]) and np.array_equal(outs["3"][B], outs["1"][B]), B
+        for g in (0, B - 1):
+            ref = np.zeros(n + 1, np.uint32)
+            oracle.lib().orc_key_switch(keys.ksk, x[g], ref)
+            assert np.array_equal(outs["3"][B][g], ref), (B, g)
+
+
 OPS = ["NAND", "AND", "OR", "XOR", "NOT"]
 
 
