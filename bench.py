@@ -50,18 +50,19 @@ def design_figures(key_slices):
 
 def fft64_figures():
     """Per-gate work of the FFT64 mode (fft64.cuh; DESIGN.md sections 2 and 5), counted per lane from the code and confirmed by ncu
-    (4340 FP64 warp instructions per gate and CMUX): a forward transform of 512 complex points = 9 stages x 8 butterflies x 6
-    DFMA-class operations = 432 per lane (the digits enter through I2F.F64.S8, not on the FP64 pipe's DFMA count), an inverse =
+    (4429 FP64 warp instructions per gate and CMUX): a forward transform of 512 complex points = 9 stages x 8 butterflies x 6
+    DFMA-class operations = 432 per lane + 16 (stage 4 is computed output by output on the load side of the transpose; the digits
+    enter through I2F.F64.S8, not on the FP64 pipe's DFMA count) = 448, an inverse =
     482 per lane (trivial twiddles in its first stages, untwist and rounding), one spectrum x key multiply-accumulate = 64 per
     lane; per CMUX 6 forward + 2 inverse + 12 multiply-accumulates.
     Shared-memory bytes per gate and CMUX: 8 transposes x 16 KB, 96 KB of key read from the ring, 60 KB of per-lane twiddle rows,
     22 KB for the source words (rotated reads, digit byte planes), 16 KB accumulator update."""
-    fwd, inv, mac = 432 * 32, 482 * 32, 64 * 32
+    fwd, inv, mac = 448 * 32, 482 * 32, 64 * 32
     per_cmux = 6 * fwd + 2 * inv + 12 * mac
     smem = (8 * 16 + 96 + 60 + 22 + 16) * 1024
-    # issue slots: a DFMA-class instruction keeps the issue port for two cycles (profiles/r02_dfma_mix.json); the other 3911 warp
+    # issue slots: a DFMA-class instruction keeps the issue port for two cycles (profiles/r02_dfma_mix.json); the other 3241 warp
     # instructions of a gate and CMUX (ncu, profiles/r02_ncu_blind_rotate_f64_latest.txt) take one each
-    issue = 2 * per_cmux / 32 + 3911
+    issue = 2 * per_cmux / 32 + 3241
     return {"transforms_per_cmux": 8, "fp64_ops_per_gate": 635 * per_cmux, "smem_bytes_per_gate": 635 * smem,
             "issue_cycles_per_gate": 635 * issue, "bk_bytes_device": 635 * 12 * 512 * 16}
 
@@ -600,7 +601,7 @@ def run_gpu(args):
                                       "achieved": per_gpu_gps_kernel * fig["issue_cycles_per_gate"] / 1e9, "peak": issue_peak / 1e9, "unit": "G issue cycles/s",
                                       "frac": per_gpu_gps_kernel * fig["issue_cycles_per_gate"] / issue_peak, "peak_kind": "148 SM x 4 schedulers x SM clock",
                                       "issue_cycles_per_gate": fig["issue_cycles_per_gate"], "roof_gates_per_s": issue_peak / fig["issue_cycles_per_gate"],
-                                      "note": "2 x 4324 FP64 + 3911 other warp instructions per gate and CMUX; measured DFMA + FFMA mixes add up instead of "
+                                      "note": "2 x 4420 FP64 + 3241 other warp instructions per gate and CMUX; measured DFMA + FFMA mixes add up instead of "
                                               "overlapping (profiles/r02_dfma_mix.json), and a third warp per scheduler does not raise the issue rate"}
             line["int_roofline"] = dict(line["fp64_roofline"], note="FFT64 mode: the arithmetic runs on the FP64 pipe, whose issue rate equals the IMAD rate "
                                         "(profiles/intpipe_r01b.json); see fp64_roofline / smem_roofline")

@@ -36,9 +36,11 @@ __device__ __forceinline__ void f64_exchange(const cd (&send)[8], cd (&recv)[8])
         recv[m].im = __shfl_xor_sync(0xffffffffu, send[m].im, 1);
     }
 }
-// forward transform of the 16 values a lane holds (natural order j = 32 r + lane) -> spectrum (position p = 16 lane + register)
-// PREFETCH: the per-lane twiddle rows of pass B are requested before pass A (32 registers for the length of pass A and the
-// transpose; +3 % in the throughput kernel)
+// forward transform of the 16 values a lane holds (natural order j = 32 r + lane) -> spectrum (position p = 16 lane + register):
+// pass A (stages 0..3 in registers), transpose, stage 4 on the load side (each lane reads both operands of its 16 butterflies
+// and computes its output of each), pass B (stages 5..8 in registers).  No lane-pair exchange.
+// PREFETCH: the per-lane twiddle rows are requested before pass A (36 registers for the length of pass A and the transpose;
+// +3 % in the throughput kernel)
 template <bool PREFETCH = true>
 __device__ __forceinline__ void f64_forward(int lane, cd (&x)[16], cd16* S, const cd16* tb, cd (&y)[16]) {
     F64TwB tw;
@@ -46,14 +48,10 @@ __device__ __forceinline__ void f64_forward(int lane, cd (&x)[16], cd16* S, cons
     f64_fwd_passA(x);
     f64_t1_store(lane, x, S);
     __syncwarp();
-    f64_t1_load(lane, S, x);
-    __syncwarp();   // the scratch is free for the next transform
     if (!PREFETCH) f64_fwd_twB(lane, tb, tw);
-    f64_fwd_passB(x, tw);
-    cd send[8], recv[8];
-    f64_x_send(lane, x, send);
-    f64_exchange(send, recv);
-    f64_fwd_x_bfly(lane, x, recv, tb, y);
+    f64_t1_load_cross(lane, S, tw.w[0], y);
+    __syncwarp();   // the scratch is free for the next transform
+    f64_fwd_passB(y, tw);
 }
 
 // inverse transform of one output spectrum (destroyed), rounded to the exact integers and added to the accumulator polynomial

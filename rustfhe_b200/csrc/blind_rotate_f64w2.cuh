@@ -1,9 +1,9 @@
 // blind_rotate_f64w2.cuh -- K5F2, FFT64 throughput blind rotation with one gate on TWO warps (included by engine.cu only).
 //   gate pre-combination + 635 x CMUX + sample extract (tfhe.rs:27-113, trgsw.rs:264-322, trlwe.rs:110-121)
-// K5F (one warp per gate, 16 values per lane) is bound by issue slots: 4 340 FP64 instructions (two issue cycles each) and 3 911
-// others per gate and CMUX, a third of the others being the select / shuffle instructions of the lane-pair exchange stage that a
-// 16-values-per-lane transform needs.  With 8 values per thread on two warps a transform is three radix-8
-// passes and two transposes through shared memory (the transform of the latency kernel, blind_rotate_f64l2.cuh): no exchange
+// K5F (one warp per gate, 16 values per lane) is bound by issue slots, and a 16-values-per-lane transform has one stage that
+// pairs values of two lanes (shuffles and selects; when this kernel was written K5F paid 128 of them per transform, it now takes
+// the forward's on the load side of its transpose).  With 8 values per thread on two warps a transform is three
+// radix-8 passes and two transposes through shared memory (the transform of the latency kernel, blind_rotate_f64l2.cuh): no such
 // stage, the per-thread twiddles are 4 + 4 loads, and the two output spectra of a gate are 64 registers per thread instead of
 // 128 -- so G gates = 2 G warps fit an SM with more than two warps per scheduler.
 // Per step and gate: both polynomials' masked source words (16 per thread and polynomial, thread-private: thread t needs the

@@ -55,7 +55,7 @@ struct alignas(16) cd16 { double re, im; };   // what the tables, the transposes
 
 constexpr int F64_PTS = 512;                 // complex points per polynomial
 constexpr int F64_PER_LANE = 16;
-constexpr int F64_FWDB_ROWS = 12, F64_INVA_ROWS = 8, F64_UNTW_ROWS = 16;
+constexpr int F64_FWDB_ROWS = 9, F64_INVA_ROWS = 8, F64_UNTW_ROWS = 16;
 constexpr int F64_TAB_ELEMS = (F64_FWDB_ROWS + F64_INVA_ROWS) * 32;   // per-lane twiddle tables, [row][lane] cd16 (+ the untwist table)
 constexpr double F64_ROUND_MAGIC = 6755399441055744.0;                             // 1.5 * 2^52
 constexpr double F64_DIGIT_BIAS = 4503599627370496.0 + 32.0;                       // 2^52 + 32
@@ -173,88 +173,74 @@ TFHE_HD void f64_fwd_passA(cd (&x)[16]) {
     f64_fa_stage<2>(x, std::make_integer_sequence<int, 8>{});
     f64_fa_stage<3>(x, std::make_integer_sequence<int, 8>{});
 }
-// transpose 1: element j = 32 r + lane is stored at slot j ^ ((r & 3) << 1); lane' = 2 hi + j0 then reads j = (hi, rho, j0)
+// transpose 1: element j = 32 r + lane is stored at slot j ^ (r & 7).  Lane' = 2 hi + top then needs BOTH halves of the block
+// hi = j >> 5 (elements (hi, top' = 0 / 1, q), q = j & 15) for stage 4, whose butterflies pair top' = 0 with top' = 1: it reads
+// the 32 elements and computes only ITS output of every butterfly (f64_t1_load_cross) -- the two lanes of a pair read the same
+// addresses (16 distinct 16-byte words per instruction, two per bank group: two wavefronts).  A 16-values-per-lane transform of
+// 512 points has one stage that pairs values of two lanes; taken here, on the load side of the transpose, it costs 16 loads and
+// 16 operations more than half of its butterflies, instead of 32 shuffles and 96 selects after pass B.
 TFHE_HD void f64_t1_store(int lane, const cd (&x)[16], cd16* S) {
-    cd16* b[4];   // the swizzle only touches bits 1..2 of the lane: four bases, everything else is an immediate offset
+    cd16* b[8];   // the swizzle only touches bits 0..2 of the lane: eight bases, everything else is an immediate offset
 #pragma unroll
-    for (int k = 0; k < 4; k++) b[k] = S + (lane ^ (k << 1));
+    for (int k = 0; k < 8; k++) b[k] = S + (lane ^ k);
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         cd16 v; v.re = x[r].re; v.im = x[r].im;
-        b[r & 3][32 * r] = v;
+        b[r & 7][32 * r] = v;
     }
 }
-TFHE_HD void f64_t1_load(int lane, const cd16* S, cd (&x)[16]) {
-    const int hi = lane >> 1, j0 = lane & 1;
-    const int base = ((hi << 5) | j0) ^ ((hi & 3) << 1);
-    const cd16* b[4];   // (rho << 1) touches bits 1..4, the swizzle bits 1..2: XOR on bits 1..2, plain offset on bits 3..4
+// stage 4 on the load side: x[q] = a_q + w b_q, w = +- twiddle of node (4, hi) (the sign is the lane's top bit, in the table)
+TFHE_HD void f64_t1_load_cross(int lane, const cd16* S, const cd16& w, cd (&x)[16]) {
+    const int hi = lane >> 1;
+    const cd16* b[8];
 #pragma unroll
-    for (int k = 0; k < 4; k++) b[k] = S + (base ^ (k << 1));
+    for (int k = 0; k < 8; k++) b[k] = S + ((hi << 5) | (k ^ (hi & 7)));
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const int rho = (k >> 1) | ((k & 1) << 3);   // 0, 8, 1, 9, ...: the operands of the first butterflies of pass B arrive first
-        const cd16 v = b[rho & 3][(rho >> 2) << 3];
-        x[rho].re = v.re; x[rho].im = v.im;
+        const int q = (k >> 1) | ((k & 1) << 3);   // 0, 8, 1, 9, ...: the operands of the first butterflies of pass B arrive first
+        const cd16 A = b[q & 7][q & 8], B = b[q & 7][16 + (q & 8)];
+        x[q].re = F_FMA(w.re, B.re, F_FMA(-w.im, B.im, A.re));
+        x[q].im = F_FMA(w.re, B.im, F_FMA(w.im, B.re, A.im));
     }
 }
-// pass B: stages 4..7 on rho, per-lane twiddles tb[t * 32 + lane].  The eight rows are loaded by f64_fwd_twB BEFORE the
-// transpose (nothing can be hoisted above a warp barrier by the compiler), so their latency is under pass A and the transpose.
-struct F64TwB { cd16 w[8]; };
+// pass B: stages 5..8 on the register index q = j & 15, per-lane twiddles tb[t * 32 + lane] (row 0 is stage 4's).  The rows are
+// loaded by f64_fwd_twB BEFORE the transpose (nothing can be hoisted above a warp barrier by the compiler), so their latency is
+// under pass A and the transpose.
+struct F64TwB { cd16 w[9]; };
 TFHE_HD void f64_fwd_twB(int lane, const cd16* tb, F64TwB& t) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) t.w[k] = tb[k * 32 + lane];
+    for (int k = 0; k < 9; k++) t.w[k] = tb[k * 32 + lane];
 }
 TFHE_HD void f64_fwd_passB(cd (&x)[16], const F64TwB& tw) {
     {
-        const cd16 w = tw.w[0];
+        const cd16 w = tw.w[1];
 #pragma unroll
         for (int t = 0; t < 8; t++) bf_w(x[t], x[t + 8], w.re, w.im);
     }
     {
-        const cd16 w = tw.w[1];
+        const cd16 w = tw.w[2];
 #pragma unroll
         for (int t = 0; t < 4; t++) { bf_w(x[t], x[t + 4], w.re, w.im); bf_iw(x[8 + t], x[12 + t], w.re, w.im); }
     }
 #pragma unroll
     for (int c2 = 0; c2 < 2; c2++) {
-        const cd16 w = tw.w[2 + c2];
+        const cd16 w = tw.w[3 + c2];
 #pragma unroll
         for (int t = 0; t < 2; t++) { bf_w(x[8 * c2 + t], x[8 * c2 + t + 2], w.re, w.im); bf_iw(x[8 * c2 + 4 + t], x[8 * c2 + 6 + t], w.re, w.im); }
     }
 #pragma unroll
     for (int c2 = 0; c2 < 4; c2++) {
-        const cd16 w = tw.w[4 + c2];
+        const cd16 w = tw.w[5 + c2];
         bf_w(x[4 * c2], x[4 * c2 + 1], w.re, w.im);
         bf_iw(x[4 * c2 + 2], x[4 * c2 + 3], w.re, w.im);
     }
 }
-TFHE_HD void f64_fwd_passB(int lane, cd (&x)[16], const cd16* tb) {
-    F64TwB tw;
-    f64_fwd_twB(lane, tb, tw);
-    f64_fwd_passB(x, tw);
-}
-// stage 8, the lane-pair exchange.  Lane j0 owns the butterflies rho = 8 j0 + m, m < 8: it keeps its own operand of those and
-// needs the partner's; it sends the operand it holds of the partner's butterflies.
+// the lane-pair exchange of the INVERSE transform's stage 4: lane parity j0 owns the butterflies m + 8 j0; it sends the operand
+// it holds of the partner's butterflies
 TFHE_HD void f64_x_send(int lane, const cd (&x)[16], cd (&send)[8]) {
     const bool odd = lane & 1;
 #pragma unroll
     for (int m = 0; m < 8; m++) { send[m].re = odd ? x[m].re : x[m + 8].re; send[m].im = odd ? x[m].im : x[m + 8].im; }
-}
-TFHE_HD void f64_fwd_x_bfly(int lane, const cd (&x)[16], const cd (&recv)[8], const cd16* tb, cd (&y)[16]) {
-    const bool odd = lane & 1;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const cd16 w = tb[(8 + q) * 32 + lane];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int m = 2 * q + e;
-            cd a, b;   // a = element with j0 = 0, b = element with j0 = 1 of rho = 8 j0(lane) + m
-            a.re = odd ? recv[m].re : x[m].re; a.im = odd ? recv[m].im : x[m].im;
-            b.re = odd ? x[m + 8].re : recv[m].re; b.im = odd ? x[m + 8].im : recv[m].im;
-            if (e == 0) bf_w(a, b, w.re, w.im); else bf_iw(a, b, w.re, w.im);
-            y[2 * m] = a; y[2 * m + 1] = b;
-        }
-    }
 }
 
 // pointwise multiply-accumulate: acc[k] += y[k] * key[k * 32 + lane]; one half (registers 8 H .. 8 H + 7, 4 KB of key) at a time

@@ -155,10 +155,13 @@ void emul_cmux_rotate_t2(const uint32_t* dev, uint32_t* acc, uint32_t abar, uint
 static void f64_forward_all_lanes(cd (*x)[16], cd16* S, cd (*y)[16]) {
     const cd16* tb = reinterpret_cast<const cd16*>(h_f64_fwdB);
     static_assert(sizeof(cd16) == 16, "cd16 layout");
-    cd send[32][8];
     for (int lane = 0; lane < 32; lane++) { f64_fwd_passA(x[lane]); f64_t1_store(lane, x[lane], S); }
-    for (int lane = 0; lane < 32; lane++) { f64_t1_load(lane, S, x[lane]); f64_fwd_passB(lane, x[lane], tb); f64_x_send(lane, x[lane], send[lane]); }
-    for (int lane = 0; lane < 32; lane++) f64_fwd_x_bfly(lane, x[lane], send[lane ^ 1], tb, y[lane]);
+    for (int lane = 0; lane < 32; lane++) {
+        F64TwB tw;
+        f64_fwd_twB(lane, tb, tw);
+        f64_t1_load_cross(lane, S, tw.w[0], y[lane]);
+        f64_fwd_passB(y[lane], tw);
+    }
 }
 void emul_key_transform_f64(const uint32_t* trgsw, double* dev) {
     std::vector<cd16> S(512);
