@@ -91,20 +91,31 @@ struct F64Ring {
     long total;        // chunks the CTA consumes
     int active;        // warps of the CTA that own a gate
     long period;       // 0: chunk n of the stream is chunk n of the key; > 0: chunk n is chunk n % period (one TRGSW used over and over)
+    uint32_t full32;   // shared-window address of full[0]; empty[] and left[] follow it (set by f64_ring_addr)
 };
+__device__ __forceinline__ void f64_ring_addr(F64Ring& rg) { rg.full32 = smem_u32(rg.full); }   // after full / empty / left are laid out back to back
 // consumer side: wait for chunk n, run `use(slot)`, hand the slot back.  The LAST warp to leave a slot refills it with chunk
 // n + F64_RING: no warp is the producer, so the warps of a CTA may drift up to a ring apart (they are started staggered so that
 // the transposes and key reads of one gate fall under the arithmetic of another).
+__device__ __forceinline__ void mbar_wait32(uint32_t b, uint32_t parity) {   // the barrier by its shared-window address
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT32_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT32_%=;\n\t}" ::"r"(b), "r"(parity) : "memory");
+}
 template <class F>
 __device__ __forceinline__ void f64_with_chunk(const F64Ring& rg, long n, int lane, F&& use) {
     const int s = (int)(n & (F64_RING - 1));
     const uint32_t par = (uint32_t)((n / F64_RING) & 1);
-    mbar_wait(rg.full + s, par);
+    mbar_wait32(rg.full32 + 8u * (uint32_t)s, par);   // 32-bit shared addresses, converted once per kernel (a generic pointer costs a conversion per use)
     use(rg.slot + (size_t)s * F64_SLOT_ELEMS);
     __syncwarp();
     if (lane == 0) {
-        mbar_arrive(rg.empty + s);
-        if (atomicAdd(rg.left + s, 1u) == (uint32_t)(rg.active - 1)) {
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(rg.full32 + 8u * (uint32_t)(F64_RING + s)) : "memory");   // empty[s]
+        uint32_t before;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(before) : "r"(rg.full32 + 16u * (uint32_t)F64_RING + 4u * (uint32_t)s) : "memory");   // left[s]
+        if (before == (uint32_t)(rg.active - 1)) {
             rg.left[s] = 0;
             if (n + F64_RING < rg.total) {
                 mbar_wait(rg.empty + s, par);   // every warp's reads of the slot are ordered before the copy that overwrites it
@@ -126,6 +137,7 @@ __global__ void __launch_bounds__(F64_GATES * 32, F64_CTAS_PER_SM) blind_rotate_
     rg.full = reinterpret_cast<uint64_t*>(rg.slot + (size_t)F64_RING * F64_SLOT_ELEMS);
     rg.empty = rg.full + F64_RING;
     rg.left = reinterpret_cast<uint32_t*>(rg.empty + F64_RING);
+    f64_ring_addr(rg);
     const int gl = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* gbase = smem_raw + F64_SHARED_BYTES + (size_t)gl * F64_GATE_SMEM_BYTES;
     uint32_t* acc = reinterpret_cast<uint32_t*>(gbase);
@@ -293,6 +305,7 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel
     rg.full = reinterpret_cast<uint64_t*>(rg.slot + (size_t)F64_RING * F64_SLOT_ELEMS);
     rg.empty = rg.full + F64_RING;
     rg.left = reinterpret_cast<uint32_t*>(rg.empty + F64_RING);
+    f64_ring_addr(rg);
     const int gl = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* gbase = smem_raw + F64_SHARED_BYTES + (size_t)gl * F64_GATE_SMEM_BYTES;
     uint32_t* acc = reinterpret_cast<uint32_t*>(gbase);

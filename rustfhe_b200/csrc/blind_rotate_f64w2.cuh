@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(F64W2_THREADS, 1) blind_rotate_f64w2_kernel(co
     rg.full = reinterpret_cast<uint64_t*>(rg.slot + (size_t)F64_RING * F64_SLOT_ELEMS);
     rg.empty = rg.full + F64_RING;
     rg.left = reinterpret_cast<uint32_t*>(rg.empty + F64_RING);
+    f64_ring_addr(rg);
     const int gl = threadIdx.x >> 6, t = threadIdx.x & 63, lane = threadIdx.x & 31;
     unsigned char* gbase = smem_raw + F64W2_SHARED_BYTES + (size_t)gl * F64W2_GATE_SMEM_BYTES;
     uint32_t* acc = reinterpret_cast<uint32_t*>(gbase);
