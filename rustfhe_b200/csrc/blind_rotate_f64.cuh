@@ -406,6 +406,128 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel
 }
 
 // =====================================================================================================
+// K5FXI: external products / cmux with ONE TRGSW PER ITEM in the FFT64 arithmetic (TRGSWRepF::cross / cmux on a fresh TRGSW,
+// trgsw.rs:264-322; BASELINE config 3):  out[g] = TRGSW[g] (x) (in[g] - in0[g]) + in0[g].
+// There is no key to share: a warp transforms the twelve polynomials of its item's TRGSW itself, straight from their torus words
+// in global memory (18 forward + 2 inverse transforms per product instead of 8).  The spectrum of a digit polynomial waits in
+// shared memory (on the accumulator's space: both polynomials' digit planes are taken first) while the two key polynomials of
+// its row are transformed in the registers and multiplied in; 1 / 512 and the byte scale of the digits go onto the sums.
+// =====================================================================================================
+constexpr int XPI_WARPS = 8;
+constexpr int XPI_WARP_BYTES = 2 * 1024 * 4 /*input / digit spectrum / result*/ + 512 * 16 /*transpose scratch*/ + 12 * 32 * 16 /*digit planes of both polynomials*/;
+constexpr int XPI_SMEM_BYTES = (F64_TAB_ELEMS + F64_UNTW_ROWS * 32) * 16 + XPI_WARPS * XPI_WARP_BYTES;
+static_assert(XPI_SMEM_BYTES <= 227 * 1024, "per-item external product: shared memory of one SM");
+__global__ void __launch_bounds__(XPI_WARPS * 32, 1) external_product_item_f64_kernel(const BrArgs a, const uint32_t* __restrict__ trgsw /*[B][6][2][1024]*/) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd16* tab = reinterpret_cast<cd16*>(smem_raw);
+    const cd16* tb = tab;
+    const cd16* ta = tab + F64_FWDB_ROWS * 32;
+    const cd16* ut = tab + F64_TAB_ELEMS;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem_raw + (F64_TAB_ELEMS + F64_UNTW_ROWS * 32) * 16 + (size_t)w * XPI_WARP_BYTES;
+    uint32_t* acc = reinterpret_cast<uint32_t*>(wbase);
+    cd16* Y = reinterpret_cast<cd16*>(wbase) + lane;   // the digit spectrum, lane-private, on the accumulator's space
+    cd16* S = reinterpret_cast<cd16*>(wbase + 2 * 1024 * 4);
+    uint4* D = reinterpret_cast<uint4*>(wbase + 2 * 1024 * 4 + 512 * 16);
+    {
+        double* t = reinterpret_cast<double*>(tab);
+        for (int k = threadIdx.x; k < F64_FWDB_ROWS * 64; k += blockDim.x) t[k] = g_f64_fwdB[k];
+        for (int k = threadIdx.x; k < F64_INVA_ROWS * 64; k += blockDim.x) t[F64_FWDB_ROWS * 64 + k] = g_f64_invA[k];
+        for (int k = threadIdx.x; k < F64_UNTW_ROWS * 64; k += blockDim.x) t[(F64_FWDB_ROWS + F64_INVA_ROWS) * 64 + k] = g_f64_untw[k];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (long g = (long)blockIdx.x * XPI_WARPS + w; g < a.B; g += (long)gridDim.x * XPI_WARPS) {
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(a.trlwe_in + (size_t)g * 2048) + lane;
+            uint4* dst = reinterpret_cast<uint4*>(acc) + lane;
+            uint4 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) v[q] = src[32 * q];
+            if (a.trlwe_in0) {   // cmux: rep_1 - rep_0
+                const uint4* sub = reinterpret_cast<const uint4*>(a.trlwe_in0 + (size_t)g * 2048) + lane;
+#pragma unroll
+                for (int q = 0; q < 16; q++) { const uint4 t = sub[32 * q]; v[q].x -= t.x; v[q].y -= t.y; v[q].z -= t.z; v[q].w -= t.w; }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; q++) dst[32 * q] = v[q];
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int pw = 0; pw < 2; pw++) {   // the digit planes of both polynomials: the accumulator's space is free afterwards
+            uint32_t u[32];
+            t2_u<false>(lane, acc + pw * 1024, 0u, a.mask, u);
+            u4 re, im;
+            uint4* Dp = D + pw * 6 * 32 + lane;
+            f64_pack_plane<0>(u, re, im);
+            Dp[0 * 32] = make_uint4(re.x, re.y, re.z, re.w); Dp[1 * 32] = make_uint4(im.x, im.y, im.z, im.w);
+            f64_pack_plane<1>(u, re, im);
+            Dp[2 * 32] = make_uint4(re.x, re.y, re.z, re.w); Dp[3 * 32] = make_uint4(im.x, im.y, im.z, im.w);
+            f64_pack_plane<2>(u, re, im);
+            Dp[4 * 32] = make_uint4(re.x, re.y, re.z, re.w); Dp[5 * 32] = make_uint4(im.x, im.y, im.z, im.w);
+        }
+        __syncwarp();   // every lane has read its source words (other lanes' rows of acc): Y may overwrite them
+        cd s0[16], s1[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) { s0[k].re = 0.0; s0[k].im = 0.0; s1[k].re = 0.0; s1[k].im = 0.0; }
+        const uint32_t* item = trgsw + (size_t)g * (12 * 1024);
+#pragma unroll 1
+        for (int j = 0; j < 6; j++) {
+            cd x[16], y[16];
+            {
+                const uint4 a4 = D[(2 * j) * 32 + lane], b4 = D[(2 * j + 1) * 32 + lane];
+                u4 re, im;
+                re.x = a4.x; re.y = a4.y; re.z = a4.z; re.w = a4.w; im.x = b4.x; im.y = b4.y; im.z = b4.z; im.w = b4.w;
+                f64_digits(re, im, x);
+            }
+            f64_forward(lane, x, S, tb, y);
+#pragma unroll
+            for (int k = 0; k < 16; k++) { cd16 v; v.re = y[k].re; v.im = y[k].im; Y[32 * k] = v; }
+            f64_key_input(lane, item + (size_t)(2 * j) * 1024, x);
+            f64_forward(lane, x, S, tb, y);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const cd16 d = Y[32 * k];
+                s0[k].re = F_FMA(d.re, y[k].re, F_FMA(-d.im, y[k].im, s0[k].re));
+                s0[k].im = F_FMA(d.re, y[k].im, F_FMA(d.im, y[k].re, s0[k].im));
+            }
+            f64_key_input(lane, item + (size_t)(2 * j + 1) * 1024, x);
+            f64_forward(lane, x, S, tb, y);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const cd16 d = Y[32 * k];
+                s1[k].re = F_FMA(d.re, y[k].re, F_FMA(-d.im, y[k].im, s1[k].re));
+                s1[k].im = F_FMA(d.re, y[k].im, F_FMA(d.im, y[k].re, s1[k].im));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) {   // 1 / 512 of the inverse transform and 1 / 4 of the digit bytes: an exact power of two
+            s0[k].re = F_MUL(s0[k].re, F64_KEY_SCALE); s0[k].im = F_MUL(s0[k].im, F64_KEY_SCALE);
+            s1[k].re = F_MUL(s1[k].re, F64_KEY_SCALE); s1[k].im = F_MUL(s1[k].im, F64_KEY_SCALE);
+        }
+        __syncwarp();
+        f64_inverse_acc<true>(lane, s0, S, ta, ut, acc);
+        f64_inverse_acc<true>(lane, s1, S, ta, ut, acc + 1024);
+        __syncwarp();
+        {
+            uint4* dst = reinterpret_cast<uint4*>(a.trlwe_out + (size_t)g * 2048) + lane;
+            const uint4* res = reinterpret_cast<const uint4*>(acc) + lane;
+            uint4 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) v[q] = res[32 * q];
+            if (a.trlwe_in0) {   // cmux: ... + rep_0
+                const uint4* add = reinterpret_cast<const uint4*>(a.trlwe_in0 + (size_t)g * 2048) + lane;
+#pragma unroll
+                for (int q = 0; q < 16; q++) { const uint4 t = add[32 * q]; v[q].x += t.x; v[q].y += t.y; v[q].z += t.z; v[q].w += t.w; }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; q++) dst[32 * q] = v[q];
+        }
+        __syncwarp();
+    }
+}
+
+// =====================================================================================================
 // K7F: exact negacyclic product a * d mod (X^N + 1, 2^32) in the FFT64 arithmetic (Polynomial::fft_cross, math.rs:337-347;
 // Spqlios_poly_mul, spqlios-wrapper.cpp:38-53; BASELINE config 3).  a = torus words taken as centred 32-bit integers, |d| <= 192:
 // a coefficient of the product is below 1024 * 2^31 * 192 < 2^49, as in the external product.  One product per warp (two forward

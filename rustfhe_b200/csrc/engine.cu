@@ -261,6 +261,8 @@ int tfhe_b200_ctx_create(const tfhe_b200_params* p, int device, tfhe_b200_ctx** 
         return bail("smem attr (f64 polymul)", e);
     if ((e = cudaFuncSetAttribute(external_product_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f64_smem_bytes())) != cudaSuccess)
         return bail("smem attr (f64 external product)", e);
+    if ((e = cudaFuncSetAttribute(external_product_item_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XPI_SMEM_BYTES)) != cudaSuccess)
+        return bail("smem attr (f64 external product, per-item TRGSW)", e);
     if (const char* v = getenv("TFHE_B200_F64_LATENCY")) ctx->f64_latency = atoi(v);
     if (const char* v = getenv("TFHE_B200_F64_CLUSTER")) ctx->f64_cluster = atoi(v);
     if ((e = cudaFuncSetAttribute(blind_rotate_f64_latency3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64L3_SMEM_BYTES)) != cudaSuccess)
@@ -1055,13 +1057,13 @@ int tfhe_b200_decrypt_bits_device(tfhe_b200_ctx* ctx, const uint8_t* s0, const u
 // external product / cmux on device pointers: transform the TRGSW samples into slot scratch, then one CMUX step per product
 static int run_extprod(tfhe_b200_ctx* ctx, Slot* s, const uint32_t* trgsw_dev, size_t ntrgsw, const uint32_t* rep1, const uint32_t* rep0,
                        uint32_t* out, size_t B, cudaStream_t st) {
-    RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, ntrgsw * BK_STEP_WORDS * 4));
     BrArgs a{};
     a.bkdev = s->scratch; a.mask = ctx->prm.decomp_mask; a.mu = ctx->prm.mu; a.B = (long)B; a.split = (long)B; a.nsteps = 1;
     a.trlwe_in = rep1; a.trlwe_in0 = rep0; a.trlwe_out = out; a.ntrgsw = (long)ntrgsw; a.ns = ctx->ns_int();
     const bool rows16 = (((uintptr_t)rep1 | (uintptr_t)rep0 | (uintptr_t)out) & 15) == 0;   // the FFT64 kernel moves its rows as 16-byte words
     if (ctx->key_slices == 1 && ntrgsw == 1 && B > (size_t)ctx->sm_count && rows16) {   // FFT64, one shared TRGSW: persistent CTAs, one product per warp
-        cd16* kx = reinterpret_cast<cd16*>(s->scratch);   // 96 KB of the slot scratch (BK_STEP_WORDS * 4 = 144 KB were reserved above)
+        RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, (size_t)BK_STEP_WORDS * 4));
+        cd16* kx = reinterpret_cast<cd16*>(s->scratch);   // 96 KB of the slot scratch
         bk_transform_f64_kernel<<<(12 + KTF_WARPS - 1) / KTF_WARPS, KTF_WARPS * 32, 0, st>>>(trgsw_dev, kx, 12);
         const long ngroups = ((long)B + F64_GATES - 1) / F64_GATES;
         const unsigned grid = (unsigned)std::min<long>(ngroups, (long)ctx->sm_count);
@@ -1070,6 +1072,16 @@ static int run_extprod(tfhe_b200_ctx* ctx, Slot* s, const uint32_t* trgsw_dev, s
         CK(cudaGetLastError());
         return TFHE_B200_OK;
     }
+    if (ctx->key_slices == 1 && ntrgsw == B && B > (size_t)ctx->sm_count && rows16) {   // FFT64, one TRGSW per item: the warp transforms it itself
+        const long nct = ((long)B + XPI_WARPS - 1) / XPI_WARPS;
+        const unsigned grid = (unsigned)std::min<long>(nct, (long)ctx->sm_count);
+        external_product_item_f64_kernel<<<grid, XPI_WARPS * 32, XPI_SMEM_BYTES, st>>>(a, trgsw_dev);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return TFHE_B200_OK;
+    }
+    RC(grow(ctx, (void**)&s->scratch, &s->scratch_cap, ntrgsw * BK_STEP_WORDS * 4));   // the NTT kernels read transformed TRGSWs from the slot scratch
+    a.bkdev = s->scratch;
     if (a.ns == 2 && B > (size_t)ctx->sm_count) {   // two slices, throughput shape: the two-warps-per-product kernel, six products per CTA
         const int npolys = (int)ntrgsw * 12;
         bk_transform_t2_kernel<<<(npolys + KT_WARPS - 1) / KT_WARPS, KT_WARPS * 32, 0, st>>>(trgsw_dev, s->scratch, npolys);

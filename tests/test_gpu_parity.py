@@ -111,6 +111,32 @@ def test_external_product_large_batch_shared_trgsw(engine, oracle, rng):
     assert np.array_equal(small, out[:40])
 
 
+def test_external_product_large_batch_per_item_trgsw(engine, oracle, rng):
+    """config 3(ii) with one TRGSW per item at throughput size (in the default mode external_product_item_f64_kernel: a warp
+    transforms its item's twelve TRGSW polynomials itself; ragged last round), plain product and cmux form, bit-exact vs the
+    integer oracle on a sample -- including an all-digits -32 input against a TRGSW of +-2^31 words -- and identical to the
+    small-batch path."""
+    B = 8 * 148 + 5
+    trlwe, rep0 = u32(rng, B, 2, N), u32(rng, B, 2, N)
+    trgsw = u32(rng, B, 6, 2, N)
+    trlwe[1] = 0x7DF7C000            # all digits -32
+    trgsw[1] = 0x80000000            # extreme key words
+    out = engine.external_product_batch(trgsw, trlwe)
+    cm = engine.cmux_batch(trgsw, trlwe, rep0)
+    idx = np.concatenate([[0, 1, B - 1, B - 2], rng.choice(B, 5, replace=False)])
+    for g in idx:
+        ref = np.zeros(2 * N, np.uint32)
+        oracle.lib().orc_external_product_exact(trgsw[g].reshape(-1), trlwe[g].reshape(-1), 0x02084000, ref)
+        assert np.array_equal(out[g].reshape(-1), ref), g
+        oracle.lib().orc_external_product_exact(trgsw[g].reshape(-1), (trlwe[g] - rep0[g]).reshape(-1), 0x02084000, ref)
+        assert np.array_equal(cm[g].reshape(-1), ref + rep0[g].reshape(-1)), g
+    # the small-batch path of this mode (two-slice NTT kernel) agrees on every ordinary item; item 1 (all key words 2^31, all
+    # digits -32) is outside the bound that path is exact for (mode 3 is the worst-case-exact one, test_exact_mode_three_key_slices)
+    small = engine.external_product_batch(trgsw[:40], trlwe[:40])
+    keep = np.arange(40) != 1
+    assert np.array_equal(small[keep], out[:40][keep])
+
+
 def test_external_product_vs_reference_fft(engine, oracle, rng):
     """P1: against the reference's own FFT (oracle/_ref): |diff| <= 2 ulp per coefficient (measured -1/0/+1)."""
     if not oracle.ref_init():
