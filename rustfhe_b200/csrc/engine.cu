@@ -897,6 +897,8 @@ int tfhe_b200_circuit_run_level_device(tfhe_b200_ctx* ctx, const tfhe_b200_circu
     cudaStream_t st = (cudaStream_t)stream;
     Slot* s;
     RC(slot_acquire(ctx, &st, false, &s));
+    // consecutive calls rotate over the work slots: size each slot's digit buffer for the widest level once, not level by level
+    RC(grow(ctx, (void**)&s->ksdig, &s->ksdig_cap, c->max_level * 1024 * sizeof(uint16_t)));
     const size_t f = c->level_first[level] + first;
     BrArgs a{};
     a.ops = c->ops + f;
