@@ -247,6 +247,7 @@ struct tfhe_b200_group_circuit {
     std::vector<size_t> level_gates;
     size_t n_wires = 0, max_level = 0, shard_min = 0;
     uint64_t sharded_levels = 0, replicated_levels = 0;   // of the last run
+    std::vector<uint32_t> trivial;                        // host source of the constant wires' ciphertexts
     int32_t* out_idx = nullptr;                           // device 0: the output wires of a run and their gathered rows
     uint32_t* out_rows = nullptr;
     size_t out_cap = 0;
@@ -315,9 +316,9 @@ int tfhe_b200_group_circuit_create(tfhe_b200_group* g, size_t n_levels, const si
 }
 // inputs_host [n_inputs][n+1] = wires 0 .. n_inputs-1 (uploaded to device 0 once and broadcast over NCCL); constant wires are
 // set to trivial ciphertexts on every device; outputs_host [n_out][n+1] = the wires out_wires[], gathered on device 0.
-int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* c, const uint32_t* inputs_host, size_t n_inputs,
-                                const int32_t* const_wires, const uint8_t* const_bits, size_t n_consts, const int32_t* out_wires, size_t n_out,
-                                uint32_t* outputs_host) {
+static int group_circuit_run_impl(tfhe_b200_group* g, tfhe_b200_group_circuit* c, const uint32_t* inputs_host, size_t n_inputs,
+                                  const int32_t* const_wires, const uint8_t* const_bits, size_t n_consts, const int32_t* out_wires, size_t n_out,
+                                  uint32_t* outputs_host) {
     if (!g || !c || (n_inputs && !inputs_host) || (n_consts && (!const_wires || !const_bits)) || (n_out && (!out_wires || !outputs_host)))
         return TFHE_B200_ERR_PARAM;
     if (n_inputs > c->n_wires) { g->err = "group_circuit_run: more inputs than wires"; return TFHE_B200_ERR_PARAM; }
@@ -326,7 +327,8 @@ int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* c, 
     for (size_t k = 0; k < n_out; k++)
         if (out_wires[k] < 0 || (size_t)out_wires[k] >= c->n_wires) { g->err = "group_circuit_run: output wire out of range"; return TFHE_B200_ERR_PARAM; }
     const int n = (int)g->ctx.size();
-    std::vector<uint32_t> trivial(2 * CT_WORDS, 0u);   // [0] = Zero, [1] = One: (b, a) = (-+1/8, 0)  (tlwe.rs:181-186); alive until the final sync
+    std::vector<uint32_t>& trivial = c->trivial;   // [0] = Zero, [1] = One: (b, a) = (-+1/8, 0)  (tlwe.rs:181-186); lives with the circuit:
+    trivial.assign(2 * CT_WORDS, 0u);              // the asynchronous copies below may still read it when an error returns early
     trivial[0] = 0u - g->mu;
     trivial[CT_WORDS] = g->mu;
     for (int r = 0; r < n; r++) {
@@ -404,6 +406,20 @@ int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* c, 
         GCK(cudaMemcpyAsync(outputs_host, c->out_rows, n_out * CT_WORDS * 4, cudaMemcpyDeviceToHost, g->stream[0]));
     }
     return sync_streams(g);
+}
+int tfhe_b200_group_circuit_run(tfhe_b200_group* g, tfhe_b200_group_circuit* c, const uint32_t* inputs_host, size_t n_inputs,
+                                const int32_t* const_wires, const uint8_t* const_bits, size_t n_consts, const int32_t* out_wires, size_t n_out,
+                                uint32_t* outputs_host) {
+    const int rc = group_circuit_run_impl(g, c, inputs_host, n_inputs, const_wires, const_bits, n_consts, out_wires, n_out, outputs_host);
+    if (rc != TFHE_B200_OK && g) {   // an error half way: nothing enqueued so far may outlive the caller's buffers
+        const std::string first = g->err;
+        for (size_t r = 0; r < g->ctx.size(); r++) {
+            cudaSetDevice(g->devices[r]);
+            cudaStreamSynchronize(g->stream[r]);
+        }
+        g->err = first;
+    }
+    return rc;
 }
 int tfhe_b200_group_circuit_stats(const tfhe_b200_group_circuit* c, uint64_t* sharded_levels, uint64_t* replicated_levels, size_t* shard_min) {
     if (!c) return TFHE_B200_ERR_PARAM;
