@@ -94,6 +94,16 @@ def test_group_circuit_one_device_matches_device_circuit(engine, keys, rng):
         gc.close()
         assert np.array_equal(got, want)
         assert np.array_equal(keys.decrypt(got), nl.simulate(bits))
+        # an output wire outside the table is refused with an error code (and the group stays usable)
+        import dataclasses
+        gc = Cq.GroupCircuit(g, nl)
+        gc.netlist = dataclasses.replace(nl, outputs=[nl.n_wires + 5])
+        with pytest.raises(R.TfheError) as ei:
+            gc.run(cts)
+        assert "out of range" in str(ei.value)
+        gc.netlist = nl
+        assert np.array_equal(gc.run(cts), want)
+        gc.close()
         # constants only (a nander expression): trivial ciphertexts are set on the device, no inputs are uploaded
         ex = Cq.expr_to_netlist(Cq.parse_logic_expr("!(1&0)^(0|1)&1"))
         gc = Cq.GroupCircuit(g, ex)
