@@ -252,7 +252,7 @@ def run_extras(eng, R, K, torch, dev, stream, dx, dy, s0, rank, world, dist):
         o = torch.empty_like(a)
         t = timed(lambda: eng.negacyclic_mul_batch_device(a.data_ptr(), d.data_ptr(), o.data_ptr(), B3, stream.cuda_stream))
         if eng.stats()["key_slices"] == 1:   # FFT64: polymul_f64_kernel, two forward + one inverse transform per product, I/O straight from HBM
-            issue_pm = 2 * (2 * 432 + 482 + 16 * 6) + 700
+            issue_pm = 2 * 1468 + 660   # ncu (profiles/r02_ncu_polymul_f64.txt): 1468 FP64 (2 x 448 + 482 + 96 per lane) + 660 other warp instructions per product
             out["config3_negacyclic_mul"] = {"batch": B3, "products_per_s": B3 / t, "issue_roofline_frac": B3 / t * issue_pm / (148 * 4 * 1.965e9),
                                              "hbm_gbs": B3 / t * 3 * 4096 / 1e9, "note": "FFT64 arithmetic, one product per warp"}
         else:
@@ -263,7 +263,7 @@ def run_extras(eng, R, K, torch, dev, stream, dx, dy, s0, rank, world, dist):
         trg1 = u32(1, 6, 2, 1024)
         t = timed(lambda: eng.external_product_batch_device(trg1.data_ptr(), 1, trl.data_ptr(), res.data_ptr(), B3, stream.cuda_stream))
         if eng.stats()["key_slices"] == 1:   # FFT64: the persistent external_product_f64_kernel, bound by issue slots like the gate kernel
-            issue_xp = fft64_figures()["issue_cycles_per_gate"] / 635.0
+            issue_xp = 2 * 4415 + 2620   # ncu (profiles/r02_ncu_external_product_f64.txt): FP64 + other warp instructions per product
             out["config3_external_product_shared_trgsw"] = {"batch": B3, "products_per_s": B3 / t, "issue_roofline_frac": B3 / t * issue_xp / (148 * 4 * 1.965e9),
                                                             "hbm_gbs": B3 / t * 2 * 8192 / 1e9,
                                                             "note": "FFT64 arithmetic, one product per warp, the TRGSW transformed inside the call and kept on the key ring"}

@@ -38,8 +38,8 @@ def main():
     # FFT64 arithmetic (the default): both kernels are bound by issue slots like the gate kernel (bench.py fft64_figures; a DFMA holds
     # the issue port for two cycles): cycles per product = 2 x FP64 instructions + the others
     issue_peak = 148 * 4 * 1.965e9
-    issue_pm = 2 * (2 * 432 + 482 + 16 * 6) + 700
-    issue_xp = 2 * (6 * 432 + 2 * 482 + 12 * 64) + 3911
+    issue_pm = 2 * 1468 + 660      # ncu, profiles/r02_ncu_polymul_f64.txt: FP64 + other warp instructions per product
+    issue_xp = 2 * 4415 + 2620     # ncu, profiles/r02_ncu_external_product_f64.txt
     dev = torch.device("cuda", 0)
     st = torch.cuda.current_stream()
     g = torch.Generator(device=dev).manual_seed(7)
