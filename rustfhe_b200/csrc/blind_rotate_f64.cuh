@@ -317,10 +317,12 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel
     rg.total = mine * 6;
     rg.active = F64_GATES;   // every warp takes part in every round (a warp without a product repeats the last one and does not store)
     rg.period = 6;
+    uint64_t* inbar = reinterpret_cast<uint64_t*>(gbase + 2 * 1024 * 4 + 512 * 16 + 6 * 32 * 16);   // this warp's "next input has landed"
+    if (lane == 0) mbar_init(inbar, 1);
     if (threadIdx.x == 0) {
         for (int s = 0; s < F64_RING; s++) { mbar_init(rg.full + s, 1); mbar_init(rg.empty + s, F64_GATES); rg.left[s] = 0; }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (lane == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     {
         double* t = reinterpret_cast<double*>(tab);
         for (int k = threadIdx.x; k < F64_FWDB_ROWS * 64; k += blockDim.x) t[k] = g_f64_fwdB[k];
@@ -332,11 +334,20 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel
         for (long n = 0; n < F64_RING && n < rg.total; n++)
             bulk_fetch(rg.slot + (size_t)n * F64_SLOT_ELEMS, rg.key + (size_t)(n % 6) * F64_SLOT_ELEMS, F64_CHUNK_BYTES, rg.full + n);
     long n = 0;
+    // plain products (no rep_0): the result goes straight to global memory from the inverse transforms, so the input buffer is free
+    // once both polynomials' digit planes exist -- the NEXT product's input is fetched into it by one bulk (TMA) copy under the rest
+    // of this product (three forward and two inverse transforms)
+    const bool plain = a.trlwe_in0 == nullptr;
+    bool have_input = false;
+    uint32_t in_par = 0;
 #pragma unroll 1
     for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const long want = grp * F64_GATES + gl;
         const long g = want < a.B ? want : a.B - 1;
-        {   // 16 independent 16-byte loads per lane (one memory latency per product, not one per 128-byte row)
+        if (have_input) {
+            mbar_wait(inbar, in_par);
+            in_par ^= 1u;
+        } else {   // 16 independent 16-byte loads per lane (one memory latency per product, not one per 128-byte row)
             const uint4* src = reinterpret_cast<const uint4*>(a.trlwe_in + (size_t)g * 2048) + lane;
             uint4* dst = reinterpret_cast<uint4*>(acc) + lane;
             uint4 v[16];
@@ -367,6 +378,15 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel
                 f64_pack_plane<2>(u, re, im);
                 D[4 * 32 + lane] = make_uint4(re.x, re.y, re.z, re.w); D[5 * 32 + lane] = make_uint4(im.x, im.y, im.z, im.w);
             }
+            if (pw == 1) {
+                const long nxt = want + (long)gridDim.x * F64_GATES;
+                have_input = plain && nxt < a.B;
+                __syncwarp();   // every lane has taken its source words
+                if (have_input && lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    bulk_fetch(acc, a.trlwe_in + (size_t)nxt * 2048, 2048u * 4u, inbar);
+                }
+            }
 #pragma unroll 1
             for (int dw = 0; dw < 3; dw++) {
                 cd x[16], y[16];
@@ -384,10 +404,11 @@ __global__ void __launch_bounds__(F64_GATES * 32, 1) external_product_f64_kernel
                 n++;
             }
         }
-        f64_inverse_acc<true>(lane, s0, S, ta, ut, acc);
-        f64_inverse_acc<true>(lane, s1, S, ta, ut, acc + 1024);
+        uint32_t* ao = (plain && want < a.B) ? a.trlwe_out + (size_t)g * 2048 : acc;   // (a warp without a product has no next input either)
+        f64_inverse_acc<true>(lane, s0, S, ta, ut, ao);
+        f64_inverse_acc<true>(lane, s1, S, ta, ut, ao + 1024);
         __syncwarp();
-        if (want < a.B) {
+        if (!plain && want < a.B) {
             uint4* dst = reinterpret_cast<uint4*>(a.trlwe_out + (size_t)g * 2048) + lane;
             const uint4* res = reinterpret_cast<const uint4*>(acc) + lane;
             uint4 v[16];
