@@ -492,6 +492,9 @@ __global__ void __launch_bounds__(XPI_WARPS * 32, 1) external_product_item_f64_k
 #pragma unroll
         for (int k = 0; k < 16; k++) { s0[k].re = 0.0; s0[k].im = 0.0; s1[k].re = 0.0; s1[k].im = 0.0; }
         const uint32_t* item = trgsw + (size_t)g * (12 * 1024);
+        // every key polynomial (4 KB = 32 lines of 128 bytes, one per lane) is requested into L1 while the previous transform runs
+        auto prefetch_poly = [&](int q) { asm volatile("prefetch.global.L1 [%0];" ::"l"(item + (size_t)q * 1024 + lane * 32)); };
+        prefetch_poly(0);
 #pragma unroll 1
         for (int j = 0; j < 6; j++) {
             cd x[16], y[16];
@@ -505,6 +508,7 @@ __global__ void __launch_bounds__(XPI_WARPS * 32, 1) external_product_item_f64_k
 #pragma unroll
             for (int k = 0; k < 16; k++) { cd16 v; v.re = y[k].re; v.im = y[k].im; Y[32 * k] = v; }
             f64_key_input(lane, item + (size_t)(2 * j) * 1024, x);
+            prefetch_poly(2 * j + 1);
             f64_forward(lane, x, S, tb, y);
 #pragma unroll
             for (int k = 0; k < 16; k++) {
@@ -513,6 +517,7 @@ __global__ void __launch_bounds__(XPI_WARPS * 32, 1) external_product_item_f64_k
                 s0[k].im = F_FMA(d.re, y[k].im, F_FMA(d.im, y[k].re, s0[k].im));
             }
             f64_key_input(lane, item + (size_t)(2 * j + 1) * 1024, x);
+            if (j < 5) prefetch_poly(2 * j + 2);
             f64_forward(lane, x, S, tb, y);
 #pragma unroll
             for (int k = 0; k < 16; k++) {
