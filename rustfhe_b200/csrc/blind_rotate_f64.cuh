@@ -583,10 +583,18 @@ __global__ void __launch_bounds__(PMF_WARPS * 32, 1) polymul_f64_kernel(const ui
     for (long g = (long)blockIdx.x * PMF_WARPS + w; g < B; g += (long)gridDim.x * PMF_WARPS) {
         cd x[16], y[16];
         f64_key_input(lane, a + (size_t)g * 1024, x);
+        const int32_t* dp = d + (size_t)g * 1024;
+        {   // the second operand into L1 and the next product's operands into L2 while the first transform runs (one 128-byte line per lane)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(dp + lane * 32));
+            const long gn = g + (long)gridDim.x * PMF_WARPS;
+            if (gn < B) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a + (size_t)gn * 1024 + lane * 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(d + (size_t)gn * 1024 + lane * 32));
+            }
+        }
         f64_forward(lane, x, S, tb, y);
 #pragma unroll
         for (int k = 0; k < 16; k++) { cd16 v; v.re = y[k].re; v.im = y[k].im; Y[32 * k] = v; }
-        const int32_t* dp = d + (size_t)g * 1024;
 #pragma unroll
         for (int r = 0; r < 16; r++) { x[r].re = (double)dp[32 * r + lane]; x[r].im = (double)dp[512 + 32 * r + lane]; }
         f64_forward(lane, x, S, tb, y);
