@@ -78,7 +78,10 @@ __device__ __forceinline__ void f64_inverse_acc(int lane, cd (&sp)[16], cd16* S,
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         if (REPLACE) { ao[32 * r + lane] = lo[r]; ao[512 + 32 * r + lane] = hi[r]; }
-        else { ao[32 * r + lane] += lo[r]; ao[512 + 32 * r + lane] += hi[r]; }
+        else {   // one shared-memory reduction per word instead of load + add + store (-128 instructions per gate and CMUX, -0.7 % time)
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(ao + 32 * r + lane)), "r"(lo[r]) : "memory");
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(ao + 512 + 32 * r + lane)), "r"(hi[r]) : "memory");
+        }
     }
 }
 
