@@ -41,6 +41,8 @@ constexpr int F64L2_SMEM_BYTES = F64L2_TAB_ELEMS * 16 + 2 * 1024 * 4 /*acc*/ + F
                                  F64L2_KEY_BYTES + 2 * 1024 * 4 /*masked source words*/ + 640 * 2 /*abar*/ + 16 /*mbarrier*/;
 static_assert(F64L2_SMEM_BYTES <= 227 * 1024, "one gate must fit the shared memory of one SM");
 
+// accumulator word += v as one shared-memory reduction: nothing to wait for (a load + add + store has the load's latency in the step's chain)
+__device__ __forceinline__ void l2_red_add(uint32_t* p, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
 __device__ __forceinline__ void l2_store(cd16* p, const cd& v) { cd16 t; t.re = v.re; t.im = v.im; *p = t; }
 __device__ __forceinline__ void l2_load(const cd16* p, cd& v) { const cd16 t = *p; v.re = t.re; v.im = t.im; }
 
@@ -218,8 +220,8 @@ __global__ void __launch_bounds__(F64L2_THREADS, 1) blind_rotate_f64_latency2_ke
                 const cd16 u = tut[e * 64 + t];
                 const double zr = F_FMA(y[e].re, u.re, -F_MUL(y[e].im, u.im));
                 const double zi = F_FMA(y[e].re, u.im, F_MUL(y[e].im, u.re));
-                ao[t + 64 * e] += f64_low_word(F_ADD(zr, F64_ROUND_MAGIC));
-                ao[512 + t + 64 * e] += f64_low_word(F_ADD(zi, F64_ROUND_MAGIC));
+                l2_red_add(ao + t + 64 * e, f64_low_word(F_ADD(zr, F64_ROUND_MAGIC)));
+                l2_red_add(ao + 512 + t + 64 * e, f64_low_word(F_ADD(zi, F64_ROUND_MAGIC)));
             }
         }
         __syncthreads();   // acc is complete before the next step's rotated reads
@@ -446,8 +448,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F64L3_THREADS, 1) bl
                 const cd16 u = tut[e * 64 + t];
                 const double zr = F_FMA(y[e].re, u.re, -F_MUL(y[e].im, u.im));
                 const double zi = F_FMA(y[e].re, u.im, F_MUL(y[e].im, u.re));
-                acc[t + 64 * e] += f64_low_word(F_ADD(zr, F64_ROUND_MAGIC));
-                acc[512 + t + 64 * e] += f64_low_word(F_ADD(zi, F64_ROUND_MAGIC));
+                l2_red_add(acc + t + 64 * e, f64_low_word(F_ADD(zr, F64_ROUND_MAGIC)));
+                l2_red_add(acc + 512 + t + 64 * e, f64_low_word(F_ADD(zi, F64_ROUND_MAGIC)));
             }
         }
         __syncthreads();   // my accumulator polynomial is complete before the next step's rotated reads

@@ -88,8 +88,8 @@ __device__ __forceinline__ void f64w2_inverse_acc(int t, cd (&y)[8], cd16* bufA,
         const cd16 u = tut[e * 64 + t];
         const double zr = F_FMA(y[e].re, u.re, -F_MUL(y[e].im, u.im));
         const double zi = F_FMA(y[e].re, u.im, F_MUL(y[e].im, u.re));
-        ao[t + 64 * e] += f64_low_word(F_ADD(zr, F64_ROUND_MAGIC));
-        ao[512 + t + 64 * e] += f64_low_word(F_ADD(zi, F64_ROUND_MAGIC));
+        l2_red_add(ao + t + 64 * e, f64_low_word(F_ADD(zr, F64_ROUND_MAGIC)));
+        l2_red_add(ao + 512 + t + 64 * e, f64_low_word(F_ADD(zi, F64_ROUND_MAGIC)));
     }
 }
 
