@@ -60,9 +60,9 @@ def fft64_figures():
     fwd, inv, mac = 448 * 32, 482 * 32, 64 * 32
     per_cmux = 6 * fwd + 2 * inv + 12 * mac
     smem = (8 * 16 + 96 + 60 + 22 + 16) * 1024
-    # issue slots: a DFMA-class instruction keeps the issue port for two cycles (profiles/r02_dfma_mix.json); the other 3241 warp
+    # issue slots: a DFMA-class instruction keeps the issue port for two cycles (profiles/r02_dfma_mix.json); the other 3113 warp
     # instructions of a gate and CMUX (ncu, profiles/r02_ncu_blind_rotate_f64_latest.txt) take one each
-    issue = 2 * per_cmux / 32 + 3241
+    issue = 2 * per_cmux / 32 + 3113
     return {"transforms_per_cmux": 8, "fp64_ops_per_gate": 635 * per_cmux, "smem_bytes_per_gate": 635 * smem,
             "issue_cycles_per_gate": 635 * issue, "bk_bytes_device": 635 * 12 * 512 * 16}
 
@@ -601,7 +601,7 @@ def run_gpu(args):
                                       "achieved": per_gpu_gps_kernel * fig["issue_cycles_per_gate"] / 1e9, "peak": issue_peak / 1e9, "unit": "G issue cycles/s",
                                       "frac": per_gpu_gps_kernel * fig["issue_cycles_per_gate"] / issue_peak, "peak_kind": "148 SM x 4 schedulers x SM clock",
                                       "issue_cycles_per_gate": fig["issue_cycles_per_gate"], "roof_gates_per_s": issue_peak / fig["issue_cycles_per_gate"],
-                                      "note": "2 x 4420 FP64 + 3241 other warp instructions per gate and CMUX; measured DFMA + FFMA mixes add up instead of "
+                                      "note": "2 x 4420 FP64 + 3113 other warp instructions per gate and CMUX; measured DFMA + FFMA mixes add up instead of "
                                               "overlapping (profiles/r02_dfma_mix.json), and a third warp per scheduler does not raise the issue rate"}
             line["int_roofline"] = dict(line["fp64_roofline"], note="FFT64 mode: the arithmetic runs on the FP64 pipe, whose issue rate equals the IMAD rate "
                                         "(profiles/intpipe_r01b.json); see fp64_roofline / smem_roofline")
