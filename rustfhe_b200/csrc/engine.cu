@@ -581,8 +581,16 @@ static int launch_keyswitch(tfhe_b200_ctx* ctx, const uint16_t* dig, uint32_t* o
         keyswitch_kernel<<<grid, dim3(KS_THREADS, KS_GROUPS), 0, st>>>(reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B, idxo);
     } else if (ctx->ks_variant == 3) {   // producer / consumer pipeline over the staged rows, one warp per gate (default)
         const long tiles = (B + KSP_GATES - 1) / KSP_GATES;
+        // slices of the key indices: the count (8 .. 128) whose tiles x slices CTAs run in the fewest index-steps, two CTAs per SM:
+        // whole waves matter -- 1024 gates = 64 tiles: 8 slices are 512 CTAs = 1.73 waves of 128 indices, 9 slices 1.95 waves of 114
+        const long slots = 2L * ctx->sm_count;
         int isplit = KS_ISPLIT_MIN;
-        while (isplit < 128 && tiles * isplit < 2L * ctx->sm_count) isplit *= 2;
+        long best = LONG_MAX;
+        for (int y = KS_ISPLIT_MIN; y <= 128; y++) {
+            const long waves = (tiles * y + slots - 1) / slots;
+            const long cost = waves * ((1024 + y - 1) / y + 6);   // + 6: start-up of a CTA (digits, pipeline fill) in index-steps
+            if (cost < best) { best = cost; isplit = y; }
+        }
         keyswitch_p_kernel<KSP_GATES, KSP_RING><<<dim3((unsigned)tiles, isplit), (KSP_GATES + 1) * 32, KsP<KSP_GATES, KSP_RING>::SMEM_BYTES, st>>>(
             reinterpret_cast<const uint4*>(ctx->kskdev), dig, out, B, idxo);
     } else {                      // the same with one __syncthreads per stage instead of empty barriers (TFHE_B200_KS_VARIANT=2)

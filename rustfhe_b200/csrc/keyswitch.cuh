@@ -186,8 +186,10 @@ __global__ void __launch_bounds__((NG + 1) * 32) keyswitch_p_kernel(const uint4*
     uint64_t* empty = full + RING;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long g0 = (long)blockIdx.x * NG;
-    const int ichunk = 1024 / (int)gridDim.y;
-    const int i0 = blockIdx.y * ichunk;
+    // the 1024 key indices are cut into gridDim.y nearly equal slices (any count from KS_ISPLIT_MIN to 128, not only powers of two:
+    // the host picks the count that fills the SMs in whole waves)
+    const int i0 = (int)(((long)blockIdx.y * 1024) / (long)gridDim.y);
+    const int ichunk = (int)((((long)blockIdx.y + 1) * 1024) / (long)gridDim.y) - i0;
     const int nstages = ichunk * (8 / KS2_LV);
     constexpr int SPI = 8 / KS2_LV;   // stages per key index
     for (int t = threadIdx.x; t < ichunk * NG; t += (NG + 1) * 32) {
