@@ -68,8 +68,9 @@ __global__ void __launch_bounds__(KS_THREADS* KS_GROUPS) keyswitch_kernel(const 
 // the digit is CTA-uniform but every thread tests it).  Here a warp owns one gate and all 159 chunks of its output row
 // (5 per lane): the digit picks the ROW ADDRESS in shared memory, so per (gate, digit) there are two instructions of
 // select and five (LDS.128 + 4 adds) instead of 5 warps x 12.  The rows of a stage (4 levels x 3 multiples of one key
-// index = 30 KB) are copied once per CTA with cp.async into a 3-deep ring (one __syncthreads per stage) and consumed by
-// the 16 gates of the tile.
+// index = 30 KB) are copied once per CTA by one bulk (TMA) copy into a 3-deep ring (one __syncthreads per stage) and consumed
+// by the 16 gates of the tile.  Kept as TFHE_B200_KS_VARIANT=2; the shipped kernel is K6p below (the same rows behind a
+// producer / consumer ring).
 #if !defined(KS2_NG)
 #define KS2_NG 16
 #endif
