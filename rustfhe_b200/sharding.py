@@ -60,3 +60,48 @@ def evaluate_sharded(gate_fn, in0, in1, rank, world, gather=True, ops=None):
     dist.all_gather(parts, mine)
     out = np.concatenate([p.cpu().numpy().view(np.uint32)[:b[1] - b[0]] for p, b in zip(parts, bounds)], axis=0)
     return out
+
+
+def evaluate_circuit_sharded(level_fn, netlist, inputs, rank, world, shard_min=75):
+    """A levelised netlist with one process per GPU (the torch.distributed counterpart of tfhe_b200_group_circuit_run):
+    every rank keeps the whole wire table; a level of at least `shard_min` gates is cut into contiguous shards (rustfhe_b200.
+    circuit.level_plan), each rank evaluates its shard and ONE all_gather per level exchanges the level's outputs (2544 B per
+    gate); narrower levels are evaluated by every rank on its own copy, without an exchange.
+    `level_fn(ops, in0_rows, in1_rows) -> out_rows` is the per-rank engine call (tfhe_b200_gate_batch_mixed)."""
+    import torch
+    import torch.distributed as dist
+    from . import circuit as Cq
+    W = inputs.shape[1] if netlist.n_inputs else 636
+    wires = np.zeros((netlist.n_wires, W), np.uint32)
+    if netlist.n_inputs:
+        wires[:netlist.n_inputs] = inputs
+    for w, bit in netlist.consts.items():
+        wires[w, 0] = 0x20000000 if bit else 0xE0000000
+    sizes, ops, i0, i1, o = Cq._flatten_levels(netlist)
+    plan = Cq.level_plan(sizes, world, shard_min)
+    first = 0
+    stats = {"sharded_levels": 0, "replicated_levels": 0}
+    for width, (kind, what) in zip(sizes, plan):
+        sl = slice(first, first + width)
+        first += width
+        if width == 0:
+            continue
+        if kind == "replicated":
+            wires[o[sl]] = level_fn(ops[sl], wires[i0[sl]], wires[i1[sl]])
+            stats["replicated_levels"] += 1
+            continue
+        f, c = what[rank]
+        mine = level_fn(ops[sl][f:f + c], wires[i0[sl][f:f + c]], wires[i1[sl][f:f + c]]) if c else np.zeros((0, W), np.uint32)
+        per = max(cnt for _, cnt in what)
+        pad = np.zeros((per, W), np.uint32)
+        pad[:c] = mine
+        t = torch.from_numpy(pad.view(np.int32))
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        rows = np.concatenate([p.cpu().numpy().view(np.uint32)[:cnt] for p, (_, cnt) in zip(parts, what)], axis=0)
+        wires[o[sl]] = rows
+        stats["sharded_levels"] += 1
+    return (wires[netlist.outputs] if netlist.outputs else wires), stats
+

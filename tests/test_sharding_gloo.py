@@ -69,3 +69,59 @@ def test_two_rank_key_replication_and_sharded_gates():
     assert res[0][1] == res[1][1], "key replicas differ"
     assert res[0][2] and res[1][2], "sharded evaluation decrypted wrong"
     assert res[0][3] == res[1][3], "gathered outputs differ between ranks"
+
+
+def _circuit_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rustfhe_b200 import circuit as Cq
+        from rustfhe_b200.sharding import evaluate_circuit_sharded
+        MU = 0x20000000
+        calls = []
+
+        def level_fn(ops, a, b):   # stand-in for tfhe_b200_gate_batch_mixed on TRIVIAL ciphertexts (word 0 = +-1/8, the rest 0)
+            x, y = (a[:, 0] < 2 ** 31).astype(np.uint8), (b[:, 0] < 2 ** 31).astype(np.uint8)
+            table = {Cq.NAND: 1 - (x & y), Cq.AND: x & y, Cq.OR: x | y, Cq.XOR: x ^ y, Cq.NOT: 1 - x}
+            out = np.zeros_like(a)
+            for k, op in enumerate(ops):
+                out[k, 0] = MU if table[int(op)][k] else (2 ** 32 - MU)
+            calls.append(len(ops))
+            return out
+        nl = Cq.side_by_side(Cq.prefix_adder(8), 6)
+        r = np.random.default_rng(3)
+        bits = r.integers(0, 2, nl.n_inputs).astype(np.uint8)
+        cts = np.zeros((nl.n_inputs, 4), np.uint32)
+        cts[:, 0] = np.where(bits == 1, MU, 2 ** 32 - MU)
+        out, stats = evaluate_circuit_sharded(level_fn, nl, cts, rank, world, shard_min=40)
+        got = (out[:, 0] < 2 ** 31).astype(np.uint8)
+        sizes = [sum(len(o) for (_, _, o) in lev.values()) for lev in nl.levels()]
+        plan = Cq.level_plan(sizes, world, 40)
+        want_calls = [w if kind == "replicated" else what[rank][1] for w, (kind, what) in zip(sizes, plan)]
+        q.put((rank, bool(np.array_equal(got, nl.simulate(bits))), stats, calls == want_calls, out[:, 0].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_circuit_levels():
+    """evaluate_circuit_sharded (the one-process-per-GPU form of the group circuit): wide levels are cut over the ranks and their
+    outputs exchanged by one all_gather per level, narrow levels are evaluated by every rank; both ranks end with the same,
+    correct outputs, and each rank's engine saw exactly its shards."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + (os.getpid() % 40)
+    procs = [ctx.Process(target=_circuit_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    assert res[0][1] and res[1][1], "sharded circuit evaluated wrong"
+    assert res[0][2] == res[1][2] and res[0][2]["sharded_levels"] > 0 and res[0][2]["replicated_levels"] > 0
+    assert res[0][3] and res[1][3], "a rank evaluated gates outside its shards"
+    assert res[0][4] == res[1][4], "outputs differ between ranks"
