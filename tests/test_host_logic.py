@@ -387,3 +387,35 @@ def test_deterministic_gaussian_matches_libm_and_is_gaussian(oracle):
         xs.append(got / 2.0 ** 17)
     xs = np.array(xs)
     assert abs(xs.mean()) < 0.06 and abs(xs.std() - 1) < 0.05
+
+
+def test_fft64_forward_transpose_address_pattern():
+    """The shared-memory address pattern of the forward transform's transpose (fft64.cuh: f64_t1_store / f64_t1_load_cross),
+    restated from its index arithmetic: every 16-byte element is written once and read by exactly the two lanes of a pair; a store
+    instruction touches 32 distinct elements, four per 128-byte bank row (4 wavefronts = the minimum for 512 bytes); a load
+    instruction touches 16 distinct elements -- the two lanes of a pair read the same one -- two per bank row (2 wavefronts)."""
+    slot = lambda j: j ^ ((j >> 5) & 7)                      # element j = 32 r + lane is stored at slot j ^ (r & 7)
+    written = set()
+    for r in range(16):                                       # one STS.128 per register r
+        addrs = [slot(32 * r + lane) for lane in range(32)]
+        assert len(set(addrs)) == 32
+        groups = np.bincount([a % 8 for a in addrs], minlength=8)   # 8 elements of 16 bytes = one 128-byte bank row
+        assert groups.max() == 4
+        written.update(addrs)
+    assert written == set(range(512))
+    readers = {}
+    for top2 in range(2):                                     # which operand of the stage-4 butterfly
+        for q in range(16):                                   # one LDS.128 per (operand, register q)
+            addrs = []
+            for lane in range(32):
+                hi = lane >> 1
+                j = 32 * hi + 16 * top2 + q
+                # f64_t1_load_cross: base (hi << 5) | ((q & 7) ^ (hi & 7)), immediates (q & 8) and 16 for the second operand
+                a = ((hi << 5) | ((q & 7) ^ (hi & 7))) + (q & 8) + 16 * top2
+                assert a == slot(j)
+                addrs.append(a)
+                readers.setdefault(a, set()).add(lane)
+            distinct = sorted(set(addrs))
+            assert len(distinct) == 16
+            assert np.bincount([a % 8 for a in distinct], minlength=8).max() == 2
+    assert all(len(v) == 2 and max(v) - min(v) == 1 for v in readers.values()) and len(readers) == 512
